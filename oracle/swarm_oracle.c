@@ -1,0 +1,695 @@
+/*
+ * swarm_oracle.c -- CPU restatement of the reference's drone-swarm env step.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This file is the parity ORACLE for the CUDA path:
+ * a plain scalar C restatement of the algorithm in the reference repo
+ *   nusRying/Multi-Agent-RL-for-Autonomous-Drone-Swarms
+ *     src/swarm_marl/envs/common.py            (DroneEnvConfig)
+ *     src/swarm_marl/envs/drone_swarm_env.py   (DroneSwarmEnv)
+ *     src/swarm_marl/envs/single_drone_env.py  (SingleDroneEnv)
+ * plus the numpy pieces those files lean on (np.random.default_rng = SeedSequence
+ * + PCG64 XSL-RR 128/64, Generator.uniform, np.linalg.norm's two code paths,
+ * np.mean's pairwise summation, NEP-50 weak-scalar comparisons).  Every function
+ * cites the reference file:line it follows.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load it; the product
+ * package never does.
+ *
+ * PARITY PIN: tests/test_oracle_golden.py checks this file bit-for-bit against
+ * the .npz fixtures under tests/golden/, which oracle/gen_golden.py produced by importing the
+ * UNMODIFIED reference (numpy 2.3.5, OpenBLAS 0.3.30 x86-64) in the build
+ * container; tests/test_oracle_vs_reference.py re-checks live when
+ * /root/reference is present.
+ *
+ * Arithmetic rules restated here (traps T1-T6):
+ *  T1 norm1d  = np.linalg.norm(vec3)  -> sqrt(x.dot(x)) -> OpenBLAS sdot (x86-64
+ *               kernel/x86_64/sdot.c tail loop: `double dot; dot += y[i]*x[i]` with
+ *               the product rounded to f32 first) -> cast f32 -> sqrtf.
+ *  T2 normAxis = np.linalg.norm(A, axis=k) -> sqrt(add.reduce(A*A)) = sequential f32.
+ *  T3 thresholds: np.float32-vs-Python-float compares round the Python float to f32;
+ *               Python-float-vs-Python-float compares (goal radius) stay in double.
+ *  T4 rewards are Python floats (double); np.mean uses numpy's 8-lane pairwise sum.
+ *  T5 argsort ties: this oracle breaks ties by lowest index (np.argsort's default
+ *               introsort/simd-sort is not stable; ties are counted by the tests).
+ *  T6 parked (goal-reached) drones: neighbours yes, colliders / formation no.
+ *
+ * Build: see oracle/Makefile  (gcc -O2 -ffp-contract=off -fno-fast-math).
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------- */
+/* Config: mirror of DroneEnvConfig (envs/common.py:7-25) + num_drones        */
+/* (drone_swarm_env.py:32) + oracle-only switches.                            */
+/* ------------------------------------------------------------------------- */
+typedef struct OracleConfig {
+    double world_size, dt, max_speed, max_accel, collision_radius, goal_radius;
+    double obstacle_radius, desired_spacing;
+    double reward_progress_scale, reward_goal, reward_collision, reward_formation_scale;
+    int32_t max_steps, num_obstacles, sensed_obstacles, neighbor_k;
+    int32_t num_drones;
+    int32_t env_kind;  /* 0 = SingleDroneEnv, 1 = DroneSwarmEnv */
+    int32_t norm_mode; /* 0 = BLAS sdot (double accumulate), 1 = sequential f32 */
+    int32_t reserved;
+} OracleConfig;
+
+/* One batch of E environments, arrays laid out exactly like the reference's
+ * numpy attributes with a leading env axis. */
+typedef struct OracleBatch {
+    int32_t num_envs;
+    int32_t pad;
+    float *positions;    /* [E][N][3]  DroneSwarmEnv.positions  (drone_swarm_env.py:59) */
+    float *velocities;   /* [E][N][3]  .velocities (:60) */
+    float *goal;         /* [E][3]     .goal (:61) */
+    float *obstacles;    /* [E][M][3]  .obstacles (:62) */
+    int32_t *step_count; /* [E]        .step_count (:63) */
+    uint8_t *active;     /* [E][N]     membership of drone_i in .agents (:39,169-172) */
+    uint64_t *rng;       /* [E][4]     PCG64 {state_hi, state_lo, inc_hi, inc_lo} */
+    /* outputs of the last reset/step */
+    float *obs;          /* [E][N][D]  D = 9 + 4K + 4S (swarm) or 9 + 4S (single) */
+    double *reward;      /* [E][N]     Python-float rewards */
+    float *dist;         /* [E][N]     info["distance_to_goal"] (f32-valued) */
+    uint8_t *terminated; /* [E][N] */
+    uint8_t *truncated;  /* [E][N] */
+    uint8_t *reached;    /* [E][N]     info["reached_goal"] */
+    uint8_t *collision;  /* [E][N]     info["collision"] */
+    uint8_t *obs_valid;  /* [E][N]     1 where the reference would put agent i in the obs dict */
+    uint8_t *all_terminated; /* [E]    terminated["__all__"] */
+    uint8_t *all_truncated;  /* [E]    truncated["__all__"] */
+    float *global_state; /* [E][6N+3]  info["global_state"] (drone_swarm_env.py:293-302) */
+} OracleBatch;
+
+/* ------------------------------------------------------------------------- */
+/* numpy.random: SeedSequence + PCG64 + Generator.uniform                     */
+/* (used by `np.random.default_rng(seed)` drone_swarm_env.py:35,66-67 and      */
+/*  single_drone_env.py:31,55-57)                                              */
+/* ------------------------------------------------------------------------- */
+typedef unsigned __int128 u128;
+
+#define SS_INIT_A 0x43b0d7e5u
+#define SS_MULT_A 0x931e8875u
+#define SS_INIT_B 0x8b51f9ddu
+#define SS_MULT_B 0x58f38dedu
+#define SS_MIX_L 0xca01f9ddu
+#define SS_MIX_R 0x4973f715u
+#define SS_XSHIFT 16
+#define SS_POOL 4
+
+static uint32_t ss_hashmix(uint32_t value, uint32_t *hash_const) {
+    value ^= *hash_const;
+    *hash_const *= SS_MULT_A;
+    value *= *hash_const;
+    value ^= value >> SS_XSHIFT;
+    return value;
+}
+
+static uint32_t ss_mix(uint32_t x, uint32_t y) {
+    uint32_t r = SS_MIX_L * x - SS_MIX_R * y;
+    r ^= r >> SS_XSHIFT;
+    return r;
+}
+
+/* numpy/random/bit_generator.pyx: SeedSequence.mix_entropy + generate_state(4, uint64)
+ * followed by PCG64's pcg64_set_seed / pcg_setseq_128_srandom_r. */
+void oracle_seed(uint64_t seed, uint64_t rng[4]) {
+    uint32_t entropy[2];
+    int n_ent = 1;
+    entropy[0] = (uint32_t)(seed & 0xffffffffu);
+    entropy[1] = (uint32_t)(seed >> 32);
+    if (entropy[1] != 0) n_ent = 2;
+
+    uint32_t pool[SS_POOL];
+    uint32_t hc = SS_INIT_A;
+    for (int i = 0; i < SS_POOL; ++i) pool[i] = ss_hashmix(i < n_ent ? entropy[i] : 0u, &hc);
+    for (int s = 0; s < SS_POOL; ++s)
+        for (int d = 0; d < SS_POOL; ++d)
+            if (s != d) pool[d] = ss_mix(pool[d], ss_hashmix(pool[s], &hc));
+    /* (entropy longer than the pool does not occur for 64-bit seeds) */
+
+    uint32_t words[8];
+    hc = SS_INIT_B;
+    for (int i = 0; i < 8; ++i) {
+        uint32_t v = pool[i % SS_POOL];
+        v ^= hc;
+        hc *= SS_MULT_B;
+        v *= hc;
+        v ^= v >> SS_XSHIFT;
+        words[i] = v;
+    }
+    uint64_t w64[4];
+    for (int i = 0; i < 4; ++i) w64[i] = (uint64_t)words[2 * i] | ((uint64_t)words[2 * i + 1] << 32);
+
+    const u128 mult = ((u128)2549297995355413924ULL << 64) | (u128)4865540595714422341ULL;
+    u128 initstate = ((u128)w64[0] << 64) | w64[1];
+    u128 initseq = ((u128)w64[2] << 64) | w64[3];
+    u128 inc = (initseq << 1) | 1u;
+    u128 state = 0;
+    state = state * mult + inc;
+    state += initstate;
+    state = state * mult + inc;
+    rng[0] = (uint64_t)(state >> 64);
+    rng[1] = (uint64_t)state;
+    rng[2] = (uint64_t)(inc >> 64);
+    rng[3] = (uint64_t)inc;
+}
+
+/* pcg64_next64: advance, then XSL-RR output of the new state. */
+uint64_t oracle_pcg64_next(uint64_t rng[4]) {
+    const u128 mult = ((u128)2549297995355413924ULL << 64) | (u128)4865540595714422341ULL;
+    u128 state = ((u128)rng[0] << 64) | rng[1];
+    u128 inc = ((u128)rng[2] << 64) | rng[3];
+    state = state * mult + inc;
+    rng[0] = (uint64_t)(state >> 64);
+    rng[1] = (uint64_t)state;
+    uint64_t hi = rng[0], lo = rng[1];
+    uint64_t x = hi ^ lo;
+    unsigned rot = (unsigned)(hi >> 58);
+    return (x >> rot) | (x << ((-rot) & 63));
+}
+
+/* Generator.uniform(low, high) -> random_uniform: low + (high-low) * next_double,
+ * next_double = (next_uint64 >> 11) * 2^-53; then `.astype(np.float32)`
+ * (drone_swarm_env.py:72-80, single_drone_env.py:59-66). */
+static float draw_uniform_f32(uint64_t rng[4], double lo, double range) {
+    double u = (double)(oracle_pcg64_next(rng) >> 11) * (1.0 / 9007199254740992.0);
+    volatile double scaled = range * u; /* no FMA contraction */
+    double v = lo + scaled;
+    return (float)v;
+}
+
+/* ------------------------------------------------------------------------- */
+/* np.linalg.norm restatements (T1, T2)                                       */
+/* ------------------------------------------------------------------------- */
+static float norm1d(const OracleConfig *c, float x, float y, float z) {
+    /* np.linalg.norm(vec) with axis=None: sqrt(vec.dot(vec)) */
+    volatile float px = x * x, py = y * y, pz = z * z;
+    float s;
+    if (c->norm_mode == 0) {
+        volatile double acc = 0.0;
+        acc = acc + (double)px;
+        acc = acc + (double)py;
+        acc = acc + (double)pz;
+        s = (float)acc;
+    } else {
+        volatile float a = px + py;
+        s = a + pz;
+    }
+    return sqrtf(s);
+}
+
+static float norm_axis(float x, float y, float z) {
+    /* np.linalg.norm(A, axis=-1): sqrt(add.reduce(A*A, axis)) -- sequential f32 */
+    volatile float px = x * x, py = y * y, pz = z * z;
+    volatile float a = px + py;
+    volatile float s = a + pz;
+    return sqrtf(s);
+}
+
+/* np.add.reduce over a contiguous double vector: numpy's pairwise_sum
+ * (numpy/_core/src/umath/loops_utils.h.src) -- what np.mean uses at
+ * drone_swarm_env.py:222. */
+static double np_pairwise_sum(const double *a, int n) {
+    if (n < 8) {
+        double r = -0.0;
+        for (int i = 0; i < n; ++i) r += a[i];
+        return r;
+    } else if (n <= 128) {
+        double r[8];
+        int i;
+        for (i = 0; i < 8; ++i) r[i] = a[i];
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int k = 0; k < 8; ++k) r[k] += a[i + k];
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res += a[i];
+        return res;
+    } else {
+        int n2 = n / 2;
+        n2 -= n2 % 8;
+        return np_pairwise_sum(a, n2) + np_pairwise_sum(a + n2, n - n2);
+    }
+}
+
+static int obs_dim(const OracleConfig *c) {
+    /* drone_swarm_env.py:41-45 ; single_drone_env.py:33 */
+    return c->env_kind == 1 ? 9 + 4 * c->neighbor_k + 4 * c->sensed_obstacles
+                            : 9 + 4 * c->sensed_obstacles;
+}
+
+/* ------------------------------------------------------------------------- */
+/* Observation pieces                                                         */
+/* ------------------------------------------------------------------------- */
+
+/* _nearest_obstacle_features  drone_swarm_env.py:273-291 / single_drone_env.py:142-159 */
+static void nearest_obstacle_features(const OracleConfig *c, const float *own, const float *obst,
+                                      float *out) {
+    int S = c->sensed_obstacles, M = c->num_obstacles;
+    for (int k = 0; k < 4 * S; ++k) out[k] = 0.0f;
+    if (M == 0 || S <= 0) return;
+    float *dist = (float *)malloc(sizeof(float) * (size_t)M);
+    int *order = (int *)malloc(sizeof(int) * (size_t)M);
+    for (int m = 0; m < M; ++m) {
+        float rx = obst[3 * m] - own[0], ry = obst[3 * m + 1] - own[1], rz = obst[3 * m + 2] - own[2];
+        dist[m] = norm_axis(rx, ry, rz);
+        order[m] = m;
+    }
+    /* stable insertion sort == argsort with lowest-index tie break */
+    for (int a = 1; a < M; ++a) {
+        int key = order[a], b = a - 1;
+        while (b >= 0 && dist[order[b]] > dist[key]) { order[b + 1] = order[b]; --b; }
+        order[b + 1] = key;
+    }
+    int k = S < M ? S : M;
+    for (int q = 0; q < k; ++q) {
+        int m = order[q];
+        out[4 * q + 0] = obst[3 * m] - own[0];
+        out[4 * q + 1] = obst[3 * m + 1] - own[1];
+        out[4 * q + 2] = obst[3 * m + 2] - own[2];
+        out[4 * q + 3] = dist[m];
+    }
+    free(dist);
+    free(order);
+}
+
+/* _nearest_neighbor_features  drone_swarm_env.py:245-271 (all drones j != i, parked included) */
+static void nearest_neighbor_features(const OracleConfig *c, const float *pos, int index, float *out) {
+    int K = c->neighbor_k, N = c->num_drones;
+    for (int k = 0; k < 4 * K; ++k) out[k] = 0.0f;
+    if (N <= 1 || K <= 0) return;
+    int n = N - 1;
+    float *dist = (float *)malloc(sizeof(float) * (size_t)n);
+    int *who = (int *)malloc(sizeof(int) * (size_t)n);
+    int *order = (int *)malloc(sizeof(int) * (size_t)n);
+    const float *own = pos + 3 * index;
+    int cnt = 0;
+    for (int j = 0; j < N; ++j) {
+        if (j == index) continue;
+        float vx = pos[3 * j] - own[0], vy = pos[3 * j + 1] - own[1], vz = pos[3 * j + 2] - own[2];
+        dist[cnt] = norm1d(c, vx, vy, vz);
+        who[cnt] = j;
+        order[cnt] = cnt;
+        ++cnt;
+    }
+    for (int a = 1; a < n; ++a) {
+        int key = order[a], b = a - 1;
+        while (b >= 0 && dist[order[b]] > dist[key]) { order[b + 1] = order[b]; --b; }
+        order[b + 1] = key;
+    }
+    int k = K < n ? K : n;
+    for (int q = 0; q < k; ++q) {
+        int j = who[order[q]];
+        out[4 * q + 0] = pos[3 * j] - own[0];
+        out[4 * q + 1] = pos[3 * j + 1] - own[1];
+        out[4 * q + 2] = pos[3 * j + 2] - own[2];
+        out[4 * q + 3] = dist[order[q]];
+    }
+    free(dist);
+    free(who);
+    free(order);
+}
+
+/* _build_obs  drone_swarm_env.py:226-243 / single_drone_env.py:128-140 */
+static void build_obs(const OracleConfig *c, const float *pos, const float *vel, const float *goal,
+                      const float *obst, int index, float *out) {
+    const float *p = pos + 3 * index, *v = vel + 3 * index;
+    out[0] = p[0]; out[1] = p[1]; out[2] = p[2];
+    out[3] = v[0]; out[4] = v[1]; out[5] = v[2];
+    out[6] = goal[0] - p[0]; out[7] = goal[1] - p[1]; out[8] = goal[2] - p[2];
+    int off = 9;
+    if (c->env_kind == 1) {
+        nearest_neighbor_features(c, pos, index, out + off);
+        off += 4 * c->neighbor_k;
+    }
+    nearest_obstacle_features(c, p, obst, out + off);
+}
+
+/* _distance_to_goal  drone_swarm_env.py:176-177 / single_drone_env.py:113-114 */
+static float distance_to_goal(const OracleConfig *c, const float *goal, const float *p) {
+    return norm1d(c, goal[0] - p[0], goal[1] - p[1], goal[2] - p[2]);
+}
+
+/* _global_state  drone_swarm_env.py:293-302 */
+static void global_state(const OracleConfig *c, const float *pos, const float *vel, const float *goal,
+                         float *out) {
+    int N = c->num_drones;
+    memcpy(out, pos, sizeof(float) * 3 * (size_t)N);
+    memcpy(out + 3 * N, vel, sizeof(float) * 3 * (size_t)N);
+    memcpy(out + 6 * N, goal, sizeof(float) * 3);
+}
+
+/* _clip_speed  drone_swarm_env.py:179-183 / single_drone_env.py:116-120 */
+static void clip_speed(const OracleConfig *c, float *v) {
+    float speed = norm1d(c, v[0], v[1], v[2]);
+    float vmax = (float)c->max_speed; /* np.float32 <= python float -> f32 compare (NEP 50) */
+    if (speed <= vmax || speed < (float)1e-8) return;
+    for (int k = 0; k < 3; ++k) {
+        volatile float q = v[k] / speed;
+        v[k] = q * vmax;
+    }
+}
+
+static float clipf(float x, float lo, float hi) {
+    /* np.clip == minimum(maximum(x, lo), hi); NaN propagates */
+    if (x < lo) return lo;
+    if (x > hi) return hi;
+    return x;
+}
+
+/* integrate block  drone_swarm_env.py:103-111 / single_drone_env.py:74-84 */
+static void integrate(const OracleConfig *c, const float *action, float *p, float *v) {
+    float amax = (float)c->max_accel, dt = (float)c->dt;
+    for (int k = 0; k < 3; ++k) {
+        float a = clipf(action[k], -1.0f, 1.0f);
+        volatile float accel = a * amax;
+        volatile float dv = accel * dt;
+        v[k] = v[k] + dv;
+    }
+    clip_speed(c, v);
+    for (int k = 0; k < 3; ++k) {
+        volatile float dp = v[k] * dt;
+        p[k] = p[k] + dp;
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* Per-env views                                                              */
+/* ------------------------------------------------------------------------- */
+typedef struct EnvView {
+    float *pos, *vel, *goal, *obst;
+    int32_t *step_count;
+    uint8_t *active;
+    uint64_t *rng;
+    float *obs, *dist, *gs;
+    double *reward;
+    uint8_t *terminated, *truncated, *reached, *collision, *obs_valid, *all_term, *all_trunc;
+} EnvView;
+
+static EnvView view(const OracleConfig *c, const OracleBatch *b, int e) {
+    int N = c->num_drones, M = c->num_obstacles, D = obs_dim(c);
+    EnvView v;
+    v.pos = b->positions + (size_t)e * N * 3;
+    v.vel = b->velocities + (size_t)e * N * 3;
+    v.goal = b->goal + (size_t)e * 3;
+    v.obst = b->obstacles + (size_t)e * M * 3;
+    v.step_count = b->step_count + e;
+    v.active = b->active + (size_t)e * N;
+    v.rng = b->rng + (size_t)e * 4;
+    v.obs = b->obs + (size_t)e * N * D;
+    v.dist = b->dist + (size_t)e * N;
+    v.gs = b->global_state ? b->global_state + (size_t)e * (6 * N + 3) : NULL;
+    v.reward = b->reward + (size_t)e * N;
+    v.terminated = b->terminated + (size_t)e * N;
+    v.truncated = b->truncated + (size_t)e * N;
+    v.reached = b->reached + (size_t)e * N;
+    v.collision = b->collision + (size_t)e * N;
+    v.obs_valid = b->obs_valid + (size_t)e * N;
+    v.all_term = b->all_terminated + e;
+    v.all_trunc = b->all_truncated + e;
+    return v;
+}
+
+/* obs + info for every drone of one env (what reset() returns, and what the
+ * batched contract reports after set_state):  drone_swarm_env.py:82-89. */
+static void observe_env(const OracleConfig *c, EnvView *v) {
+    int N = c->num_drones, D = obs_dim(c);
+    for (int i = 0; i < N; ++i) {
+        build_obs(c, v->pos, v->vel, v->goal, v->obst, i, v->obs + (size_t)i * D);
+        v->dist[i] = distance_to_goal(c, v->goal, v->pos + 3 * i);
+        v->obs_valid[i] = c->env_kind == 1 ? v->active[i] : 1;
+        v->reward[i] = 0.0;
+        v->terminated[i] = v->truncated[i] = v->reached[i] = v->collision[i] = 0;
+    }
+    *v->all_term = 0;
+    *v->all_trunc = 0;
+    if (v->gs) global_state(c, v->pos, v->vel, v->goal, v->gs);
+}
+
+/* reset  drone_swarm_env.py:65-90 / single_drone_env.py:53-71.
+ * Draw order: positions (N,3) -> goal (3,) -> obstacles (M,3). */
+static void reset_env(const OracleConfig *c, EnvView *v) {
+    int N = c->num_drones, M = c->num_obstacles;
+    double bound = c->world_size / 2.0;
+    double lo = -bound, range = bound - (-bound);
+    for (int i = 0; i < N; ++i) v->active[i] = 1;
+    *v->step_count = 0;
+    for (int k = 0; k < 3 * N; ++k) v->pos[k] = draw_uniform_f32(v->rng, lo, range);
+    for (int k = 0; k < 3 * N; ++k) v->vel[k] = 0.0f;
+    for (int k = 0; k < 3; ++k) v->goal[k] = draw_uniform_f32(v->rng, lo, range);
+    for (int k = 0; k < 3 * M; ++k) v->obst[k] = draw_uniform_f32(v->rng, lo, range);
+    observe_env(c, v);
+}
+
+/* _collision_mask  drone_swarm_env.py:185-208 (over active drones only) */
+static void collision_mask(const OracleConfig *c, const EnvView *v, uint8_t *collided) {
+    int N = c->num_drones, M = c->num_obstacles;
+    float thr_obst = (float)(c->collision_radius + c->obstacle_radius); /* array <= py float */
+    float thr_pair = (float)(2.0 * c->collision_radius);                /* np.float32 <= py float */
+    for (int i = 0; i < N; ++i) collided[i] = 0;
+    for (int i = 0; i < N; ++i) {
+        if (!v->active[i]) continue;
+        for (int m = 0; m < M; ++m) {
+            float d = norm_axis(v->pos[3 * i] - v->obst[3 * m], v->pos[3 * i + 1] - v->obst[3 * m + 1],
+                                v->pos[3 * i + 2] - v->obst[3 * m + 2]);
+            if (d <= thr_obst) collided[i] = 1;
+        }
+    }
+    for (int i = 0; i < N; ++i) {
+        if (!v->active[i]) continue;
+        for (int j = i + 1; j < N; ++j) {
+            if (!v->active[j]) continue;
+            float d = norm1d(c, v->pos[3 * i] - v->pos[3 * j], v->pos[3 * i + 1] - v->pos[3 * j + 1],
+                             v->pos[3 * i + 2] - v->pos[3 * j + 2]);
+            if (d <= thr_pair) { collided[i] = 1; collided[j] = 1; }
+        }
+    }
+}
+
+/* _formation_penalties  drone_swarm_env.py:210-224 */
+static void formation_penalties(const OracleConfig *c, const EnvView *v, double *pen) {
+    int N = c->num_drones, n_active = 0;
+    for (int i = 0; i < N; ++i) { pen[i] = 0.0; n_active += v->active[i] ? 1 : 0; }
+    if (n_active <= 1) return;
+    double *errs = (double *)malloc(sizeof(double) * (size_t)N);
+    for (int i = 0; i < N; ++i) {
+        if (!v->active[i]) continue;
+        int n = 0;
+        for (int j = 0; j < N; ++j) {
+            if (j == i || !v->active[j]) continue;
+            double d = (double)norm1d(c, v->pos[3 * i] - v->pos[3 * j], v->pos[3 * i + 1] - v->pos[3 * j + 1],
+                                      v->pos[3 * i + 2] - v->pos[3 * j + 2]);
+            errs[n++] = fabs(d - c->desired_spacing);
+        }
+        if (n > 0) {
+            double spacing_error = np_pairwise_sum(errs, n) / (double)n;
+            pen[i] = -c->reward_formation_scale * spacing_error;
+        }
+    }
+    free(errs);
+}
+
+/* DroneSwarmEnv.step  drone_swarm_env.py:92-174.  `action` is [N][3] f32 (a missing
+ * dict key is a zero row, :104). */
+static void step_swarm_env(const OracleConfig *c, EnvView *v, const float *action) {
+    int N = c->num_drones, D = obs_dim(c);
+    int n_active = 0;
+    for (int i = 0; i < N; ++i) n_active += v->active[i] ? 1 : 0;
+    for (int i = 0; i < N; ++i) {
+        v->reward[i] = 0.0;
+        v->terminated[i] = v->truncated[i] = v->reached[i] = v->collision[i] = v->obs_valid[i] = 0;
+    }
+    if (n_active == 0) { /* :94-95 */
+        *v->all_term = 1;
+        *v->all_trunc = 0;
+        return;
+    }
+    double *prev = (double *)malloc(sizeof(double) * (size_t)N);
+    double *curr = (double *)malloc(sizeof(double) * (size_t)N);
+    double *pen = (double *)malloc(sizeof(double) * (size_t)N);
+    uint8_t *collided = (uint8_t *)malloc((size_t)N);
+
+    for (int i = 0; i < N; ++i) /* :98-101 */
+        if (v->active[i]) prev[i] = (double)distance_to_goal(c, v->goal, v->pos + 3 * i);
+    for (int i = 0; i < N; ++i) /* :103-111 */
+        if (v->active[i]) integrate(c, action + 3 * i, v->pos + 3 * i, v->vel + 3 * i);
+    float bound = (float)(c->world_size / 2.0); /* :113-117, all drones */
+    for (int k = 0; k < 3 * N; ++k) v->pos[k] = clipf(v->pos[k], -bound, bound);
+    *v->step_count += 1; /* :118 */
+
+    for (int i = 0; i < N; ++i) /* :120-127 */
+        if (v->active[i]) {
+            curr[i] = (double)distance_to_goal(c, v->goal, v->pos + 3 * i);
+            v->reached[i] = curr[i] <= c->goal_radius; /* Python-float (double) compare, T3 */
+        }
+    collision_mask(c, v, collided);
+    formation_penalties(c, v, pen);
+
+    int any_collision = 0;
+    for (int i = 0; i < N; ++i) if (v->active[i] && collided[i]) any_collision = 1; /* :137 */
+    int time_limit = *v->step_count >= c->max_steps;                                 /* :138 */
+    int n_next = 0;
+    uint8_t *next_active = (uint8_t *)calloc((size_t)N, 1);
+
+    for (int i = 0; i < N; ++i) { /* :141-162 */
+        if (!v->active[i]) continue;
+        double progress = (prev[i] - curr[i]) * c->reward_progress_scale;
+        double reward = progress + pen[i];
+        if (v->reached[i]) reward += c->reward_goal;
+        if (collided[i]) reward += c->reward_collision;
+        v->reward[i] = reward;
+        int done_agent = v->reached[i] || collided[i];
+        v->terminated[i] = (uint8_t)done_agent;
+        v->truncated[i] = (uint8_t)(time_limit && !done_agent);
+        v->collision[i] = collided[i];
+        v->dist[i] = (float)curr[i];
+        if (!done_agent && !time_limit && !any_collision) {
+            build_obs(c, v->pos, v->vel, v->goal, v->obst, i, v->obs + (size_t)i * D);
+            v->obs_valid[i] = 1;
+            next_active[i] = 1;
+            ++n_next;
+        }
+    }
+    int all_reached = n_next == 0 && !any_collision && !time_limit; /* :164 */
+    int episode_done = all_reached || any_collision;
+    *v->all_term = (uint8_t)episode_done;
+    *v->all_trunc = (uint8_t)(time_limit && !episode_done);
+    if (*v->all_term || *v->all_trunc) memset(v->active, 0, (size_t)N); /* :169-170 */
+    else memcpy(v->active, next_active, (size_t)N);                     /* :171-172 */
+    if (v->gs) global_state(c, v->pos, v->vel, v->goal, v->gs);
+
+    free(prev); free(curr); free(pen); free(collided); free(next_active);
+}
+
+/* SingleDroneEnv.step  single_drone_env.py:73-111 */
+static void step_single_env(const OracleConfig *c, EnvView *v, const float *action) {
+    int M = c->num_obstacles;
+    double prev = (double)distance_to_goal(c, v->goal, v->pos); /* :77 */
+    integrate(c, action, v->pos, v->vel);                        /* :74-75, 79-82 */
+    float bound = (float)(c->world_size / 2.0);
+    for (int k = 0; k < 3; ++k) v->pos[k] = clipf(v->pos[k], -bound, bound); /* :83-87 */
+    *v->step_count += 1;                                                       /* :89 */
+    double curr = (double)distance_to_goal(c, v->goal, v->pos);               /* :91 */
+    double reward = (prev - curr) * c->reward_progress_scale;                  /* :92 */
+    int reached = curr <= c->goal_radius;                                      /* :93 */
+    int collision = 0;                                                         /* :122-126 */
+    float thr = (float)(c->obstacle_radius + c->collision_radius);
+    for (int m = 0; m < M; ++m) {
+        float d = norm_axis(v->obst[3 * m] - v->pos[0], v->obst[3 * m + 1] - v->pos[1],
+                            v->obst[3 * m + 2] - v->pos[2]);
+        if (d <= thr) collision = 1;
+    }
+    if (reached) reward += c->reward_goal;       /* :97-98 */
+    if (collision) reward += c->reward_collision; /* :99-100 */
+    v->reward[0] = reward;
+    v->terminated[0] = (uint8_t)(reached || collision);               /* :102 */
+    v->truncated[0] = (uint8_t)(*v->step_count >= c->max_steps);      /* :103 (not masked) */
+    v->reached[0] = (uint8_t)reached;
+    v->collision[0] = (uint8_t)collision;
+    v->dist[0] = (float)curr;
+    v->obs_valid[0] = 1;
+    build_obs(c, v->pos, v->vel, v->goal, v->obst, 0, v->obs); /* :105 */
+    *v->all_term = v->terminated[0];
+    *v->all_trunc = v->truncated[0];
+    if (v->gs) global_state(c, v->pos, v->vel, v->goal, v->gs);
+}
+
+/* ------------------------------------------------------------------------- */
+/* Batch entry points (ctypes)                                                */
+/* ------------------------------------------------------------------------- */
+int oracle_obs_dim(const OracleConfig *c) { return obs_dim(c); }
+
+void oracle_seed_batch(const OracleBatch *b, const uint64_t *seeds) {
+    for (int e = 0; e < b->num_envs; ++e) oracle_seed(seeds[e], b->rng + (size_t)e * 4);
+}
+
+void oracle_reset_batch(const OracleConfig *c, const OracleBatch *b, const uint8_t *mask) {
+    for (int e = 0; e < b->num_envs; ++e) {
+        if (mask && !mask[e]) continue;
+        EnvView v = view(c, b, e);
+        reset_env(c, &v);
+    }
+}
+
+void oracle_observe_batch(const OracleConfig *c, const OracleBatch *b) {
+    for (int e = 0; e < b->num_envs; ++e) {
+        EnvView v = view(c, b, e);
+        observe_env(c, &v);
+    }
+}
+
+/* ep_done_out[e] (nullable) = 1 where the episode ended on this step; with
+ * auto_reset the env is then reset (rng stream continues, like RLlib calling
+ * env.reset() with no seed) and obs/dist/obs_valid/global_state hold the reset
+ * observation while reward/flags keep the terminal step's values. */
+static void step_range(const OracleConfig *c, const OracleBatch *b, const float *actions, int auto_reset,
+                       int e0, int e1) {
+    int N = c->num_drones;
+    for (int e = e0; e < e1; ++e) {
+        EnvView v = view(c, b, e);
+        const float *act = actions + (size_t)e * N * 3;
+        if (c->env_kind == 1) step_swarm_env(c, &v, act);
+        else step_single_env(c, &v, act);
+        if (auto_reset && (*v.all_term || *v.all_trunc)) {
+            /* keep terminal reward / flags, replace obs + info with the reset ones */
+            double *rew = (double *)malloc(sizeof(double) * (size_t)N);
+            uint8_t *fl = (uint8_t *)malloc((size_t)N * 4);
+            memcpy(rew, v.reward, sizeof(double) * (size_t)N);
+            memcpy(fl, v.terminated, (size_t)N);
+            memcpy(fl + N, v.truncated, (size_t)N);
+            memcpy(fl + 2 * N, v.reached, (size_t)N);
+            memcpy(fl + 3 * N, v.collision, (size_t)N);
+            uint8_t at = *v.all_term, atr = *v.all_trunc;
+            reset_env(c, &v);
+            memcpy(v.reward, rew, sizeof(double) * (size_t)N);
+            memcpy(v.terminated, fl, (size_t)N);
+            memcpy(v.truncated, fl + N, (size_t)N);
+            memcpy(v.reached, fl + 2 * N, (size_t)N);
+            memcpy(v.collision, fl + 3 * N, (size_t)N);
+            *v.all_term = at;
+            *v.all_trunc = atr;
+            free(rew);
+            free(fl);
+        }
+    }
+}
+
+typedef struct StepJob {
+    const OracleConfig *c;
+    const OracleBatch *b;
+    const float *actions;
+    int auto_reset, e0, e1;
+} StepJob;
+
+static void *step_worker(void *arg) {
+    StepJob *j = (StepJob *)arg;
+    step_range(j->c, j->b, j->actions, j->auto_reset, j->e0, j->e1);
+    return NULL;
+}
+
+void oracle_step_batch(const OracleConfig *c, const OracleBatch *b, const float *actions, int auto_reset,
+                       int num_threads) {
+    int E = b->num_envs;
+    if (num_threads <= 1 || E < 2 * num_threads) {
+        step_range(c, b, actions, auto_reset, 0, E);
+        return;
+    }
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)num_threads);
+    StepJob *jobs = (StepJob *)malloc(sizeof(StepJob) * (size_t)num_threads);
+    for (int t = 0; t < num_threads; ++t) {
+        jobs[t].c = c; jobs[t].b = b; jobs[t].actions = actions; jobs[t].auto_reset = auto_reset;
+        jobs[t].e0 = (int)((int64_t)E * t / num_threads);
+        jobs[t].e1 = (int)((int64_t)E * (t + 1) / num_threads);
+        pthread_create(&th[t], NULL, step_worker, &jobs[t]);
+    }
+    for (int t = 0; t < num_threads; ++t) pthread_join(th[t], NULL);
+    free(th);
+    free(jobs);
+}
+
+#ifdef __cplusplus
+}
+#endif
