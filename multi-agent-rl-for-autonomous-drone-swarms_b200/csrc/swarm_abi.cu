@@ -1,0 +1,389 @@
+// swarm_abi.cu -- the extern "C" surface declared in include/swarm_b200.h.
+// Host logic only: config validation, derivation of the float32 constants the reference's numpy
+// expressions effectively use, PCG64 jump table, launch geometry, the chunked host-buffer path.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "swarm_internal.h"
+
+using namespace swarm;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return fail(SWARM_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr int kHostChunks = 4;
+
+}  // namespace
+
+struct SwarmHandle {
+    SwarmConfig cfg;
+    DevParams base;          // everything but the buffer pointers / per-launch fields
+    int kmax, smax;
+    int device;
+    int num_sms;
+    int blocks_per_sm;
+    size_t smem_bytes;
+    JumpEntry* jump_dev;
+    int64_t launches;
+    // host-buffer path
+    cudaStream_t chunk_stream[kHostChunks];
+    cudaEvent_t chunk_done[kHostChunks];
+    float* actions_dev;      // [E][N][3] staging for swarm_step_host
+    bool host_path_ready;
+};
+
+namespace {
+
+int obs_dim_of(const SwarmConfig& c) {
+    return c.env_kind == SWARM_KIND_SWARM ? 9 + 4 * c.neighbor_k + 4 * c.sensed_obstacles
+                                          : 9 + 4 * c.sensed_obstacles;
+}
+
+int validate(const SwarmConfig* c) {
+    if (!c) return fail(SWARM_E_NULL, "config is NULL");
+    if (c->abi_version != SWARM_ABI_VERSION)
+        return fail(SWARM_E_INVALID, "abi_version %d != %d", c->abi_version, SWARM_ABI_VERSION);
+    if (c->env_kind != SWARM_KIND_SINGLE && c->env_kind != SWARM_KIND_SWARM)
+        return fail(SWARM_E_INVALID, "env_kind %d unknown", c->env_kind);
+    if (c->num_envs < 1) return fail(SWARM_E_INVALID, "num_envs must be >= 1");
+    if (c->num_drones < 1) return fail(SWARM_E_INVALID, "num_drones must be >= 1");
+    if (c->env_kind == SWARM_KIND_SINGLE && c->num_drones != 1)
+        return fail(SWARM_E_INVALID, "SWARM_KIND_SINGLE needs num_drones == 1");
+    if (c->num_drones > SWARM_MAX_DRONES)
+        return fail(SWARM_E_UNSUPPORTED, "num_drones %d > %d", c->num_drones, SWARM_MAX_DRONES);
+    if (c->num_obstacles < 0 || c->num_obstacles > 64)
+        return fail(SWARM_E_UNSUPPORTED, "num_obstacles %d outside [0, 64]", c->num_obstacles);
+    if (c->sensed_obstacles < 0 || c->sensed_obstacles > SWARM_MAX_SENSED)
+        return fail(SWARM_E_UNSUPPORTED, "sensed_obstacles %d outside [0, %d]", c->sensed_obstacles, SWARM_MAX_SENSED);
+    if (c->neighbor_k < 0 || c->neighbor_k > SWARM_MAX_NEIGHBOR_K)
+        return fail(SWARM_E_UNSUPPORTED, "neighbor_k %d outside [0, %d]", c->neighbor_k, SWARM_MAX_NEIGHBOR_K);
+    if (c->norm_mode != 0 && c->norm_mode != 1) return fail(SWARM_E_INVALID, "norm_mode must be 0 or 1");
+    if ((int64_t)c->num_envs * c->num_drones > (int64_t)1 << 30)
+        return fail(SWARM_E_UNSUPPORTED, "num_envs * num_drones too large");
+    return SWARM_OK;
+}
+
+// largest float32 <= x: a float32-valued Python float d satisfies (d <= x) in double iff d <= this
+float f32_floor_of(double x) {
+    float f = (float)x;
+    if ((double)f > x) f = std::nextafterf(f, -INFINITY);
+    return f;
+}
+
+void build_jump_table(int n_draws, std::vector<JumpEntry>& out) {
+    typedef unsigned __int128 u128;
+    const u128 mult = ((u128)2549297995355413924ULL << 64) | (u128)4865540595714422341ULL;
+    out.resize((size_t)n_draws + 1);
+    u128 a = 1, g = 0;  // A^0, G_0
+    for (int k = 0; k <= n_draws; ++k) {
+        out[(size_t)k].a_hi = (unsigned long long)(a >> 64);
+        out[(size_t)k].a_lo = (unsigned long long)a;
+        out[(size_t)k].g_hi = (unsigned long long)(g >> 64);
+        out[(size_t)k].g_lo = (unsigned long long)g;
+        g = g * mult + 1;  // G_{k+1} = A G_k + 1
+        a = a * mult;
+    }
+}
+
+void fill_params(const SwarmConfig& c, DevParams& p) {
+    memset(&p, 0, sizeof(p));
+    p.E = c.num_envs; p.N = c.num_drones; p.M = c.num_obstacles;
+    p.K = c.env_kind == SWARM_KIND_SWARM ? c.neighbor_k : 0;
+    p.S = c.sensed_obstacles;
+    p.D = obs_dim_of(c);
+    p.R = 6 * p.N + 3;
+    p.G = p.N <= 32 ? 32 / p.N : 1;
+    p.nslots = (p.N + 31) / 32;
+    p.n_tab = p.N <= 32 ? 32 : p.N;
+    p.m_pad = p.M > 0 ? p.M : 1;
+    p.n_draws = 3 * p.N + 3 + 3 * p.M;
+    p.smem_per_warp = (2 * p.n_tab + p.G + p.G * p.m_pad) * 16 + 32 * p.D * 4;
+    p.max_steps = c.max_steps;
+    // float32 constants (numpy NEP 50: a Python float meeting a float32 array / scalar is cast to f32)
+    p.amax = (float)c.max_accel;                       // drone_swarm_env.py:107
+    p.dt = (float)c.dt;                                // :109, :111
+    p.vmax = (float)c.max_speed;                       // :181, :183
+    p.eps_speed = (float)1e-8;                         // :181
+    p.bound = (float)(c.world_size / 2.0);             // :113-117
+    p.thr_goal = f32_floor_of(c.goal_radius);          // :124-127 Python-float compare
+    p.thr_obst = (float)(c.collision_radius + c.obstacle_radius);  // :196-197
+    p.thr_pair = (float)(2.0 * c.collision_radius);    // :205
+    p.k_p = c.reward_progress_scale; p.r_goal = c.reward_goal; p.r_col = c.reward_collision;
+    p.neg_k_f = -c.reward_formation_scale; p.d_star = c.desired_spacing;
+    const double bound = c.world_size / 2.0;           // :71
+    p.rng_lo = -bound; p.rng_range = bound - (-bound); // Generator.uniform(low, high): high - low
+}
+
+int bind_buffers(const SwarmHandle* h, const SwarmBuffers* b, DevParams& p) {
+    if (!b) return fail(SWARM_E_NULL, "buffers is NULL");
+    p = h->base;
+    if (!b->pos4 || !b->vel4 || !b->goal4 || !b->obst4 || !b->step_count || !b->rng || !b->ep_return || !b->obs ||
+        !b->reward || !b->dist || !b->terminated || !b->truncated || !b->reached || !b->collision ||
+        !b->obs_valid || !b->all_terminated || !b->all_truncated)
+        return fail(SWARM_E_NULL, "a required SwarmBuffers pointer is NULL");
+    if ((reinterpret_cast<uintptr_t>(b->pos4) | reinterpret_cast<uintptr_t>(b->vel4) |
+         reinterpret_cast<uintptr_t>(b->goal4) | reinterpret_cast<uintptr_t>(b->obst4) |
+         reinterpret_cast<uintptr_t>(b->obs)) & 15u)
+        return fail(SWARM_E_INVALID, "pos4 / vel4 / goal4 / obst4 / obs must be 16-byte aligned");
+    p.pos4 = reinterpret_cast<float4*>(b->pos4); p.vel4 = reinterpret_cast<float4*>(b->vel4);
+    p.goal4 = reinterpret_cast<float4*>(b->goal4); p.obst4 = reinterpret_cast<float4*>(b->obst4);
+    p.step_count = b->step_count; p.rng = reinterpret_cast<unsigned long long*>(b->rng);
+    p.ep_return = b->ep_return;
+    p.obs = b->obs; p.reward = b->reward; p.reward64 = b->reward64; p.dist = b->dist;
+    p.terminated = b->terminated; p.truncated = b->truncated; p.reached = b->reached;
+    p.collision = b->collision; p.obs_valid = b->obs_valid;
+    p.all_term = b->all_terminated; p.all_trunc = b->all_truncated;
+    p.gs = b->global_state; p.episode_return = b->episode_return; p.episode_length = b->episode_length;
+    p.stats = reinterpret_cast<unsigned long long*>(b->stats);
+    p.jump = h->jump_dev;
+    return SWARM_OK;
+}
+
+int launch(SwarmHandle* h, DevParams& p, int env_begin, int env_count, cudaStream_t stream) {
+    p.env_begin = env_begin;
+    p.env_count = env_count;
+    p.n_groups = (env_count + p.G - 1) / p.G;
+    const int ctas_needed = (p.n_groups + kWarpsPerCta - 1) / kWarpsPerCta;
+    const int resident = h->num_sms * h->blocks_per_sm;
+    const int grid = ctas_needed < resident ? ctas_needed : resident;
+    CUDA_TRY(launch_env_kernel(p, h->kmax, h->smax, h->cfg.norm_mode, h->cfg.env_kind, grid, h->smem_bytes, stream));
+    h->launches++;
+    return SWARM_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool active = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) {
+            if (cudaSetDevice(dev) == cudaSuccess) active = true;
+        }
+    }
+    ~DeviceGuard() { if (active) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+extern "C" {
+
+int swarm_abi_version(void) { return SWARM_ABI_VERSION; }
+
+const char* swarm_last_error(void) { return g_err; }
+
+int swarm_query_sizes(const SwarmConfig* cfg, SwarmSizes* out) {
+    int rc = validate(cfg);
+    if (rc != SWARM_OK) return rc;
+    if (!out) return fail(SWARM_E_NULL, "out is NULL");
+    const int64_t E = cfg->num_envs, N = cfg->num_drones, M = cfg->num_obstacles;
+    const int64_t D = obs_dim_of(*cfg);
+    out->obs_dim = D;
+    out->state_dim = 6 * N + 3;
+    out->pos4 = E * N * 4; out->vel4 = E * N * 4; out->goal4 = E * 4;
+    out->obst4 = E * M * 4 > 4 ? E * M * 4 : 4;
+    out->step_count = E; out->rng = E * 4; out->ep_return = E;
+    out->actions = E * N * 3; out->obs = E * N * D; out->per_agent = E * N; out->per_env = E;
+    out->global_state = E * (6 * N + 3);
+    out->stats = SWARM_STATS_WORDS;
+    return SWARM_OK;
+}
+
+int swarm_create(const SwarmConfig* cfg, SwarmHandle** out) {
+    int rc = validate(cfg);
+    if (rc != SWARM_OK) return rc;
+    if (!out) return fail(SWARM_E_NULL, "out is NULL");
+    *out = nullptr;
+    int dev = cfg->device;
+    if (dev < 0) CUDA_TRY(cudaGetDevice(&dev));
+    DeviceGuard guard(dev);
+    SwarmHandle* h = new (std::nothrow) SwarmHandle();
+    if (!h) return fail(SWARM_E_INVALID, "out of host memory");
+    h->cfg = *cfg;
+    h->device = dev;
+    h->launches = 0;
+    h->jump_dev = nullptr;
+    h->actions_dev = nullptr;
+    h->host_path_ready = false;
+    fill_params(*cfg, h->base);
+    h->kmax = h->base.K;
+    h->smax = h->base.S;
+    h->smem_bytes = (size_t)h->base.smem_per_warp * kWarpsPerCta;
+
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) { delete h; return fail(SWARM_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
+    h->num_sms = prop.multiProcessorCount;
+    if (h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
+        const size_t need = h->smem_bytes;
+        delete h;
+        return fail(SWARM_E_UNSUPPORTED, "config needs %zu B shared memory per CTA (> %zu)", need,
+                    (size_t)prop.sharedMemPerBlockOptin);
+    }
+    e = env_kernel_occupancy(h->kmax, h->smax, cfg->norm_mode, cfg->env_kind, h->smem_bytes, &h->blocks_per_sm);
+    if (e != cudaSuccess || h->blocks_per_sm < 1) {
+        delete h;
+        return fail(SWARM_E_CUDA, "kernel occupancy query failed: %s", cudaGetErrorString(e));
+    }
+    std::vector<JumpEntry> table;
+    build_jump_table(h->base.n_draws, table);
+    e = cudaMalloc(&h->jump_dev, table.size() * sizeof(JumpEntry));
+    if (e == cudaSuccess)
+        e = cudaMemcpy(h->jump_dev, table.data(), table.size() * sizeof(JumpEntry), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        if (h->jump_dev) cudaFree(h->jump_dev);
+        delete h;
+        return fail(SWARM_E_CUDA, "jump table upload failed: %s", cudaGetErrorString(e));
+    }
+    *out = h;
+    return SWARM_OK;
+}
+
+int swarm_destroy(SwarmHandle* h) {
+    if (!h) return SWARM_OK;
+    DeviceGuard guard(h->device);
+    if (h->host_path_ready) {
+        for (int c = 0; c < kHostChunks; ++c) {
+            cudaStreamDestroy(h->chunk_stream[c]);
+            cudaEventDestroy(h->chunk_done[c]);
+        }
+    }
+    if (h->actions_dev) cudaFree(h->actions_dev);
+    if (h->jump_dev) cudaFree(h->jump_dev);
+    delete h;
+    return SWARM_OK;
+}
+
+int swarm_seed(SwarmHandle* h, const SwarmBuffers* bufs, const uint64_t* seeds, const uint8_t* env_mask, void* stream) {
+    if (!h) return fail(SWARM_E_NULL, "handle is NULL");
+    if (!seeds) return fail(SWARM_E_NULL, "seeds is NULL");
+    DeviceGuard guard(h->device);
+    DevParams p;
+    int rc = bind_buffers(h, bufs, p);
+    if (rc != SWARM_OK) return rc;
+    p.seeds = reinterpret_cast<const unsigned long long*>(seeds);
+    p.env_mask = env_mask;
+    CUDA_TRY(launch_seed_kernel(p, static_cast<cudaStream_t>(stream)));
+    h->launches++;
+    return SWARM_OK;
+}
+
+int swarm_reset(SwarmHandle* h, const SwarmBuffers* bufs, const uint8_t* env_mask, void* stream) {
+    if (!h) return fail(SWARM_E_NULL, "handle is NULL");
+    DeviceGuard guard(h->device);
+    DevParams p;
+    int rc = bind_buffers(h, bufs, p);
+    if (rc != SWARM_OK) return rc;
+    p.mode = kModeReset;
+    p.env_mask = env_mask;
+    return launch(h, p, 0, p.E, static_cast<cudaStream_t>(stream));
+}
+
+int swarm_observe(SwarmHandle* h, const SwarmBuffers* bufs, void* stream) {
+    if (!h) return fail(SWARM_E_NULL, "handle is NULL");
+    DeviceGuard guard(h->device);
+    DevParams p;
+    int rc = bind_buffers(h, bufs, p);
+    if (rc != SWARM_OK) return rc;
+    p.mode = kModeObserve;
+    return launch(h, p, 0, p.E, static_cast<cudaStream_t>(stream));
+}
+
+int swarm_step(SwarmHandle* h, const SwarmBuffers* bufs, const float* actions, int auto_reset, void* stream) {
+    if (!h) return fail(SWARM_E_NULL, "handle is NULL");
+    if (!actions) return fail(SWARM_E_NULL, "actions is NULL");
+    DeviceGuard guard(h->device);
+    DevParams p;
+    int rc = bind_buffers(h, bufs, p);
+    if (rc != SWARM_OK) return rc;
+    p.mode = kModeStep;
+    p.auto_reset = auto_reset ? 1 : 0;
+    p.actions = actions;
+    return launch(h, p, 0, p.E, static_cast<cudaStream_t>(stream));
+}
+
+int swarm_step_host(SwarmHandle* h, const SwarmBuffers* bufs, const float* actions_host, const SwarmHostOut* out,
+                    int auto_reset) {
+    if (!h) return fail(SWARM_E_NULL, "handle is NULL");
+    if (!actions_host || !out) return fail(SWARM_E_NULL, "actions_host / out_host is NULL");
+    DeviceGuard guard(h->device);
+    DevParams p;
+    int rc = bind_buffers(h, bufs, p);
+    if (rc != SWARM_OK) return rc;
+    if (out->global_state && !p.gs) return fail(SWARM_E_INVALID, "host global_state requested but bufs->global_state is NULL");
+    if (!h->host_path_ready) {
+        for (int c = 0; c < kHostChunks; ++c) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&h->chunk_stream[c], cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&h->chunk_done[c], cudaEventDisableTiming));
+        }
+        CUDA_TRY(cudaMalloc(&h->actions_dev, (size_t)p.E * p.N * 3 * sizeof(float)));
+        h->host_path_ready = true;
+    }
+    // the internal chunk streams do not order against the caller's streams: drain prior work first
+    CUDA_TRY(cudaDeviceSynchronize());
+    p.mode = kModeStep;
+    p.auto_reset = auto_reset ? 1 : 0;
+    p.actions = h->actions_dev;
+    const int E = p.E, N = p.N, D = p.D, R = p.R;
+    // chunk boundaries are multiples of G so a warp's env group never straddles two launches
+    int chunks = kHostChunks;
+    int groups_total = (E + p.G - 1) / p.G;
+    if (groups_total < chunks * 64) chunks = 1;
+    const int groups_per_chunk = (groups_total + chunks - 1) / chunks;
+    for (int c = 0; c < chunks; ++c) {
+        const int e0 = c * groups_per_chunk * p.G;
+        if (e0 >= E) break;
+        const int e1 = (e0 + groups_per_chunk * p.G) < E ? (e0 + groups_per_chunk * p.G) : E;
+        const size_t ne = (size_t)(e1 - e0);
+        cudaStream_t s = h->chunk_stream[c];
+        CUDA_TRY(cudaMemcpyAsync(h->actions_dev + (size_t)e0 * N * 3, actions_host + (size_t)e0 * N * 3,
+                                 ne * N * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+        DevParams pc = p;
+        rc = launch(h, pc, e0, e1 - e0, s);
+        if (rc != SWARM_OK) return rc;
+#define D2H(field, devptr, per_env_elems, type)                                                         \
+        if (out->field)                                                                                 \
+            CUDA_TRY(cudaMemcpyAsync(out->field + (size_t)e0 * (per_env_elems), (devptr) + (size_t)e0 * (per_env_elems), \
+                                     ne * (per_env_elems) * sizeof(type), cudaMemcpyDeviceToHost, s))
+        D2H(obs, p.obs, (size_t)N * D, float);
+        D2H(reward, p.reward, (size_t)N, float);
+        D2H(dist, p.dist, (size_t)N, float);
+        D2H(terminated, p.terminated, (size_t)N, uint8_t);
+        D2H(truncated, p.truncated, (size_t)N, uint8_t);
+        D2H(reached, p.reached, (size_t)N, uint8_t);
+        D2H(collision, p.collision, (size_t)N, uint8_t);
+        D2H(obs_valid, p.obs_valid, (size_t)N, uint8_t);
+        D2H(all_terminated, p.all_term, (size_t)1, uint8_t);
+        D2H(all_truncated, p.all_trunc, (size_t)1, uint8_t);
+        D2H(global_state, p.gs, (size_t)R, float);
+#undef D2H
+        CUDA_TRY(cudaEventRecord(h->chunk_done[c], s));
+    }
+    for (int c = 0; c < chunks; ++c) {
+        if (c * groups_per_chunk * p.G >= E) break;
+        CUDA_TRY(cudaEventSynchronize(h->chunk_done[c]));
+    }
+    return SWARM_OK;
+}
+
+int64_t swarm_launch_count(const SwarmHandle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,63 @@
+// swarm_internal.h -- shared between the kernel TU and the C-ABI TU (not installed).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "swarm_b200.h"
+
+namespace swarm {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kThreadsPerCta = kWarpsPerCta * 32;
+
+enum Mode : int { kModeStep = 0, kModeReset = 1, kModeObserve = 2 };
+
+// One entry per draw count k: state_{n+k} = A^k * state_n + G_k * inc  (mod 2^128)
+struct __align__(16) JumpEntry {
+    unsigned long long a_hi, a_lo, g_hi, g_lo;
+};
+
+// Kernel parameters (passed by value; lives in the constant bank).
+struct DevParams {
+    // shapes
+    int E, N, M, K, S, D, R;      // R = 6N + 3
+    int G;                        // env instances per warp (N <= 32: 32 / N, else 1)
+    int nslots;                   // drones per lane (ceil(N / 32))
+    int n_tab;                    // float4 entries of the per-warp position / velocity tables
+    int m_pad;                    // obstacle table entries per env (max(M, 1))
+    int n_draws;                  // 3N + 3 + 3M uniform draws per reset
+    int env_begin, env_count;     // env range of this launch
+    int n_groups;                 // ceil(env_count / G)
+    int smem_per_warp;            // bytes
+    int mode;                     // Mode
+    int auto_reset;
+    int max_steps;
+    // float32 constants the reference's numpy expressions effectively use
+    float amax, dt, vmax, eps_speed, bound;
+    float thr_goal;               // largest f32 <= goal_radius (double compare of an f32-valued float)
+    float thr_obst, thr_pair;     // f32(r_c + r_o), f32(2 r_c)
+    // Python-float (double) constants
+    double k_p, r_goal, r_col, neg_k_f, d_star;
+    double rng_lo, rng_range;     // uniform(-W/2, W/2): lo, hi - lo
+    // state
+    float4* pos4; float4* vel4; float4* goal4; float4* obst4;
+    int* step_count; unsigned long long* rng; float* ep_return;
+    // inputs
+    const float* actions; const uint8_t* env_mask; const unsigned long long* seeds;
+    // outputs
+    float* obs; float* reward; double* reward64; float* dist;
+    uint8_t *terminated, *truncated, *reached, *collision, *obs_valid, *all_term, *all_trunc;
+    float* gs; float* episode_return; int* episode_length;
+    unsigned long long* stats;
+    const JumpEntry* jump;        // [n_draws + 1]
+};
+
+// kernel selection (swarm_kernels.cu)
+struct KernelChoice { int kmax, smax; };
+cudaError_t launch_env_kernel(const DevParams& p, int kmax, int smax, int norm_mode, int env_kind,
+                              int grid, size_t smem_bytes, cudaStream_t stream);
+cudaError_t env_kernel_occupancy(int kmax, int smax, int norm_mode, int env_kind, size_t smem_bytes,
+                                 int* blocks_per_sm);
+cudaError_t launch_seed_kernel(const DevParams& p, cudaStream_t stream);
+
+}  // namespace swarm

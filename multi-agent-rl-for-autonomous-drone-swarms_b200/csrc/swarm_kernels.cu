@@ -1,0 +1,788 @@
+// swarm_kernels.cu -- sm_100a kernels of the batched drone-swarm env step.
+//
+// One fused launch performs, for every env instance of the batch, the whole of
+//   DroneSwarmEnv.step   (reference src/swarm_marl/envs/drone_swarm_env.py:92-174)
+//   SingleDroneEnv.step  (reference src/swarm_marl/envs/single_drone_env.py:73-111)
+// integrate -> wall clip -> goal distance -> obstacle / pairwise distances (collision,
+// formation, k-nearest features) -> reward -> done flags -> observation rows -> global_state,
+// and, when an episode ends with auto_reset, env.reset() (drone_swarm_env.py:65-90) from the
+// env's own numpy-compatible PCG64 stream.
+//
+// Mapping.  Envs are independent, so the unit of work is a WARP: one warp owns G = 32/N env
+// instances (N <= 32; lane = env-local index * N + drone) or one env with ceil(N/32) drones per
+// lane (N > 32).  A warp keeps its envs' positions / velocities / goal / obstacles in a private
+// shared-memory slice (float4 tables: every pair-loop read is one broadcast LDS.128), needs no
+// block barrier, and transposes its 32 x D observation rows through shared memory so the
+// global writes are contiguous float4 streams.  All state traffic is float4 (coalesced 16 B).
+//
+// Arithmetic is bit-faithful to the reference's numpy expressions: explicit round-to-nearest
+// float32 ops with no FMA contraction (the TU is compiled with -fmad=false as well), float64
+// accumulation where np.linalg.norm goes through BLAS sdot, float64 reward
+// arithmetic with numpy's 8-lane pairwise summation order for np.mean (T4), lowest-index tie
+// break for the k-nearest selections (T5), parked drones as neighbours but not colliders (T6).
+#include "swarm_internal.h"
+
+namespace swarm {
+
+#define FULL_MASK 0xffffffffu
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+template <int NORM>
+__device__ __forceinline__ float norm1d(float x, float y, float z) {
+    // np.linalg.norm(vec3): sqrt(dot(v, v)), dot = BLAS sdot (f32 products, f64 accumulate)
+    const float px = __fmul_rn(x, x), py = __fmul_rn(y, y), pz = __fmul_rn(z, z);
+    float s;
+    if (NORM == 0) {
+        s = __double2float_rn(__dadd_rn(__dadd_rn((double)px, (double)py), (double)pz));
+    } else {
+        s = __fadd_rn(__fadd_rn(px, py), pz);
+    }
+    return __fsqrt_rn(s);
+}
+
+__device__ __forceinline__ float norm_axis(float x, float y, float z) {
+    // np.linalg.norm(A, axis=-1): sqrt(add.reduce(A * A)) -- sequential float32
+    return __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+}
+
+__device__ __forceinline__ float clipf(float x, float lo, float hi) {
+    // np.clip == minimum(maximum(x, lo), hi); NaN propagates
+    return x < lo ? lo : (x > hi ? hi : x);
+}
+
+// sorted (ascending) top-KM list of (distance, index); strict '<' keeps the earlier index on ties
+template <int KM>
+__device__ __forceinline__ void topk_insert(float d, int j, float (&bd)[KM], int (&bj)[KM]) {
+    bool lt[KM];
+#pragma unroll
+    for (int q = 0; q < KM; ++q) lt[q] = d < bd[q];
+#pragma unroll
+    for (int q = KM - 1; q >= 0; --q) {
+        if (q > 0) {
+            const float sd = lt[q - 1] ? bd[q - 1] : d;
+            const int sj = lt[q - 1] ? bj[q - 1] : j;
+            bd[q] = lt[q] ? sd : bd[q];
+            bj[q] = lt[q] ? sj : bj[q];
+        } else {
+            bd[0] = lt[0] ? d : bd[0];
+            bj[0] = lt[0] ? j : bj[0];
+        }
+    }
+}
+
+__device__ __forceinline__ float comp(const float4& v, int c) { return c == 0 ? v.x : (c == 1 ? v.y : v.z); }
+
+// ------------------------------------------------------------------------------------------
+// numpy PCG64 (XSL-RR 128/64) with jump-ahead, so the 3N+3+3M draws of a reset are generated
+// by 32 lanes in parallel:  state_{n+k} = A^k state_n + G_k inc.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mul128(unsigned long long ah, unsigned long long al, unsigned long long bh,
+                                       unsigned long long bl, unsigned long long& rh, unsigned long long& rl) {
+    rl = al * bl;
+    rh = __umul64hi(al, bl) + ah * bl + al * bh;
+}
+
+__device__ __forceinline__ void pcg_jump(const JumpEntry& j, unsigned long long sh, unsigned long long sl,
+                                         unsigned long long ih, unsigned long long il, unsigned long long& oh,
+                                         unsigned long long& ol) {
+    unsigned long long xh, xl, yh, yl;
+    mul128(j.a_hi, j.a_lo, sh, sl, xh, xl);
+    mul128(j.g_hi, j.g_lo, ih, il, yh, yl);
+    ol = xl + yl;
+    oh = xh + yh + (ol < xl ? 1ull : 0ull);
+}
+
+__device__ __forceinline__ float pcg_uniform_f32(unsigned long long hi, unsigned long long lo, double u_lo,
+                                                 double u_range) {
+    // Generator.uniform -> random_uniform: lo + range * ((next_uint64 >> 11) * 2^-53), then astype(f32)
+    const unsigned long long x = hi ^ lo;
+    const unsigned rot = (unsigned)(hi >> 58);
+    const unsigned long long out = (x >> rot) | (x << ((64u - rot) & 63u));
+    const double u = __dmul_rn(__ull2double_rn(out >> 11), 1.0 / 9007199254740992.0);
+    return __double2float_rn(__dadd_rn(u_lo, __dmul_rn(u_range, u)));
+}
+
+// ------------------------------------------------------------------------------------------
+// per-drone scan: obstacle distances + pairwise distances
+// ------------------------------------------------------------------------------------------
+struct ScanOut {
+    bool obst_hit, pair_hit;
+    double form_sum;  // np.add.reduce(|d - d*|) in numpy's pairwise order
+    int form_n;
+};
+
+template <int KMAX, int SMAX, int NORM, int KIND, bool STEP>
+__device__ __forceinline__ void scan_drone(const DevParams& P, const float4* __restrict__ tpos,
+                                           const float4* __restrict__ tobs, int i, float px, float py, float pz,
+                                           bool alive_i, int n_alive_env, float (&nd)[KMAX], int (&nj)[KMAX],
+                                           float (&od)[SMAX], int (&om)[SMAX], ScanOut& out) {
+    const int N = P.N, M = P.M;
+#pragma unroll
+    for (int q = 0; q < KMAX; ++q) { nd[q] = __int_as_float(0x7f800000); nj[q] = -1; }
+#pragma unroll
+    for (int q = 0; q < SMAX; ++q) { od[q] = __int_as_float(0x7f800000); om[q] = -1; }
+    out.obst_hit = false;
+    out.pair_hit = false;
+    out.form_sum = 0.0;
+    out.form_n = 0;
+
+    // ---- obstacles: _nearest_obstacle_features (:273-291) + obstacle part of _collision_mask (:190-200)
+    for (int m = 0; m < M; ++m) {
+        const float4 o = tobs[m];
+        const float d = norm_axis(__fsub_rn(o.x, px), __fsub_rn(o.y, py), __fsub_rn(o.z, pz));
+        if (STEP) out.obst_hit |= d <= P.thr_obst;
+        topk_insert<SMAX>(d, m, od, om);
+    }
+    if (KIND == SWARM_KIND_SINGLE) return;
+
+    // ---- drones: _nearest_neighbor_features (:245-271) over ALL j != i; pair part of
+    //      _collision_mask (:202-207) and _formation_penalties (:210-224) over ACTIVE pairs
+    const int n_others = N - 1;
+    if (!STEP) {
+        for (int jp = 0; jp < n_others; ++jp) {
+            const int j = jp + (jp >= i ? 1 : 0);
+            const float4 q = tpos[j];
+            const float d = norm1d<NORM>(__fsub_rn(q.x, px), __fsub_rn(q.y, py), __fsub_rn(q.z, pz));
+            topk_insert<KMAX>(d, j, nd, nj);
+        }
+        return;
+    }
+
+    if (alive_i && n_alive_env == N) {
+        // fast path: every drone active -> the j-th other drone is element j of the mean's operand,
+        // so numpy's pairwise-sum lane is static under 8x unrolling
+        const int n8 = n_others >= 8 ? (n_others & ~7) : 0;
+        double r[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) r[u] = 0.0;
+        for (int jb = 0; jb < n8; jb += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int jp = jb + u;
+                const int j = jp + (jp >= i ? 1 : 0);
+                const float4 q = tpos[j];
+                const float d = norm1d<NORM>(__fsub_rn(q.x, px), __fsub_rn(q.y, py), __fsub_rn(q.z, pz));
+                topk_insert<KMAX>(d, j, nd, nj);
+                out.pair_hit |= d <= P.thr_pair;
+                r[u] = __dadd_rn(r[u], fabs(__dsub_rn((double)d, P.d_star)));
+            }
+        }
+        double res = 0.0;
+        if (n8 > 0)
+            res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                            __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+        for (int jp = n8; jp < n_others; ++jp) {
+            const int j = jp + (jp >= i ? 1 : 0);
+            const float4 q = tpos[j];
+            const float d = norm1d<NORM>(__fsub_rn(q.x, px), __fsub_rn(q.y, py), __fsub_rn(q.z, pz));
+            topk_insert<KMAX>(d, j, nd, nj);
+            out.pair_hit |= d <= P.thr_pair;
+            res = __dadd_rn(res, fabs(__dsub_rn((double)d, P.d_star)));
+        }
+        out.form_sum = res;
+        out.form_n = n_others;
+        return;
+    }
+
+    // general path: some drones are parked (or this one is) -> compact on the fly
+    const int n_f = alive_i ? n_alive_env - 1 : 0;
+    const int n8 = n_f >= 8 ? (n_f & ~7) : 0;
+    double r[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) r[u] = 0.0;
+    double res = 0.0;
+    bool tree_done = false;
+    int cnt = 0;
+    for (int jp = 0; jp < n_others; ++jp) {
+        const int j = jp + (jp >= i ? 1 : 0);
+        const float4 q = tpos[j];
+        const float d = norm1d<NORM>(__fsub_rn(q.x, px), __fsub_rn(q.y, py), __fsub_rn(q.z, pz));
+        topk_insert<KMAX>(d, j, nd, nj);
+        if (alive_i && q.w != 0.0f) {
+            out.pair_hit |= d <= P.thr_pair;
+            const double err = fabs(__dsub_rn((double)d, P.d_star));
+            if (cnt < n8) {
+                const int lane8 = cnt & 7;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) r[u] = __dadd_rn(r[u], lane8 == u ? err : 0.0);
+            } else {
+                if (!tree_done && n8 > 0) {
+                    res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                                    __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+                }
+                tree_done = true;
+                res = __dadd_rn(res, err);
+            }
+            ++cnt;
+        }
+    }
+    if (!tree_done && n8 > 0)
+        res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                        __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    out.form_sum = res;
+    out.form_n = n_f;
+}
+
+// observation row -> this lane's row of the staging tile:  _build_obs (:226-243)
+template <int KMAX, int SMAX, int KIND>
+__device__ __forceinline__ void stage_obs_row(const DevParams& P, float* __restrict__ row,
+                                              const float4* __restrict__ tpos, const float4* __restrict__ tobs,
+                                              float px, float py, float pz, float vx, float vy, float vz, float gx,
+                                              float gy, float gz, const float (&nd)[KMAX], const int (&nj)[KMAX],
+                                              const float (&od)[SMAX], const int (&om)[SMAX]) {
+    row[0] = px; row[1] = py; row[2] = pz;
+    row[3] = vx; row[4] = vy; row[5] = vz;
+    row[6] = __fsub_rn(gx, px); row[7] = __fsub_rn(gy, py); row[8] = __fsub_rn(gz, pz);
+    int off = 9;
+    if (KIND == SWARM_KIND_SWARM) {
+#pragma unroll
+        for (int q = 0; q < KMAX; ++q) {
+            if (q < P.K) {
+                float rx = 0.f, ry = 0.f, rz = 0.f, d = 0.f;
+                if (nj[q] >= 0) {
+                    const float4 t = tpos[nj[q]];
+                    rx = __fsub_rn(t.x, px); ry = __fsub_rn(t.y, py); rz = __fsub_rn(t.z, pz);
+                    d = nd[q];
+                }
+                row[off + 4 * q + 0] = rx; row[off + 4 * q + 1] = ry;
+                row[off + 4 * q + 2] = rz; row[off + 4 * q + 3] = d;
+            }
+        }
+        off += 4 * P.K;
+    }
+#pragma unroll
+    for (int q = 0; q < SMAX; ++q) {
+        if (q < P.S) {
+            float rx = 0.f, ry = 0.f, rz = 0.f, d = 0.f;
+            if (om[q] >= 0) {
+                const float4 t = tobs[om[q]];
+                rx = __fsub_rn(t.x, px); ry = __fsub_rn(t.y, py); rz = __fsub_rn(t.z, pz);
+                d = od[q];
+            }
+            row[off + 4 * q + 0] = rx; row[off + 4 * q + 1] = ry;
+            row[off + 4 * q + 2] = rz; row[off + 4 * q + 3] = d;
+        }
+    }
+}
+
+// staged rows -> obs[base_agent .. base_agent + n_rows) as one contiguous stream
+__device__ __forceinline__ void flush_stage(const DevParams& P, const float* __restrict__ stage, long long base_agent,
+                                            int n_rows, int lane) {
+    const int total = n_rows * P.D;
+    float* dst = P.obs + base_agent * P.D;
+    if (((base_agent & 3) == 0) && ((total & 3) == 0)) {  // D = 1 (mod 4): 16-byte aligned iff base % 4 == 0
+        const float4* s4 = reinterpret_cast<const float4*>(stage);
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        for (int idx = lane; idx < (total >> 2); idx += 32) __stcs(d4 + idx, s4[idx]);
+    } else {
+        for (int idx = lane; idx < total; idx += 32) __stcs(dst + idx, stage[idx]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// the env kernel (step / reset / observe)
+// ------------------------------------------------------------------------------------------
+template <int KMAX, int SMAX, int NORM, int KIND>
+__global__ void __launch_bounds__(kThreadsPerCta) swarm_env_kernel(const DevParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    unsigned char* wb = smem_raw + (size_t)warp * P.smem_per_warp;
+    float4* tab_pos = reinterpret_cast<float4*>(wb);
+    float4* tab_vel = tab_pos + P.n_tab;
+    float4* tab_goal = tab_vel + P.n_tab;
+    float4* tab_obst = tab_goal + P.G;
+    float* stage = reinterpret_cast<float*>(tab_obst + P.G * P.m_pad);
+
+    const int N = P.N, M = P.M, G = P.G, D = P.D, nslots = P.nslots;
+    const bool small_n = N <= 32;
+    const int e_l = small_n ? lane / N : 0;      // env-local index of this lane
+    const int i_base = small_n ? lane - e_l * N : lane;
+    const unsigned env_lanes =
+        small_n ? (e_l < G ? (N == 32 ? FULL_MASK : (((1u << N) - 1u) << (e_l * N))) : 0u) : FULL_MASK;
+
+    // per-lane statistics (flushed once per warp at the end)
+    unsigned st_eps = 0, st_succ = 0, st_col = 0, st_to = 0, st_len = 0, st_asteps = 0, st_esteps = 0;
+    double st_ret = 0.0;
+
+    const int warps_total = gridDim.x * kWarpsPerCta;
+    for (int grp = blockIdx.x * kWarpsPerCta + warp; grp < P.n_groups; grp += warps_total) {
+        const int env0 = P.env_begin + grp * G;
+        const int n_env = min(G, P.env_begin + P.env_count - env0);
+        const bool lane_env_ok = e_l < n_env;
+        const int env = env0 + (lane_env_ok ? e_l : 0);
+        const float4* tpos = tab_pos + e_l * N;          // this lane's env tables
+        const float4* tobs = tab_obst + e_l * P.m_pad;
+
+        __syncwarp();  // previous group's shared-memory reads are done
+        // ---- per-env tables: goal, obstacles
+        if (lane < n_env) tab_goal[lane] = P.goal4[env0 + lane];
+        for (int idx = lane; idx < n_env * M; idx += 32) {
+            const int el = idx / M, m = idx - el * M;
+            tab_obst[el * P.m_pad + m] = P.obst4[(long long)(env0 + el) * M + m];
+        }
+        float4 g4 = lane_env_ok ? P.goal4[env] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float gx = g4.x, gy = g4.y, gz = g4.z;
+        const int sc = lane_env_ok ? P.step_count[env] : 0;
+
+        unsigned reset_envs = 0;  // bit el: env el of this group is (re)drawn in this launch
+
+        if (P.mode == kModeStep) {
+            // =========================== phase A: integrate (:98-118) ===========================
+            int n_alive_env = 0;
+            for (int slot = 0; slot < nslots; ++slot) {
+                const int i = slot * 32 + i_base;
+                const bool ok = lane_env_ok && i < N;
+                bool alive = false;
+                if (ok) {
+                    const long long a = (long long)env * N + i;
+                    float4 p = P.pos4[a];
+                    float4 v = P.vel4[a];
+                    alive = KIND == SWARM_KIND_SINGLE ? true : (p.w != 0.0f);
+                    // prev distance (:98-101)
+                    const float prev_d = norm1d<NORM>(__fsub_rn(gx, p.x), __fsub_rn(gy, p.y), __fsub_rn(gz, p.z));
+                    if (alive) {
+                        const float ax = clipf(P.actions[a * 3 + 0], -1.0f, 1.0f);
+                        const float ay = clipf(P.actions[a * 3 + 1], -1.0f, 1.0f);
+                        const float az = clipf(P.actions[a * 3 + 2], -1.0f, 1.0f);
+                        v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(ax, P.amax), P.dt));
+                        v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(ay, P.amax), P.dt));
+                        v.z = __fadd_rn(v.z, __fmul_rn(__fmul_rn(az, P.amax), P.dt));
+                        const float speed = norm1d<NORM>(v.x, v.y, v.z);  // _clip_speed (:179-183)
+                        if (!(speed <= P.vmax || speed < P.eps_speed)) {
+                            v.x = __fmul_rn(__fdiv_rn(v.x, speed), P.vmax);
+                            v.y = __fmul_rn(__fdiv_rn(v.y, speed), P.vmax);
+                            v.z = __fmul_rn(__fdiv_rn(v.z, speed), P.vmax);
+                        }
+                        p.x = __fadd_rn(p.x, __fmul_rn(v.x, P.dt));
+                        p.y = __fadd_rn(p.y, __fmul_rn(v.y, P.dt));
+                        p.z = __fadd_rn(p.z, __fmul_rn(v.z, P.dt));
+                    }
+                    // wall clip for ALL drones (:113-117); velocity is not zeroed at the wall
+                    p.x = clipf(p.x, -P.bound, P.bound);
+                    p.y = clipf(p.y, -P.bound, P.bound);
+                    p.z = clipf(p.z, -P.bound, P.bound);
+                    p.w = alive ? 1.0f : 0.0f;
+                    v.w = prev_d;
+                    tab_pos[e_l * N + i] = p;
+                    tab_vel[e_l * N + i] = v;
+                }
+                n_alive_env += __popc(__ballot_sync(FULL_MASK, ok && alive) & env_lanes);
+            }
+            __syncwarp();
+
+            // ================ phase B: distances, reward, obs rows (:120-162) ================
+            unsigned m_alive = 0, m_done = 0;  // bit = slot
+            float rew_sum = 0.0f;
+            bool any_col = false;
+            int n_cont = 0;
+            for (int slot = 0; slot < nslots; ++slot) {
+                const int i = slot * 32 + i_base;
+                const bool ok = lane_env_ok && i < N;
+                bool alive = false, reached = false, collided = false;
+                float rew32 = 0.0f;
+                if (ok) {
+                    const float4 p = tpos[i];
+                    const float4 v = tab_vel[e_l * N + i];
+                    alive = p.w != 0.0f;
+                    const float curr_d = norm1d<NORM>(__fsub_rn(gx, p.x), __fsub_rn(gy, p.y), __fsub_rn(gz, p.z));
+                    float nd[KMAX]; int nj[KMAX]; float od[SMAX]; int om[SMAX];
+                    ScanOut so;
+                    scan_drone<KMAX, SMAX, NORM, KIND, true>(P, tpos, tobs, i, p.x, p.y, p.z, alive, n_alive_env, nd,
+                                                             nj, od, om, so);
+                    reached = alive && curr_d <= P.thr_goal;           // :124-127 (double compare)
+                    collided = alive && (so.obst_hit || so.pair_hit);   // :128
+                    double reward = 0.0;
+                    if (alive) {
+                        const double progress = __dmul_rn(__dsub_rn((double)v.w, (double)curr_d), P.k_p);  // :142
+                        if (KIND == SWARM_KIND_SWARM) {
+                            double pen = 0.0;  // :210-224
+                            if (so.form_n > 0) pen = __dmul_rn(P.neg_k_f, __ddiv_rn(so.form_sum, (double)so.form_n));
+                            reward = __dadd_rn(progress, pen);  // :143
+                        } else {
+                            reward = progress;
+                        }
+                        if (reached) reward = __dadd_rn(reward, P.r_goal);   // :144-145
+                        if (collided) reward = __dadd_rn(reward, P.r_col);   // :146-147
+                    }
+                    rew32 = __double2float_rn(reward);
+                    const long long a = (long long)env * N + i;
+                    P.reward[a] = rew32;
+                    if (P.reward64) P.reward64[a] = reward;
+                    P.dist[a] = curr_d;
+                    P.reached[a] = reached ? 1 : 0;
+                    P.collision[a] = collided ? 1 : 0;
+                    stage_obs_row<KMAX, SMAX, KIND>(P, stage + lane * D, tpos, tobs, p.x, p.y, p.z, v.x, v.y, v.z, gx,
+                                                    gy, gz, nd, nj, od, om);
+                }
+                __syncwarp();
+                {
+                    const int n_rows = small_n ? n_env * N : min(32, N - slot * 32);
+                    const long long base = (long long)env0 * N + slot * 32;
+                    flush_stage(P, stage, base, n_rows, lane);
+                }
+                if (nslots > 1) __syncwarp();
+                const bool done_agent = reached || collided;
+                m_alive |= (alive ? 1u : 0u) << slot;
+                m_done |= (done_agent ? 1u : 0u) << slot;
+                any_col |= (__ballot_sync(FULL_MASK, collided) & env_lanes) != 0;
+                n_cont += __popc(__ballot_sync(FULL_MASK, alive && !done_agent) & env_lanes);
+                // deterministic per-env reward sum (segmented tree over the env's lanes)
+                float x = rew32;
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const float t = __shfl_down_sync(FULL_MASK, x, off);
+                    if (small_n ? (i_base + off < N) : true) x = __fadd_rn(x, t);
+                }
+                rew_sum = __fadd_rn(rew_sum, x);  // meaningful on the env's first lane
+            }
+
+            // ====================== env-level flags (:137-138, :164-172) ======================
+            const bool env_active = KIND == SWARM_KIND_SINGLE ? true : n_alive_env > 0;
+            const int sc_new = env_active ? sc + 1 : sc;
+            const bool time_limit = env_active && sc_new >= P.max_steps;
+            bool all_term, all_trunc, ep_over;
+            if (KIND == SWARM_KIND_SWARM) {
+                const bool all_reached = n_cont == 0 && !any_col && !time_limit;
+                const bool episode_done = all_reached || any_col;
+                all_term = env_active ? episode_done : true;  // :94-95 when no agent is left
+                all_trunc = env_active ? (time_limit && !episode_done) : false;
+                ep_over = env_active && (all_term || all_trunc);
+                if (lane_env_ok && i_base == 0 && ep_over) {
+                    st_eps++; st_succ += all_reached ? 1 : 0; st_col += any_col ? 1 : 0; st_to += all_trunc ? 1 : 0;
+                }
+            } else {
+                all_term = (m_done & 1u) != 0;   // single env: terminated (:102)
+                all_trunc = time_limit;          // truncated, not masked by terminated (:103)
+                ep_over = all_term || all_trunc;
+                if (lane_env_ok && ep_over) {
+                    st_eps++; st_to += (all_trunc && !all_term) ? 1 : 0;
+                }
+            }
+            const bool cont_ok = !time_limit && !any_col;
+            for (int slot = 0; slot < nslots; ++slot) {
+                const int i = slot * 32 + i_base;
+                if (!(lane_env_ok && i < N)) continue;
+                const bool alive = (m_alive >> slot) & 1u, done_agent = (m_done >> slot) & 1u;
+                const long long a = (long long)env * N + i;
+                bool valid, alive_next;
+                if (KIND == SWARM_KIND_SWARM) {
+                    P.terminated[a] = (alive && done_agent) ? 1 : 0;                 // :150-151
+                    P.truncated[a] = (alive && time_limit && !done_agent) ? 1 : 0;   // :152
+                    valid = alive && !done_agent && cont_ok;                         // :154
+                    alive_next = ep_over ? false : valid;                            // :169-172
+                } else {
+                    P.terminated[a] = all_term ? 1 : 0;
+                    P.truncated[a] = all_trunc ? 1 : 0;
+                    valid = true;
+                    alive_next = true;
+                }
+                P.obs_valid[a] = valid ? 1 : 0;
+                float4 p = tab_pos[e_l * N + i];
+                float4 v = tab_vel[e_l * N + i];
+                p.w = alive_next ? 1.0f : 0.0f;
+                v.w = 0.0f;
+                tab_pos[e_l * N + i] = p;  // (reset / global_state read the tables)
+                P.pos4[a] = p;
+                P.vel4[a] = v;
+            }
+            const bool need_reset = P.auto_reset && (ep_over || !env_active);
+            if (lane_env_ok && i_base == 0) {
+                st_esteps += env_active ? 1 : 0;
+                st_asteps += n_alive_env;
+                P.all_term[env] = all_term ? 1 : 0;
+                P.all_trunc[env] = all_trunc ? 1 : 0;
+                const float ret = __fadd_rn(P.ep_return[env], rew_sum);
+                if (ep_over) { st_len += sc_new; st_ret += (double)ret; }
+                if (P.episode_return) P.episode_return[env] = ep_over ? ret : 0.0f;
+                if (P.episode_length) P.episode_length[env] = ep_over ? sc_new : 0;
+                if (!need_reset) {
+                    P.step_count[env] = sc_new;
+                    P.ep_return[env] = ep_over ? 0.0f : ret;
+                }
+            }
+            reset_envs = __ballot_sync(FULL_MASK, lane_env_ok && i_base == 0 && need_reset);
+            // lane of env-local index el is el * N  ->  compress to one bit per env
+            if (small_n) {
+                unsigned packed = 0;
+                for (int el = 0; el < n_env; ++el) packed |= ((reset_envs >> (el * N)) & 1u) << el;
+                reset_envs = packed;
+            } else {
+                reset_envs = reset_envs & 1u;
+            }
+        } else {
+            // ============ reset / observe: tables straight from the state buffers ============
+            for (int slot = 0; slot < nslots; ++slot) {
+                const int i = slot * 32 + i_base;
+                if (lane_env_ok && i < N) {
+                    const long long a = (long long)env * N + i;
+                    tab_pos[e_l * N + i] = P.pos4[a];
+                    tab_vel[e_l * N + i] = P.vel4[a];
+                }
+            }
+            if (P.mode == kModeReset) {
+                const bool want = lane < n_env && (P.env_mask == nullptr || P.env_mask[env0 + lane] != 0);
+                reset_envs = __ballot_sync(FULL_MASK, want);
+            }
+        }
+        __syncwarp();
+
+        // ================================ reset (:65-80) ================================
+        if (reset_envs) {
+            for (int el = 0; el < n_env; ++el) {
+                if (!((reset_envs >> el) & 1u)) continue;
+                const int renv = env0 + el;
+                const unsigned long long sh = P.rng[(long long)renv * 4 + 0], sl = P.rng[(long long)renv * 4 + 1];
+                const unsigned long long ih = P.rng[(long long)renv * 4 + 2], il = P.rng[(long long)renv * 4 + 3];
+                for (int k = lane; k < P.n_draws; k += 32) {
+                    unsigned long long oh, ol;
+                    pcg_jump(P.jump[k + 1], sh, sl, ih, il, oh, ol);
+                    const float val = pcg_uniform_f32(oh, ol, P.rng_lo, P.rng_range);
+                    // draw order: positions (N,3) -> goal (3,) -> obstacles (M,3)
+                    if (k < 3 * N) {
+                        reinterpret_cast<float*>(tab_pos + el * N + k / 3)[k % 3] = val;
+                    } else if (k < 3 * N + 3) {
+                        reinterpret_cast<float*>(tab_goal + el)[k - 3 * N] = val;
+                    } else {
+                        const int kk = k - 3 * N - 3;
+                        reinterpret_cast<float*>(tab_obst + el * P.m_pad + kk / 3)[kk % 3] = val;
+                    }
+                }
+                for (int k = lane; k < N; k += 32) {
+                    reinterpret_cast<float*>(tab_pos + el * N + k)[3] = 1.0f;
+                    tab_vel[el * N + k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (lane == 0) {
+                    unsigned long long oh, ol;
+                    pcg_jump(P.jump[P.n_draws], sh, sl, ih, il, oh, ol);
+                    P.rng[(long long)renv * 4 + 0] = oh;
+                    P.rng[(long long)renv * 4 + 1] = ol;
+                    P.step_count[renv] = 0;
+                    P.ep_return[renv] = 0.0f;
+                    reinterpret_cast<float*>(tab_goal + el)[3] = 0.0f;
+                }
+                for (int k = lane; k < M; k += 32) reinterpret_cast<float*>(tab_obst + el * P.m_pad + k)[3] = 0.0f;
+            }
+            __syncwarp();
+            // new goal / obstacles back to the state buffers
+            if (lane < n_env && ((reset_envs >> lane) & 1u)) P.goal4[env0 + lane] = tab_goal[lane];
+            for (int idx = lane; idx < n_env * M; idx += 32) {
+                const int el = idx / M, m = idx - el * M;
+                if ((reset_envs >> el) & 1u) P.obst4[(long long)(env0 + el) * M + m] = tab_obst[el * P.m_pad + m];
+            }
+            if (lane_env_ok) { g4 = tab_goal[e_l]; gx = g4.x; gy = g4.y; gz = g4.z; }
+        }
+
+        // =========== observe pass: reset()'s obs / infos (:82-89), or swarm_observe ===========
+        const unsigned observe_envs = P.mode == kModeObserve ? FULL_MASK : reset_envs;
+        if (observe_envs) {
+            const bool mine = lane_env_ok && ((observe_envs >> e_l) & 1u);
+            const bool fresh = lane_env_ok && ((reset_envs >> e_l) & 1u);
+            for (int slot = 0; slot < nslots; ++slot) {
+                const int i = slot * 32 + i_base;
+                const bool ok = mine && i < N;
+                if (ok) {
+                    const float4 p = tpos[i];
+                    const float4 v = tab_vel[e_l * N + i];
+                    float nd[KMAX]; int nj[KMAX]; float od[SMAX]; int om[SMAX];
+                    ScanOut so;
+                    scan_drone<KMAX, SMAX, NORM, KIND, false>(P, tpos, tobs, i, p.x, p.y, p.z, true, N, nd, nj, od, om,
+                                                              so);
+                    const long long a = (long long)env * N + i;
+                    P.dist[a] = norm1d<NORM>(__fsub_rn(gx, p.x), __fsub_rn(gy, p.y), __fsub_rn(gz, p.z));
+                    P.obs_valid[a] = KIND == SWARM_KIND_SINGLE ? 1 : (p.w != 0.0f ? 1 : 0);
+                    if (fresh) {
+                        P.pos4[a] = p;
+                        P.vel4[a] = make_float4(v.x, v.y, v.z, 0.0f);
+                    }
+                    if (P.mode != kModeStep) {
+                        P.reward[a] = 0.0f;
+                        if (P.reward64) P.reward64[a] = 0.0;
+                        P.terminated[a] = 0; P.truncated[a] = 0; P.reached[a] = 0; P.collision[a] = 0;
+                    }
+                    stage_obs_row<KMAX, SMAX, KIND>(P, stage + lane * D, tpos, tobs, p.x, p.y, p.z, v.x, v.y, v.z, gx,
+                                                    gy, gz, nd, nj, od, om);
+                }
+                __syncwarp();
+                // single-slot groups restage only the observed envs' rows; the other rows of the tile
+                // still hold this step's rows, so the whole tile can be flushed again.  In reset mode
+                // with a partial mask those other rows are stale -> flush per env there.
+                if (small_n) {
+                    if (P.mode == kModeStep || observe_envs == FULL_MASK ||
+                        (reset_envs & ((1u << n_env) - 1u)) == ((1u << n_env) - 1u)) {
+                        flush_stage(P, stage, (long long)env0 * N, n_env * N, lane);
+                    } else {
+                        for (int el = 0; el < n_env; ++el)
+                            if ((observe_envs >> el) & 1u)
+                                flush_stage(P, stage + el * N * D, (long long)(env0 + el) * N, N, lane);
+                    }
+                } else if (mine) {
+                    flush_stage(P, stage, (long long)env0 * N + slot * 32, min(32, N - slot * 32), lane);
+                }
+                if (nslots > 1) __syncwarp();
+            }
+            if (P.mode != kModeStep && lane < n_env && ((observe_envs >> lane) & 1u)) {
+                P.all_term[env0 + lane] = 0;
+                P.all_trunc[env0 + lane] = 0;
+                if (P.episode_return) P.episode_return[env0 + lane] = 0.0f;
+                if (P.episode_length) P.episode_length[env0 + lane] = 0;
+            }
+        }
+
+        // ======================= global_state (:293-302), optional =======================
+        if (P.gs && (P.mode != kModeReset || reset_envs)) {
+            __syncwarp();
+            for (int el = 0; el < n_env; ++el) {
+                if (P.mode == kModeReset && !((reset_envs >> el) & 1u)) continue;
+                float* row = P.gs + (long long)(env0 + el) * P.R;
+                const float4 gg = tab_goal[el];
+                for (int r = lane; r < P.R; r += 32) {
+                    float val;
+                    if (r < 3 * N) val = comp(tab_pos[el * N + r / 3], r % 3);
+                    else if (r < 6 * N) val = comp(tab_vel[el * N + (r - 3 * N) / 3], (r - 3 * N) % 3);
+                    else val = comp(gg, r - 6 * N);
+                    __stcs(row + r, val);
+                }
+            }
+        }
+    }
+
+    // ---- statistics: one atomic per warp per counter
+    if (P.stats && P.mode == kModeStep) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            st_eps += __shfl_xor_sync(FULL_MASK, st_eps, off);
+            st_succ += __shfl_xor_sync(FULL_MASK, st_succ, off);
+            st_col += __shfl_xor_sync(FULL_MASK, st_col, off);
+            st_to += __shfl_xor_sync(FULL_MASK, st_to, off);
+            st_len += __shfl_xor_sync(FULL_MASK, st_len, off);
+            st_asteps += __shfl_xor_sync(FULL_MASK, st_asteps, off);
+            st_esteps += __shfl_xor_sync(FULL_MASK, st_esteps, off);
+            st_ret += __shfl_xor_sync(FULL_MASK, st_ret, off);
+        }
+        if (lane == 0) {
+            if (st_eps) {
+                atomicAdd(P.stats + SWARM_STAT_EPISODES, (unsigned long long)st_eps);
+                atomicAdd(P.stats + SWARM_STAT_SUCCESS, (unsigned long long)st_succ);
+                atomicAdd(P.stats + SWARM_STAT_COLLISION, (unsigned long long)st_col);
+                atomicAdd(P.stats + SWARM_STAT_TIMEOUT, (unsigned long long)st_to);
+                atomicAdd(P.stats + SWARM_STAT_LENGTH_SUM, (unsigned long long)st_len);
+                atomicAdd(reinterpret_cast<double*>(P.stats + SWARM_STAT_RETURN_SUM), st_ret);
+            }
+            atomicAdd(P.stats + SWARM_STAT_AGENT_STEPS, (unsigned long long)st_asteps);
+            atomicAdd(P.stats + SWARM_STAT_ENV_STEPS, (unsigned long long)st_esteps);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// np.random.default_rng(seed): SeedSequence(seed).generate_state(4, uint64) -> PCG64 seeding
+// (numpy/random/bit_generator.pyx, _pcg64.pyx, src/pcg64/pcg64.h)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ss_hashmix(unsigned value, unsigned& hc) {
+    value ^= hc;
+    hc *= 0x931e8875u;
+    value *= hc;
+    value ^= value >> 16;
+    return value;
+}
+__device__ __forceinline__ unsigned ss_mix(unsigned x, unsigned y) {
+    unsigned r = 0xca01f9ddu * x - 0x4973f715u * y;
+    r ^= r >> 16;
+    return r;
+}
+
+__global__ void swarm_seed_kernel(const DevParams P) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= P.E) return;
+    if (P.env_mask && !P.env_mask[e]) return;
+    const unsigned long long seed = P.seeds[e];
+    const unsigned ent0 = (unsigned)(seed & 0xffffffffull), ent1 = (unsigned)(seed >> 32);
+    const int n_ent = ent1 != 0 ? 2 : 1;
+    unsigned pool[4];
+    unsigned hc = 0x43b0d7e5u;
+    pool[0] = ss_hashmix(ent0, hc);
+    pool[1] = ss_hashmix(n_ent > 1 ? ent1 : 0u, hc);
+    pool[2] = ss_hashmix(0u, hc);
+    pool[3] = ss_hashmix(0u, hc);
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int d = 0; d < 4; ++d)
+            if (s != d) pool[d] = ss_mix(pool[d], ss_hashmix(pool[s], hc));
+    unsigned w[8];
+    hc = 0x8b51f9ddu;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        unsigned v = pool[k & 3];
+        v ^= hc;
+        hc *= 0x58f38dedu;
+        v *= hc;
+        v ^= v >> 16;
+        w[k] = v;
+    }
+    const unsigned long long s_hi = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32);
+    const unsigned long long s_lo = (unsigned long long)w[2] | ((unsigned long long)w[3] << 32);
+    const unsigned long long q_hi = (unsigned long long)w[4] | ((unsigned long long)w[5] << 32);
+    const unsigned long long q_lo = (unsigned long long)w[6] | ((unsigned long long)w[7] << 32);
+    // pcg_setseq_128_srandom_r: inc = (initseq << 1) | 1; state = 0; step; state += initstate; step
+    const unsigned long long inc_hi = (q_hi << 1) | (q_lo >> 63), inc_lo = (q_lo << 1) | 1ull;
+    const unsigned long long m_hi = 2549297995355413924ull, m_lo = 4865540595714422341ull;
+    unsigned long long st_hi = inc_hi, st_lo = inc_lo;  // 0 * mult + inc
+    st_lo += s_lo;
+    st_hi += s_hi + (st_lo < s_lo ? 1ull : 0ull);
+    unsigned long long ph, pl;
+    mul128(st_hi, st_lo, m_hi, m_lo, ph, pl);
+    st_lo = pl + inc_lo;
+    st_hi = ph + inc_hi + (st_lo < pl ? 1ull : 0ull);
+    P.rng[(long long)e * 4 + 0] = st_hi;
+    P.rng[(long long)e * 4 + 1] = st_lo;
+    P.rng[(long long)e * 4 + 2] = inc_hi;
+    P.rng[(long long)e * 4 + 3] = inc_lo;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side dispatch over the instantiated kernels
+// ------------------------------------------------------------------------------------------
+typedef void (*EnvKernel)(const DevParams);
+
+template <int KMAX, int SMAX>
+static EnvKernel pick_kernel(int norm_mode, int env_kind) {
+    if (env_kind == SWARM_KIND_SWARM)
+        return norm_mode == 0 ? swarm_env_kernel<KMAX, SMAX, 0, SWARM_KIND_SWARM>
+                              : swarm_env_kernel<KMAX, SMAX, 1, SWARM_KIND_SWARM>;
+    return norm_mode == 0 ? swarm_env_kernel<1, SMAX, 0, SWARM_KIND_SINGLE>
+                          : swarm_env_kernel<1, SMAX, 1, SWARM_KIND_SINGLE>;
+}
+
+static EnvKernel resolve(int kmax, int smax, int norm_mode, int env_kind) {
+    if (kmax <= 3 && smax <= 4) return pick_kernel<3, 4>(norm_mode, env_kind);
+    return pick_kernel<SWARM_MAX_NEIGHBOR_K, SWARM_MAX_SENSED>(norm_mode, env_kind);
+}
+
+cudaError_t launch_env_kernel(const DevParams& p, int kmax, int smax, int norm_mode, int env_kind, int grid,
+                              size_t smem_bytes, cudaStream_t stream) {
+    EnvKernel k = resolve(kmax, smax, norm_mode, env_kind);
+    cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (err != cudaSuccess) return err;
+    k<<<grid, kThreadsPerCta, smem_bytes, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t env_kernel_occupancy(int kmax, int smax, int norm_mode, int env_kind, size_t smem_bytes,
+                                 int* blocks_per_sm) {
+    EnvKernel k = resolve(kmax, smax, norm_mode, env_kind);
+    cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (err != cudaSuccess) return err;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, kThreadsPerCta, smem_bytes);
+}
+
+cudaError_t launch_seed_kernel(const DevParams& p, cudaStream_t stream) {
+    const int threads = 128;
+    swarm_seed_kernel<<<(p.E + threads - 1) / threads, threads, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace swarm

@@ -1,0 +1,275 @@
+"""SwarmEngine -- batched, device-resident drone-swarm env step (host side of the C ABI).
+
+One engine = E independent instances of the reference's `DroneSwarmEnv` (kind="swarm",
+reference src/swarm_marl/envs/drone_swarm_env.py:17) or `SingleDroneEnv` (kind="single",
+src/swarm_marl/envs/single_drone_env.py:12) living on one GPU.  PyTorch is used only to own
+device memory and streams; every computation is a hand-written sm_100a kernel behind
+include/swarm_b200.h.  There is no fallback path: without the built library this module
+raises on import of the binding.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any
+
+import numpy as np
+import torch
+
+from . import _abi
+from .config import DroneEnvConfig
+
+
+class SwarmEngine:
+    """E env instances stepped by one fused kernel launch.
+
+    Tensors (all on `device`, leading env axis):
+      pos4 [E,N,4] f32 (x,y,z,alive)   vel4 [E,N,4]   goal4 [E,4]   obst4 [E,M,4]
+      step_count [E] i32   rng [E,4] i64 (numpy PCG64 words)   ep_return [E] f32
+      obs [E,N,D] f32   reward [E,N] f32   dist [E,N] f32
+      terminated / truncated / reached / collision / obs_valid [E,N] u8
+      all_terminated / all_truncated [E] u8   global_state [E,6N+3] f32
+      episode_return [E] f32 / episode_length [E] i32 (episode that ended on this step)
+    """
+
+    def __init__(self, num_envs: int, config: dict[str, Any] | None = None, kind: str = "swarm",
+                 device: str | torch.device = "cuda", global_state: bool = True, reward64: bool = False,
+                 norm_mode: int = 0):
+        if kind not in ("swarm", "single"):
+            raise ValueError(f"kind must be 'swarm' or 'single', got {kind!r}")
+        self._lib = _abi.load()
+        raw = dict(config or {})
+        self.kind = kind
+        # drone_swarm_env.py:32-34: num_drones is popped, the rest goes through DroneEnvConfig.from_dict
+        self.num_drones = int(raw.pop("num_drones", 3)) if kind == "swarm" else 1
+        raw.pop("num_drones", None)
+        self.cfg = DroneEnvConfig.from_dict(raw)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("SwarmEngine runs on CUDA devices only (there is no CPU path)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.E, self.N, self.M = int(num_envs), self.num_drones, int(self.cfg.num_obstacles)
+        self.K = int(self.cfg.neighbor_k) if kind == "swarm" else 0
+        self.S = int(self.cfg.sensed_obstacles)
+
+        c = _abi.SwarmConfig()
+        c.abi_version = _abi.ABI_VERSION
+        c.env_kind = _abi.KIND_SWARM if kind == "swarm" else _abi.KIND_SINGLE
+        c.num_envs, c.num_drones, c.num_obstacles = self.E, self.N, self.M
+        c.sensed_obstacles, c.neighbor_k = self.S, int(self.cfg.neighbor_k)
+        c.max_steps, c.norm_mode, c.device = int(self.cfg.max_steps), int(norm_mode), self.device.index
+        for name in _abi._DOUBLES:
+            setattr(c, name, float(getattr(self.cfg, name)))
+        self._c = c
+        sz = _abi.SwarmSizes()
+        _abi.check(self._lib.swarm_query_sizes(C.byref(c), C.byref(sz)), "swarm_query_sizes")
+        self.D, self.R = int(sz.obs_dim), int(sz.state_dim)
+        self._handle = C.c_void_p()
+        _abi.check(self._lib.swarm_create(C.byref(c), C.byref(self._handle)), "swarm_create")
+
+        E, N, M, D, R = self.E, self.N, self.M, self.D, self.R
+        dev = self.device
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)  # noqa: E731
+        self.pos4 = z((E, N, 4), torch.float32)
+        self.vel4 = z((E, N, 4), torch.float32)
+        self.goal4 = z((E, 4), torch.float32)
+        self._obst4_storage = z((E, max(M, 1), 4), torch.float32)  # never empty, even when M == 0
+        self.obst4 = self._obst4_storage[:, :M]
+        self.step_count = z((E,), torch.int32)
+        self.rng = z((E, 4), torch.int64)
+        self.ep_return = z((E,), torch.float32)
+        self.obs = z((E, N, D), torch.float32)
+        self.reward = z((E, N), torch.float32)
+        self.reward64 = z((E, N), torch.float64) if reward64 else None
+        self.dist = z((E, N), torch.float32)
+        self.terminated = z((E, N), torch.uint8)
+        self.truncated = z((E, N), torch.uint8)
+        self.reached = z((E, N), torch.uint8)
+        self.collision = z((E, N), torch.uint8)
+        self.obs_valid = z((E, N), torch.uint8)
+        self.all_terminated = z((E,), torch.uint8)
+        self.all_truncated = z((E,), torch.uint8)
+        self.global_state = z((E, R), torch.float32) if global_state else None
+        self.episode_return = z((E,), torch.float32)
+        self.episode_length = z((E,), torch.int32)
+        self.stats_words = z((len(_abi.STAT_NAMES),), torch.int64)
+        self.pos4[..., 3] = 1.0
+        self._actions_dev = None
+        self._bufs = self._make_buffers()
+        self._host = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _make_buffers(self) -> _abi.SwarmBuffers:
+        b = _abi.SwarmBuffers()
+        for name in _abi.BUFFER_FIELDS:
+            t = self._obst4_storage if name == "obst4" else (
+                self.stats_words if name == "stats" else getattr(self, name))
+            setattr(b, name, None if t is None else t.data_ptr())
+        return b
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def close(self):
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            self._lib.swarm_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ reference-shaped views
+    @property
+    def positions(self) -> torch.Tensor:   # DroneSwarmEnv.positions (drone_swarm_env.py:59)
+        return self.pos4[..., :3]
+
+    @property
+    def velocities(self) -> torch.Tensor:  # .velocities (:60)
+        return self.vel4[..., :3]
+
+    @property
+    def goal(self) -> torch.Tensor:        # .goal (:61)
+        return self.goal4[:, :3]
+
+    @property
+    def obstacles(self) -> torch.Tensor:   # .obstacles (:62)
+        return self.obst4[..., :3]
+
+    @property
+    def alive(self) -> torch.Tensor:       # membership in .agents (:39, :169-172)
+        return self.pos4[..., 3] != 0
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.swarm_launch_count(self._handle))
+
+    # ------------------------------------------------------------------ API
+    def seed(self, seeds, env_mask: torch.Tensor | None = None):
+        """`np.random.default_rng(seed)` per env (drone_swarm_env.py:35 / reset(seed=...) :66-67)."""
+        if torch.is_tensor(seeds):
+            s = seeds.to(device=self.device, dtype=torch.int64).contiguous()
+        else:
+            arr = np.ascontiguousarray(np.broadcast_to(np.asarray(seeds, dtype=np.uint64), (self.E,)))
+            s = torch.from_numpy(arr.view(np.int64)).to(self.device)
+        if s.numel() != self.E:
+            raise ValueError(f"need {self.E} seeds, got {s.numel()}")
+        m = self._mask(env_mask)
+        _abi.check(self._lib.swarm_seed(self._handle, C.byref(self._bufs), s.data_ptr(),
+                                        None if m is None else m.data_ptr(), self._stream()), "swarm_seed")
+        self._keep = (s, m)
+
+    def _mask(self, env_mask):
+        if env_mask is None:
+            return None
+        m = torch.as_tensor(env_mask, device=self.device).to(torch.uint8).contiguous()
+        if m.numel() != self.E:
+            raise ValueError(f"env_mask needs {self.E} entries")
+        return m
+
+    def reset(self, env_mask: torch.Tensor | None = None):
+        """`env.reset()` for the masked envs (all when None): drone_swarm_env.py:65-90."""
+        m = self._mask(env_mask)
+        _abi.check(self._lib.swarm_reset(self._handle, C.byref(self._bufs), None if m is None else m.data_ptr(),
+                                         self._stream()), "swarm_reset")
+        self._keep = m
+        return self.obs
+
+    def observe(self):
+        """Recompute obs / dist / global_state from the (externally written) state."""
+        _abi.check(self._lib.swarm_observe(self._handle, C.byref(self._bufs), self._stream()), "swarm_observe")
+        return self.obs
+
+    def step(self, actions: torch.Tensor, auto_reset: bool = True):
+        """`env.step(action_dict)` for every env: drone_swarm_env.py:92-174.
+
+        actions: [E,N,3] float32 CUDA tensor (a drone without an action gets a zero row)."""
+        if not (torch.is_tensor(actions) and actions.is_cuda):
+            raise TypeError("actions must be a CUDA tensor (use step_host for host buffers)")
+        a = actions.to(dtype=torch.float32).contiguous()
+        if a.numel() != self.E * self.N * 3:
+            raise ValueError(f"actions must have shape [{self.E},{self.N},3]")
+        _abi.check(self._lib.swarm_step(self._handle, C.byref(self._bufs), a.data_ptr(), int(auto_reset),
+                                        self._stream()), "swarm_step")
+        self._keep = a
+        return self.obs, self.reward, self.terminated, self.truncated
+
+    def set_state(self, positions=None, velocities=None, goal=None, obstacles=None, alive=None, step_count=None,
+                  observe: bool = True):
+        """State injection (parity runs): arrays shaped like the reference attributes + env axis."""
+        dev = self.device
+        if positions is not None:
+            self.pos4[..., :3] = torch.as_tensor(positions, dtype=torch.float32, device=dev).reshape(self.E, self.N, 3)
+        if velocities is not None:
+            self.vel4[..., :3] = torch.as_tensor(velocities, dtype=torch.float32, device=dev).reshape(self.E, self.N, 3)
+        if goal is not None:
+            self.goal4[:, :3] = torch.as_tensor(goal, dtype=torch.float32, device=dev).reshape(self.E, 3)
+        if obstacles is not None and self.M:
+            self.obst4[..., :3] = torch.as_tensor(obstacles, dtype=torch.float32, device=dev).reshape(self.E, self.M, 3)
+        if alive is not None:
+            self.pos4[..., 3] = torch.as_tensor(alive, device=dev).reshape(self.E, self.N).to(torch.float32)
+        if step_count is not None:
+            self.step_count[:] = torch.as_tensor(step_count, dtype=torch.int32, device=dev)
+        if observe:
+            self.observe()
+
+    # ------------------------------------------------------------------ host-buffer (end-to-end) path
+    def host_buffers(self, with_global_state: bool = True) -> dict[str, np.ndarray]:
+        """Pinned host arrays for `step_host` (allocated once)."""
+        if self._host is None:
+            E, N, D, R = self.E, self.N, self.D, self.R
+            pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()  # noqa: E731
+            h = dict(actions=pin((E, N, 3), torch.float32), obs=pin((E, N, D), torch.float32),
+                     reward=pin((E, N), torch.float32), dist=pin((E, N), torch.float32))
+            for name in ("terminated", "truncated", "reached", "collision", "obs_valid"):
+                h[name] = pin((E, N), torch.uint8)
+            h["all_terminated"] = pin((E,), torch.uint8)
+            h["all_truncated"] = pin((E,), torch.uint8)
+            if with_global_state and self.global_state is not None:
+                h["global_state"] = pin((E, R), torch.float32)
+            self._host = h
+        return self._host
+
+    def step_host(self, actions_host=None, auto_reset: bool = True, outputs: tuple[str, ...] | None = None):
+        """One step through HOST buffers: H2D actions, kernel, D2H outputs (chunk-pipelined in the
+        library).  `actions_host`: [E,N,3] float32 numpy / CPU tensor, or None to use the pinned
+        `host_buffers()['actions']` in place.  Returns the dict of pinned host tensors."""
+        h = self.host_buffers()
+        if actions_host is not None:
+            src = torch.as_tensor(actions_host, dtype=torch.float32).reshape(self.E, self.N, 3)
+            h["actions"].copy_(src)
+        out = _abi.SwarmHostOut()
+        names = outputs if outputs is not None else tuple(n for n in _abi.HOST_OUT_FIELDS if n in h)
+        for name in names:
+            setattr(out, name, h[name].data_ptr())
+        _abi.check(self._lib.swarm_step_host(self._handle, C.byref(self._bufs), h["actions"].data_ptr(),
+                                             C.byref(out), int(auto_reset)), "swarm_step_host")
+        return h
+
+    def host_bytes_per_step(self, outputs: tuple[str, ...] | None = None) -> tuple[int, int]:
+        h = self.host_buffers()
+        names = outputs if outputs is not None else tuple(n for n in _abi.HOST_OUT_FIELDS if n in h)
+        return h["actions"].numel() * 4, sum(h[n].numel() * h[n].element_size() for n in names)
+
+    # ------------------------------------------------------------------ statistics
+    def stats(self) -> dict[str, float]:
+        """Running episode statistics accumulated on the device (one D2H copy of 64 bytes)."""
+        w = self.stats_words.cpu().numpy()
+        out = {n: int(w[i]) for i, n in enumerate(_abi.STAT_NAMES)}
+        out["return_sum"] = float(w[5:6].view(np.float64)[0])
+        return out
+
+    def reset_stats(self):
+        self.stats_words.zero_()
+
+    def algorithmic_bytes_per_agent_step(self) -> float:
+        """unpadded logical bytes one agent-step must move."""
+        N, M, D = self.N, self.M, self.D
+        per_agent = 36 + 24 + 4 * D + 4 + 2 + 6
+        per_env = 12 + 12 * M + 4 + 4 + 2
+        if self.kind == "swarm" and self.global_state is not None:
+            per_agent += 24
+            per_env += 12
+        return per_agent + per_env / N

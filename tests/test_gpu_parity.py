@@ -1,0 +1,222 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against (a) the golden
+fixtures recorded from the unmodified reference and (b) the C oracle on seeded inputs.
+
+Bar (BASELINE.json north_star): fp32 state / obs / reward within 1e-5 relative over 1000
+steps, flags bit-exact up to counted 1-ulp threshold cases.  What is asserted here is
+stronger: state, observations, float64 rewards, distances, flags, global_state and the reset
+draws are BIT-EXACT; the only tolerated difference is the order of exactly tied distances in
+the k-nearest blocks (np.argsort is not stable), which is validated and counted.
+"""
+import numpy as np
+import pytest
+
+import parity_util as pu
+
+pytestmark = pytest.mark.gpu
+
+
+def _backend(*a, **k):
+    from engine_backend import EngineBackend
+    return EngineBackend(*a, **k)
+
+
+@pytest.mark.parametrize("name", pu.golden_names())
+def test_cuda_matches_reference_golden(name):
+    g = pu.load_golden(name)
+    m = g["meta"]
+    b = _backend(len(g["seeds"]), m["config"], kind=m["kind"])
+    assert b.D == m["D"]
+    stats = pu.replay_and_compare(b, g)
+    assert stats["steps"] == m["T"]
+    # float32 reward output == float32(reference float64 reward)
+    b2 = _backend(len(g["seeds"]), m["config"], kind=m["kind"], reward64=False)
+    pu.replay_and_compare(b2, g, reward_dtype=np.float32, steps=200)
+
+
+CASES = [
+    # kind, cfg, E, T, action scale
+    ("swarm", {"num_drones": 8, "num_obstacles": 4}, 4096, 60, 1.5),                      # C2 full size
+    ("swarm", {"num_drones": 16, "num_obstacles": 8}, 2048, 40, 1.5),                     # C3 shape
+    ("swarm", {"num_drones": 32, "num_obstacles": 8}, 1024, 40, 1.0),                     # C4 shape, world 20
+    ("swarm", {"num_drones": 32, "num_obstacles": 8, "world_size": 44.0}, 512, 60, 1.5),  # C4 density-matched
+    ("swarm", {"num_drones": 128, "num_obstacles": 8, "world_size": 70.0}, 64, 12, 1.0),  # C5 shape
+    ("swarm", {"num_drones": 3, "num_obstacles": 0, "max_steps": 30}, 1000, 80, 1.0),     # ragged warp packing
+    ("swarm", {"num_drones": 5, "num_obstacles": 8, "max_steps": 25, "world_size": 24.0}, 777, 60, 1.0),
+    ("swarm", {"num_drones": 12, "num_obstacles": 3, "neighbor_k": 5, "sensed_obstacles": 2}, 333, 40, 1.2),
+    ("swarm", {"num_drones": 20, "num_obstacles": 6, "neighbor_k": 8, "sensed_obstacles": 8}, 100, 40, 1.2),
+    ("swarm", {"num_drones": 40, "num_obstacles": 5, "world_size": 50.0}, 50, 30, 1.2),   # two slots, ragged
+    ("swarm", {"num_drones": 1, "num_obstacles": 2, "max_steps": 20}, 500, 50, 1.0),
+    ("single", {"num_obstacles": 8, "max_steps": 50}, 5000, 120, 1.5),                    # C1 batched
+    ("single", {"num_obstacles": 0, "max_steps": 10}, 33, 30, 1.0),
+]
+
+
+@pytest.mark.parametrize("kind,cfg,E,T,scale", CASES)
+def test_cuda_matches_oracle_seeded(kind, cfg, E, T, scale):
+    import swarm_oracle as so
+    from parity_util import assert_biteq, obs_row_ok_up_to_ties
+
+    b = _backend(E, cfg, kind=kind)
+    o = so.OracleSwarm(E, cfg, kind=kind)
+    seeds = np.arange(1000, 1000 + E, dtype=np.uint64)
+    b.seed(seeds)
+    o.seed(seeds)
+    b.reset()
+    o.reset()
+    rng = np.random.default_rng(42)
+    N = o.N
+    ties = 0
+    for t in range(-1, T):
+        if t >= 0:
+            if t % 3 == 2:  # goal seeking: parks drones, reaches goals
+                d = o.goal[:, None, :] - o.positions
+                d = d / np.maximum(np.linalg.norm(d, axis=2, keepdims=True), 1e-6)
+                act = (d * 1.2 + rng.normal(0, 0.3, size=(E, N, 3))).astype(np.float32)
+            else:
+                act = rng.uniform(-scale, scale, size=(E, N, 3)).astype(np.float32)
+            b.step(act, auto_reset=True)
+            o.step(act, auto_reset=True, num_threads=8)
+        for name in ("positions", "velocities", "goal", "obstacles", "step_count", "reward", "dist", "terminated",
+                     "truncated", "reached", "collision", "obs_valid", "all_terminated", "all_truncated",
+                     "global_state", "active"):
+            assert_biteq(name, getattr(b, name), getattr(o, name), t)
+        valid = o.obs_valid.astype(bool)
+        bo, oo = b.obs, o.obs
+        diff = np.argwhere((pu.bits(bo) != pu.bits(oo)).any(axis=2) & valid)
+        for e, i in diff:
+            assert obs_row_ok_up_to_ties(kind, {**so.DEFAULTS, **cfg}, o.positions[e], o.velocities[e], o.goal[e],
+                                         o.obstacles[e], i, bo[e, i]), f"obs row beyond ties at step {t} env {e} drone {i}"
+            ties += 1
+    print(f"{kind} {cfg}: E={E} T={T} bit-exact; tie rows {ties}")
+
+
+def test_no_auto_reset_and_dead_env_contract():
+    """Without auto-reset an ended swarm episode leaves no active agent; further steps return
+    terminated['__all__'] = True and nothing else (drone_swarm_env.py:94-95)."""
+    import swarm_oracle as so
+    from parity_util import assert_biteq
+
+    cfg = {"num_drones": 4, "num_obstacles": 6, "max_steps": 12, "world_size": 10.0}
+    E = 256
+    b = _backend(E, cfg)
+    o = so.OracleSwarm(E, cfg)
+    seeds = np.arange(E, dtype=np.uint64)
+    for x in (b, o):
+        x.seed(seeds)
+        x.reset()
+    rng = np.random.default_rng(3)
+    for t in range(30):
+        act = rng.uniform(-1, 1, size=(E, 4, 3)).astype(np.float32)
+        b.step(act, auto_reset=False)
+        o.step(act, auto_reset=False)
+        for name in ("positions", "velocities", "step_count", "reward", "terminated", "truncated", "obs_valid",
+                     "all_terminated", "all_truncated", "active"):
+            assert_biteq(name, getattr(b, name), getattr(o, name), t)
+    assert o.all_terminated.all() and not o.active.any()
+    # partial reset by mask, continuing each env's stream
+    mask = (np.arange(E) % 3 == 0).astype(np.uint8)
+    b.reset(mask)
+    o.reset(mask)
+    for name in ("positions", "velocities", "goal", "obstacles", "step_count", "obs_valid", "active", "dist"):
+        assert_biteq(name, getattr(b, name), getattr(o, name), "masked reset")
+    m = mask.astype(bool)
+    assert np.array_equal(pu.bits(b.obs[m]), pu.bits(o.obs[m]))
+
+
+def test_state_injection_and_observe():
+    import swarm_oracle as so
+    from parity_util import assert_biteq
+
+    cfg = {"num_drones": 6, "num_obstacles": 5}
+    E = 128
+    b = _backend(E, cfg)
+    o = so.OracleSwarm(E, cfg)
+    rng = np.random.default_rng(11)
+    o.positions[:] = rng.uniform(-10, 10, o.positions.shape).astype(np.float32)
+    o.velocities[:] = rng.uniform(-2, 2, o.velocities.shape).astype(np.float32)
+    o.goal[:] = rng.uniform(-10, 10, o.goal.shape).astype(np.float32)
+    o.obstacles[:] = rng.uniform(-10, 10, o.obstacles.shape).astype(np.float32)
+    o.active[:] = rng.integers(0, 2, o.active.shape)
+    o.observe()
+    b.eng.set_state(o.positions, o.velocities, o.goal, o.obstacles, alive=o.active)
+    for name in ("obs", "dist", "obs_valid", "global_state"):
+        assert_biteq(name, getattr(b, name), getattr(o, name), "observe")
+
+
+def test_norm_mode_sequential_f32():
+    """norm_mode=1 (BLAS builds whose sdot accumulates in float32) against the oracle's same switch."""
+    import swarm_oracle as so
+    from parity_util import assert_biteq
+
+    cfg = {"num_drones": 8, "num_obstacles": 4}
+    E = 200
+    b = _backend(E, cfg, norm_mode=1)
+    o = so.OracleSwarm(E, cfg, norm_mode=1)
+    seeds = np.arange(E, dtype=np.uint64)
+    for x in (b, o):
+        x.seed(seeds)
+        x.reset()
+    rng = np.random.default_rng(5)
+    for t in range(40):
+        act = rng.uniform(-1.5, 1.5, size=(E, 8, 3)).astype(np.float32)
+        b.step(act)
+        o.step(act, auto_reset=True)
+        for name in ("positions", "velocities", "reward", "terminated", "truncated", "obs_valid", "dist"):
+            assert_biteq(name, getattr(b, name), getattr(o, name), t)
+
+
+def test_step_host_matches_device_step():
+    """The host-buffer (end-to-end) entry point returns what the device-resident step computes."""
+    import torch
+    import swarm_b200
+
+    cfg = {"num_drones": 8, "num_obstacles": 4}
+    E = 4096
+    a = swarm_b200.SwarmEngine(E, cfg, device="cuda:0")
+    b = swarm_b200.SwarmEngine(E, cfg, device="cuda:0")
+    seeds = np.arange(E, dtype=np.uint64)
+    for x in (a, b):
+        x.seed(seeds)
+        x.reset()
+    rng = np.random.default_rng(9)
+    for t in range(25):
+        act = rng.uniform(-1.5, 1.5, size=(E, 8, 3)).astype(np.float32)
+        a.step(torch.from_numpy(act).cuda())
+        h = b.step_host(act)
+        torch.cuda.synchronize()
+        for name in ("obs", "reward", "dist", "terminated", "truncated", "reached", "collision", "obs_valid",
+                     "all_terminated", "all_truncated", "global_state"):
+            assert np.array_equal(pu.bits(h[name].numpy()), pu.bits(getattr(a, name).cpu().numpy())), (name, t)
+
+
+def test_engine_stats_and_episode_outputs():
+    import torch
+    import swarm_b200
+
+    cfg = {"num_drones": 4, "num_obstacles": 8, "max_steps": 15, "world_size": 12.0}
+    E, T = 512, 64
+    eng = swarm_b200.SwarmEngine(E, cfg, device="cuda:0")
+    eng.seed(np.arange(E, dtype=np.uint64))
+    eng.reset()
+    rng = np.random.default_rng(1)
+    eps = 0
+    ret_sum = 0.0
+    len_sum = 0
+    running = np.zeros(E, np.float64)
+    for t in range(T):
+        act = torch.from_numpy(rng.uniform(-1, 1, size=(E, 4, 3)).astype(np.float32)).cuda()
+        eng.step(act)
+        done = (eng.all_terminated | eng.all_truncated).cpu().numpy().astype(bool)
+        running += eng.reward.cpu().numpy().astype(np.float64).sum(axis=1)
+        er = eng.episode_return.cpu().numpy()
+        el = eng.episode_length.cpu().numpy()
+        assert np.all(el[~done] == 0)
+        np.testing.assert_allclose(er[done], running[done], rtol=1e-4, atol=1e-3)
+        eps += int(done.sum())
+        ret_sum += float(er[done].sum())
+        len_sum += int(el[done].sum())
+        running[done] = 0.0
+    st = eng.stats()
+    assert st["episodes"] == eps and st["length_sum"] == len_sum and st["env_steps"] == E * T
+    assert st["success"] + st["collision"] + st["timeout"] == eps
+    np.testing.assert_allclose(st["return_sum"], ret_sum, rtol=1e-5)
