@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- agent-steps/s of the batched swarm step (+obs+reward+done+global_state).
+
+Contract (driver):  python bench.py --gpus N --steps K --warmup W   (torchrun for N > 1)
+prints ONE JSON line on rank 0.
+
+Workload = BASELINE.json configs[3] ("C4", the config the metric is quoted on): 32-drone swarm,
+8 obstacles, reference-default DroneEnvConfig (world 20, K=3, S=4, max_steps 400), 65536 env
+instances PER GPU (weak scaling; the whole of C4 fits one GPU), i.i.d. U(-1,1) float32 actions
+read from device memory, auto-reset on, global_state emitted.  A "step" is one fused launch that
+advances every env instance once.  The per-step working set (~0.5 GB) exceeds the 126 MB L2.
+
+  value     device-resident throughput: actions applied (device counter) / CUDA-event time, max over ranks
+  e2e       same metric through the host-buffer C-ABI call (pinned H2D actions + D2H of every output)
+  roofline  algorithmic bytes (B = 244 + (34 + 12 M)/N per slot-step) / kernel time vs measured HBM peak
+  cpu_baseline  the C oracle (a port of the reference's algorithm) on all host cores, bounded sample
+
+`--impl reference` times that CPU port alone (the reference is pure Python: there is no
+oracle/_ref to compile, and /root/reference does not exist on the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (kind, config, default envs per GPU)
+    "c4": ("swarm", {"num_drones": 32, "num_obstacles": 8}, 65536),
+    "c4_w44": ("swarm", {"num_drones": 32, "num_obstacles": 8, "world_size": 44.0}, 65536),
+    "c2": ("swarm", {"num_drones": 8, "num_obstacles": 4}, 262144),
+    "c3": ("swarm", {"num_drones": 16, "num_obstacles": 8}, 131072),
+    "c5": ("swarm", {"num_drones": 128, "num_obstacles": 8}, 8192),
+    "c5_w70": ("swarm", {"num_drones": 128, "num_obstacles": 8, "world_size": 70.0}, 8192),
+    "c1": ("single", {"num_obstacles": 8}, 1048576),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def cpu_port_rate(kind, cfg, n_envs, budget_s, threads):
+    """Times the C oracle (port of the reference algorithm) on the host cores: bounded sample."""
+    import swarm_oracle as so
+
+    o = so.OracleSwarm(n_envs, cfg, kind=kind)
+    o.seed(np.arange(n_envs, dtype=np.uint64))
+    o.reset()
+    rng = np.random.default_rng(1000)
+    acts = [rng.uniform(-1, 1, size=(n_envs, o.N, 3)).astype(np.float32) for _ in range(4)]
+    o.step(acts[0], auto_reset=True, num_threads=threads)  # warm
+    steps, agent_steps = 0, 0
+    t0 = time.perf_counter()
+    while True:
+        agent_steps += int(o.active.sum()) if kind == "swarm" else n_envs
+        o.step(acts[steps % 4], auto_reset=True, num_threads=threads)
+        steps += 1
+        if time.perf_counter() - t0 >= budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return agent_steps / dt, steps, dt
+
+
+def run_reference_arm(args, kind, cfg, wl_name):
+    """--impl reference: the CPU port, all host threads, same config / metric / unit."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import swarm_oracle as so
+
+    threads = len(os.sched_getaffinity(0))
+    n_envs = args.cpu_envs
+    o = so.OracleSwarm(n_envs, cfg, kind=kind)
+    o.seed(np.arange(n_envs, dtype=np.uint64))
+    o.reset()
+    rng = np.random.default_rng(1000)
+    acts = [rng.uniform(-1, 1, size=(n_envs, o.N, 3)).astype(np.float32) for _ in range(4)]
+    for w in range(args.warmup):
+        o.step(acts[w % 4], auto_reset=True, num_threads=threads)
+    agent_steps = 0
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        agent_steps += int(o.active.sum()) if kind == "swarm" else n_envs
+        o.step(acts[k % 4], auto_reset=True, num_threads=threads)
+    dt = time.perf_counter() - t0
+    val = agent_steps / dt
+    sample = f"{n_envs} env instances x {args.steps} steps of the {wl_name} config per step-batch, {threads} threads"
+    line = {
+        "impl": "reference", "metric": "agent_steps_per_sec", "value": val, "unit": "agent-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(wl_name, kind, cfg, n_envs, 1),
+        "cpu_baseline": {"value": val, "unit": "agent-steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference is pure Python (cannot travel to the GPU box); this is oracle/swarm_oracle.c, a scalar C "
+                "port of its algorithm pinned bit-exact to fixtures recorded from it",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(name, kind, cfg, envs_per_gpu, n_gpus):
+    full = {"world_size": 20.0, "max_steps": 400, "neighbor_k": 3, "sensed_obstacles": 4}
+    full.update(cfg)
+    return {"workload": f"{name}: {kind} env, N={full.get('num_drones', 1)} drones, M={full['num_obstacles']} "
+                        f"obstacles, K={full['neighbor_k']}, S={full['sensed_obstacles']}, world {full['world_size']}, "
+                        f"{envs_per_gpu} env instances per GPU x {n_gpus} GPU(s), U(-1,1) actions, auto-reset, "
+                        f"global_state on, domain randomisation off",
+            "envs_per_gpu": envs_per_gpu, "num_drones": full.get("num_drones", 1),
+            "num_obstacles": full["num_obstacles"], "parallelism": f"env-sharded x{n_gpus}, no data-path collective",
+            "l2_policy": "per-step working set larger than L2 (no flush needed)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs-per-gpu", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=12)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-envs", type=int, default=2048)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-global-state", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    kind, cfg, default_envs = WORKLOADS[args.workload]
+    E = args.envs_per_gpu or default_envs
+
+    if args.impl == "reference":
+        if args.steps > 200:
+            args.steps = 200
+        run_reference_arm(args, kind, cfg, args.workload)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import swarm_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    eng = swarm_b200.SwarmEngine(E, cfg, kind=kind, device=dev, global_state=not args.no_global_state)
+    N = eng.N
+    # env e of rank r is global env r*E + e: seeds are a function of the GLOBAL env index
+    eng.seed(np.arange(rank * E, (rank + 1) * E, dtype=np.uint64))
+    eng.reset()
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    n_act = 4
+    actions = [torch.rand((E, N, 3), generator=gen, device=dev) * 2.0 - 1.0 for _ in range(n_act)]
+
+    for w in range(args.warmup):
+        eng.step(actions[w % n_act], auto_reset=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    eng.reset_stats()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for k in range(args.steps):
+        eng.step(actions[k % n_act], auto_reset=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    launches = eng.launch_count - launches0
+    elapsed_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    st = eng.stats()
+    agent_steps = st["agent_steps"]           # actions actually applied (device counter)
+    slot_steps = E * N * args.steps
+
+    # the one collective of the path: the episode-statistics reduction (NCCL, tiny)
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([agent_steps, slot_steps, st["episodes"], launches], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    elapsed_ms = float(t.item())
+    agent_steps_all, slot_steps_all, episodes_all, launches_all = (float(x) for x in tot.tolist())
+    value = agent_steps_all / (elapsed_ms * 1e-3)
+
+    # ---- end-to-end through host buffers
+    e2e = None
+    if not args.no_e2e:
+        h = eng.host_buffers()
+        host_actions = [a.cpu().pin_memory() for a in actions[:2]]   # the caller's pinned action buffers
+        for w in range(3):
+            eng.step_host(host_actions[w % 2], auto_reset=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        eng.reset_stats()
+        t0 = time.perf_counter()
+        ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ee0.record()
+        for k in range(args.e2e_steps):
+            out = eng.step_host(host_actions[k % 2], auto_reset=True)
+            _ = float(out["reward"][0, 0])               # host reads the result
+        ee1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        dev_ms = ee0.elapsed_time(ee1)
+        e2e_ms = max(wall * 1e3, dev_ms)
+        e2e_steps_done = eng.stats()["agent_steps"]
+        te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        se = torch.tensor([e2e_steps_done], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            dist.all_reduce(se, op=dist.ReduceOp.SUM)
+        h2d, d2h = eng.host_bytes_per_step()
+        e2e = {"value": float(se.item()) / (float(te.item()) * 1e-3), "unit": "agent-steps/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
+               "ms_per_step": float(te.item()) / args.e2e_steps,
+               "path": "swarm_step_host: pinned host actions -> H2D -> fused step -> D2H of obs, reward, dist, "
+                       "5 flag arrays, __all__ flags, global_state (4 env-axis chunks on side streams)"}
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        B = eng.algorithmic_bytes_per_agent_step()
+        kernel_ms = elapsed_ms / args.steps
+        bytes_per_launch = B * E * N
+        achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(prof):
+            try:
+                traffic = json.load(open(prof)).get(args.workload, {}).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": "agent_steps_per_sec", "value": value, "unit": "agent-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.workload, kind, cfg, E, world),
+            "slot_steps_per_sec": slot_steps_all / (elapsed_ms * 1e-3),
+            "episodes_in_timed_region": episodes_all,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "bytes_per_agent_step": B, "bytes_per_launch": bytes_per_launch,
+                         "kernel": "swarm_env_kernel (one fused launch per step)", "kernel_ms": kernel_ms},
+            "e2e": e2e,
+            "gpu_launches": int(launches_all),
+            "clocks": clocks,
+        }
+        if not args.no_cpu:
+            threads = len(os.sched_getaffinity(0))
+            rate, csteps, cdt = cpu_port_rate(kind, cfg, args.cpu_envs, args.cpu_seconds, threads)
+            line["cpu_baseline"] = {
+                "value": rate, "unit": "agent-steps/s", "cores": threads, "kind": "port",
+                "sample": f"{args.cpu_envs} env instances x {csteps} steps of the same config in {cdt:.1f} s "
+                          f"(oracle/swarm_oracle.c, scalar C port of the reference algorithm, {threads} threads)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

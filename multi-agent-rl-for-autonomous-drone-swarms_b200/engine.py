@@ -152,7 +152,7 @@ class SwarmEngine:
         if torch.is_tensor(seeds):
             s = seeds.to(device=self.device, dtype=torch.int64).contiguous()
         else:
-            arr = np.ascontiguousarray(np.broadcast_to(np.asarray(seeds, dtype=np.uint64), (self.E,)))
+            arr = np.array(np.broadcast_to(np.asarray(seeds, dtype=np.uint64), (self.E,)))  # writable copy
             s = torch.from_numpy(arr.view(np.int64)).to(self.device)
         if s.numel() != self.E:
             raise ValueError(f"need {self.E} seeds, got {s.numel()}")
@@ -237,14 +237,18 @@ class SwarmEngine:
         library).  `actions_host`: [E,N,3] float32 numpy / CPU tensor, or None to use the pinned
         `host_buffers()['actions']` in place.  Returns the dict of pinned host tensors."""
         h = self.host_buffers()
+        act = h["actions"]
         if actions_host is not None:
             src = torch.as_tensor(actions_host, dtype=torch.float32).reshape(self.E, self.N, 3)
-            h["actions"].copy_(src)
+            if src.is_pinned() and src.is_contiguous():
+                act = src                      # already page-locked: DMA straight from the caller's buffer
+            else:
+                h["actions"].copy_(src)
         out = _abi.SwarmHostOut()
         names = outputs if outputs is not None else tuple(n for n in _abi.HOST_OUT_FIELDS if n in h)
         for name in names:
             setattr(out, name, h[name].data_ptr())
-        _abi.check(self._lib.swarm_step_host(self._handle, C.byref(self._bufs), h["actions"].data_ptr(),
+        _abi.check(self._lib.swarm_step_host(self._handle, C.byref(self._bufs), act.data_ptr(),
                                              C.byref(out), int(auto_reset)), "swarm_step_host")
         return h
 

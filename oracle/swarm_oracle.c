@@ -48,6 +48,9 @@ extern "C" {
 /* Config: mirror of DroneEnvConfig (envs/common.py:7-25) + num_drones        */
 /* (drone_swarm_env.py:32) + oracle-only switches.                            */
 /* ------------------------------------------------------------------------- */
+#define ORACLE_MAX_DRONES 1024   /* scratch bound of this restatement */
+#define ORACLE_MAX_OBSTACLES 256
+
 typedef struct OracleConfig {
     double world_size, dt, max_speed, max_accel, collision_radius, goal_radius;
     double obstacle_radius, desired_spacing;
@@ -251,8 +254,8 @@ static void nearest_obstacle_features(const OracleConfig *c, const float *own, c
     int S = c->sensed_obstacles, M = c->num_obstacles;
     for (int k = 0; k < 4 * S; ++k) out[k] = 0.0f;
     if (M == 0 || S <= 0) return;
-    float *dist = (float *)malloc(sizeof(float) * (size_t)M);
-    int *order = (int *)malloc(sizeof(int) * (size_t)M);
+    float dist[ORACLE_MAX_OBSTACLES];
+    int order[ORACLE_MAX_OBSTACLES];
     for (int m = 0; m < M; ++m) {
         float rx = obst[3 * m] - own[0], ry = obst[3 * m + 1] - own[1], rz = obst[3 * m + 2] - own[2];
         dist[m] = norm_axis(rx, ry, rz);
@@ -272,8 +275,6 @@ static void nearest_obstacle_features(const OracleConfig *c, const float *own, c
         out[4 * q + 2] = obst[3 * m + 2] - own[2];
         out[4 * q + 3] = dist[m];
     }
-    free(dist);
-    free(order);
 }
 
 /* _nearest_neighbor_features  drone_swarm_env.py:245-271 (all drones j != i, parked included) */
@@ -282,9 +283,8 @@ static void nearest_neighbor_features(const OracleConfig *c, const float *pos, i
     for (int k = 0; k < 4 * K; ++k) out[k] = 0.0f;
     if (N <= 1 || K <= 0) return;
     int n = N - 1;
-    float *dist = (float *)malloc(sizeof(float) * (size_t)n);
-    int *who = (int *)malloc(sizeof(int) * (size_t)n);
-    int *order = (int *)malloc(sizeof(int) * (size_t)n);
+    float dist[ORACLE_MAX_DRONES];
+    int who[ORACLE_MAX_DRONES], order[ORACLE_MAX_DRONES];
     const float *own = pos + 3 * index;
     int cnt = 0;
     for (int j = 0; j < N; ++j) {
@@ -308,9 +308,6 @@ static void nearest_neighbor_features(const OracleConfig *c, const float *pos, i
         out[4 * q + 2] = pos[3 * j + 2] - own[2];
         out[4 * q + 3] = dist[order[q]];
     }
-    free(dist);
-    free(who);
-    free(order);
 }
 
 /* _build_obs  drone_swarm_env.py:226-243 / single_drone_env.py:128-140 */
@@ -474,7 +471,7 @@ static void formation_penalties(const OracleConfig *c, const EnvView *v, double 
     int N = c->num_drones, n_active = 0;
     for (int i = 0; i < N; ++i) { pen[i] = 0.0; n_active += v->active[i] ? 1 : 0; }
     if (n_active <= 1) return;
-    double *errs = (double *)malloc(sizeof(double) * (size_t)N);
+    double errs[ORACLE_MAX_DRONES];
     for (int i = 0; i < N; ++i) {
         if (!v->active[i]) continue;
         int n = 0;
@@ -489,7 +486,6 @@ static void formation_penalties(const OracleConfig *c, const EnvView *v, double 
             pen[i] = -c->reward_formation_scale * spacing_error;
         }
     }
-    free(errs);
 }
 
 /* DroneSwarmEnv.step  drone_swarm_env.py:92-174.  `action` is [N][3] f32 (a missing
