@@ -38,7 +38,6 @@ constexpr int kHostChunks = 4;
 struct SwarmHandle {
     SwarmConfig cfg;
     DevParams base;          // everything but the buffer pointers / per-launch fields
-    int kmax, smax;
     int device;
     int num_sms;
     int blocks_per_sm;
@@ -166,7 +165,7 @@ int launch(SwarmHandle* h, DevParams& p, int env_begin, int env_count, cudaStrea
     const int ctas_needed = (p.n_groups + kWarpsPerCta - 1) / kWarpsPerCta;
     const int resident = h->num_sms * h->blocks_per_sm;
     const int grid = ctas_needed < resident ? ctas_needed : resident;
-    CUDA_TRY(launch_env_kernel(p, h->kmax, h->smax, h->cfg.norm_mode, h->cfg.env_kind, grid, h->smem_bytes, stream));
+    CUDA_TRY(launch_env_kernel(p, h->cfg.norm_mode, h->cfg.env_kind, grid, h->smem_bytes, stream));
     h->launches++;
     return SWARM_OK;
 }
@@ -224,8 +223,6 @@ int swarm_create(const SwarmConfig* cfg, SwarmHandle** out) {
     h->actions_dev = nullptr;
     h->host_path_ready = false;
     fill_params(*cfg, h->base);
-    h->kmax = h->base.K;
-    h->smax = h->base.S;
     h->smem_bytes = (size_t)h->base.smem_per_warp * kWarpsPerCta;
 
     cudaDeviceProp prop;
@@ -238,7 +235,7 @@ int swarm_create(const SwarmConfig* cfg, SwarmHandle** out) {
         return fail(SWARM_E_UNSUPPORTED, "config needs %zu B shared memory per CTA (> %zu)", need,
                     (size_t)prop.sharedMemPerBlockOptin);
     }
-    e = env_kernel_occupancy(h->kmax, h->smax, cfg->norm_mode, cfg->env_kind, h->smem_bytes, &h->blocks_per_sm);
+    e = env_kernel_occupancy(h->base, cfg->norm_mode, cfg->env_kind, h->smem_bytes, &h->blocks_per_sm);
     if (e != cudaSuccess || h->blocks_per_sm < 1) {
         delete h;
         return fail(SWARM_E_CUDA, "kernel occupancy query failed: %s", cudaGetErrorString(e));

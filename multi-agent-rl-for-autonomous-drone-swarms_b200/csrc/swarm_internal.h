@@ -9,6 +9,7 @@ namespace swarm {
 
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreadsPerCta = kWarpsPerCta * 32;
+constexpr int kMinBlocksPerSm = 3;  // register budget: 65536 / (3 * 256) = 85 per thread
 
 enum Mode : int { kModeStep = 0, kModeReset = 1, kModeObserve = 2 };
 
@@ -53,10 +54,9 @@ struct DevParams {
 };
 
 // kernel selection (swarm_kernels.cu)
-struct KernelChoice { int kmax, smax; };
-cudaError_t launch_env_kernel(const DevParams& p, int kmax, int smax, int norm_mode, int env_kind,
-                              int grid, size_t smem_bytes, cudaStream_t stream);
-cudaError_t env_kernel_occupancy(int kmax, int smax, int norm_mode, int env_kind, size_t smem_bytes,
+cudaError_t launch_env_kernel(const DevParams& p, int norm_mode, int env_kind, int grid, size_t smem_bytes,
+                              cudaStream_t stream);
+cudaError_t env_kernel_occupancy(const DevParams& p, int norm_mode, int env_kind, size_t smem_bytes,
                                  int* blocks_per_sm);
 cudaError_t launch_seed_kernel(const DevParams& p, cudaStream_t stream);
 

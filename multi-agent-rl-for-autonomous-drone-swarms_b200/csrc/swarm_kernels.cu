@@ -11,9 +11,9 @@
 // Mapping.  Envs are independent, so the unit of work is a WARP: one warp owns G = 32/N env
 // instances (N <= 32; lane = env-local index * N + drone) or one env with ceil(N/32) drones per
 // lane (N > 32).  A warp keeps its envs' positions / velocities / goal / obstacles in a private
-// shared-memory slice (float4 tables: every pair-loop read is one broadcast LDS.128), needs no
-// block barrier, and transposes its 32 x D observation rows through shared memory so the
-// global writes are contiguous float4 streams.  All state traffic is float4 (coalesced 16 B).
+// shared-memory slice (float4 tables: every pair-loop read is one LDS.128), needs no block
+// barrier, and transposes its 32 x D observation rows through shared memory so the global
+// writes are contiguous float4 streams.  All state traffic is float4 (coalesced 16 B).
 //
 // Arithmetic is bit-faithful to the reference's numpy expressions: explicit round-to-nearest
 // float32 ops with no FMA contraction (the TU is compiled with -fmad=false as well), float64
@@ -25,26 +25,40 @@
 namespace swarm {
 
 #define FULL_MASK 0xffffffffu
+#define F32_INF __int_as_float(0x7f800000)
 
 // ------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------
+// sum of squares exactly as np.linalg.norm(vec3) forms it before the sqrt
 template <int NORM>
-__device__ __forceinline__ float norm1d(float x, float y, float z) {
-    // np.linalg.norm(vec3): sqrt(dot(v, v)), dot = BLAS sdot (f32 products, f64 accumulate)
+__device__ __forceinline__ float sumsq1d(float x, float y, float z) {
+    // sqrt(dot(v, v)), dot = BLAS sdot: float32 products, float64 accumulate, cast back to float32
     const float px = __fmul_rn(x, x), py = __fmul_rn(y, y), pz = __fmul_rn(z, z);
-    float s;
-    if (NORM == 0) {
-        s = __double2float_rn(__dadd_rn(__dadd_rn((double)px, (double)py), (double)pz));
-    } else {
-        s = __fadd_rn(__fadd_rn(px, py), pz);
-    }
-    return __fsqrt_rn(s);
+    if (NORM == 0) return __double2float_rn(__dadd_rn(__dadd_rn((double)px, (double)py), (double)pz));
+    return __fadd_rn(__fadd_rn(px, py), pz);
 }
 
-__device__ __forceinline__ float norm_axis(float x, float y, float z) {
+__device__ __forceinline__ float sumsq_axis(float x, float y, float z) {
     // np.linalg.norm(A, axis=-1): sqrt(add.reduce(A * A)) -- sequential float32
-    return __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+    return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+}
+
+template <int NORM>
+__device__ __forceinline__ float norm1d(float x, float y, float z) {
+    return __fsqrt_rn(sumsq1d<NORM>(x, y, z));
+}
+
+// IEEE round-to-nearest sqrt for 2^-101 <= s < inf: the branch-free fast path of sqrt.rn.f32
+// (MUFU.RSQ seed + one residual correction); callers check the range once per block of values.
+#define SQRT_FAST_MIN 3.944304526105059e-31f /* 2^-101 */
+__device__ __forceinline__ float sqrt_rn_fast(float s) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(s));
+    const float g = __fmul_rn(s, y);
+    const float h = __fmul_rn(y, 0.5f);
+    const float r = __fmaf_rn(-g, g, s);
+    return __fmaf_rn(r, h, g);
 }
 
 __device__ __forceinline__ float clipf(float x, float lo, float hi) {
@@ -71,8 +85,6 @@ __device__ __forceinline__ void topk_insert(float d, int j, float (&bd)[KM], int
         }
     }
 }
-
-__device__ __forceinline__ float comp(const float4& v, int c) { return c == 0 ? v.x : (c == 1 ? v.y : v.z); }
 
 // ------------------------------------------------------------------------------------------
 // numpy PCG64 (XSL-RR 128/64) with jump-ahead, so the 3N+3+3M draws of a reset are generated
@@ -113,74 +125,123 @@ struct ScanOut {
     int form_n;
 };
 
-template <int KMAX, int SMAX, int NORM, int KIND, bool STEP>
+__device__ __forceinline__ double tree8(const double (&r)[8]) {
+    return __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                     __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+}
+
+// Eight consecutive "other drones" jp = jb .. jb+7 of drone i (jp skips i: j = jp + (jp >= i)).
+// FORM 0: k-nearest only; 1: r[u] += |d - d*| (numpy pairwise lane u); 2: res += ... in order.
+template <int KT, int NORM, bool FULL, int FORM>
+__device__ __forceinline__ void pair_block8(const float4* __restrict__ tpos, int jb, int n_others, int i, float px,
+                                            float py, float pz, float (&nd)[KT], int (&nj)[KT], double (&r)[8],
+                                            double& res, double d_star) {
+    float s[8];
+    bool valid[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int jp = jb + u;
+        valid[u] = FULL || jp < n_others;
+        const int j = valid[u] ? jp + (jp >= i ? 1 : 0) : i;
+        const float4 q = tpos[j];
+        const float ss = sumsq1d<NORM>(__fsub_rn(q.x, px), __fsub_rn(q.y, py), __fsub_rn(q.z, pz));
+        s[u] = valid[u] ? ss : 1.0f;
+    }
+    const float smin = fminf(fminf(fminf(s[0], s[1]), fminf(s[2], s[3])), fminf(fminf(s[4], s[5]), fminf(s[6], s[7])));
+    float d[8];
+    if (smin >= SQRT_FAST_MIN) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) d[u] = sqrt_rn_fast(s[u]);
+    } else {  // coincident drones (d == 0) or denormal range: full IEEE path
+#pragma unroll
+        for (int u = 0; u < 8; ++u) d[u] = __fsqrt_rn(s[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        topk_insert<KT>(valid[u] ? d[u] : F32_INF, jb + u, nd, nj);
+        if (FORM != 0) {
+            const double err = fabs(__dsub_rn((double)d[u], d_star));
+            if (FORM == 1) r[u] = __dadd_rn(r[u], err);
+            else res = __dadd_rn(res, valid[u] ? err : 0.0);
+        }
+    }
+}
+
+template <int ST, bool FULL>
+__device__ __forceinline__ void obst_block4(const float4* __restrict__ tobs, int mb, int M, float px, float py, float pz,
+                                            float (&od)[ST], int (&om)[ST]) {
+    float s[4];
+    bool valid[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        valid[u] = FULL || mb + u < M;
+        const float4 o = tobs[valid[u] ? mb + u : 0];
+        const float ss = sumsq_axis(__fsub_rn(o.x, px), __fsub_rn(o.y, py), __fsub_rn(o.z, pz));
+        s[u] = valid[u] ? ss : 1.0f;
+    }
+    const float smin = fminf(fminf(s[0], s[1]), fminf(s[2], s[3]));
+    float d[4];
+    if (smin >= SQRT_FAST_MIN) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) d[u] = sqrt_rn_fast(s[u]);
+    } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) d[u] = __fsqrt_rn(s[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) topk_insert<ST>(valid[u] ? d[u] : F32_INF, mb + u, od, om);
+}
+
+// KT / ST: capacity of the k-nearest lists (>= K, S).  nj holds "other" indices jp (see above).
+template <int KT, int ST, int NORM, int KIND, bool STEP>
 __device__ __forceinline__ void scan_drone(const DevParams& P, const float4* __restrict__ tpos,
                                            const float4* __restrict__ tobs, int i, float px, float py, float pz,
-                                           bool alive_i, int n_alive_env, float (&nd)[KMAX], int (&nj)[KMAX],
-                                           float (&od)[SMAX], int (&om)[SMAX], ScanOut& out) {
+                                           bool alive_i, int n_alive_env, float (&nd)[KT], int (&nj)[KT],
+                                           float (&od)[ST], int (&om)[ST], ScanOut& out) {
     const int N = P.N, M = P.M;
 #pragma unroll
-    for (int q = 0; q < KMAX; ++q) { nd[q] = __int_as_float(0x7f800000); nj[q] = -1; }
+    for (int q = 0; q < KT; ++q) { nd[q] = F32_INF; nj[q] = -1; }
 #pragma unroll
-    for (int q = 0; q < SMAX; ++q) { od[q] = __int_as_float(0x7f800000); om[q] = -1; }
-    out.obst_hit = false;
+    for (int q = 0; q < ST; ++q) { od[q] = F32_INF; om[q] = -1; }
     out.pair_hit = false;
     out.form_sum = 0.0;
     out.form_n = 0;
 
     // ---- obstacles: _nearest_obstacle_features (:273-291) + obstacle part of _collision_mask (:190-200)
-    for (int m = 0; m < M; ++m) {
-        const float4 o = tobs[m];
-        const float d = norm_axis(__fsub_rn(o.x, px), __fsub_rn(o.y, py), __fsub_rn(o.z, pz));
-        if (STEP) out.obst_hit |= d <= P.thr_obst;
-        topk_insert<SMAX>(d, m, od, om);
+    {
+        int mb = 0;
+        for (; mb + 4 <= M; mb += 4) obst_block4<ST, true>(tobs, mb, M, px, py, pz, od, om);
+        if (mb < M) obst_block4<ST, false>(tobs, mb, M, px, py, pz, od, om);
     }
+    out.obst_hit = od[0] <= P.thr_obst;  // nearest obstacle decides; +inf when M == 0
     if (KIND == SWARM_KIND_SINGLE) return;
 
     // ---- drones: _nearest_neighbor_features (:245-271) over ALL j != i; pair part of
     //      _collision_mask (:202-207) and _formation_penalties (:210-224) over ACTIVE pairs
     const int n_others = N - 1;
+    double r[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) r[u] = 0.0;
+    double res = 0.0;
+
     if (!STEP) {
-        for (int jp = 0; jp < n_others; ++jp) {
-            const int j = jp + (jp >= i ? 1 : 0);
-            const float4 q = tpos[j];
-            const float d = norm1d<NORM>(__fsub_rn(q.x, px), __fsub_rn(q.y, py), __fsub_rn(q.z, pz));
-            topk_insert<KMAX>(d, j, nd, nj);
-        }
+        int jb = 0;
+        for (; jb + 8 <= n_others; jb += 8)
+            pair_block8<KT, NORM, true, 0>(tpos, jb, n_others, i, px, py, pz, nd, nj, r, res, 0.0);
+        if (jb < n_others) pair_block8<KT, NORM, false, 0>(tpos, jb, n_others, i, px, py, pz, nd, nj, r, res, 0.0);
         return;
     }
 
     if (alive_i && n_alive_env == N) {
-        // fast path: every drone active -> the j-th other drone is element j of the mean's operand,
+        // fast path: every drone active -> the jp-th other drone is element jp of the mean's operand,
         // so numpy's pairwise-sum lane is static under 8x unrolling
+        const double d_star = P.d_star;
         const int n8 = n_others >= 8 ? (n_others & ~7) : 0;
-        double r[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) r[u] = 0.0;
-        for (int jb = 0; jb < n8; jb += 8) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int jp = jb + u;
-                const int j = jp + (jp >= i ? 1 : 0);
-                const float4 q = tpos[j];
-                const float d = norm1d<NORM>(__fsub_rn(q.x, px), __fsub_rn(q.y, py), __fsub_rn(q.z, pz));
-                topk_insert<KMAX>(d, j, nd, nj);
-                out.pair_hit |= d <= P.thr_pair;
-                r[u] = __dadd_rn(r[u], fabs(__dsub_rn((double)d, P.d_star)));
-            }
-        }
-        double res = 0.0;
-        if (n8 > 0)
-            res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                            __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-        for (int jp = n8; jp < n_others; ++jp) {
-            const int j = jp + (jp >= i ? 1 : 0);
-            const float4 q = tpos[j];
-            const float d = norm1d<NORM>(__fsub_rn(q.x, px), __fsub_rn(q.y, py), __fsub_rn(q.z, pz));
-            topk_insert<KMAX>(d, j, nd, nj);
-            out.pair_hit |= d <= P.thr_pair;
-            res = __dadd_rn(res, fabs(__dsub_rn((double)d, P.d_star)));
-        }
+        for (int jb = 0; jb < n8; jb += 8)
+            pair_block8<KT, NORM, true, 1>(tpos, jb, n_others, i, px, py, pz, nd, nj, r, res, d_star);
+        if (n8 > 0) res = tree8(r);
+        if (n8 < n_others) pair_block8<KT, NORM, false, 2>(tpos, n8, n_others, i, px, py, pz, nd, nj, r, res, d_star);
+        out.pair_hit = nd[0] <= P.thr_pair;  // nearest drone decides (all drones active here)
         out.form_sum = res;
         out.form_n = n_others;
         return;
@@ -189,17 +250,13 @@ __device__ __forceinline__ void scan_drone(const DevParams& P, const float4* __r
     // general path: some drones are parked (or this one is) -> compact on the fly
     const int n_f = alive_i ? n_alive_env - 1 : 0;
     const int n8 = n_f >= 8 ? (n_f & ~7) : 0;
-    double r[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) r[u] = 0.0;
-    double res = 0.0;
     bool tree_done = false;
     int cnt = 0;
     for (int jp = 0; jp < n_others; ++jp) {
         const int j = jp + (jp >= i ? 1 : 0);
         const float4 q = tpos[j];
         const float d = norm1d<NORM>(__fsub_rn(q.x, px), __fsub_rn(q.y, py), __fsub_rn(q.z, pz));
-        topk_insert<KMAX>(d, j, nd, nj);
+        topk_insert<KT>(d, jp, nd, nj);
         if (alive_i && q.w != 0.0f) {
             out.pair_hit |= d <= P.thr_pair;
             const double err = fabs(__dsub_rn((double)d, P.d_star));
@@ -208,41 +265,37 @@ __device__ __forceinline__ void scan_drone(const DevParams& P, const float4* __r
 #pragma unroll
                 for (int u = 0; u < 8; ++u) r[u] = __dadd_rn(r[u], lane8 == u ? err : 0.0);
             } else {
-                if (!tree_done && n8 > 0) {
-                    res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                                    __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-                }
+                if (!tree_done && n8 > 0) res = tree8(r);
                 tree_done = true;
                 res = __dadd_rn(res, err);
             }
             ++cnt;
         }
     }
-    if (!tree_done && n8 > 0)
-        res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                        __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    if (!tree_done && n8 > 0) res = tree8(r);
     out.form_sum = res;
     out.form_n = n_f;
 }
 
 // observation row -> this lane's row of the staging tile:  _build_obs (:226-243)
-template <int KMAX, int SMAX, int KIND>
+template <int KT, int ST, bool EXACT, int KIND>
 __device__ __forceinline__ void stage_obs_row(const DevParams& P, float* __restrict__ row,
-                                              const float4* __restrict__ tpos, const float4* __restrict__ tobs,
+                                              const float4* __restrict__ tpos, const float4* __restrict__ tobs, int i,
                                               float px, float py, float pz, float vx, float vy, float vz, float gx,
-                                              float gy, float gz, const float (&nd)[KMAX], const int (&nj)[KMAX],
-                                              const float (&od)[SMAX], const int (&om)[SMAX]) {
+                                              float gy, float gz, const float (&nd)[KT], const int (&nj)[KT],
+                                              const float (&od)[ST], const int (&om)[ST]) {
+    const int K = EXACT ? KT : P.K, S = EXACT ? ST : P.S;
     row[0] = px; row[1] = py; row[2] = pz;
     row[3] = vx; row[4] = vy; row[5] = vz;
     row[6] = __fsub_rn(gx, px); row[7] = __fsub_rn(gy, py); row[8] = __fsub_rn(gz, pz);
     int off = 9;
     if (KIND == SWARM_KIND_SWARM) {
 #pragma unroll
-        for (int q = 0; q < KMAX; ++q) {
-            if (q < P.K) {
+        for (int q = 0; q < KT; ++q) {
+            if (q < K) {
                 float rx = 0.f, ry = 0.f, rz = 0.f, d = 0.f;
                 if (nj[q] >= 0) {
-                    const float4 t = tpos[nj[q]];
+                    const float4 t = tpos[nj[q] + (nj[q] >= i ? 1 : 0)];
                     rx = __fsub_rn(t.x, px); ry = __fsub_rn(t.y, py); rz = __fsub_rn(t.z, pz);
                     d = nd[q];
                 }
@@ -250,11 +303,11 @@ __device__ __forceinline__ void stage_obs_row(const DevParams& P, float* __restr
                 row[off + 4 * q + 2] = rz; row[off + 4 * q + 3] = d;
             }
         }
-        off += 4 * P.K;
+        off += 4 * K;
     }
 #pragma unroll
-    for (int q = 0; q < SMAX; ++q) {
-        if (q < P.S) {
+    for (int q = 0; q < ST; ++q) {
+        if (q < S) {
             float rx = 0.f, ry = 0.f, rz = 0.f, d = 0.f;
             if (om[q] >= 0) {
                 const float4 t = tobs[om[q]];
@@ -268,10 +321,10 @@ __device__ __forceinline__ void stage_obs_row(const DevParams& P, float* __restr
 }
 
 // staged rows -> obs[base_agent .. base_agent + n_rows) as one contiguous stream
-__device__ __forceinline__ void flush_stage(const DevParams& P, const float* __restrict__ stage, long long base_agent,
-                                            int n_rows, int lane) {
-    const int total = n_rows * P.D;
-    float* dst = P.obs + base_agent * P.D;
+__device__ __forceinline__ void flush_stage(float* __restrict__ obs, int D, const float* __restrict__ stage,
+                                            long long base_agent, int n_rows, int lane) {
+    const int total = n_rows * D;
+    float* dst = obs + base_agent * D;
     if (((base_agent & 3) == 0) && ((total & 3) == 0)) {  // D = 1 (mod 4): 16-byte aligned iff base % 4 == 0
         const float4* s4 = reinterpret_cast<const float4*>(stage);
         float4* d4 = reinterpret_cast<float4*>(dst);
@@ -281,11 +334,20 @@ __device__ __forceinline__ void flush_stage(const DevParams& P, const float* __r
     }
 }
 
+// global_state row pieces of one drone: [pos.ravel | vel.ravel | goal] (:293-302)
+__device__ __forceinline__ void write_gs_drone(float* __restrict__ row, int N, int i, float px, float py, float pz,
+                                               float vx, float vy, float vz) {
+    __stcs(row + 3 * i + 0, px); __stcs(row + 3 * i + 1, py); __stcs(row + 3 * i + 2, pz);
+    __stcs(row + 3 * N + 3 * i + 0, vx); __stcs(row + 3 * N + 3 * i + 1, vy); __stcs(row + 3 * N + 3 * i + 2, vz);
+}
+
 // ------------------------------------------------------------------------------------------
 // the env kernel (step / reset / observe)
+//   KT, ST  capacity of the k-nearest lists; EXACT: K == KT and S == ST (D is compile-time)
+//   SMALLN  N <= 32: one drone per lane, drone state stays in registers between the phases
 // ------------------------------------------------------------------------------------------
-template <int KMAX, int SMAX, int NORM, int KIND>
-__global__ void __launch_bounds__(kThreadsPerCta) swarm_env_kernel(const DevParams P) {
+template <int KT, int ST, bool EXACT, int NORM, int KIND, bool SMALLN>
+__global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_kernel(const DevParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -296,12 +358,13 @@ __global__ void __launch_bounds__(kThreadsPerCta) swarm_env_kernel(const DevPara
     float4* tab_obst = tab_goal + P.G;
     float* stage = reinterpret_cast<float*>(tab_obst + P.G * P.m_pad);
 
-    const int N = P.N, M = P.M, G = P.G, D = P.D, nslots = P.nslots;
-    const bool small_n = N <= 32;
-    const int e_l = small_n ? lane / N : 0;      // env-local index of this lane
-    const int i_base = small_n ? lane - e_l * N : lane;
+    const int N = P.N, M = P.M, G = P.G;
+    const int D = EXACT ? (KIND == SWARM_KIND_SWARM ? 9 + 4 * KT + 4 * ST : 9 + 4 * ST) : P.D;
+    const int nslots = SMALLN ? 1 : P.nslots;
+    const int e_l = SMALLN ? lane / N : 0;  // env-local index of this lane
+    const int i_base = SMALLN ? lane - e_l * N : lane;
     const unsigned env_lanes =
-        small_n ? (e_l < G ? (N == 32 ? FULL_MASK : (((1u << N) - 1u) << (e_l * N))) : 0u) : FULL_MASK;
+        SMALLN ? (e_l < G ? (N == 32 ? FULL_MASK : (((1u << N) - 1u) << (e_l * N))) : 0u) : FULL_MASK;
 
     // per-lane statistics (flushed once per warp at the end)
     unsigned st_eps = 0, st_succ = 0, st_col = 0, st_to = 0, st_len = 0, st_asteps = 0, st_esteps = 0;
@@ -313,8 +376,9 @@ __global__ void __launch_bounds__(kThreadsPerCta) swarm_env_kernel(const DevPara
         const int n_env = min(G, P.env_begin + P.env_count - env0);
         const bool lane_env_ok = e_l < n_env;
         const int env = env0 + (lane_env_ok ? e_l : 0);
-        const float4* tpos = tab_pos + e_l * N;          // this lane's env tables
+        const float4* tpos = tab_pos + e_l * N;  // this lane's env tables
         const float4* tobs = tab_obst + e_l * P.m_pad;
+        float* gs_row = P.gs ? P.gs + (long long)env * P.R : nullptr;
 
         __syncwarp();  // previous group's shared-memory reads are done
         // ---- per-env tables: goal, obstacles
@@ -332,6 +396,7 @@ __global__ void __launch_bounds__(kThreadsPerCta) swarm_env_kernel(const DevPara
         if (P.mode == kModeStep) {
             // =========================== phase A: integrate (:98-118) ===========================
             int n_alive_env = 0;
+            float4 p_reg = make_float4(0.f, 0.f, 0.f, 0.f), v_reg = p_reg;  // SMALLN: this lane's drone
             for (int slot = 0; slot < nslots; ++slot) {
                 const int i = slot * 32 + i_base;
                 const bool ok = lane_env_ok && i < N;
@@ -367,7 +432,8 @@ __global__ void __launch_bounds__(kThreadsPerCta) swarm_env_kernel(const DevPara
                     p.w = alive ? 1.0f : 0.0f;
                     v.w = prev_d;
                     tab_pos[e_l * N + i] = p;
-                    tab_vel[e_l * N + i] = v;
+                    if (SMALLN) { p_reg = p; v_reg = v; }
+                    else tab_vel[e_l * N + i] = v;
                 }
                 n_alive_env += __popc(__ballot_sync(FULL_MASK, ok && alive) & env_lanes);
             }
@@ -384,14 +450,14 @@ __global__ void __launch_bounds__(kThreadsPerCta) swarm_env_kernel(const DevPara
                 bool alive = false, reached = false, collided = false;
                 float rew32 = 0.0f;
                 if (ok) {
-                    const float4 p = tpos[i];
-                    const float4 v = tab_vel[e_l * N + i];
+                    const float4 p = SMALLN ? p_reg : tpos[i];
+                    const float4 v = SMALLN ? v_reg : tab_vel[e_l * N + i];
                     alive = p.w != 0.0f;
                     const float curr_d = norm1d<NORM>(__fsub_rn(gx, p.x), __fsub_rn(gy, p.y), __fsub_rn(gz, p.z));
-                    float nd[KMAX]; int nj[KMAX]; float od[SMAX]; int om[SMAX];
+                    float nd[KT]; int nj[KT]; float od[ST]; int om[ST];
                     ScanOut so;
-                    scan_drone<KMAX, SMAX, NORM, KIND, true>(P, tpos, tobs, i, p.x, p.y, p.z, alive, n_alive_env, nd,
-                                                             nj, od, om, so);
+                    scan_drone<KT, ST, NORM, KIND, true>(P, tpos, tobs, i, p.x, p.y, p.z, alive, n_alive_env, nd, nj,
+                                                         od, om, so);
                     reached = alive && curr_d <= P.thr_goal;           // :124-127 (double compare)
                     collided = alive && (so.obst_hit || so.pair_hit);   // :128
                     double reward = 0.0;
@@ -414,16 +480,16 @@ __global__ void __launch_bounds__(kThreadsPerCta) swarm_env_kernel(const DevPara
                     P.dist[a] = curr_d;
                     P.reached[a] = reached ? 1 : 0;
                     P.collision[a] = collided ? 1 : 0;
-                    stage_obs_row<KMAX, SMAX, KIND>(P, stage + lane * D, tpos, tobs, p.x, p.y, p.z, v.x, v.y, v.z, gx,
-                                                    gy, gz, nd, nj, od, om);
+                    stage_obs_row<KT, ST, EXACT, KIND>(P, stage + lane * D, tpos, tobs, i, p.x, p.y, p.z, v.x, v.y,
+                                                       v.z, gx, gy, gz, nd, nj, od, om);
                 }
                 __syncwarp();
                 {
-                    const int n_rows = small_n ? n_env * N : min(32, N - slot * 32);
+                    const int n_rows = SMALLN ? n_env * N : min(32, N - slot * 32);
                     const long long base = (long long)env0 * N + slot * 32;
-                    flush_stage(P, stage, base, n_rows, lane);
+                    flush_stage(P.obs, D, stage, base, n_rows, lane);
                 }
-                if (nslots > 1) __syncwarp();
+                if (!SMALLN) __syncwarp();
                 const bool done_agent = reached || collided;
                 m_alive |= (alive ? 1u : 0u) << slot;
                 m_done |= (done_agent ? 1u : 0u) << slot;
@@ -434,7 +500,7 @@ __global__ void __launch_bounds__(kThreadsPerCta) swarm_env_kernel(const DevPara
 #pragma unroll
                 for (int off = 16; off >= 1; off >>= 1) {
                     const float t = __shfl_down_sync(FULL_MASK, x, off);
-                    if (small_n ? (i_base + off < N) : true) x = __fadd_rn(x, t);
+                    if (SMALLN ? (i_base + off < N) : true) x = __fadd_rn(x, t);
                 }
                 rew_sum = __fadd_rn(rew_sum, x);  // meaningful on the env's first lane
             }
@@ -461,6 +527,7 @@ __global__ void __launch_bounds__(kThreadsPerCta) swarm_env_kernel(const DevPara
                     st_eps++; st_to += (all_trunc && !all_term) ? 1 : 0;
                 }
             }
+            const bool need_reset = P.auto_reset && (ep_over || !env_active);
             const bool cont_ok = !time_limit && !any_col;
             for (int slot = 0; slot < nslots; ++slot) {
                 const int i = slot * 32 + i_base;
@@ -479,16 +546,17 @@ __global__ void __launch_bounds__(kThreadsPerCta) swarm_env_kernel(const DevPara
                     valid = true;
                     alive_next = true;
                 }
-                P.obs_valid[a] = valid ? 1 : 0;
-                float4 p = tab_pos[e_l * N + i];
-                float4 v = tab_vel[e_l * N + i];
-                p.w = alive_next ? 1.0f : 0.0f;
-                v.w = 0.0f;
-                tab_pos[e_l * N + i] = p;  // (reset / global_state read the tables)
-                P.pos4[a] = p;
-                P.vel4[a] = v;
+                if (!need_reset) {  // (a reset env rewrites all of this in the observe pass)
+                    P.obs_valid[a] = valid ? 1 : 0;
+                    float4 p = SMALLN ? p_reg : tab_pos[e_l * N + i];
+                    float4 v = SMALLN ? v_reg : tab_vel[e_l * N + i];
+                    p.w = alive_next ? 1.0f : 0.0f;
+                    v.w = 0.0f;
+                    P.pos4[a] = p;
+                    P.vel4[a] = v;
+                    if (gs_row) write_gs_drone(gs_row, N, i, p.x, p.y, p.z, v.x, v.y, v.z);
+                }
             }
-            const bool need_reset = P.auto_reset && (ep_over || !env_active);
             if (lane_env_ok && i_base == 0) {
                 st_esteps += env_active ? 1 : 0;
                 st_asteps += n_alive_env;
@@ -501,11 +569,11 @@ __global__ void __launch_bounds__(kThreadsPerCta) swarm_env_kernel(const DevPara
                 if (!need_reset) {
                     P.step_count[env] = sc_new;
                     P.ep_return[env] = ep_over ? 0.0f : ret;
+                    if (gs_row) { __stcs(gs_row + 6 * N + 0, gx); __stcs(gs_row + 6 * N + 1, gy); __stcs(gs_row + 6 * N + 2, gz); }
                 }
             }
             reset_envs = __ballot_sync(FULL_MASK, lane_env_ok && i_base == 0 && need_reset);
-            // lane of env-local index el is el * N  ->  compress to one bit per env
-            if (small_n) {
+            if (SMALLN) {  // leader lane of env-local index el is el * N -> one bit per env
                 unsigned packed = 0;
                 for (int el = 0; el < n_env; ++el) packed |= ((reset_envs >> (el * N)) & 1u) << el;
                 reset_envs = packed;
@@ -586,10 +654,9 @@ __global__ void __launch_bounds__(kThreadsPerCta) swarm_env_kernel(const DevPara
                 if (ok) {
                     const float4 p = tpos[i];
                     const float4 v = tab_vel[e_l * N + i];
-                    float nd[KMAX]; int nj[KMAX]; float od[SMAX]; int om[SMAX];
+                    float nd[KT]; int nj[KT]; float od[ST]; int om[ST];
                     ScanOut so;
-                    scan_drone<KMAX, SMAX, NORM, KIND, false>(P, tpos, tobs, i, p.x, p.y, p.z, true, N, nd, nj, od, om,
-                                                              so);
+                    scan_drone<KT, ST, NORM, KIND, false>(P, tpos, tobs, i, p.x, p.y, p.z, true, N, nd, nj, od, om, so);
                     const long long a = (long long)env * N + i;
                     P.dist[a] = norm1d<NORM>(__fsub_rn(gx, p.x), __fsub_rn(gy, p.y), __fsub_rn(gz, p.z));
                     P.obs_valid[a] = KIND == SWARM_KIND_SINGLE ? 1 : (p.w != 0.0f ? 1 : 0);
@@ -602,49 +669,36 @@ __global__ void __launch_bounds__(kThreadsPerCta) swarm_env_kernel(const DevPara
                         if (P.reward64) P.reward64[a] = 0.0;
                         P.terminated[a] = 0; P.truncated[a] = 0; P.reached[a] = 0; P.collision[a] = 0;
                     }
-                    stage_obs_row<KMAX, SMAX, KIND>(P, stage + lane * D, tpos, tobs, p.x, p.y, p.z, v.x, v.y, v.z, gx,
-                                                    gy, gz, nd, nj, od, om);
+                    if (gs_row) write_gs_drone(gs_row, N, i, p.x, p.y, p.z, v.x, v.y, v.z);
+                    stage_obs_row<KT, ST, EXACT, KIND>(P, stage + lane * D, tpos, tobs, i, p.x, p.y, p.z, v.x, v.y, v.z,
+                                                       gx, gy, gz, nd, nj, od, om);
+                }
+                if (mine && i_base == 0 && slot == 0 && gs_row) {
+                    __stcs(gs_row + 6 * N + 0, gx); __stcs(gs_row + 6 * N + 1, gy); __stcs(gs_row + 6 * N + 2, gz);
                 }
                 __syncwarp();
                 // single-slot groups restage only the observed envs' rows; the other rows of the tile
                 // still hold this step's rows, so the whole tile can be flushed again.  In reset mode
                 // with a partial mask those other rows are stale -> flush per env there.
-                if (small_n) {
+                if (SMALLN) {
                     if (P.mode == kModeStep || observe_envs == FULL_MASK ||
                         (reset_envs & ((1u << n_env) - 1u)) == ((1u << n_env) - 1u)) {
-                        flush_stage(P, stage, (long long)env0 * N, n_env * N, lane);
+                        flush_stage(P.obs, D, stage, (long long)env0 * N, n_env * N, lane);
                     } else {
                         for (int el = 0; el < n_env; ++el)
                             if ((observe_envs >> el) & 1u)
-                                flush_stage(P, stage + el * N * D, (long long)(env0 + el) * N, N, lane);
+                                flush_stage(P.obs, D, stage + el * N * D, (long long)(env0 + el) * N, N, lane);
                     }
                 } else if (mine) {
-                    flush_stage(P, stage, (long long)env0 * N + slot * 32, min(32, N - slot * 32), lane);
+                    flush_stage(P.obs, D, stage, (long long)env0 * N + slot * 32, min(32, N - slot * 32), lane);
                 }
-                if (nslots > 1) __syncwarp();
+                if (!SMALLN) __syncwarp();
             }
             if (P.mode != kModeStep && lane < n_env && ((observe_envs >> lane) & 1u)) {
                 P.all_term[env0 + lane] = 0;
                 P.all_trunc[env0 + lane] = 0;
                 if (P.episode_return) P.episode_return[env0 + lane] = 0.0f;
                 if (P.episode_length) P.episode_length[env0 + lane] = 0;
-            }
-        }
-
-        // ======================= global_state (:293-302), optional =======================
-        if (P.gs && (P.mode != kModeReset || reset_envs)) {
-            __syncwarp();
-            for (int el = 0; el < n_env; ++el) {
-                if (P.mode == kModeReset && !((reset_envs >> el) & 1u)) continue;
-                float* row = P.gs + (long long)(env0 + el) * P.R;
-                const float4 gg = tab_goal[el];
-                for (int r = lane; r < P.R; r += 32) {
-                    float val;
-                    if (r < 3 * N) val = comp(tab_pos[el * N + r / 3], r % 3);
-                    else if (r < 6 * N) val = comp(tab_vel[el * N + (r - 3 * N) / 3], (r - 3 * N) % 3);
-                    else val = comp(gg, r - 6 * N);
-                    __stcs(row + r, val);
-                }
             }
         }
     }
@@ -748,32 +802,35 @@ __global__ void swarm_seed_kernel(const DevParams P) {
 // ------------------------------------------------------------------------------------------
 typedef void (*EnvKernel)(const DevParams);
 
-template <int KMAX, int SMAX>
-static EnvKernel pick_kernel(int norm_mode, int env_kind) {
-    if (env_kind == SWARM_KIND_SWARM)
-        return norm_mode == 0 ? swarm_env_kernel<KMAX, SMAX, 0, SWARM_KIND_SWARM>
-                              : swarm_env_kernel<KMAX, SMAX, 1, SWARM_KIND_SWARM>;
-    return norm_mode == 0 ? swarm_env_kernel<1, SMAX, 0, SWARM_KIND_SINGLE>
-                          : swarm_env_kernel<1, SMAX, 1, SWARM_KIND_SINGLE>;
+template <int KT, int ST, bool EXACT, int KIND>
+static EnvKernel pick2(int norm_mode, bool small_n) {
+    if (norm_mode == 0)
+        return small_n ? swarm_env_kernel<KT, ST, EXACT, 0, KIND, true> : swarm_env_kernel<KT, ST, EXACT, 0, KIND, false>;
+    return small_n ? swarm_env_kernel<KT, ST, EXACT, 1, KIND, true> : swarm_env_kernel<KT, ST, EXACT, 1, KIND, false>;
 }
 
-static EnvKernel resolve(int kmax, int smax, int norm_mode, int env_kind) {
-    if (kmax <= 3 && smax <= 4) return pick_kernel<3, 4>(norm_mode, env_kind);
-    return pick_kernel<SWARM_MAX_NEIGHBOR_K, SWARM_MAX_SENSED>(norm_mode, env_kind);
+static EnvKernel resolve(int k, int s, int norm_mode, int env_kind, int n) {
+    const bool small_n = n <= 32;
+    if (env_kind == SWARM_KIND_SWARM) {
+        if (k == 3 && s == 4) return pick2<3, 4, true, SWARM_KIND_SWARM>(norm_mode, small_n);
+        return pick2<SWARM_MAX_NEIGHBOR_K, SWARM_MAX_SENSED, false, SWARM_KIND_SWARM>(norm_mode, small_n);
+    }
+    if (s == 4) return pick2<1, 4, true, SWARM_KIND_SINGLE>(norm_mode, true);
+    return pick2<1, SWARM_MAX_SENSED, false, SWARM_KIND_SINGLE>(norm_mode, true);
 }
 
-cudaError_t launch_env_kernel(const DevParams& p, int kmax, int smax, int norm_mode, int env_kind, int grid,
-                              size_t smem_bytes, cudaStream_t stream) {
-    EnvKernel k = resolve(kmax, smax, norm_mode, env_kind);
+cudaError_t launch_env_kernel(const DevParams& p, int norm_mode, int env_kind, int grid, size_t smem_bytes,
+                              cudaStream_t stream) {
+    EnvKernel k = resolve(p.K, p.S, norm_mode, env_kind, p.N);
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (err != cudaSuccess) return err;
     k<<<grid, kThreadsPerCta, smem_bytes, stream>>>(p);
     return cudaGetLastError();
 }
 
-cudaError_t env_kernel_occupancy(int kmax, int smax, int norm_mode, int env_kind, size_t smem_bytes,
+cudaError_t env_kernel_occupancy(const DevParams& p, int norm_mode, int env_kind, size_t smem_bytes,
                                  int* blocks_per_sm) {
-    EnvKernel k = resolve(kmax, smax, norm_mode, env_kind);
+    EnvKernel k = resolve(p.K, p.S, norm_mode, env_kind, p.N);
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (err != cudaSuccess) return err;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, kThreadsPerCta, smem_bytes);
