@@ -136,7 +136,7 @@ enum {
 
 /* Host-side output pointers for swarm_step_host (any may be NULL = do not copy back). */
 typedef struct SwarmHostOut {
-    float *obs; float *reward; float *dist;
+    float *obs; float *reward; double *reward64; float *dist;
     uint8_t *terminated; uint8_t *truncated; uint8_t *reached; uint8_t *collision; uint8_t *obs_valid;
     uint8_t *all_terminated; uint8_t *all_truncated;
     float *global_state;

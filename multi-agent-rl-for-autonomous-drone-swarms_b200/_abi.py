@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libswarm_b200.so")
+LIB_PATH = os.environ.get("SWARM_B200_LIB") or os.path.join(_PKG_DIR, "libswarm_b200.so")  # override: tuning builds
 
 ABI_VERSION = 1
 KIND_SINGLE, KIND_SWARM = 0, 1
@@ -44,7 +44,7 @@ class SwarmBuffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in BUFFER_FIELDS]
 
 
-HOST_OUT_FIELDS = ("obs", "reward", "dist", "terminated", "truncated", "reached", "collision", "obs_valid",
+HOST_OUT_FIELDS = ("obs", "reward", "reward64", "dist", "terminated", "truncated", "reached", "collision", "obs_valid",
                    "all_terminated", "all_truncated", "global_state")
 
 

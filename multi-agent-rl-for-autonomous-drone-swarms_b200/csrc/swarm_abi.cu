@@ -362,6 +362,10 @@ int swarm_step_host(SwarmHandle* h, const SwarmBuffers* bufs, const float* actio
                                      ne * (per_env_elems) * sizeof(type), cudaMemcpyDeviceToHost, s))
         D2H(obs, p.obs, (size_t)N * D, float);
         D2H(reward, p.reward, (size_t)N, float);
+        if (out->reward64 && p.reward64) {
+            CUDA_TRY(cudaMemcpyAsync(out->reward64 + (size_t)e0 * N, p.reward64 + (size_t)e0 * N, ne * N * sizeof(double),
+                                     cudaMemcpyDeviceToHost, s));
+        }
         D2H(dist, p.dist, (size_t)N, float);
         D2H(terminated, p.terminated, (size_t)N, uint8_t);
         D2H(truncated, p.truncated, (size_t)N, uint8_t);

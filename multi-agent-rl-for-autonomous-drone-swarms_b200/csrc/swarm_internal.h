@@ -7,9 +7,15 @@
 
 namespace swarm {
 
-constexpr int kWarpsPerCta = 8;
+#ifndef SWARM_WARPS_PER_CTA
+#define SWARM_WARPS_PER_CTA 8
+#endif
+#ifndef SWARM_MIN_BLOCKS
+#define SWARM_MIN_BLOCKS 3  // register budget: 65536 / (3 * 256) = 85 per thread
+#endif
+constexpr int kWarpsPerCta = SWARM_WARPS_PER_CTA;
 constexpr int kThreadsPerCta = kWarpsPerCta * 32;
-constexpr int kMinBlocksPerSm = 3;  // register budget: 65536 / (3 * 256) = 85 per thread
+constexpr int kMinBlocksPerSm = SWARM_MIN_BLOCKS;
 
 enum Mode : int { kModeStep = 0, kModeReset = 1, kModeObserve = 2 };
 

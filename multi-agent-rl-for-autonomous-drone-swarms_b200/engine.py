@@ -223,6 +223,8 @@ class SwarmEngine:
             pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()  # noqa: E731
             h = dict(actions=pin((E, N, 3), torch.float32), obs=pin((E, N, D), torch.float32),
                      reward=pin((E, N), torch.float32), dist=pin((E, N), torch.float32))
+            if self.reward64 is not None:
+                h["reward64"] = pin((E, N), torch.float64)
             for name in ("terminated", "truncated", "reached", "collision", "obs_valid"):
                 h[name] = pin((E, N), torch.uint8)
             h["all_terminated"] = pin((E,), torch.uint8)

@@ -1,0 +1,230 @@
+"""Reference-compatible env classes backed by the CUDA engine (the drop-in façade).
+
+`DroneSwarmEnv` / `SingleDroneEnv` keep the reference's constructor, `reset` / `step` contract,
+dict population rules and public attributes, so an env creator `lambda cfg: DroneSwarmEnv(cfg)`
+registered with `ray.tune.registry.register_env` (reference scripts/train_ctde.py:125,
+scripts/evaluate_protocol.py:362-364, :427-431) or direct construction works unchanged:
+
+    reference src/swarm_marl/envs/drone_swarm_env.py   DroneSwarmEnv   :17-302
+    reference src/swarm_marl/envs/single_drone_env.py  SingleDroneEnv  :12-159
+
+Each instance is one env (E = 1) stepped through the host-buffer C-ABI entry point; all
+arithmetic runs in the sm_100a kernels (no CPU path).  For throughput use `SwarmEngine`
+(thousands of env instances per launch) -- the façade exists for API compatibility.
+"""
+from __future__ import annotations
+
+import os
+from typing import Any
+
+import numpy as np
+
+from .config import DroneEnvConfig
+
+try:  # gymnasium is optional here (it is not installed in the build image)
+    import gymnasium as _gym
+    from gymnasium import spaces as _spaces
+
+    _GymEnv = _gym.Env
+    Box = _spaces.Box
+except ModuleNotFoundError:  # pragma: no cover - exercised in this image
+    class _GymEnv:  # type: ignore[no-redef]
+        metadata: dict = {"render_modes": []}
+
+        def reset(self, *, seed=None, options=None):
+            return None
+
+    class Box:  # type: ignore[no-redef]
+        """Minimal `gymnasium.spaces.Box` stand-in: shape / dtype / low / high / sample / contains."""
+
+        def __init__(self, low, high, shape=None, dtype=np.float32, seed=None):
+            self.dtype = np.dtype(dtype)
+            self.shape = tuple(shape) if shape is not None else np.shape(low)
+            self.low = np.broadcast_to(np.asarray(low, dtype=self.dtype), self.shape).copy()
+            self.high = np.broadcast_to(np.asarray(high, dtype=self.dtype), self.shape).copy()
+            self._rng = np.random.default_rng(seed)
+
+        def sample(self):
+            lo = np.where(np.isfinite(self.low), self.low, -1.0)
+            hi = np.where(np.isfinite(self.high), self.high, 1.0)
+            return self._rng.uniform(lo, hi).astype(self.dtype)
+
+        def contains(self, x):
+            x = np.asarray(x)
+            return x.shape == self.shape and bool(np.all(x >= self.low) and np.all(x <= self.high))
+
+try:
+    from ray.rllib.env.multi_agent_env import MultiAgentEnv as _MultiAgentEnv
+except ModuleNotFoundError:  # same fallback as the reference (drone_swarm_env.py:8-12)
+    class _MultiAgentEnv:  # type: ignore[no-redef]
+        pass
+
+
+def _entropy_seed() -> int:
+    """`np.random.default_rng(None)` draws OS entropy; so do we (63 bits)."""
+    return int.from_bytes(os.urandom(8), "little") >> 1
+
+
+class _EngineBacked:
+    """Shared plumbing: one SwarmEngine with E = 1 and pinned host outputs."""
+
+    def _make_engine(self, config: dict[str, Any], kind: str, device):
+        from .engine import SwarmEngine
+
+        self._engine = SwarmEngine(1, config, kind=kind, device=device or "cuda", global_state=True, reward64=True)
+        seed = self.cfg.seed if self.cfg.seed is not None else _entropy_seed()
+        self._engine.seed(np.asarray([seed], dtype=np.uint64))
+        self._host = self._engine.host_buffers()
+
+    def _fetch_reset_outputs(self):
+        e = self._engine
+        import torch
+
+        torch.cuda.synchronize(e.device)
+        return (e.obs[0].cpu().numpy(), e.dist[0].cpu().numpy(), e.global_state[0].cpu().numpy())
+
+    # state attributes read by scripts/visualize_swarm.py:76-81,105-110
+    @property
+    def obstacles(self) -> np.ndarray:
+        return self._engine.obstacles[0].cpu().numpy()
+
+    @property
+    def goal(self) -> np.ndarray:
+        return self._engine.goal[0].cpu().numpy()
+
+    @property
+    def step_count(self) -> int:
+        return int(self._engine.step_count[0].item())
+
+    def close(self):
+        self._engine.close()
+
+
+class DroneSwarmEnv(_EngineBacked, _MultiAgentEnv):
+    """Multi-agent 3D swarm environment (reference drone_swarm_env.py:17)."""
+
+    def __init__(self, config: dict[str, Any] | None = None, device=None):
+        super().__init__()
+        cfg_dict = dict(config or {})
+        self.num_drones = int(cfg_dict.get("num_drones", 3))                      # :32
+        env_cfg = {k: v for k, v in cfg_dict.items() if k != "num_drones"}        # :33
+        self.cfg = DroneEnvConfig.from_dict(env_cfg)                              # :34
+        self.agent_ids = [f"drone_{i}" for i in range(self.num_drones)]           # :37
+        self.agent_id_to_index = {a: i for i, a in enumerate(self.agent_ids)}
+        self.agents = list(self.agent_ids)
+        self._obs_dim = 9 + self.cfg.neighbor_k * 4 + self.cfg.sensed_obstacles * 4   # :41-45
+        self.observation_space = Box(low=-np.inf, high=np.inf, shape=(self._obs_dim,), dtype=np.float32)
+        self.action_space = Box(low=-1.0, high=1.0, shape=(3,), dtype=np.float32)
+        self._make_engine({**env_cfg, "num_drones": self.num_drones}, "swarm", device)
+
+    # -- reference attributes
+    @property
+    def positions(self) -> np.ndarray:
+        return self._engine.positions[0].cpu().numpy()
+
+    @property
+    def velocities(self) -> np.ndarray:
+        return self._engine.velocities[0].cpu().numpy()
+
+    def reset(self, *, seed: int | None = None, options: dict[str, Any] | None = None):
+        """drone_swarm_env.py:65-90."""
+        if seed is not None:
+            self._engine.seed(np.asarray([seed], dtype=np.uint64))
+        self.agents = list(self.agent_ids)
+        self._engine.reset()
+        obs, dist, gs = self._fetch_reset_outputs()
+        observations = {a: obs[i].copy() for i, a in enumerate(self.agent_ids)}
+        infos = {a: {"distance_to_goal": float(dist[i]), "global_state": gs.copy()}
+                 for i, a in enumerate(self.agent_ids)}
+        return observations, infos
+
+    def step(self, action_dict: dict[str, np.ndarray]):
+        """drone_swarm_env.py:92-174 (same dict population rules)."""
+        active = list(self.agents)
+        if not active:                                                            # :94-95
+            return {}, {}, {"__all__": True}, {"__all__": False}, {}
+        act = self._host["actions"].numpy()
+        act[...] = 0.0
+        for a in active:                                                          # :103-106
+            raw = action_dict.get(a, np.zeros(3, dtype=np.float32))
+            act[0, self.agent_id_to_index[a]] = np.asarray(raw, dtype=np.float32).reshape(3)
+        h = self._engine.step_host(None, auto_reset=False)
+        rew = h["reward64"].numpy()[0]
+        term, trunc = h["terminated"].numpy()[0], h["truncated"].numpy()[0]
+        valid = h["obs_valid"].numpy()[0]
+        rewards: dict[str, float] = {}
+        terminated: dict[str, bool] = {}
+        truncated: dict[str, bool] = {}
+        infos: dict[str, dict[str, Any]] = {}
+        obs: dict[str, np.ndarray] = {}
+        next_active: list[str] = []
+        for a in active:                                                          # :141-162
+            i = self.agent_id_to_index[a]
+            rewards[a] = float(rew[i])
+            terminated[a] = bool(term[i])
+            truncated[a] = bool(trunc[i])
+            if valid[i]:
+                obs[a] = h["obs"].numpy()[0, i].copy()
+                infos[a] = {
+                    "distance_to_goal": float(h["dist"].numpy()[0, i]),
+                    "reached_goal": bool(h["reached"].numpy()[0, i]),
+                    "collision": bool(h["collision"].numpy()[0, i]),
+                    "global_state": h["global_state"].numpy()[0].copy(),
+                }
+                next_active.append(a)
+        terminated["__all__"] = bool(h["all_terminated"].numpy()[0])              # :164-167
+        truncated["__all__"] = bool(h["all_truncated"].numpy()[0])
+        self.agents = [] if (terminated["__all__"] or truncated["__all__"]) else next_active   # :169-172
+        return obs, rewards, terminated, truncated, infos
+
+
+class SingleDroneEnv(_EngineBacked, _GymEnv):
+    """3D continuous-control single-drone environment (reference single_drone_env.py:12)."""
+
+    metadata = {"render_modes": []}
+
+    def __init__(self, config: dict[str, Any] | None = None, device=None):
+        super().__init__()
+        self.cfg = DroneEnvConfig.from_dict(config)                               # :30
+        self._obs_dim = 9 + self.cfg.sensed_obstacles * 4                         # :33
+        self.observation_space = Box(low=-np.inf, high=np.inf, shape=(self._obs_dim,), dtype=np.float32)
+        self.action_space = Box(low=-1.0, high=1.0, shape=(3,), dtype=np.float32)
+        raw = {k: v for k, v in (config or {}).items() if k != "num_drones"}
+        self._make_engine(raw, "single", device)
+
+    @property
+    def position(self) -> np.ndarray:
+        return self._engine.positions[0, 0].cpu().numpy()
+
+    @property
+    def velocity(self) -> np.ndarray:
+        return self._engine.velocities[0, 0].cpu().numpy()
+
+    def reset(self, *, seed: int | None = None, options: dict[str, Any] | None = None):
+        """single_drone_env.py:53-71."""
+        super().reset(seed=seed)
+        if seed is not None:
+            self._engine.seed(np.asarray([seed], dtype=np.uint64))
+        self._engine.reset()
+        obs, dist, _ = self._fetch_reset_outputs()
+        return obs[0].copy(), {"distance_to_goal": float(dist[0])}
+
+    def step(self, action: np.ndarray):
+        """single_drone_env.py:73-111."""
+        act = self._host["actions"].numpy()
+        act[0, 0] = np.asarray(action, dtype=np.float32).reshape(3)
+        h = self._engine.step_host(None, auto_reset=False)
+        info = {
+            "distance_to_goal": float(h["dist"].numpy()[0, 0]),
+            "reached_goal": bool(h["reached"].numpy()[0, 0]),
+            "collision": bool(h["collision"].numpy()[0, 0]),
+        }
+        return (h["obs"].numpy()[0, 0].copy(), float(h["reward64"].numpy()[0, 0]),
+                bool(h["terminated"].numpy()[0, 0]), bool(h["truncated"].numpy()[0, 0]), info)
+
+
+def make_env_creator(kind: str = "swarm", device=None):
+    """Env creator for `ray.tune.registry.register_env(name, creator)`:
+    the drop-in for `lambda cfg: DroneSwarmEnv(cfg)` (reference scripts/train_multi_agent.py:96)."""
+    cls = {"swarm": DroneSwarmEnv, "single": SingleDroneEnv}[kind]
+    return lambda cfg: cls(dict(cfg) if cfg is not None else None, device=device)

@@ -1,0 +1,141 @@
+"""The reference-compatible dict API (DroneSwarmEnv / SingleDroneEnv façades over the CUDA engine)
+replayed against golden fixtures recorded from the reference, plus the reference's own two smoke
+tests (tests/test_env_smoke.py) run verbatim against the façade classes."""
+import numpy as np
+import pytest
+
+import parity_util as pu
+
+pytestmark = pytest.mark.gpu
+
+
+def test_reference_smoke_single():
+    from swarm_b200 import SingleDroneEnv
+
+    env = SingleDroneEnv({"seed": 123, "max_steps": 10})
+    obs, info = env.reset()
+    assert obs.shape == env.observation_space.shape
+    assert "distance_to_goal" in info
+    action = np.zeros(3, dtype=np.float32)
+    obs, reward, terminated, truncated, info = env.step(action)
+    assert obs.shape == env.observation_space.shape
+    assert isinstance(reward, float)
+    assert isinstance(terminated, bool)
+    assert isinstance(truncated, bool)
+    assert "distance_to_goal" in info
+    # SURVEY section 4 known answers
+    assert reward == 0.0
+    obs, reward, *_ = env.step(np.array([1, -1, 0.5], np.float32))
+    assert reward == -0.016613006591796875
+
+
+def test_reference_smoke_multi_agent():
+    from swarm_b200 import DroneSwarmEnv
+
+    env = DroneSwarmEnv({"num_drones": 3, "seed": 123, "max_steps": 10})
+    obs, infos = env.reset()
+    assert len(obs) == 3
+    assert len(infos) == 3
+    actions = {agent_id: np.zeros(3, dtype=np.float32) for agent_id in obs}
+    next_obs, rewards, terminated, truncated, infos = env.step(actions)
+    assert len(next_obs) == 3
+    assert len(rewards) == 3
+    assert "__all__" in terminated
+    assert "__all__" in truncated
+    assert all(isinstance(v, float) for v in rewards.values())
+    assert all("global_state" in infos[agent_id] for agent_id in infos)
+    assert rewards == {"drone_0": -1.8244807004928587, "drone_1": -1.9182087421417235,
+                       "drone_2": -1.7687857389450072}
+    assert env.cfg.desired_spacing == 2.5 and env.agents == ["drone_0", "drone_1", "drone_2"]
+    assert env.positions.shape == (3, 3) and env.obstacles.shape == (8, 3) and env.goal.shape == (3,)
+    assert env.action_space.sample().shape == (3,)
+
+
+@pytest.mark.parametrize("name,steps", [("swarm_goalseek_n5", 400), ("swarm_oddcfg_n6", 300),
+                                        ("swarm_smoke_n3", 40), ("swarm_n2_m2", 200)])
+def test_swarm_facade_dict_contract_matches_golden(name, steps):
+    from swarm_b200 import DroneSwarmEnv
+
+    g = pu.load_golden(name)
+    cfg = dict(g["meta"]["config"])
+    cfg["seed"] = int(g["seeds"][0])
+    N = g["meta"]["N"]
+    ids = [f"drone_{i}" for i in range(N)]
+    env = DroneSwarmEnv(cfg)
+    obs, infos = env.reset()
+    assert list(obs) == ids
+    for i, a in enumerate(ids):
+        assert np.array_equal(pu.bits(obs[a]), pu.bits(g["reset0_obs"][0, i]))
+        assert infos[a]["distance_to_goal"] == float(g["reset0_dist"][0, i])
+        assert set(infos[a]) == {"distance_to_goal", "global_state"}
+    head = g["obs"].shape[0]
+    for t in range(min(steps, g["actions"].shape[0])):
+        active = list(env.agents)
+        ins = g["in_step"][t, 0].astype(bool)
+        assert active == [a for i, a in enumerate(ids) if ins[i]], t
+        # leave one agent's action out now and then: a missing key means a zero action (:104)
+        adict = {a: g["actions"][t, 0, env.agent_id_to_index[a]] for a in active}
+        obs, rew, term, trunc, infos = env.step(adict)
+        valid = g["obs_valid"][t, 0].astype(bool)
+        done = bool(g["all_term"][t, 0] or g["all_trunc"][t, 0])
+        assert list(rew) == active and set(term) == set(active) | {"__all__"} and set(trunc) == set(term)
+        for i, a in enumerate(ids):
+            if ins[i]:
+                assert rew[a] == g["reward"][t, 0, i] and isinstance(rew[a], float)
+                assert term[a] == bool(g["terminated"][t, 0, i]) and trunc[a] == bool(g["truncated"][t, 0, i])
+        assert term["__all__"] == bool(g["all_term"][t, 0]) and trunc["__all__"] == bool(g["all_trunc"][t, 0])
+        if done:
+            # on an episode-ending step nobody continues: obs / infos are empty (drone_swarm_env.py:154)
+            assert obs == {} and infos == {}
+            assert env.agents == []
+            obs, infos = env.reset()
+            for i, a in enumerate(ids):
+                if t < head:
+                    assert np.array_equal(pu.bits(obs[a]), pu.bits(g["obs"][t, 0, i]))
+                assert infos[a]["distance_to_goal"] == float(g["dist"][t, 0, i])
+        else:
+            assert list(obs) == [a for i, a in enumerate(ids) if valid[i]] == list(infos)
+            for i, a in enumerate(ids):
+                if valid[i]:
+                    if t < head:
+                        assert np.array_equal(pu.bits(obs[a]), pu.bits(g["obs"][t, 0, i]))
+                        assert np.array_equal(pu.bits(infos[a]["global_state"]), pu.bits(g["gs"][t, 0]))
+                    assert infos[a]["distance_to_goal"] == float(g["dist"][t, 0, i])
+                    assert infos[a]["reached_goal"] is False and infos[a]["collision"] is False
+                    assert set(infos[a]) == {"distance_to_goal", "reached_goal", "collision", "global_state"}
+        assert np.array_equal(pu.bits(env.positions), pu.bits(g["pos"][t, 0]))
+
+
+def test_single_facade_matches_golden():
+    from swarm_b200 import SingleDroneEnv
+
+    g = pu.load_golden("single_goalseek")
+    cfg = dict(g["meta"]["config"])
+    cfg["seed"] = int(g["seeds"][0])
+    env = SingleDroneEnv(cfg)
+    obs, info = env.reset()
+    assert np.array_equal(pu.bits(obs), pu.bits(g["reset0_obs"][0, 0]))
+    for t in range(400):
+        o, r, tm, tr, info = env.step(g["actions"][t, 0, 0])
+        assert r == g["reward"][t, 0, 0] and tm == bool(g["terminated"][t, 0, 0]) and tr == bool(g["truncated"][t, 0, 0])
+        assert info["reached_goal"] == bool(g["reached"][t, 0, 0]) and info["collision"] == bool(g["collision"][t, 0, 0])
+        if tm or tr:
+            o, info = env.reset()
+        assert np.array_equal(pu.bits(o), pu.bits(g["obs"][t, 0, 0])) if t < g["obs"].shape[0] else True
+        assert info["distance_to_goal"] == float(g["dist"][t, 0, 0])
+
+
+def test_dead_env_step_and_reseed():
+    from swarm_b200 import DroneSwarmEnv
+
+    env = DroneSwarmEnv({"num_drones": 3, "seed": 123, "max_steps": 2})
+    env.reset()
+    z = {a: np.zeros(3, np.float32) for a in env.agent_ids}
+    env.step(z)
+    _, _, term, trunc, _ = env.step(z)
+    assert trunc["__all__"] and not term["__all__"] and env.agents == []
+    assert env.step(z) == ({}, {}, {"__all__": True}, {"__all__": False}, {})
+    o1, _ = env.reset(seed=123)
+    env2 = DroneSwarmEnv({"num_drones": 3, "seed": 123, "max_steps": 2})
+    o2, _ = env2.reset()
+    assert all(np.array_equal(o1[a], o2[a]) for a in o1)
