@@ -117,6 +117,18 @@ void fill_params(const SwarmConfig& c, DevParams& p) {
     p.m_pad = p.M > 0 ? p.M : 1;
     p.n_draws = 3 * p.N + 3 + 3 * p.M;
     p.smem_per_warp = (2 * p.n_tab + p.G + p.G * p.m_pad) * 16 + 32 * p.D * 4;
+    if (p.N <= 32) {
+        // distance-matrix rows: stride >= N - 1, = 1 (mod 4) so row reads are conflict-free and the
+        // symmetric writes are at most 2-way conflicted; the matrix aliases the obs staging tile
+        int srow = p.N - 1 > 1 ? p.N - 1 : 1;
+        while ((srow & 3) != 1) ++srow;
+        p.srow = srow;
+        const int region = 32 * p.D > 32 * srow + 8 ? 32 * p.D : 32 * srow + 8;
+        p.stage_off = (2 * p.n_tab + p.G + p.G * p.m_pad) * 4;
+        p.smem_per_warp = p.stage_off * 4 + ((region + 3) & ~3) * 4;
+    }
+    p.n_others = (double)(p.N - 1);
+    p.inv_n_others = p.N > 1 ? 1.0 / (double)(p.N - 1) : 0.0;
     p.max_steps = c.max_steps;
     // float32 constants (numpy NEP 50: a Python float meeting a float32 array / scalar is cast to f32)
     p.amax = (float)c.max_accel;                       // drone_swarm_env.py:107

@@ -36,6 +36,8 @@ struct DevParams {
     int env_begin, env_count;     // env range of this launch
     int n_groups;                 // ceil(env_count / G)
     int smem_per_warp;            // bytes
+    int srow;                     // N <= 32 kernel: row stride (floats) of the per-warp distance matrix
+    int stage_off;                // N <= 32 kernel: float offset of the staging / matrix region in the warp slice
     int mode;                     // Mode
     int auto_reset;
     int max_steps;
@@ -46,6 +48,7 @@ struct DevParams {
     // Python-float (double) constants
     double k_p, r_goal, r_col, neg_k_f, d_star;
     double rng_lo, rng_range;     // uniform(-W/2, W/2): lo, hi - lo
+    double n_others, inv_n_others;  // N - 1 and RN(1 / (N - 1)) for the mean of the formation errors
     // state
     float4* pos4; float4* vel4; float4* goal4; float4* obst4;
     int* step_count; unsigned long long* rng; float* ep_return;
