@@ -43,6 +43,7 @@ struct SwarmHandle {
     int blocks_per_sm;
     size_t smem_bytes;
     JumpEntry* jump_dev;
+    uint8_t* reset_mask_dev;  // [E]
     int64_t launches;
     // host-buffer path
     cudaStream_t chunk_stream[kHostChunks];
@@ -120,7 +121,7 @@ void fill_params(const SwarmConfig& c, DevParams& p) {
     if (p.N <= 32) {
         // distance-matrix rows: stride >= N - 1, = 1 (mod 4) so row reads are conflict-free and the
         // symmetric writes are at most 2-way conflicted; the matrix aliases the obs staging tile
-        int srow = p.N - 1 > 1 ? p.N - 1 : 1;
+        int srow = ((p.N - 1 + 7) & ~7) > 1 ? ((p.N - 1 + 7) & ~7) : 1;  // rows are padded to whole blocks of 8
         while ((srow & 3) != 1) ++srow;
         p.srow = srow;
         const int region = 32 * p.D > 32 * srow + 8 ? 32 * p.D : 32 * srow + 8;
@@ -167,6 +168,7 @@ int bind_buffers(const SwarmHandle* h, const SwarmBuffers* b, DevParams& p) {
     p.gs = b->global_state; p.episode_return = b->episode_return; p.episode_length = b->episode_length;
     p.stats = reinterpret_cast<unsigned long long*>(b->stats);
     p.jump = h->jump_dev;
+    p.reset_mask = h->reset_mask_dev;
     return SWARM_OK;
 }
 
@@ -179,6 +181,15 @@ int launch(SwarmHandle* h, DevParams& p, int env_begin, int env_count, cudaStrea
     const int grid = ctas_needed < resident ? ctas_needed : resident;
     CUDA_TRY(launch_env_kernel(p, h->cfg.norm_mode, h->cfg.env_kind, grid, h->smem_bytes, stream));
     h->launches++;
+    if (p.mode == kModeStep && p.auto_reset && p.N <= 32) {
+        // N <= 32: the auto-reset runs as a second, tiny launch (kept out of the step kernel so each
+        // launch's instruction working set fits the SM instruction cache)
+        DevParams q = p;
+        q.mode = kModeAutoReset;
+        q.env_mask = h->reset_mask_dev;
+        CUDA_TRY(launch_env_kernel(q, h->cfg.norm_mode, h->cfg.env_kind, grid, h->smem_bytes, stream));
+        h->launches++;
+    }
     return SWARM_OK;
 }
 
@@ -232,10 +243,11 @@ int swarm_create(const SwarmConfig* cfg, SwarmHandle** out) {
     h->device = dev;
     h->launches = 0;
     h->jump_dev = nullptr;
+    h->reset_mask_dev = nullptr;
     h->actions_dev = nullptr;
     h->host_path_ready = false;
     fill_params(*cfg, h->base);
-    h->smem_bytes = (size_t)h->base.smem_per_warp * kWarpsPerCta;
+    h->smem_bytes = (size_t)h->base.smem_per_warp * kWarpsPerCta + (size_t)kWarpsPerCta * SWARM_STATS_WORDS * 8;
 
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, dev);
@@ -257,10 +269,13 @@ int swarm_create(const SwarmConfig* cfg, SwarmHandle** out) {
     e = cudaMalloc(&h->jump_dev, table.size() * sizeof(JumpEntry));
     if (e == cudaSuccess)
         e = cudaMemcpy(h->jump_dev, table.data(), table.size() * sizeof(JumpEntry), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&h->reset_mask_dev, (size_t)cfg->num_envs);
+    if (e == cudaSuccess) e = cudaMemset(h->reset_mask_dev, 0, (size_t)cfg->num_envs);
     if (e != cudaSuccess) {
         if (h->jump_dev) cudaFree(h->jump_dev);
+        if (h->reset_mask_dev) cudaFree(h->reset_mask_dev);
         delete h;
-        return fail(SWARM_E_CUDA, "jump table upload failed: %s", cudaGetErrorString(e));
+        return fail(SWARM_E_CUDA, "jump table / reset mask allocation failed: %s", cudaGetErrorString(e));
     }
     *out = h;
     return SWARM_OK;
@@ -277,6 +292,7 @@ int swarm_destroy(SwarmHandle* h) {
     }
     if (h->actions_dev) cudaFree(h->actions_dev);
     if (h->jump_dev) cudaFree(h->jump_dev);
+    if (h->reset_mask_dev) cudaFree(h->reset_mask_dev);
     delete h;
     return SWARM_OK;
 }

@@ -17,7 +17,7 @@ constexpr int kWarpsPerCta = SWARM_WARPS_PER_CTA;
 constexpr int kThreadsPerCta = kWarpsPerCta * 32;
 constexpr int kMinBlocksPerSm = SWARM_MIN_BLOCKS;
 
-enum Mode : int { kModeStep = 0, kModeReset = 1, kModeObserve = 2 };
+enum Mode : int { kModeStep = 0, kModeReset = 1, kModeObserve = 2, kModeAutoReset = 3 };  // 3: reset that keeps the step's reward / flags
 
 // One entry per draw count k: state_{n+k} = A^k * state_n + G_k * inc  (mod 2^128)
 struct __align__(16) JumpEntry {
@@ -59,6 +59,7 @@ struct DevParams {
     uint8_t *terminated, *truncated, *reached, *collision, *obs_valid, *all_term, *all_trunc;
     float* gs; float* episode_return; int* episode_length;
     unsigned long long* stats;
+    uint8_t* reset_mask;          // [E] N <= 32 step kernel -> aux kernel: env needs its auto-reset
     const JumpEntry* jump;        // [n_draws + 1]
 };
 

@@ -743,7 +743,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
 // The matrix aliases the observation staging tile.  Step, auto-reset and observe share one copy
 // of the scan code through a small warp-uniform state machine.
 // ------------------------------------------------------------------------------------------
-enum SmallStage : int { kStageStepScan = 0, kStageReset = 1, kStageObserveScan = 2 };
+enum SmallMode : int { kSmallStep = 0, kSmallAux = 1 };  // aux = reset / auto-reset / observe launches
 
 __device__ __forceinline__ double mean_markstein(double sum, double n, double inv_n) {
     // RN(sum / n) for a small integer n: two residual corrections with y = RN(1/n) (Markstein);
@@ -755,7 +755,12 @@ __device__ __forceinline__ double mean_markstein(double sum, double n, double in
     return __fma_rn(r, inv_n, q);
 }
 
-template <int KT, int ST, bool EXACT, int NORM, int KIND>
+// The step kernel (MODE = kSmallStep) contains no reset / observe code and the aux kernel no
+// reward / flag code: the instruction working set of each launch stays inside the SM's
+// instruction cache (the fused single-kernel version measured 82 % icc hit rate).  With
+// auto_reset the step launch writes a per-env reset mask and the host enqueues the aux kernel
+// right behind it on the same stream.
+template <int KT, int ST, bool EXACT, int NORM, int KIND, int MODE>
 __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_kernel_small(const DevParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5;
@@ -775,13 +780,14 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
     const unsigned env_lanes = e_l < G ? (N == 32 ? FULL_MASK : (((1u << N) - 1u) << e_base)) : 0u;
     const int n_others = N - 1;
     const int n8 = n_others >= 8 ? (n_others & ~7) : 0;
+    const int n_pad = (n_others + 7) & ~7;  // matrix rows are padded with +inf to whole blocks of 8
     const int half = N >> 1;
     float* drow = region + lane * srow;  // this drone's row of the distance matrix
-    float* srow_obs = region + lane * D; // ... and its row of the staging tile
 
-    unsigned st_asteps = 0, st_esteps = 0;
-    unsigned st_eps = 0, st_succ = 0, st_col = 0, st_to = 0, st_len = 0;
-    double st_ret = 0.0;
+    // per-warp statistics live in shared memory (leader lanes update them; flushed once at the end)
+    unsigned long long* wstats =
+        reinterpret_cast<unsigned long long*>(smem_raw + (size_t)kWarpsPerCta * P.smem_per_warp) + warp * SWARM_STATS_WORDS;
+    if (MODE == kSmallStep && lane < SWARM_STATS_WORDS) wstats[lane] = 0ull;
 
     const int warps_total = gridDim.x * kWarpsPerCta;
     for (int grp = blockIdx.x * kWarpsPerCta + warp; grp < P.n_groups; grp += warps_total) {
@@ -789,37 +795,42 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
         const int n_env = min(G, P.env_begin + P.env_count - env0);
         const bool lane_ok = e_l < n_env;
         const int env = env0 + (lane_ok ? e_l : 0);
-        const long long a0 = (long long)env0 * N;     // first agent of the group
-        const long long a = a0 + (lane_ok ? lane : 0); // this lane's agent
+        const long long a0 = (long long)env0 * N;      // first agent of the group
+        const long long a = a0 + (lane_ok ? lane : 0);  // this lane's agent
         const float4* tobs = tab_obst + e_l * P.m_pad;
         const bool leader = lane_ok && i == 0;
+        const unsigned ok_lanes = __ballot_sync(FULL_MASK, lane_ok);
+
+        unsigned reset_envs = 0;  // aux: bit el = env el is (re)drawn
+        if (MODE == kSmallAux && P.mode != kModeObserve) {
+            const bool want = lane < n_env && (P.env_mask == nullptr || P.env_mask[env0 + lane] != 0);
+            reset_envs = __ballot_sync(FULL_MASK, want);
+            if (reset_envs == 0) continue;  // nothing to reset in this group
+        }
 
         __syncwarp();  // the previous group is done with the shared-memory slice
         // ---- loads (all issued before first use)
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f), v = p, g4 = p;
-        float ax = 0.f, ay = 0.f, az = 0.f;
+        float ax = 0.f, ay = 0.f, az = 0.f, ep_ret = 0.f;
         int sc = 0;
         if (lane_ok) {
             p = P.pos4[a];
             v = P.vel4[a];
             g4 = P.goal4[env];
-            sc = P.step_count[env];
-            if (P.mode == kModeStep) {
+            if (MODE == kSmallStep) {
+                sc = P.step_count[env];
+                ep_ret = P.ep_return[env];
                 ax = P.actions[a * 3 + 0]; ay = P.actions[a * 3 + 1]; az = P.actions[a * 3 + 2];
             }
         }
         for (int idx = lane; idx < n_env * M; idx += 32) tab_obst[idx] = P.obst4[(long long)env0 * M + idx];
         float gx = g4.x, gy = g4.y, gz = g4.z;
 
-        bool alive = false;
+        bool alive = KIND == SWARM_KIND_SINGLE ? lane_ok : (lane_ok && p.w != 0.0f);
         float prev_d = 0.f;
-        int stage = kStageObserveScan;
-        unsigned reset_envs = 0;   // bit el: env el is (re)drawn in this launch
-        unsigned out_lanes = 0;    // lanes whose obs row is staged in the current pass
-        if (P.mode == kModeStep) {
-            stage = kStageStepScan;
+        unsigned out_lanes = ok_lanes;  // lanes whose obs row is produced by this launch
+        if (MODE == kSmallStep) {
             // =========================== phase A: integrate (:98-118) ===========================
-            alive = KIND == SWARM_KIND_SINGLE ? lane_ok : (lane_ok && p.w != 0.0f);
             prev_d = norm1d<NORM>(__fsub_rn(gx, p.x), __fsub_rn(gy, p.y), __fsub_rn(gz, p.z));  // :98-101
             if (alive) {
                 ax = clipf(ax, -1.0f, 1.0f); ay = clipf(ay, -1.0f, 1.0f); az = clipf(az, -1.0f, 1.0f);
@@ -840,208 +851,260 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
             p.x = clipf(p.x, -P.bound, P.bound);
             p.y = clipf(p.y, -P.bound, P.bound);
             p.z = clipf(p.z, -P.bound, P.bound);
-            out_lanes = __ballot_sync(FULL_MASK, lane_ok);
-        } else {
-            alive = KIND == SWARM_KIND_SINGLE ? lane_ok : (lane_ok && p.w != 0.0f);
-            if (P.mode == kModeReset) {
-                const bool want = lane < n_env && (P.env_mask == nullptr || P.env_mask[env0 + lane] != 0);
-                reset_envs = __ballot_sync(FULL_MASK, want);
-                stage = kStageReset;
-            } else {
-                out_lanes = __ballot_sync(FULL_MASK, lane_ok);
-            }
         }
         if (lane_ok) tab_pos[lane] = make_float4(p.x, p.y, p.z, alive ? 1.0f : 0.0f);
-        const unsigned alive_mask = __ballot_sync(FULL_MASK, alive);
-        const int n_alive_env = __popc(alive_mask & env_lanes);
+        tab_vel[lane] = make_float4(v.x, v.y, v.z, prev_d);  // parked here while the scans need the registers
 
-        // per-step results kept across the passes
-        float rew32 = 0.f;
-        bool reached = false, collided = false;
-
-        while (true) {
-            if (stage == kStageReset) {
-                // ================================ reset (:65-80) ================================
-                if (reset_envs == 0) break;
-                if (lane < n_env) tab_goal[lane] = P.goal4[env0 + lane];
-                for (int el = 0; el < n_env; ++el) {
-                    if (!((reset_envs >> el) & 1u)) continue;
-                    const int renv = env0 + el;
-                    const unsigned long long sh = P.rng[(long long)renv * 4 + 0], sl = P.rng[(long long)renv * 4 + 1];
-                    const unsigned long long ih = P.rng[(long long)renv * 4 + 2], il = P.rng[(long long)renv * 4 + 3];
-                    for (int k = lane; k < P.n_draws; k += 32) {
-                        unsigned long long oh, ol;
-                        pcg_jump(P.jump[k + 1], sh, sl, ih, il, oh, ol);
-                        const float val = pcg_uniform_f32(oh, ol, P.rng_lo, P.rng_range);
-                        // draw order: positions (N,3) -> goal (3,) -> obstacles (M,3)
-                        if (k < 3 * N) {
-                            reinterpret_cast<float*>(tab_pos + el * N + k / 3)[k % 3] = val;
-                        } else if (k < 3 * N + 3) {
-                            reinterpret_cast<float*>(tab_goal + el)[k - 3 * N] = val;
-                        } else {
-                            const int kk = k - 3 * N - 3;
-                            reinterpret_cast<float*>(tab_obst + el * P.m_pad + kk / 3)[kk % 3] = val;
-                        }
-                    }
-                    if (lane < N) reinterpret_cast<float*>(tab_pos + el * N + lane)[3] = 1.0f;
-                    if (lane == 0) {
-                        unsigned long long oh, ol;
-                        pcg_jump(P.jump[P.n_draws], sh, sl, ih, il, oh, ol);
-                        P.rng[(long long)renv * 4 + 0] = oh;
-                        P.rng[(long long)renv * 4 + 1] = ol;
-                        P.step_count[renv] = 0;
-                        P.ep_return[renv] = 0.0f;
-                        reinterpret_cast<float*>(tab_goal + el)[3] = 0.0f;
-                    }
-                    for (int k = lane; k < M; k += 32) reinterpret_cast<float*>(tab_obst + el * P.m_pad + k)[3] = 0.0f;
-                }
-                __syncwarp();
-                const bool fresh = lane_ok && ((reset_envs >> e_l) & 1u);
-                if (lane < n_env && ((reset_envs >> lane) & 1u)) P.goal4[env0 + lane] = tab_goal[lane];
-                for (int idx = lane; idx < n_env * M; idx += 32)
-                    if ((reset_envs >> (idx / M)) & 1u) P.obst4[(long long)env0 * M + idx] = tab_obst[idx];
-                if (fresh) {
-                    p = tab_pos[lane];
-                    v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    g4 = tab_goal[e_l]; gx = g4.x; gy = g4.y; gz = g4.z;
-                    alive = true;
-                    P.pos4[a] = p;
-                    P.vel4[a] = v;
-                }
-                out_lanes = __ballot_sync(FULL_MASK, fresh);
-                stage = kStageObserveScan;
-            }
-            __syncwarp();  // position / obstacle tables complete
-
-            // ========================= B1: symmetric distance matrix =========================
-            float nd[KT]; int nj[KT]; float od[ST]; int om[ST];
-#pragma unroll
-            for (int q = 0; q < KT; ++q) { nd[q] = F32_INF; nj[q] = -1; }
-#pragma unroll
-            for (int q = 0; q < ST; ++q) { od[q] = F32_INF; om[q] = -1; }
-            if (KIND == SWARM_KIND_SWARM) {
-                for (int r0 = 1; r0 <= half; r0 += 4) {
-                    float s[4];
-                    int jj[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int r = r0 + u;
-                        int j = i + r;
-                        j = j >= N ? j - N : j;
-                        const bool valid = r <= half && lane_ok;
-                        jj[u] = valid ? j : i;
-                        const float4 q = tab_pos[e_base + jj[u]];
-                        const float ss = sumsq1d<NORM>(__fsub_rn(q.x, p.x), __fsub_rn(q.y, p.y), __fsub_rn(q.z, p.z));
-                        s[u] = valid ? ss : 1.0f;
-                    }
-                    const float smin = fminf(fminf(s[0], s[1]), fminf(s[2], s[3]));
-                    float d[4];
-                    if (smin >= SQRT_FAST_MIN) {
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) d[u] = sqrt_rn_fast(s[u]);
-                    } else {  // coincident drones (d == 0) or denormal range: full IEEE path
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) d[u] = __fsqrt_rn(s[u]);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int r = r0 + u;
-                        const int j = jj[u];
-                        if (r <= half && lane_ok) {
-                            drow[j - (j > i ? 1 : 0)] = d[u];                     // own row, compacted column
-                            if (2 * r != N)                                        // (r == N/2: the partner does it itself)
-                                region[(e_base + j) * srow + (i - (i > j ? 1 : 0))] = d[u];  // partner's row
-                        }
+        if (MODE == kSmallAux && reset_envs) {
+            // ================================ reset (:65-80) ================================
+            __syncwarp();
+#pragma unroll 1
+            for (int el = 0; el < n_env; ++el) {
+                if (!((reset_envs >> el) & 1u)) continue;
+                const int renv = env0 + el;
+                const unsigned long long sh = P.rng[(long long)renv * 4 + 0], sl = P.rng[(long long)renv * 4 + 1];
+                const unsigned long long ih = P.rng[(long long)renv * 4 + 2], il = P.rng[(long long)renv * 4 + 3];
+#pragma unroll 1
+                for (int k = lane; k < P.n_draws; k += 32) {
+                    unsigned long long oh, ol;
+                    pcg_jump(P.jump[k + 1], sh, sl, ih, il, oh, ol);
+                    const float val = pcg_uniform_f32(oh, ol, P.rng_lo, P.rng_range);
+                    // draw order: positions (N,3) -> goal (3,) -> obstacles (M,3)
+                    if (k < 3 * N) {
+                        reinterpret_cast<float*>(tab_pos + el * N + k / 3)[k % 3] = val;
+                    } else if (k < 3 * N + 3) {
+                        reinterpret_cast<float*>(tab_goal + el)[k - 3 * N] = val;
+                    } else {
+                        const int kk = k - 3 * N - 3;
+                        reinterpret_cast<float*>(tab_obst + el * P.m_pad + kk / 3)[kk % 3] = val;
                     }
                 }
+                if (lane < N) {
+                    reinterpret_cast<float*>(tab_pos + el * N + lane)[3] = 1.0f;
+                    tab_vel[el * N + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (lane == 0) {
+                    unsigned long long oh, ol;
+                    pcg_jump(P.jump[P.n_draws], sh, sl, ih, il, oh, ol);
+                    P.rng[(long long)renv * 4 + 0] = oh;
+                    P.rng[(long long)renv * 4 + 1] = ol;
+                    P.step_count[renv] = 0;
+                    P.ep_return[renv] = 0.0f;
+                    reinterpret_cast<float*>(tab_goal + el)[3] = 0.0f;
+                }
+                for (int k = lane; k < M; k += 32) reinterpret_cast<float*>(tab_obst + el * P.m_pad + k)[3] = 0.0f;
             }
             __syncwarp();
+            const bool fresh = lane_ok && ((reset_envs >> e_l) & 1u);
+            if (lane < n_env && ((reset_envs >> lane) & 1u)) P.goal4[env0 + lane] = tab_goal[lane];
+            for (int idx = lane; idx < n_env * M; idx += 32)
+                if ((reset_envs >> (idx / M)) & 1u) P.obst4[(long long)env0 * M + idx] = tab_obst[idx];
+            if (fresh) {
+                p = tab_pos[lane];
+                g4 = tab_goal[e_l]; gx = g4.x; gy = g4.y; gz = g4.z;
+                alive = true;
+                P.pos4[a] = p;
+                P.vel4[a] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            out_lanes = __ballot_sync(FULL_MASK, fresh);
+        }
+        const unsigned alive_mask = __ballot_sync(FULL_MASK, alive);
+        const int n_alive_env = __popc(alive_mask & env_lanes);
+        __syncwarp();  // position / obstacle tables complete
 
-            // ================ B2: own row in ascending order: k-nearest + formation ================
-            bool pair_hit = false;
-            double form_sum = 0.0;
-            int form_n = 0;
-            if (KIND == SWARM_KIND_SWARM && lane_ok) {
-                if (stage != kStageStepScan || (alive && n_alive_env == N)) {
-                    // every drone active: column c is element c of np.mean's operand (:210-224)
-                    const double d_star = P.d_star;
-                    double r8[8];
+        // ========================= B1: symmetric distance matrix =========================
+        if (KIND == SWARM_KIND_SWARM) {
+            // Round r pairs drone i with j = i + r (wrapping inside the env).  Rounds 1 .. N/2 cover
+            // every unordered pair; for even N the last round is visited from both ends, which only
+            // stores the same value twice.  All addresses are (select of two lane constants) + r * stride.
+            const int wrap_at = N - i;  // r >= wrap_at  <=>  i + r wraps
+            const float4* tp_nw = tab_pos + lane;  // partner position, no wrap / wrap
+            const float4* tp_w = tp_nw - N;
+            float* own_nw = drow + (i - 1);        // own row, column j - 1 (j > i) / j (j < i)
+            float* own_w = drow + (i - N);
+            float* par_nw = drow + i;              // partner row j, column i (i < j) / i - 1 (i > j)
+            float* par_w = drow - N * srow + (i - 1);
+            int r0 = 1;
+#pragma unroll 1
+            for (; r0 + 3 <= half; r0 += 4) {
+                float s[4];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) r8[u] = 0.0;
-                    for (int cb = 0; cb < n8; cb += 8) {
+                for (int u = 0; u < 4; ++u) {
+                    const int r = r0 + u;
+                    const float4 q = (r >= wrap_at ? tp_w : tp_nw)[r];
+                    s[u] = sumsq1d<NORM>(__fsub_rn(q.x, p.x), __fsub_rn(q.y, p.y), __fsub_rn(q.z, p.z));
+                }
+                const float smin = fminf(fminf(s[0], s[1]), fminf(s[2], s[3]));
+                float d[4];
+                if (smin >= SQRT_FAST_MIN) {
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const float d = drow[cb + u];
-                            topk_insert<KT>(d, cb + u, nd, nj);
-                            r8[u] = __dadd_rn(r8[u], fabs(__dsub_rn((double)d, d_star)));
-                        }
+                    for (int u = 0; u < 4; ++u) d[u] = sqrt_rn_fast(s[u]);
+                } else {  // coincident drones (d == 0) or denormal range: full IEEE path
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) d[u] = __fsqrt_rn(s[u]);
+                }
+                if (lane_ok) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = r0 + u;
+                        const bool w = r >= wrap_at;
+                        (w ? own_w : own_nw)[r] = d[u];
+                        (w ? par_w : par_nw)[r * srow] = d[u];
                     }
-                    double res = n8 > 0 ? tree8(r8) : 0.0;
-                    if (n8 < n_others) {
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int c = n8 + u;
-                            const bool valid = c < n_others;
-                            const float d = valid ? drow[valid ? c : 0] : F32_INF;
-                            topk_insert<KT>(d, c, nd, nj);
-                            res = __dadd_rn(res, valid ? fabs(__dsub_rn((double)d, d_star)) : 0.0);
-                        }
-                    }
-                    pair_hit = nd[0] <= P.thr_pair;  // nearest drone decides (:202-207)
-                    form_sum = res;
-                    form_n = n_others;
-                } else {
-                    // some drones are parked (or this one is): compact the active ones on the fly
-                    const unsigned em = (alive_mask & env_lanes) >> e_base;  // bit j: drone j of this env active
-                    const unsigned cm = (em & ((1u << i) - 1u)) | ((em >> (i + 1)) << i);  // bit c: column c active
-                    const int n_f = alive ? n_alive_env - 1 : 0;
-                    const int nf8 = n_f >= 8 ? (n_f & ~7) : 0;
-                    double r8[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) r8[u] = 0.0;
-                    double res = 0.0;
-                    bool tree_done = false;
-                    int cnt = 0;
-                    for (int c = 0; c < n_others; ++c) {
-                        const float d = drow[c];
-                        topk_insert<KT>(d, c, nd, nj);
-                        if (alive && ((cm >> c) & 1u)) {
-                            pair_hit |= d <= P.thr_pair;
-                            const double err = fabs(__dsub_rn((double)d, P.d_star));
-                            if (cnt < nf8) {
-                                const int lane8 = cnt & 7;
-#pragma unroll
-                                for (int u = 0; u < 8; ++u) r8[u] = __dadd_rn(r8[u], lane8 == u ? err : 0.0);
-                            } else {
-                                if (!tree_done && nf8 > 0) res = tree8(r8);
-                                tree_done = true;
-                                res = __dadd_rn(res, err);
-                            }
-                            ++cnt;
-                        }
-                    }
-                    if (!tree_done && nf8 > 0) res = tree8(r8);
-                    form_sum = res;
-                    form_n = n_f;
                 }
             }
-            // ---- obstacles: _nearest_obstacle_features (:273-291) + obstacle part of _collision_mask
-            {
-                int mb = 0;
-                for (; mb + 4 <= M; mb += 4) obst_block4<ST, true>(tobs, mb, M, p.x, p.y, p.z, od, om);
-                if (mb < M) obst_block4<ST, false>(tobs, mb, M, p.x, p.y, p.z, od, om);
+#pragma unroll 1
+            for (; r0 <= half; ++r0) {  // leftover rounds (N/2 not a multiple of 4)
+                const bool w = r0 >= wrap_at;
+                const float4 q = lane_ok ? (w ? tp_w : tp_nw)[r0] : p;
+                const float dd = norm1d<NORM>(__fsub_rn(q.x, p.x), __fsub_rn(q.y, p.y), __fsub_rn(q.z, p.z));
+                if (lane_ok) {
+                    (w ? own_w : own_nw)[r0] = dd;
+                    (w ? par_w : par_nw)[r0 * srow] = dd;
+                }
             }
-            const bool obst_hit = od[0] <= P.thr_obst;
-            const float curr_d = norm1d<NORM>(__fsub_rn(gx, p.x), __fsub_rn(gy, p.y), __fsub_rn(gz, p.z));
-            __syncwarp();  // every lane is done with the distance matrix: the region becomes the obs tile
+            // pad the row to a multiple of 8 columns with +inf so B2 runs whole blocks only
+            if (lane_ok) {
+#pragma unroll
+                for (int u = 0; u < 7; ++u)
+                    if (n_others + u < n_pad) drow[n_others + u] = F32_INF;
+            }
+        }
+        __syncwarp();
 
-            // ============================ obs row -> staging tile ============================
-            if ((out_lanes >> lane) & 1u) {
-                float* row = srow_obs;
-                row[0] = p.x; row[1] = p.y; row[2] = p.z;
-                row[3] = v.x; row[4] = v.y; row[5] = v.z;
-                row[6] = __fsub_rn(gx, p.x); row[7] = __fsub_rn(gy, p.y); row[8] = __fsub_rn(gz, p.z);
-                int off = 9;
+        // ================ B2: own row in ascending order: k-nearest (+ formation) ================
+        float nd[KT]; int nj[KT];
+#pragma unroll
+        for (int q = 0; q < KT; ++q) { nd[q] = F32_INF; nj[q] = -1; }
+        bool pair_hit = false;
+        double form_sum = 0.0;
+        int form_n = 0;
+        if (KIND == SWARM_KIND_SWARM && lane_ok) {
+            if (MODE == kSmallAux) {
+#pragma unroll 1
+                for (int cb = 0; cb < n_pad; cb += 8) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) topk_insert<KT>(drow[cb + u], cb + u, nd, nj);
+                }
+            } else if (alive && n_alive_env == N) {
+                // every drone active: column c is element c of np.mean's operand (:210-224).  numpy sums
+                // columns [0, n8) in 8 lanes (tree-combined) and then adds columns [n8, N-1) in order; the
+                // last block therefore runs on fresh lanes that are added sequentially afterwards.
+                const double d_star = P.d_star;
+                double r8[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) r8[u] = 0.0;
+                double res = 0.0;
+#pragma unroll 1
+                for (int cb = 0; cb < n_pad; cb += 8) {
+                    if (cb == n8 && n8 > 0) {
+                        res = tree8(r8);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) r8[u] = 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const float d = drow[cb + u];  // +inf in the padding columns: never selected
+                        topk_insert<KT>(d, cb + u, nd, nj);
+                        r8[u] = __dadd_rn(r8[u], fabs(__dsub_rn((double)d, d_star)));
+                    }
+                }
+                if (n8 < n_others) {
+#pragma unroll
+                    for (int u = 0; u < 7; ++u) res = __dadd_rn(res, n8 + u < n_others ? r8[u] : 0.0);
+                } else if (n8 > 0) {
+                    res = tree8(r8);
+                }
+                pair_hit = nd[0] <= P.thr_pair;  // nearest drone decides (:202-207)
+                form_sum = res;
+                form_n = n_others;
+            } else {
+                // some drones are parked (or this one is): compact the active ones on the fly
+                const unsigned em = (alive_mask & env_lanes) >> e_base;  // bit j: drone j of this env active
+                const unsigned cm = (em & ((1u << i) - 1u)) | ((em >> (i + 1)) << i);  // bit c: column c active
+                const int n_f = alive ? n_alive_env - 1 : 0;
+                const int nf8 = n_f >= 8 ? (n_f & ~7) : 0;
+                double r8[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) r8[u] = 0.0;
+                double res = 0.0;
+                bool tree_done = false;
+                int cnt = 0;
+#pragma unroll 1
+                for (int c = 0; c < n_others; ++c) {
+                    const float d = drow[c];
+                    topk_insert<KT>(d, c, nd, nj);
+                    if (alive && ((cm >> c) & 1u)) {
+                        pair_hit |= d <= P.thr_pair;
+                        const double err = fabs(__dsub_rn((double)d, P.d_star));
+                        if (cnt < nf8) {
+                            const int lane8 = cnt & 7;
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) r8[u] = __dadd_rn(r8[u], lane8 == u ? err : 0.0);
+                        } else {
+                            if (!tree_done && nf8 > 0) res = tree8(r8);
+                            tree_done = true;
+                            res = __dadd_rn(res, err);
+                        }
+                        ++cnt;
+                    }
+                }
+                if (!tree_done && nf8 > 0) res = tree8(r8);
+                form_sum = res;
+                form_n = n_f;
+            }
+        }
+        // ---- obstacles: _nearest_obstacle_features (:273-291) + obstacle part of _collision_mask
+        float od[ST]; int om[ST];
+#pragma unroll
+        for (int q = 0; q < ST; ++q) { od[q] = F32_INF; om[q] = -1; }
+        {
+            int mb = 0;
+#pragma unroll 1
+            for (; mb + 4 <= M; mb += 4) obst_block4<ST, true>(tobs, mb, M, p.x, p.y, p.z, od, om);
+            if (mb < M) obst_block4<ST, false>(tobs, mb, M, p.x, p.y, p.z, od, om);
+        }
+        const float curr_d = norm1d<NORM>(__fsub_rn(gx, p.x), __fsub_rn(gy, p.y), __fsub_rn(gz, p.z));
+        __syncwarp();  // every lane is done with the distance matrix: the region becomes the obs tile
+        {
+            const float4 t = tab_vel[lane];
+            v = t; prev_d = t.w;
+        }
+
+        // ============================ obs row -> staging tile ============================
+        if ((out_lanes >> lane) & 1u) {
+            float* row = region + lane * D;
+            row[0] = p.x; row[1] = p.y; row[2] = p.z;
+            row[3] = v.x; row[4] = v.y; row[5] = v.z;
+            row[6] = __fsub_rn(gx, p.x); row[7] = __fsub_rn(gy, p.y); row[8] = __fsub_rn(gz, p.z);
+            int off = 9;
+            const bool all_slots = (KIND != SWARM_KIND_SWARM || n_others >= K) && M >= S;  // warp-uniform
+            if (all_slots) {
+                if (KIND == SWARM_KIND_SWARM) {
+#pragma unroll
+                    for (int q = 0; q < KT; ++q) {
+                        if (q < K) {
+                            const int c = nj[q];
+                            const float4 t = (c >= i ? tab_pos + e_base + 1 : tab_pos + e_base)[c];
+                            row[off + 4 * q + 0] = __fsub_rn(t.x, p.x);
+                            row[off + 4 * q + 1] = __fsub_rn(t.y, p.y);
+                            row[off + 4 * q + 2] = __fsub_rn(t.z, p.z);
+                            row[off + 4 * q + 3] = nd[q];
+                        }
+                    }
+                    off += 4 * K;
+                }
+#pragma unroll
+                for (int q = 0; q < ST; ++q) {
+                    if (q < S) {
+                        const float4 t = tobs[om[q]];
+                        row[off + 4 * q + 0] = __fsub_rn(t.x, p.x);
+                        row[off + 4 * q + 1] = __fsub_rn(t.y, p.y);
+                        row[off + 4 * q + 2] = __fsub_rn(t.z, p.z);
+                        row[off + 4 * q + 3] = od[q];
+                    }
+                }
+            } else {  // fewer candidates than slots: zero padding (:268-270, :288-290)
                 if (KIND == SWARM_KIND_SWARM) {
 #pragma unroll
                     for (int q = 0; q < KT; ++q) {
@@ -1070,127 +1133,131 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                     }
                 }
             }
-            __syncwarp();
-            if (out_lanes == __ballot_sync(FULL_MASK, lane_ok)) {
-                flush_stage(P.obs, D, region, a0, n_env * N, lane);   // whole tile, one contiguous stream
-            } else {
-                for (int el = 0; el < n_env; ++el)                     // only the (re)observed envs' rows
-                    if ((out_lanes >> (el * N)) & 1u)
-                        flush_stage(P.obs, D, region + el * N * D, a0 + el * N, N, lane);
-            }
+        }
+        __syncwarp();
+        if (out_lanes == ok_lanes) {
+            flush_stage(P.obs, D, region, a0, n_env * N, lane);  // whole tile, one contiguous stream
+        } else {
+#pragma unroll 1
+            for (int el = 0; el < n_env; ++el)  // only the (re)observed envs' rows
+                if ((out_lanes >> (el * N)) & 1u) flush_stage(P.obs, D, region + el * N * D, a0 + el * N, N, lane);
+        }
 
-            if (stage == kStageStepScan) {
-                // ===================== rewards and flags (:120-172) =====================
-                reached = alive && curr_d <= P.thr_goal;            // :124-127 (double compare)
-                collided = alive && (obst_hit || pair_hit);          // :128
-                double reward = 0.0;
-                if (alive) {
-                    const double progress = __dmul_rn(__dsub_rn((double)prev_d, (double)curr_d), P.k_p);  // :142
-                    if (KIND == SWARM_KIND_SWARM) {
-                        double pen = 0.0;  // :210-224
-                        if (form_n > 0) {
-                            const double mean = form_n == n_others ? mean_markstein(form_sum, P.n_others, P.inv_n_others)
-                                                                   : __ddiv_rn(form_sum, (double)form_n);
-                            pen = __dmul_rn(P.neg_k_f, mean);
-                        }
-                        reward = __dadd_rn(progress, pen);  // :143
-                    } else {
-                        reward = progress;
-                    }
-                    if (reached) reward = __dadd_rn(reward, P.r_goal);   // :144-145
-                    if (collided) reward = __dadd_rn(reward, P.r_col);   // :146-147
-                }
-                rew32 = __double2float_rn(reward);
-                const bool done_agent = reached || collided;
-                const bool any_col = (__ballot_sync(FULL_MASK, collided) & env_lanes) != 0;
-                const int n_cont = __popc(__ballot_sync(FULL_MASK, alive && !done_agent) & env_lanes);
-                // deterministic per-env reward sum (segmented tree over the env's lanes)
-                float x = rew32;
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) {
-                    const float t = __shfl_down_sync(FULL_MASK, x, off);
-                    if (i + off < N) x = __fadd_rn(x, t);
-                }
-                const bool env_active = KIND == SWARM_KIND_SINGLE ? true : n_alive_env > 0;
-                const int sc_new = env_active ? sc + 1 : sc;
-                const bool time_limit = env_active && sc_new >= P.max_steps;
-                bool all_term, all_trunc, ep_over, all_reached = false;
+        if (MODE == kSmallStep) {
+            // ===================== rewards and flags (:120-172) =====================
+            const bool obst_hit = od[0] <= P.thr_obst;
+            const bool reached = alive && curr_d <= P.thr_goal;       // :124-127 (double compare)
+            const bool collided = alive && (obst_hit || pair_hit);     // :128
+            double reward = 0.0;
+            if (alive) {
+                const double progress = __dmul_rn(__dsub_rn((double)prev_d, (double)curr_d), P.k_p);  // :142
                 if (KIND == SWARM_KIND_SWARM) {
-                    all_reached = n_cont == 0 && !any_col && !time_limit;
-                    const bool episode_done = all_reached || any_col;
-                    all_term = env_active ? episode_done : true;  // :94-95 when no agent is left
-                    all_trunc = env_active ? (time_limit && !episode_done) : false;
-                    ep_over = env_active && (all_term || all_trunc);
+                    double pen = 0.0;  // :210-224
+                    if (form_n > 0) {
+                        const double mean = form_n == n_others ? mean_markstein(form_sum, P.n_others, P.inv_n_others)
+                                                               : __ddiv_rn(form_sum, (double)form_n);
+                        pen = __dmul_rn(P.neg_k_f, mean);
+                    }
+                    reward = __dadd_rn(progress, pen);  // :143
                 } else {
-                    all_term = done_agent;   // single env: terminated (:102)
-                    all_trunc = time_limit;  // truncated, not masked by terminated (:103)
-                    ep_over = all_term || all_trunc;
+                    reward = progress;
                 }
-                const bool need_reset = P.auto_reset && (ep_over || !env_active);
-                if (lane_ok) {
-                    bool valid, alive_next;
-                    if (KIND == SWARM_KIND_SWARM) {
-                        P.terminated[a] = (alive && done_agent) ? 1 : 0;                 // :150-151
-                        P.truncated[a] = (alive && time_limit && !done_agent) ? 1 : 0;   // :152
-                        valid = alive && !done_agent && !time_limit && !any_col;         // :154
-                        alive_next = ep_over ? false : valid;                            // :169-172
-                    } else {
-                        P.terminated[a] = all_term ? 1 : 0;
-                        P.truncated[a] = all_trunc ? 1 : 0;
-                        valid = true;
-                        alive_next = true;
-                    }
-                    P.reward[a] = rew32;
-                    if (P.reward64) P.reward64[a] = reward;
-                    P.reached[a] = reached ? 1 : 0;
-                    P.collision[a] = collided ? 1 : 0;
-                    if (!need_reset) {  // (a reset env rewrites these in the observe pass)
-                        P.dist[a] = curr_d;
-                        P.obs_valid[a] = valid ? 1 : 0;
-                        P.pos4[a] = make_float4(p.x, p.y, p.z, alive_next ? 1.0f : 0.0f);
-                        P.vel4[a] = make_float4(v.x, v.y, v.z, 0.0f);
-                        if (P.gs) write_gs_drone(P.gs + (long long)env * P.R, N, i, p.x, p.y, p.z, v.x, v.y, v.z);
-                    }
-                }
-                if (leader) {
-                    st_esteps += env_active ? 1 : 0;
-                    st_asteps += n_alive_env;
-                    P.all_term[env] = all_term ? 1 : 0;
-                    P.all_trunc[env] = all_trunc ? 1 : 0;
-                    const float ret = __fadd_rn(P.ep_return[env], x);
-                    if (ep_over) {
-                        st_eps++; st_len += sc_new; st_ret += (double)ret;
-                        if (KIND == SWARM_KIND_SWARM) {
-                            st_succ += all_reached ? 1 : 0; st_col += any_col ? 1 : 0; st_to += all_trunc ? 1 : 0;
-                        } else {
-                            st_to += (all_trunc && !all_term) ? 1 : 0;
-                        }
-                    }
-                    if (P.episode_return) P.episode_return[env] = ep_over ? ret : 0.0f;
-                    if (P.episode_length) P.episode_length[env] = ep_over ? sc_new : 0;
-                    if (!need_reset) {
-                        P.step_count[env] = sc_new;
-                        P.ep_return[env] = ep_over ? 0.0f : ret;
-                        if (P.gs) {
-                            float* row = P.gs + (long long)env * P.R + 6 * N;
-                            __stcs(row + 0, gx); __stcs(row + 1, gy); __stcs(row + 2, gz);
-                        }
-                    }
-                }
-                const unsigned rl = __ballot_sync(FULL_MASK, leader && need_reset);
-                if (rl == 0) break;
-                reset_envs = 0;
-                for (int el = 0; el < n_env; ++el) reset_envs |= ((rl >> (el * N)) & 1u) << el;
-                stage = kStageReset;
-                __syncwarp();
-                continue;
+                if (reached) reward = __dadd_rn(reward, P.r_goal);   // :144-145
+                if (collided) reward = __dadd_rn(reward, P.r_col);   // :146-147
             }
-
+            const float rew32 = __double2float_rn(reward);
+            const bool done_agent = reached || collided;
+            const bool any_col = (__ballot_sync(FULL_MASK, collided) & env_lanes) != 0;
+            const int n_cont = __popc(__ballot_sync(FULL_MASK, alive && !done_agent) & env_lanes);
+            // deterministic per-env reward sum (segmented tree over the env's lanes)
+            float x = rew32;
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                const float t = __shfl_down_sync(FULL_MASK, x, off);
+                if (i + off < N) x = __fadd_rn(x, t);
+            }
+            const bool env_active = KIND == SWARM_KIND_SINGLE ? true : n_alive_env > 0;
+            const int sc_new = env_active ? sc + 1 : sc;
+            const bool time_limit = env_active && sc_new >= P.max_steps;
+            bool all_term, all_trunc, ep_over, all_reached = false;
+            if (KIND == SWARM_KIND_SWARM) {
+                all_reached = n_cont == 0 && !any_col && !time_limit;
+                const bool episode_done = all_reached || any_col;
+                all_term = env_active ? episode_done : true;  // :94-95 when no agent is left
+                all_trunc = env_active ? (time_limit && !episode_done) : false;
+                ep_over = env_active && (all_term || all_trunc);
+            } else {
+                all_term = done_agent;   // single env: terminated (:102)
+                all_trunc = time_limit;  // truncated, not masked by terminated (:103)
+                ep_over = all_term || all_trunc;
+            }
+            const bool need_reset = P.auto_reset && (ep_over || !env_active);
+            if (lane_ok) {
+                bool valid, alive_next;
+                if (KIND == SWARM_KIND_SWARM) {
+                    P.terminated[a] = (alive && done_agent) ? 1 : 0;                 // :150-151
+                    P.truncated[a] = (alive && time_limit && !done_agent) ? 1 : 0;   // :152
+                    valid = alive && !done_agent && !time_limit && !any_col;         // :154
+                    alive_next = ep_over ? false : valid;                            // :169-172
+                } else {
+                    P.terminated[a] = all_term ? 1 : 0;
+                    P.truncated[a] = all_trunc ? 1 : 0;
+                    valid = true;
+                    alive_next = true;
+                }
+                P.reward[a] = rew32;
+                if (P.reward64) P.reward64[a] = reward;
+                P.reached[a] = reached ? 1 : 0;
+                P.collision[a] = collided ? 1 : 0;
+                if (!need_reset) {  // (a reset env gets these from the aux launch that follows)
+                    P.dist[a] = curr_d;
+                    P.obs_valid[a] = valid ? 1 : 0;
+                    P.pos4[a] = make_float4(p.x, p.y, p.z, alive_next ? 1.0f : 0.0f);
+                    P.vel4[a] = make_float4(v.x, v.y, v.z, 0.0f);
+                    if (P.gs) write_gs_drone(P.gs + (long long)env * P.R, N, i, p.x, p.y, p.z, v.x, v.y, v.z);
+                }
+            }
+            if (leader) {
+                P.all_term[env] = all_term ? 1 : 0;
+                P.all_trunc[env] = all_trunc ? 1 : 0;
+                if (P.reset_mask) P.reset_mask[env] = need_reset ? 1 : 0;
+                const float ret = __fadd_rn(ep_ret, x);
+                if (ep_over) {  // several env leaders per warp when G > 1: shared-memory atomics
+                    atomicAdd(wstats + SWARM_STAT_EPISODES, 1ull);
+                    atomicAdd(wstats + SWARM_STAT_LENGTH_SUM, (unsigned long long)sc_new);
+                    atomicAdd(reinterpret_cast<double*>(wstats + SWARM_STAT_RETURN_SUM), (double)ret);
+                    if (KIND == SWARM_KIND_SWARM) {
+                        if (all_reached) atomicAdd(wstats + SWARM_STAT_SUCCESS, 1ull);
+                        if (any_col) atomicAdd(wstats + SWARM_STAT_COLLISION, 1ull);
+                        if (all_trunc) atomicAdd(wstats + SWARM_STAT_TIMEOUT, 1ull);
+                    } else if (all_trunc && !all_term) {
+                        atomicAdd(wstats + SWARM_STAT_TIMEOUT, 1ull);
+                    }
+                }
+                if (P.episode_return) P.episode_return[env] = ep_over ? ret : 0.0f;
+                if (P.episode_length) P.episode_length[env] = ep_over ? sc_new : 0;
+                if (!need_reset) {
+                    P.step_count[env] = sc_new;
+                    P.ep_return[env] = ep_over ? 0.0f : ret;
+                    if (P.gs) {
+                        float* row = P.gs + (long long)env * P.R + 6 * N;
+                        __stcs(row + 0, gx); __stcs(row + 1, gy); __stcs(row + 2, gz);
+                    }
+                }
+            }
+            {   // actions applied / envs stepped by this warp in this group
+                const unsigned act_envs = __ballot_sync(FULL_MASK, leader && env_active);
+                if (lane == 0) {
+                    wstats[SWARM_STAT_AGENT_STEPS] += (unsigned long long)__popc(alive_mask);
+                    wstats[SWARM_STAT_ENV_STEPS] += (unsigned long long)__popc(act_envs);
+                }
+            }
+        } else {
             // =========== observe epilogue: reset()'s obs / infos (:82-89), or swarm_observe ===========
             if ((out_lanes >> lane) & 1u) {
                 P.dist[a] = curr_d;
                 P.obs_valid[a] = KIND == SWARM_KIND_SINGLE ? 1 : (alive ? 1 : 0);
-                if (P.mode != kModeStep) {
+                if (P.mode != kModeAutoReset) {  // an explicit reset / observe clears the step outputs
                     P.reward[a] = 0.0f;
                     if (P.reward64) P.reward64[a] = 0.0;
                     P.terminated[a] = 0; P.truncated[a] = 0; P.reached[a] = 0; P.collision[a] = 0;
@@ -1200,41 +1267,27 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                     write_gs_drone(row, N, i, p.x, p.y, p.z, v.x, v.y, v.z);
                     if (i == 0) { __stcs(row + 6 * N + 0, gx); __stcs(row + 6 * N + 1, gy); __stcs(row + 6 * N + 2, gz); }
                 }
-                if (P.mode != kModeStep && i == 0) {
+                if (P.mode != kModeAutoReset && i == 0) {
                     P.all_term[env] = 0;
                     P.all_trunc[env] = 0;
                     if (P.episode_return) P.episode_return[env] = 0.0f;
                     if (P.episode_length) P.episode_length[env] = 0;
                 }
             }
-            break;
         }
     }
 
-    // ---- statistics: one atomic per warp per counter
-    if (P.stats && P.mode == kModeStep) {
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            st_eps += __shfl_xor_sync(FULL_MASK, st_eps, off);
-            st_succ += __shfl_xor_sync(FULL_MASK, st_succ, off);
-            st_col += __shfl_xor_sync(FULL_MASK, st_col, off);
-            st_to += __shfl_xor_sync(FULL_MASK, st_to, off);
-            st_len += __shfl_xor_sync(FULL_MASK, st_len, off);
-            st_asteps += __shfl_xor_sync(FULL_MASK, st_asteps, off);
-            st_esteps += __shfl_xor_sync(FULL_MASK, st_esteps, off);
-            st_ret += __shfl_xor_sync(FULL_MASK, st_ret, off);
-        }
-        if (lane == 0) {
-            if (st_eps) {
-                atomicAdd(P.stats + SWARM_STAT_EPISODES, (unsigned long long)st_eps);
-                atomicAdd(P.stats + SWARM_STAT_SUCCESS, (unsigned long long)st_succ);
-                atomicAdd(P.stats + SWARM_STAT_COLLISION, (unsigned long long)st_col);
-                atomicAdd(P.stats + SWARM_STAT_TIMEOUT, (unsigned long long)st_to);
-                atomicAdd(P.stats + SWARM_STAT_LENGTH_SUM, (unsigned long long)st_len);
-                atomicAdd(reinterpret_cast<double*>(P.stats + SWARM_STAT_RETURN_SUM), st_ret);
+    // ---- statistics: one global atomic per warp per counter
+    if (MODE == kSmallStep) {
+        __syncwarp();
+        if (P.stats && lane < SWARM_STATS_WORDS) {
+            const unsigned long long w = wstats[lane];
+            if (lane == SWARM_STAT_RETURN_SUM) {
+                const double dv = __longlong_as_double((long long)w);
+                if (dv != 0.0) atomicAdd(reinterpret_cast<double*>(P.stats + lane), dv);
+            } else if (w) {
+                atomicAdd(P.stats + lane, w);
             }
-            atomicAdd(P.stats + SWARM_STAT_AGENT_STEPS, (unsigned long long)st_asteps);
-            atomicAdd(P.stats + SWARM_STAT_ENV_STEPS, (unsigned long long)st_esteps);
         }
     }
 }
@@ -1311,31 +1364,39 @@ __global__ void swarm_seed_kernel(const DevParams P) {
 typedef void (*EnvKernel)(const DevParams);
 
 template <int KT, int ST, bool EXACT, int KIND>
-static EnvKernel pick2(int norm_mode, bool small_n) {
+static EnvKernel pick2(int norm_mode, bool small_n, bool step) {
+    if (!small_n)
+        return norm_mode == 0 ? swarm_env_kernel<KT, ST, EXACT, 0, KIND, false> : swarm_env_kernel<KT, ST, EXACT, 1, KIND, false>;
     if (norm_mode == 0)
-        return small_n ? swarm_env_kernel_small<KT, ST, EXACT, 0, KIND> : swarm_env_kernel<KT, ST, EXACT, 0, KIND, false>;
-    return small_n ? swarm_env_kernel_small<KT, ST, EXACT, 1, KIND> : swarm_env_kernel<KT, ST, EXACT, 1, KIND, false>;
+        return step ? swarm_env_kernel_small<KT, ST, EXACT, 0, KIND, kSmallStep>
+                    : swarm_env_kernel_small<KT, ST, EXACT, 0, KIND, kSmallAux>;
+    return step ? swarm_env_kernel_small<KT, ST, EXACT, 1, KIND, kSmallStep>
+                : swarm_env_kernel_small<KT, ST, EXACT, 1, KIND, kSmallAux>;
 }
 
 template <int KT, int ST, bool EXACT>
-static EnvKernel pick_single(int norm_mode) {
-    return norm_mode == 0 ? swarm_env_kernel_small<KT, ST, EXACT, 0, SWARM_KIND_SINGLE>
-                          : swarm_env_kernel_small<KT, ST, EXACT, 1, SWARM_KIND_SINGLE>;
+static EnvKernel pick_single(int norm_mode, bool step) {
+    if (norm_mode == 0)
+        return step ? swarm_env_kernel_small<KT, ST, EXACT, 0, SWARM_KIND_SINGLE, kSmallStep>
+                    : swarm_env_kernel_small<KT, ST, EXACT, 0, SWARM_KIND_SINGLE, kSmallAux>;
+    return step ? swarm_env_kernel_small<KT, ST, EXACT, 1, SWARM_KIND_SINGLE, kSmallStep>
+                : swarm_env_kernel_small<KT, ST, EXACT, 1, SWARM_KIND_SINGLE, kSmallAux>;
 }
 
-static EnvKernel resolve(int k, int s, int norm_mode, int env_kind, int n) {
-    const bool small_n = n <= 32;
+static EnvKernel resolve(const DevParams& p, int norm_mode, int env_kind) {
+    const bool small_n = p.N <= 32;
+    const bool step = p.mode == kModeStep;
     if (env_kind == SWARM_KIND_SWARM) {
-        if (k == 3 && s == 4) return pick2<3, 4, true, SWARM_KIND_SWARM>(norm_mode, small_n);
-        return pick2<SWARM_MAX_NEIGHBOR_K, SWARM_MAX_SENSED, false, SWARM_KIND_SWARM>(norm_mode, small_n);
+        if (p.K == 3 && p.S == 4) return pick2<3, 4, true, SWARM_KIND_SWARM>(norm_mode, small_n, step);
+        return pick2<SWARM_MAX_NEIGHBOR_K, SWARM_MAX_SENSED, false, SWARM_KIND_SWARM>(norm_mode, small_n, step);
     }
-    if (s == 4) return pick_single<1, 4, true>(norm_mode);
-    return pick_single<1, SWARM_MAX_SENSED, false>(norm_mode);
+    if (p.S == 4) return pick_single<1, 4, true>(norm_mode, step);
+    return pick_single<1, SWARM_MAX_SENSED, false>(norm_mode, step);
 }
 
 cudaError_t launch_env_kernel(const DevParams& p, int norm_mode, int env_kind, int grid, size_t smem_bytes,
                               cudaStream_t stream) {
-    EnvKernel k = resolve(p.K, p.S, norm_mode, env_kind, p.N);
+    EnvKernel k = resolve(p, norm_mode, env_kind);
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (err != cudaSuccess) return err;
     k<<<grid, kThreadsPerCta, smem_bytes, stream>>>(p);
@@ -1344,7 +1405,7 @@ cudaError_t launch_env_kernel(const DevParams& p, int norm_mode, int env_kind, i
 
 cudaError_t env_kernel_occupancy(const DevParams& p, int norm_mode, int env_kind, size_t smem_bytes,
                                  int* blocks_per_sm) {
-    EnvKernel k = resolve(p.K, p.S, norm_mode, env_kind, p.N);
+    EnvKernel k = resolve(p, norm_mode, env_kind);
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (err != cudaSuccess) return err;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, kThreadsPerCta, smem_bytes);
