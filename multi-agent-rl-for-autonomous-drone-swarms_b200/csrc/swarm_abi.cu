@@ -44,6 +44,9 @@ struct SwarmHandle {
     size_t smem_bytes;
     JumpEntry* jump_dev;
     uint8_t* reset_mask_dev;  // [E]
+    unsigned* reset_count_dev;  // [(kHostChunks + 1) * 2] per launch slot, two parities
+    int* reset_list_dev;        // [number of groups]
+    unsigned step_parity[kHostChunks + 1];
     int64_t launches;
     // host-buffer path
     cudaStream_t chunk_stream[kHostChunks];
@@ -125,8 +128,9 @@ void fill_params(const SwarmConfig& c, DevParams& p) {
         while ((srow & 3) != 1) ++srow;
         p.srow = srow;
         const int region = 32 * p.D > 32 * srow + 8 ? 32 * p.D : 32 * srow + 8;
-        p.stage_off = (2 * p.n_tab + p.G + p.G * p.m_pad) * 4;
-        p.smem_per_warp = p.stage_off * 4 + ((region + 3) & ~3) * 4;
+        // inbox: pos4[32] vel4[32] goal4[G] obst4[G*m_pad] actions[96 f32] step_count[G] ep_return[G]
+        p.inbox_bytes = ((64 + p.G + p.G * p.m_pad) * 16 + 384 + 8 * p.G + 15) & ~15;
+        p.smem_per_warp = 2 * p.inbox_bytes + ((region + 3) & ~3) * 4;
     }
     p.n_others = (double)(p.N - 1);
     p.inv_n_others = p.N > 1 ? 1.0 / (double)(p.N - 1) : 0.0;
@@ -172,13 +176,22 @@ int bind_buffers(const SwarmHandle* h, const SwarmBuffers* b, DevParams& p) {
     return SWARM_OK;
 }
 
-int launch(SwarmHandle* h, DevParams& p, int env_begin, int env_count, cudaStream_t stream) {
+int launch(SwarmHandle* h, DevParams& p, int env_begin, int env_count, cudaStream_t stream, int slot = 0) {
     p.env_begin = env_begin;
     p.env_count = env_count;
     p.n_groups = (env_count + p.G - 1) / p.G;
     const int ctas_needed = (p.n_groups + kWarpsPerCta - 1) / kWarpsPerCta;
     const int resident = h->num_sms * h->blocks_per_sm;
     const int grid = ctas_needed < resident ? ctas_needed : resident;
+    if (p.mode == kModeStep && p.auto_reset && p.N <= 32) {
+        // the step kernel lists the groups that need a reset; counters alternate between steps so the
+        // aux launch can zero the next one while nobody uses it
+        const unsigned par = h->step_parity[slot];
+        p.reset_count = h->reset_count_dev + 2 * slot + par;
+        p.reset_count_other = h->reset_count_dev + 2 * slot + (par ^ 1u);
+        p.reset_list = h->reset_list_dev + env_begin / p.G;
+        h->step_parity[slot] = par ^ 1u;
+    }
     CUDA_TRY(launch_env_kernel(p, h->cfg.norm_mode, h->cfg.env_kind, grid, h->smem_bytes, stream));
     h->launches++;
     if (p.mode == kModeStep && p.auto_reset && p.N <= 32) {
@@ -244,6 +257,9 @@ int swarm_create(const SwarmConfig* cfg, SwarmHandle** out) {
     h->launches = 0;
     h->jump_dev = nullptr;
     h->reset_mask_dev = nullptr;
+    h->reset_count_dev = nullptr;
+    h->reset_list_dev = nullptr;
+    for (int c = 0; c <= kHostChunks; ++c) h->step_parity[c] = 0;
     h->actions_dev = nullptr;
     h->host_path_ready = false;
     fill_params(*cfg, h->base);
@@ -271,9 +287,15 @@ int swarm_create(const SwarmConfig* cfg, SwarmHandle** out) {
         e = cudaMemcpy(h->jump_dev, table.data(), table.size() * sizeof(JumpEntry), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&h->reset_mask_dev, (size_t)cfg->num_envs);
     if (e == cudaSuccess) e = cudaMemset(h->reset_mask_dev, 0, (size_t)cfg->num_envs);
+    const size_t n_groups_all = ((size_t)cfg->num_envs + h->base.G - 1) / h->base.G;
+    if (e == cudaSuccess) e = cudaMalloc(&h->reset_count_dev, sizeof(unsigned) * 2 * (kHostChunks + 1));
+    if (e == cudaSuccess) e = cudaMemset(h->reset_count_dev, 0, sizeof(unsigned) * 2 * (kHostChunks + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&h->reset_list_dev, sizeof(int) * (n_groups_all + 1));
     if (e != cudaSuccess) {
         if (h->jump_dev) cudaFree(h->jump_dev);
         if (h->reset_mask_dev) cudaFree(h->reset_mask_dev);
+        if (h->reset_count_dev) cudaFree(h->reset_count_dev);
+        if (h->reset_list_dev) cudaFree(h->reset_list_dev);
         delete h;
         return fail(SWARM_E_CUDA, "jump table / reset mask allocation failed: %s", cudaGetErrorString(e));
     }
@@ -293,6 +315,8 @@ int swarm_destroy(SwarmHandle* h) {
     if (h->actions_dev) cudaFree(h->actions_dev);
     if (h->jump_dev) cudaFree(h->jump_dev);
     if (h->reset_mask_dev) cudaFree(h->reset_mask_dev);
+    if (h->reset_count_dev) cudaFree(h->reset_count_dev);
+    if (h->reset_list_dev) cudaFree(h->reset_list_dev);
     delete h;
     return SWARM_OK;
 }
@@ -382,7 +406,7 @@ int swarm_step_host(SwarmHandle* h, const SwarmBuffers* bufs, const float* actio
         CUDA_TRY(cudaMemcpyAsync(h->actions_dev + (size_t)e0 * N * 3, actions_host + (size_t)e0 * N * 3,
                                  ne * N * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
         DevParams pc = p;
-        rc = launch(h, pc, e0, e1 - e0, s);
+        rc = launch(h, pc, e0, e1 - e0, s, c + 1);
         if (rc != SWARM_OK) return rc;
 #define D2H(field, devptr, per_env_elems, type)                                                         \
         if (out->field)                                                                                 \

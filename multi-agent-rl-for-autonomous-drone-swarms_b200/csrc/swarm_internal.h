@@ -37,7 +37,7 @@ struct DevParams {
     int n_groups;                 // ceil(env_count / G)
     int smem_per_warp;            // bytes
     int srow;                     // N <= 32 kernel: row stride (floats) of the per-warp distance matrix
-    int stage_off;                // N <= 32 kernel: float offset of the staging / matrix region in the warp slice
+    int inbox_bytes;              // N <= 32 kernel: bytes of one input inbox (two per warp, then the staging region)
     int mode;                     // Mode
     int auto_reset;
     int max_steps;
@@ -60,6 +60,9 @@ struct DevParams {
     float* gs; float* episode_return; int* episode_length;
     unsigned long long* stats;
     uint8_t* reset_mask;          // [E] N <= 32 step kernel -> aux kernel: env needs its auto-reset
+    unsigned* reset_count;        // number of groups on reset_list (this step's counter)
+    unsigned* reset_count_other;  // the next step's counter (zeroed by the aux launch)
+    int* reset_list;              // first env of every group with an env to reset
     const JumpEntry* jump;        // [n_draws + 1]
 };
 

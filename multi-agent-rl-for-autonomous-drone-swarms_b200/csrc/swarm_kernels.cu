@@ -743,6 +743,15 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
 // The matrix aliases the observation staging tile.  Step, auto-reset and observe share one copy
 // of the scan code through a small warp-uniform state machine.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(unsigned saddr, const void* g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async4(unsigned saddr, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 enum SmallMode : int { kSmallStep = 0, kSmallAux = 1 };  // aux = reset / auto-reset / observe launches
 
 __device__ __forceinline__ double mean_markstein(double sum, double n, double inv_n) {
@@ -765,11 +774,12 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    float4* tab_pos = reinterpret_cast<float4*>(smem_raw + (size_t)warp * P.smem_per_warp);
-    float4* tab_vel = tab_pos + 32;
-    float4* tab_goal = tab_vel + 32;
-    float4* tab_obst = tab_goal + P.G;
-    float* region = reinterpret_cast<float*>(tab_pos) + P.stage_off;  // distance matrix / obs staging tile
+    // Per-warp slice: two "inboxes" (the next group's inputs land in one by cp.async while the current
+    // group is processed out of the other) + the distance-matrix / obs-staging region.
+    //   inbox: pos4[32] | vel4[32] | goal4[G] | obst4[G * m_pad] | actions[32 * 3] | step_count[G] | ep_return[G]
+    unsigned char* wslice = smem_raw + (size_t)warp * P.smem_per_warp;
+    float* region = reinterpret_cast<float*>(wslice + 2 * (size_t)P.inbox_bytes);  // distance matrix / obs staging tile
+    const int goal_off = 64, obst_off = 64 + P.G, act_off4 = 64 + P.G + P.G * P.m_pad;  // in float4 units
 
     const int N = P.N, M = P.M, G = P.G, srow = P.srow;
     const int K = EXACT ? KT : P.K, S = EXACT ? ST : P.S;
@@ -782,24 +792,63 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
     const int n8 = n_others >= 8 ? (n_others & ~7) : 0;
     const int n_pad = (n_others + 7) & ~7;  // matrix rows are padded with +inf to whole blocks of 8
     const int half = N >> 1;
-    float* drow = region + lane * srow;  // this drone's row of the distance matrix
-
     // per-warp statistics live in shared memory (leader lanes update them; flushed once at the end)
     unsigned long long* wstats =
         reinterpret_cast<unsigned long long*>(smem_raw + (size_t)kWarpsPerCta * P.smem_per_warp) + warp * SWARM_STATS_WORDS;
     if (MODE == kSmallStep && lane < SWARM_STATS_WORDS) wstats[lane] = 0ull;
 
     const int warps_total = gridDim.x * kWarpsPerCta;
-    for (int grp = blockIdx.x * kWarpsPerCta + warp; grp < P.n_groups; grp += warps_total) {
+    const int gwarp = blockIdx.x * kWarpsPerCta + warp;
+    // aux launches behind a step (auto-reset) walk the compacted list of groups that asked for a reset
+    const bool listed = MODE == kSmallAux && P.mode == kModeAutoReset;
+    const int n_iter = listed ? (int)*reinterpret_cast<const volatile unsigned*>(P.reset_count) : P.n_groups;
+    if (listed && gwarp == 0 && lane == 0) *P.reset_count_other = 0u;  // the next step's counter
+
+    // cp.async prefetch of one group's inputs into an inbox (step kernel only)
+    auto prefetch = [&](int grp, int buf) {
         const int env0 = P.env_begin + grp * G;
+        const int n_env = min(G, P.env_begin + P.env_count - env0);
+        const int n_ag = n_env * N;
+        const long long a0 = (long long)env0 * N;
+        unsigned char* ib = wslice + (size_t)buf * P.inbox_bytes;
+        const unsigned sbase = (unsigned)__cvta_generic_to_shared(ib);
+        if (lane < n_ag) {
+            cp_async16(sbase + lane * 16, P.pos4 + a0 + lane);
+            cp_async16(sbase + 512 + lane * 16, P.vel4 + a0 + lane);
+        }
+        if (lane < n_env) {
+            cp_async16(sbase + goal_off * 16 + lane * 16, P.goal4 + env0 + lane);
+            cp_async4(sbase + (act_off4 * 16 + 384) + lane * 4, P.step_count + env0 + lane);
+            cp_async4(sbase + (act_off4 * 16 + 384 + 4 * G) + lane * 4, P.ep_return + env0 + lane);
+        }
+        for (int idx = lane; idx < n_env * M; idx += 32)
+            cp_async16(sbase + obst_off * 16 + idx * 16, P.obst4 + (long long)env0 * M + idx);
+        const float* act = P.actions + a0 * 3;
+        if ((((G * N) | n_ag) & 3) == 0) {  // 16-byte aligned, whole 16-byte chunks
+            if (lane * 4 < n_ag * 3) cp_async16(sbase + act_off4 * 16 + lane * 16, act + lane * 4);
+        } else {
+            for (int idx = lane; idx < n_ag * 3; idx += 32) cp_async4(sbase + act_off4 * 16 + idx * 4, act + idx);
+        }
+        cp_async_commit();
+    };
+    int buf = 0;
+    if (MODE == kSmallStep && gwarp < n_iter) prefetch(gwarp, 0);
+
+    for (int it = gwarp; it < n_iter; it += warps_total, buf ^= 1) {
+        const int env0 = listed ? P.reset_list[it] : P.env_begin + it * G;
         const int n_env = min(G, P.env_begin + P.env_count - env0);
         const bool lane_ok = e_l < n_env;
         const int env = env0 + (lane_ok ? e_l : 0);
         const long long a0 = (long long)env0 * N;      // first agent of the group
         const long long a = a0 + (lane_ok ? lane : 0);  // this lane's agent
-        const float4* tobs = tab_obst + e_l * P.m_pad;
         const bool leader = lane_ok && i == 0;
         const unsigned ok_lanes = __ballot_sync(FULL_MASK, lane_ok);
+        float4* tab_pos = reinterpret_cast<float4*>(wslice + (size_t)buf * P.inbox_bytes);
+        float4* tab_vel = tab_pos + 32;
+        float4* tab_goal = tab_pos + goal_off;
+        float4* tab_obst = tab_pos + obst_off;
+        const float4* tobs = tab_obst + e_l * P.m_pad;
+        float* drow = region + lane * srow;  // this drone's row of the distance matrix
 
         unsigned reset_envs = 0;  // aux: bit el = env el is (re)drawn
         if (MODE == kSmallAux && P.mode != kModeObserve) {
@@ -808,22 +857,32 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
             if (reset_envs == 0) continue;  // nothing to reset in this group
         }
 
-        __syncwarp();  // the previous group is done with the shared-memory slice
-        // ---- loads (all issued before first use)
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f), v = p, g4 = p;
         float ax = 0.f, ay = 0.f, az = 0.f, ep_ret = 0.f;
         int sc = 0;
-        if (lane_ok) {
-            p = P.pos4[a];
-            v = P.vel4[a];
-            g4 = P.goal4[env];
-            if (MODE == kSmallStep) {
-                sc = P.step_count[env];
-                ep_ret = P.ep_return[env];
-                ax = P.actions[a * 3 + 0]; ay = P.actions[a * 3 + 1]; az = P.actions[a * 3 + 2];
+        if (MODE == kSmallStep) {
+            cp_async_wait_all();
+            __syncwarp();  // this group's inbox is complete; the other inbox is free again
+            if (it + warps_total < n_iter) prefetch(it + warps_total, buf ^ 1);
+            if (lane_ok) {
+                p = tab_pos[lane];
+                v = tab_vel[lane];
+                g4 = tab_goal[e_l];
+                const float* act = reinterpret_cast<const float*>(tab_pos + act_off4);
+                ax = act[lane * 3 + 0]; ay = act[lane * 3 + 1]; az = act[lane * 3 + 2];
+                sc = reinterpret_cast<const int*>(act + 96)[e_l];
+                ep_ret = (act + 96 + G)[e_l];
             }
+            __syncwarp();  // everyone has read its inputs before positions are overwritten in place
+        } else {
+            __syncwarp();  // the previous group is done with the shared-memory slice
+            if (lane_ok) {
+                p = P.pos4[a];
+                v = P.vel4[a];
+                g4 = P.goal4[env];
+            }
+            for (int idx = lane; idx < n_env * M; idx += 32) tab_obst[idx] = P.obst4[(long long)env0 * M + idx];
         }
-        for (int idx = lane; idx < n_env * M; idx += 32) tab_obst[idx] = P.obst4[(long long)env0 * M + idx];
         float gx = g4.x, gy = g4.y, gz = g4.z;
 
         bool alive = KIND == SWARM_KIND_SINGLE ? lane_ok : (lane_ok && p.w != 0.0f);
@@ -1244,6 +1303,10 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                         __stcs(row + 0, gx); __stcs(row + 1, gy); __stcs(row + 2, gz);
                     }
                 }
+            }
+            if (P.auto_reset) {  // groups with an env to reset go on the list the aux launch walks
+                const unsigned rl = __ballot_sync(FULL_MASK, leader && need_reset);
+                if (rl != 0 && lane == 0) P.reset_list[atomicAdd(P.reset_count, 1u)] = env0;
             }
             {   // actions applied / envs stepped by this warp in this group
                 const unsigned act_envs = __ballot_sync(FULL_MASK, leader && env_active);
