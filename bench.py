@@ -126,7 +126,7 @@ def cpu_port_rate(kind, cfg, n_envs, budget_s, threads):
     return agent_steps / dt, steps, dt
 
 
-def run_reference_arm(args, kind, cfg, wl_name):
+def run_reference_arm(args, kind, cfg, wl_name, default_envs):
     """--impl reference: the CPU port, all host threads, same config / metric / unit."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -149,12 +149,13 @@ def run_reference_arm(args, kind, cfg, wl_name):
         o.step(acts[k % 4], auto_reset=True, num_threads=threads)
     dt = time.perf_counter() - t0
     val = agent_steps / dt
-    sample = f"{n_envs} env instances x {args.steps} steps of the {wl_name} config per step-batch, {threads} threads"
+    sample = (f"each step = {n_envs} env instances of the {wl_name} config (bounded sample of the {default_envs} "
+              f"per GPU the GPU arm steps), {args.steps} steps, {threads} threads; oracle/swarm_oracle.c")
     line = {
         "impl": "reference", "metric": "agent_steps_per_sec", "value": val, "unit": "agent-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(wl_name, kind, cfg, n_envs, 1),
+        "config": workload_config(wl_name, kind, cfg, default_envs, args.gpus),
         "cpu_baseline": {"value": val, "unit": "agent-steps/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -199,7 +200,7 @@ def main():
     if args.impl == "reference":
         if args.steps > 200:
             args.steps = 200
-        run_reference_arm(args, kind, cfg, args.workload)
+        run_reference_arm(args, kind, cfg, args.workload, E)
         return
 
     import torch
