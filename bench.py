@@ -7,8 +7,8 @@ prints ONE JSON line on rank 0.
 Workload = BASELINE.json configs[3] ("C4", the config the metric is quoted on): 32-drone swarm,
 8 obstacles, reference-default DroneEnvConfig (world 20, K=3, S=4, max_steps 400), 65536 env
 instances PER GPU (weak scaling; the whole of C4 fits one GPU), i.i.d. U(-1,1) float32 actions
-read from device memory, auto-reset on, global_state emitted.  A "step" is one fused launch that
-advances every env instance once.  The per-step working set (~0.5 GB) exceeds the 126 MB L2.
+read from device memory, auto-reset on, global_state emitted.  A "step" advances every env instance
+once (step launch + the tiny auto-reset launch enqueued behind it).  The per-step working set (~0.5 GB) exceeds the 126 MB L2.
 
   value     device-resident throughput: actions applied (device counter) / CUDA-event time, max over ranks
   e2e       same metric through the host-buffer C-ABI call (pinned H2D actions + D2H of every output)
@@ -316,7 +316,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_agent_step": B, "bytes_per_launch": bytes_per_launch,
-                         "kernel": "swarm_env_kernel (one fused launch per step)", "kernel_ms": kernel_ms},
+                         "kernel": "swarm_env_kernel_small step launch + aux (auto-reset) launch; achieved uses the time of both",
+                         "kernel_ms": kernel_ms},
             "e2e": e2e,
             "gpu_launches": int(launches_all),
             "clocks": clocks,
