@@ -4,7 +4,8 @@ Drop-in for ONE hot path of nusRying/Multi-Agent-RL-for-Autonomous-Drone-Swarms:
 reset/step of `DroneSwarmEnv` / `SingleDroneEnv` (reference src/swarm_marl/envs/), computed by
 hand-written sm_100a kernels behind the C ABI in include/swarm_b200.h.
 
-    SwarmEngine      batched tensor API (E env instances per GPU, one fused launch per step)
+    SwarmEngine      batched tensor API (E env instances per GPU, one step launch + a tiny auto-reset launch)
+    evaluate_batched reference evaluation protocol (SR / CFR / TTG / FE / PE) for E episodes at once
     DroneSwarmEnv    reference-compatible multi-agent env (dict API) backed by the engine
     SingleDroneEnv   reference-compatible single-agent env backed by the engine
     DroneEnvConfig   mirror of the reference's config dataclass
@@ -24,6 +25,9 @@ def __getattr__(name):
     if name in ("DroneSwarmEnv", "SingleDroneEnv", "make_env_creator", "VectorSwarmEnv"):
         from . import envs
         return getattr(envs, name)
+    if name == "evaluate_batched":
+        from .evaluation import evaluate_batched
+        return evaluate_batched
     if name in ("ShardedSwarm", "shard_range"):
         from . import distributed
         return getattr(distributed, name)

@@ -215,6 +215,27 @@ class SwarmEngine:
         if observe:
             self.observe()
 
+    # ------------------------------------------------------------------ (de)serialisation
+    _STATE_KEYS = ("pos4", "vel4", "goal4", "obst4", "step_count", "rng", "ep_return", "stats_words")
+
+    def state_dict(self) -> dict[str, Any]:
+        """Everything needed to continue every env bit-for-bit (the reference never checkpoints env
+        state; RLlib resumes only the policy).  CPU tensors, safe to `torch.save`."""
+        torch.cuda.synchronize(self.device)
+        out = {k: getattr(self, k).detach().cpu().clone() for k in self._STATE_KEYS}
+        out["meta"] = dict(kind=self.kind, E=self.E, N=self.N, M=self.M, K=self.K, S=self.S)
+        return out
+
+    def load_state_dict(self, state: dict[str, Any], observe: bool = True):
+        meta = state.get("meta", {})
+        mine = dict(kind=self.kind, E=self.E, N=self.N, M=self.M, K=self.K, S=self.S)
+        if meta and meta != mine:
+            raise ValueError(f"state_dict is for {meta}, this engine is {mine}")
+        for k in self._STATE_KEYS:
+            getattr(self, k).copy_(state[k].to(self.device))
+        if observe:
+            self.observe()
+
     # ------------------------------------------------------------------ host-buffer (end-to-end) path
     def host_buffers(self, with_global_state: bool = True) -> dict[str, np.ndarray]:
         """Pinned host arrays for `step_host` (allocated once)."""
