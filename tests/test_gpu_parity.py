@@ -294,13 +294,11 @@ def test_batched_evaluator_matches_reference_loop_on_facade():
     cfg = {"num_drones": 4, "num_obstacles": 6, "max_steps": 60, "world_size": 14.0}
     E, base = 24, 500
 
-    def policy_np(obs):  # deterministic goal seeking from the local observation
-        g = obs[6:9]
-        return (1.5 * g / max(float(np.linalg.norm(g)), 1e-6)).astype(np.float32)
+    def policy_np(obs):  # bang-bang goal seeking from the local observation (exactly reproducible)
+        return np.sign(obs[6:9]).astype(np.float32)
 
     def policy_t(obs, valid):
-        g = obs[..., 6:9]
-        return 1.5 * g / torch.linalg.vector_norm(g, dim=-1, keepdim=True).clamp(min=1e-6)
+        return torch.sign(obs[..., 6:9])
 
     def dist(a, b):
         return float(np.linalg.norm(a - b))
