@@ -198,8 +198,6 @@ def main():
     E = args.envs_per_gpu or default_envs
 
     if args.impl == "reference":
-        if args.steps > 200:
-            args.steps = 200
         run_reference_arm(args, kind, cfg, args.workload, E)
         return
 
