@@ -46,6 +46,17 @@ WORKLOADS = {
 }
 
 
+# configs/domain_randomization_v1.yaml:9-60 of the reference (control_delay_steps excluded: not implemented)
+DR_V1 = {"mass_scale": (0.85, 1.15), "max_accel_scale": (0.90, 1.10), "max_speed_scale": (0.90, 1.10),
+         "dt_scale": (0.95, 1.05), "obstacle_radius_scale": (0.9, 1.1), "world_size_scale": (0.95, 1.05),
+         "thrust_noise_std": 0.03, "position_noise_std": 0.02, "velocity_noise_std": 0.02,
+         "obstacle_distance_noise_std": 0.03}
+
+
+def dr_enabled(args):
+    return args.dr == "on"
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -155,7 +166,7 @@ def run_reference_arm(args, kind, cfg, wl_name, default_envs):
         "impl": "reference", "metric": "agent_steps_per_sec", "value": val, "unit": "agent-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(wl_name, kind, cfg, default_envs, args.gpus),
+        "config": workload_config(wl_name, kind, cfg, default_envs, args.gpus, dr_enabled(args)),
         "cpu_baseline": {"value": val, "unit": "agent-steps/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -165,13 +176,13 @@ def run_reference_arm(args, kind, cfg, wl_name, default_envs):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(name, kind, cfg, envs_per_gpu, n_gpus):
+def workload_config(name, kind, cfg, envs_per_gpu, n_gpus, dr=False):
     full = {"world_size": 20.0, "max_steps": 400, "neighbor_k": 3, "sensed_obstacles": 4}
     full.update(cfg)
     return {"workload": f"{name}: {kind} env, N={full.get('num_drones', 1)} drones, M={full['num_obstacles']} "
                         f"obstacles, K={full['neighbor_k']}, S={full['sensed_obstacles']}, world {full['world_size']}, "
                         f"{envs_per_gpu} env instances per GPU x {n_gpus} GPU(s), U(-1,1) actions, auto-reset, "
-                        f"global_state on, domain randomisation off",
+                        f"global_state on, domain randomisation {'on (domain_randomization_v1 ranges, no control delay)' if dr else 'off'}",
             "envs_per_gpu": envs_per_gpu, "num_drones": full.get("num_drones", 1),
             "num_obstacles": full["num_obstacles"], "parallelism": f"env-sharded x{n_gpus}, no data-path collective",
             "l2_policy": "per-step working set larger than L2 (no flush needed)"}
@@ -191,6 +202,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-global-state", action="store_true")
+    ap.add_argument("--dr", default="auto", choices=["auto", "on", "off"],
+                    help="domain randomisation (domain_randomization_v1 ranges); auto = on for c4 (BASELINE configs[3])")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -213,7 +226,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    eng = swarm_b200.SwarmEngine(E, cfg, kind=kind, device=dev, global_state=not args.no_global_state)
+    eng = swarm_b200.SwarmEngine(E, cfg, kind=kind, device=dev, global_state=not args.no_global_state,
+                                 domain_randomization=DR_V1 if dr_enabled(args) else None, dr_seed=2026,
+                                 env_index_base=rank * E)
     N = eng.N
     # env e of rank r is global env r*E + e: seeds are a function of the GLOBAL env index
     eng.seed(np.arange(rank * E, (rank + 1) * E, dtype=np.uint64))
@@ -308,7 +323,7 @@ def main():
             "metric": "agent_steps_per_sec", "value": value, "unit": "agent-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.workload, kind, cfg, E, world),
+            "config": workload_config(args.workload, kind, cfg, E, world, dr_enabled(args)),
             "slot_steps_per_sec": slot_steps_all / (elapsed_ms * 1e-3),
             "episodes_in_timed_region": episodes_all,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

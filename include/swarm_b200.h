@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SWARM_ABI_VERSION 1
+#define SWARM_ABI_VERSION 2
 
 enum {
     SWARM_OK = 0,
@@ -66,6 +66,18 @@ typedef struct SwarmConfig {
     double world_size, dt, max_speed, max_accel, collision_radius, goal_radius;
     double obstacle_radius, desired_spacing;
     double reward_progress_scale, reward_goal, reward_collision, reward_formation_scale;
+    /* ---- domain randomisation (reference configs/domain_randomization_v1.yaml:9-60).  No reference
+     * code consumes that file, so the semantics are this library's and parity is
+     * pinned only against oracle/swarm_oracle.c; with dr_enabled == 0 nothing below is read and the
+     * step is bit-identical to the reference. */
+    int32_t dr_enabled;
+    int32_t dr_reserved;
+    uint64_t dr_seed;         /* key of the counter-based (Philox4x32-10) DR streams */
+    int64_t env_index_base;   /* global index of this handle's env 0 (streams do not depend on sharding) */
+    double dr_mass_scale[2], dr_max_accel_scale[2], dr_max_speed_scale[2], dr_dt_scale[2];
+    double dr_obstacle_radius_scale[2], dr_world_size_scale[2];   /* uniform [min, max], per env per episode */
+    double dr_thrust_noise_std;             /* multiplicative Gaussian on the clipped action, per drone per step */
+    double dr_position_noise_std, dr_velocity_noise_std, dr_obstacle_distance_noise_std;  /* additive, on the obs */
 } SwarmConfig;
 
 /* Element counts of every buffer, as a function of the config (swarm_query_sizes). */
@@ -85,6 +97,7 @@ typedef struct SwarmSizes {
     int64_t per_env;       /* E      (all_terminated, all_truncated, episode outputs) */
     int64_t global_state;  /* E*(6N+3) float32 */
     int64_t stats;         /* SWARM_STATS_WORDS uint64 */
+    int64_t dr_params;     /* E*8 float32 */
 } SwarmSizes;
 
 /* Device pointers.  State is structure-of-arrays with one float4 per drone so every state
@@ -119,6 +132,8 @@ typedef struct SwarmBuffers {
     float *episode_return;   /* [E]    nullable: return of the episode that ended on this step */
     int32_t *episode_length; /* [E]    nullable: its length in steps (0 when no episode ended) */
     uint64_t *stats;     /* [SWARM_STATS_WORDS] nullable: running counters, see SWARM_STAT_* */
+    float *dr_params;    /* [E][8] state, required when dr_enabled: per-env per-episode constants
+                            {max_accel, max_speed, dt, bound, obstacle threshold, episode key, world, 0} */
 } SwarmBuffers;
 
 /* stats block (uint64 words; SWARM_STAT_RETURN_SUM holds a double's bit pattern) */
@@ -184,6 +199,9 @@ int swarm_step_host(SwarmHandle *h, const SwarmBuffers *bufs, const float *actio
 
 /* Number of kernel launches this handle has enqueued so far (bench bookkeeping). */
 int64_t swarm_launch_count(const SwarmHandle *h);
+
+/* The 4096-entry standard-normal quantile table the DR noise is drawn from (host, for tests). */
+int swarm_dr_quantile_table(float *out4096);
 
 #ifdef __cplusplus
 }

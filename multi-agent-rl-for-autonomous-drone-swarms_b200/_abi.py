@@ -11,7 +11,7 @@ import os
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SWARM_B200_LIB") or os.path.join(_PKG_DIR, "libswarm_b200.so")  # override: tuning builds
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 KIND_SINGLE, KIND_SWARM = 0, 1
 MAX_DRONES, MAX_NEIGHBOR_K, MAX_SENSED = 128, 8, 8
 
@@ -23,21 +23,30 @@ _DOUBLES = ("world_size", "dt", "max_speed", "max_accel", "collision_radius", "g
             "reward_formation_scale")
 
 
+DR_RANGES = ("dr_mass_scale", "dr_max_accel_scale", "dr_max_speed_scale", "dr_dt_scale",
+             "dr_obstacle_radius_scale", "dr_world_size_scale")
+DR_STDS = ("dr_thrust_noise_std", "dr_position_noise_std", "dr_velocity_noise_std",
+           "dr_obstacle_distance_noise_std")
+
+
 class SwarmConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("abi_version", "env_kind", "num_envs", "num_drones", "num_obstacles",
                                          "sensed_obstacles", "neighbor_k", "max_steps", "norm_mode", "device")] + \
-               [(n, C.c_double) for n in _DOUBLES]
+               [(n, C.c_double) for n in _DOUBLES] + \
+               [("dr_enabled", C.c_int32), ("dr_reserved", C.c_int32), ("dr_seed", C.c_uint64),
+                ("env_index_base", C.c_int64)] + \
+               [(n, C.c_double * 2) for n in DR_RANGES] + [(n, C.c_double) for n in DR_STDS]
 
 
 class SwarmSizes(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("obs_dim", "state_dim", "pos4", "vel4", "goal4", "obst4", "step_count",
                                          "rng", "ep_return", "actions", "obs", "per_agent", "per_env",
-                                         "global_state", "stats")]
+                                         "global_state", "stats", "dr_params")]
 
 
 BUFFER_FIELDS = ("pos4", "vel4", "goal4", "obst4", "step_count", "rng", "ep_return", "obs", "reward", "reward64",
                  "dist", "terminated", "truncated", "reached", "collision", "obs_valid", "all_terminated",
-                 "all_truncated", "global_state", "episode_return", "episode_length", "stats")
+                 "all_truncated", "global_state", "episode_return", "episode_length", "stats", "dr_params")
 
 
 class SwarmBuffers(C.Structure):
@@ -53,7 +62,8 @@ class SwarmHostOut(C.Structure):
 
 
 EXPORTS = ("swarm_abi_version", "swarm_last_error", "swarm_create", "swarm_destroy", "swarm_query_sizes",
-           "swarm_seed", "swarm_reset", "swarm_observe", "swarm_step", "swarm_step_host", "swarm_launch_count")
+           "swarm_seed", "swarm_reset", "swarm_observe", "swarm_step", "swarm_step_host", "swarm_launch_count",
+           "swarm_dr_quantile_table")
 
 
 class SwarmError(RuntimeError):
@@ -87,6 +97,8 @@ def load():
     lib.swarm_step_host.argtypes = [vp, C.POINTER(SwarmBuffers), vp, C.POINTER(SwarmHostOut), i32]
     lib.swarm_launch_count.argtypes = [vp]
     lib.swarm_launch_count.restype = C.c_int64
+    lib.swarm_dr_quantile_table.argtypes = [vp]
+    lib.swarm_dr_quantile_table.restype = i32
     for name in ("swarm_create", "swarm_destroy", "swarm_query_sizes", "swarm_seed", "swarm_reset",
                  "swarm_observe", "swarm_step", "swarm_step_host"):
         getattr(lib, name).restype = i32

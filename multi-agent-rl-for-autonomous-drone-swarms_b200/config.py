@@ -36,3 +36,44 @@ class DroneEnvConfig:
             return cls()
         names = {f.name for f in fields(cls)}
         return cls(**{k: v for k, v in raw.items() if k in names})
+
+
+DR_RANGE_KEYS = ("mass_scale", "max_accel_scale", "max_speed_scale", "dt_scale", "obstacle_radius_scale",
+                 "world_size_scale")
+DR_STD_KEYS = ("thrust_noise_std", "position_noise_std", "velocity_noise_std", "obstacle_distance_noise_std")
+
+
+def flatten_domain_randomization(spec: dict[str, Any] | None) -> dict[str, Any]:
+    """Normalise a domain-randomisation spec to {range key: (min, max), std key: sigma}.
+
+    Accepts the flat form itself, or the document shape of the reference's
+    `configs/domain_randomization_v1.yaml:9-60` (`randomization: {dynamics|actuation|sensing|
+    environment: {<key>: {distribution, min, max | std}}}`).  No reference code reads that file, so
+    what each key DOES is defined by this engine.  `control_delay_steps` is not
+    implemented and is rejected rather than silently ignored unless it is the no-delay setting."""
+    if not spec:
+        return {}
+    flat: dict[str, Any] = {}
+    groups = spec.get("randomization") if isinstance(spec.get("randomization"), dict) else None
+    items = {}
+    if groups is not None:
+        for g in groups.values():
+            if isinstance(g, dict):
+                items.update(g)
+    else:
+        items = dict(spec)
+    for k, v in items.items():
+        if k in DR_RANGE_KEYS:
+            lo, hi = (v["min"], v["max"]) if isinstance(v, dict) else v
+            flat[k] = (float(lo), float(hi))
+        elif k in DR_STD_KEYS:
+            flat[k] = float(v["std"]) if isinstance(v, dict) else float(v)
+        elif k == "control_delay_steps":
+            vals = v.get("values", [0]) if isinstance(v, dict) else v
+            probs = v.get("probs") if isinstance(v, dict) else None
+            live = [x for j, x in enumerate(vals) if probs is None or probs[j] > 0]
+            if any(int(x) != 0 for x in live):
+                raise NotImplementedError("control_delay_steps > 0 is not implemented by the engine")
+        elif groups is None:
+            raise KeyError(f"unknown domain-randomisation key {k!r}")
+    return flat

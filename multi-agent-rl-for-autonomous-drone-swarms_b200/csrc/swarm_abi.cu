@@ -46,6 +46,7 @@ struct SwarmHandle {
     uint8_t* reset_mask_dev;  // [E]
     unsigned* reset_count_dev;  // [(kHostChunks + 1) * 2] per launch slot, two parities
     int* reset_list_dev;        // [number of groups]
+    float* qtable_dev;          // [4096] (domain randomisation only)
     unsigned step_parity[kHostChunks + 1];
     int64_t launches;
     // host-buffer path
@@ -81,6 +82,18 @@ int validate(const SwarmConfig* c) {
     if (c->neighbor_k < 0 || c->neighbor_k > SWARM_MAX_NEIGHBOR_K)
         return fail(SWARM_E_UNSUPPORTED, "neighbor_k %d outside [0, %d]", c->neighbor_k, SWARM_MAX_NEIGHBOR_K);
     if (c->norm_mode != 0 && c->norm_mode != 1) return fail(SWARM_E_INVALID, "norm_mode must be 0 or 1");
+    if (c->dr_enabled) {
+        if (c->num_drones > 32 || c->norm_mode != 0)
+            return fail(SWARM_E_UNSUPPORTED, "domain randomisation needs num_drones <= 32 and norm_mode 0");
+        const double* rng[6] = {c->dr_mass_scale, c->dr_max_accel_scale, c->dr_max_speed_scale, c->dr_dt_scale,
+                                c->dr_obstacle_radius_scale, c->dr_world_size_scale};
+        for (int k = 0; k < 6; ++k)
+            if (!(rng[k][0] > 0.0) || !(rng[k][1] >= rng[k][0]))
+                return fail(SWARM_E_INVALID, "domain randomisation range %d must satisfy 0 < min <= max", k);
+        if (c->dr_thrust_noise_std < 0 || c->dr_position_noise_std < 0 || c->dr_velocity_noise_std < 0 ||
+            c->dr_obstacle_distance_noise_std < 0)
+            return fail(SWARM_E_INVALID, "domain randomisation noise std must be >= 0");
+    }
     if ((int64_t)c->num_envs * c->num_drones > (int64_t)1 << 30)
         return fail(SWARM_E_UNSUPPORTED, "num_envs * num_drones too large");
     return SWARM_OK;
@@ -91,6 +104,37 @@ float f32_floor_of(double x) {
     float f = (float)x;
     if ((double)f > x) f = std::nextafterf(f, -INFINITY);
     return f;
+}
+
+// Standard-normal quantiles z_k = Phi^-1((k + 0.5) / 4096): the DR noise is a 12-bit table lookup, so
+// the CUDA path and the C oracle produce identical noise without depending on libm / MUFU rounding.
+double inv_norm_cdf(double p) {  // Acklam's rational approximation
+    static const double a[] = {-3.969683028665376e+01, 2.209460984245205e+02, -2.759285104469687e+02,
+                               1.383577518672690e+02, -3.066479806614716e+01, 2.506628277459239e+00};
+    static const double b[] = {-5.447609879822406e+01, 1.615858368580409e+02, -1.556989798598866e+02,
+                               6.680131188771972e+01, -1.328068155288572e+01};
+    static const double c[] = {-7.784894002430293e-03, -3.223964580411365e-01, -2.400758277161838e+00,
+                               -2.549732539343734e+00, 4.374664141464968e+00, 2.938163982698783e+00};
+    static const double d[] = {7.784695709041462e-03, 3.224671290700398e-01, 2.445134137142996e+00,
+                               3.754408661907416e+00};
+    const double plow = 0.02425;
+    if (p < plow) {
+        const double q = std::sqrt(-2.0 * std::log(p));
+        return (((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) /
+               ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1.0);
+    }
+    if (p > 1.0 - plow) {
+        const double q = std::sqrt(-2.0 * std::log(1.0 - p));
+        return -(((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) /
+               ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1.0);
+    }
+    const double q = p - 0.5, r = q * q;
+    return (((((a[0] * r + a[1]) * r + a[2]) * r + a[3]) * r + a[4]) * r + a[5]) * q /
+           (((((b[0] * r + b[1]) * r + b[2]) * r + b[3]) * r + b[4]) * r + 1.0);
+}
+
+void build_qtable(float* out) {
+    for (int k = 0; k < 4096; ++k) out[k] = (float)inv_norm_cdf(((double)k + 0.5) / 4096.0);
 }
 
 void build_jump_table(int n_draws, std::vector<JumpEntry>& out) {
@@ -129,8 +173,23 @@ void fill_params(const SwarmConfig& c, DevParams& p) {
         p.srow = srow;
         const int region = 32 * p.D > 32 * srow + 8 ? 32 * p.D : 32 * srow + 8;
         // inbox: pos4[32] vel4[32] goal4[G] obst4[G*m_pad] actions[96 f32] step_count[G] ep_return[G]
+        // (+ 32 B of per-env DR constants per env when domain randomisation is on)
         p.inbox_bytes = ((64 + p.G + p.G * p.m_pad) * 16 + 384 + 8 * p.G + 15) & ~15;
+        if (c.dr_enabled) p.inbox_bytes += 32 * p.G;
         p.smem_per_warp = 2 * p.inbox_bytes + ((region + 3) & ~3) * 4;
+    }
+    p.dr_enabled = c.dr_enabled ? 1 : 0;
+    if (p.dr_enabled) {
+        p.dr_key0 = (unsigned)(c.dr_seed & 0xffffffffu);
+        p.dr_key1 = (unsigned)(c.dr_seed >> 32);
+        p.env_index_base = c.env_index_base;
+        const double* rng[6] = {c.dr_mass_scale, c.dr_max_accel_scale, c.dr_max_speed_scale, c.dr_dt_scale,
+                                c.dr_obstacle_radius_scale, c.dr_world_size_scale};
+        for (int k = 0; k < 6; ++k) { p.dr_lo[k] = rng[k][0]; p.dr_span[k] = rng[k][1] - rng[k][0]; }
+        p.dr_max_accel = c.max_accel; p.dr_max_speed = c.max_speed; p.dr_dt = c.dt; p.dr_world = c.world_size;
+        p.dr_r_c = c.collision_radius; p.dr_r_o = c.obstacle_radius;
+        p.dr_std_thrust = (float)c.dr_thrust_noise_std; p.dr_std_pos = (float)c.dr_position_noise_std;
+        p.dr_std_vel = (float)c.dr_velocity_noise_std; p.dr_std_obst = (float)c.dr_obstacle_distance_noise_std;
     }
     p.n_others = (double)(p.N - 1);
     p.inv_n_others = p.N > 1 ? 1.0 / (double)(p.N - 1) : 0.0;
@@ -173,6 +232,12 @@ int bind_buffers(const SwarmHandle* h, const SwarmBuffers* b, DevParams& p) {
     p.stats = reinterpret_cast<unsigned long long*>(b->stats);
     p.jump = h->jump_dev;
     p.reset_mask = h->reset_mask_dev;
+    if (p.dr_enabled) {
+        if (!b->dr_params) return fail(SWARM_E_NULL, "dr_params is required when dr_enabled");
+        if (reinterpret_cast<uintptr_t>(b->dr_params) & 15u) return fail(SWARM_E_INVALID, "dr_params must be 16-byte aligned");
+        p.dr_params = reinterpret_cast<float4*>(b->dr_params);
+        p.dr_qtable = h->qtable_dev;
+    }
     return SWARM_OK;
 }
 
@@ -239,6 +304,7 @@ int swarm_query_sizes(const SwarmConfig* cfg, SwarmSizes* out) {
     out->actions = E * N * 3; out->obs = E * N * D; out->per_agent = E * N; out->per_env = E;
     out->global_state = E * (6 * N + 3);
     out->stats = SWARM_STATS_WORDS;
+    out->dr_params = E * 8;
     return SWARM_OK;
 }
 
@@ -259,6 +325,7 @@ int swarm_create(const SwarmConfig* cfg, SwarmHandle** out) {
     h->reset_mask_dev = nullptr;
     h->reset_count_dev = nullptr;
     h->reset_list_dev = nullptr;
+    h->qtable_dev = nullptr;
     for (int c = 0; c <= kHostChunks; ++c) h->step_parity[c] = 0;
     h->actions_dev = nullptr;
     h->host_path_ready = false;
@@ -291,11 +358,18 @@ int swarm_create(const SwarmConfig* cfg, SwarmHandle** out) {
     if (e == cudaSuccess) e = cudaMalloc(&h->reset_count_dev, sizeof(unsigned) * 2 * (kHostChunks + 1));
     if (e == cudaSuccess) e = cudaMemset(h->reset_count_dev, 0, sizeof(unsigned) * 2 * (kHostChunks + 1));
     if (e == cudaSuccess) e = cudaMalloc(&h->reset_list_dev, sizeof(int) * (n_groups_all + 1));
+    if (e == cudaSuccess && cfg->dr_enabled) {
+        std::vector<float> qt(4096);
+        build_qtable(qt.data());
+        e = cudaMalloc(&h->qtable_dev, 4096 * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpy(h->qtable_dev, qt.data(), 4096 * sizeof(float), cudaMemcpyHostToDevice);
+    }
     if (e != cudaSuccess) {
         if (h->jump_dev) cudaFree(h->jump_dev);
         if (h->reset_mask_dev) cudaFree(h->reset_mask_dev);
         if (h->reset_count_dev) cudaFree(h->reset_count_dev);
         if (h->reset_list_dev) cudaFree(h->reset_list_dev);
+        if (h->qtable_dev) cudaFree(h->qtable_dev);
         delete h;
         return fail(SWARM_E_CUDA, "jump table / reset mask allocation failed: %s", cudaGetErrorString(e));
     }
@@ -317,6 +391,7 @@ int swarm_destroy(SwarmHandle* h) {
     if (h->reset_mask_dev) cudaFree(h->reset_mask_dev);
     if (h->reset_count_dev) cudaFree(h->reset_count_dev);
     if (h->reset_list_dev) cudaFree(h->reset_list_dev);
+    if (h->qtable_dev) cudaFree(h->qtable_dev);
     delete h;
     return SWARM_OK;
 }
@@ -438,5 +513,11 @@ int swarm_step_host(SwarmHandle* h, const SwarmBuffers* bufs, const float* actio
 }
 
 int64_t swarm_launch_count(const SwarmHandle* h) { return h ? h->launches : 0; }
+
+int swarm_dr_quantile_table(float* out4096) {
+    if (!out4096) return fail(SWARM_E_NULL, "out is NULL");
+    build_qtable(out4096);
+    return SWARM_OK;
+}
 
 }  // extern "C"

@@ -64,6 +64,15 @@ struct DevParams {
     unsigned* reset_count_other;  // the next step's counter (zeroed by the aux launch)
     int* reset_list;              // first env of every group with an env to reset
     const JumpEntry* jump;        // [n_draws + 1]
+    // ---- domain randomisation (N <= 32 kernels, norm_mode 0)
+    int dr_enabled;
+    unsigned dr_key0, dr_key1;    // Philox key = dr_seed
+    long long env_index_base;
+    double dr_lo[6], dr_span[6];  // mass, max_accel, max_speed, dt, obstacle_radius, world_size: min, max - min
+    double dr_max_accel, dr_max_speed, dr_dt, dr_world, dr_r_c, dr_r_o;
+    float dr_std_thrust, dr_std_pos, dr_std_vel, dr_std_obst;
+    float4* dr_params;            // [E][2] float4
+    const float* dr_qtable;       // [4096] standard-normal quantiles
 };
 
 // kernel selection (swarm_kernels.cu)

@@ -752,6 +752,24 @@ __device__ __forceinline__ void cp_async4(unsigned saddr, const void* g) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// Philox4x32-10 (Salmon et al.), the counter-based generator of the domain-randomisation streams
+__device__ __forceinline__ uint4 philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0,
+                                                unsigned k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ unsigned u4_get(const uint4& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
+// stream ids of the per-step DR draws (counter word 3 = drone | stream << 16)
+#define DR_STREAM_THRUST 0u
+#define DR_STREAM_SENSOR 1u  /* + n / 4 for the n-th sensor normal */
+#define DR_CTR_EPISODE 0xD5D5D5D5u
+
 enum SmallMode : int { kSmallStep = 0, kSmallAux = 1 };  // aux = reset / auto-reset / observe launches
 
 __device__ __forceinline__ double mean_markstein(double sum, double n, double inv_n) {
@@ -777,7 +795,7 @@ __host__ __device__ constexpr int small_srow(int n) {
     return s;
 }
 
-template <int KT, int ST, bool EXACT, int NORM, int KIND, int MODE, int NT>
+template <int KT, int ST, bool EXACT, int NORM, int KIND, int MODE, int NT, bool DR>
 __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_kernel_small(const DevParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5;
@@ -790,7 +808,8 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
     const int N = NT ? NT : P.N, M = P.M, G = NT ? 32 / NT : P.G, srow = NT ? small_srow(NT) : P.srow;
     const int K = EXACT ? KT : P.K, S = EXACT ? ST : P.S;
     const int D = EXACT ? (KIND == SWARM_KIND_SWARM ? 9 + 4 * KT + 4 * ST : 9 + 4 * ST) : P.D;
-    const int goal_off = 64, obst_off = 64 + G, act_off4 = 64 + G + G * P.m_pad;  // inbox offsets, float4 units
+    const int goal_off = 64, obst_off = 64 + G, dr_off4 = 64 + G + G * P.m_pad;     // inbox offsets, float4 units
+    const int act_off4 = dr_off4 + (DR ? 2 * G : 0);
     const int e_l = lane / N;
     const int i = lane - e_l * N;
     const int e_base = e_l * N;  // first lane of this lane's env
@@ -830,6 +849,9 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
         }
         for (int idx = lane; idx < n_env * M; idx += 32)
             cp_async16(sbase + obst_off * 16 + idx * 16, P.obst4 + (long long)env0 * M + idx);
+        if (DR)
+            for (int idx = lane; idx < 2 * n_env; idx += 32)
+                cp_async16(sbase + dr_off4 * 16 + idx * 16, P.dr_params + (long long)env0 * 2 + idx);
         const float* act = P.actions + a0 * 3;
         if ((((G * N) | n_ag) & 3) == 0) {  // 16-byte aligned, whole 16-byte chunks
             if (lane * 4 < n_ag * 3) cp_async16(sbase + act_off4 * 16 + lane * 16, act + lane * 4);
@@ -891,6 +913,16 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
             for (int idx = lane; idx < n_env * M; idx += 32) tab_obst[idx] = P.obst4[(long long)env0 * M + idx];
         }
         float gx = g4.x, gy = g4.y, gz = g4.z;
+        // per-env dynamics constants: the config's, or this episode's randomised ones
+        float c_amax = P.amax, c_vmax = P.vmax, c_dt = P.dt, c_bound = P.bound, c_thr_obst = P.thr_obst;
+        unsigned ekey = 0u;
+        if (DR && lane_ok) {
+            const float4* drp = MODE == kSmallStep ? tab_pos + dr_off4 + 2 * e_l : P.dr_params + (long long)env * 2;
+            const float4 d0 = drp[0], d1 = drp[1];
+            c_amax = d0.x; c_vmax = d0.y; c_dt = d0.z; c_bound = d0.w;
+            c_thr_obst = d1.x; ekey = __float_as_uint(d1.y);
+        }
+        const unsigned genv = DR ? (unsigned)(P.env_index_base + env) : 0u;
 
         bool alive = KIND == SWARM_KIND_SINGLE ? lane_ok : (lane_ok && p.w != 0.0f);
         float prev_d = 0.f;
@@ -900,24 +932,33 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
             prev_d = norm1d<NORM>(__fsub_rn(gx, p.x), __fsub_rn(gy, p.y), __fsub_rn(gz, p.z));  // :98-101
             if (alive) {
                 ax = clipf(ax, -1.0f, 1.0f); ay = clipf(ay, -1.0f, 1.0f); az = clipf(az, -1.0f, 1.0f);
-                v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(ax, P.amax), P.dt));
-                v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(ay, P.amax), P.dt));
-                v.z = __fadd_rn(v.z, __fmul_rn(__fmul_rn(az, P.amax), P.dt));
-                const float speed = norm1d<NORM>(v.x, v.y, v.z);  // _clip_speed (:179-183)
-                if (!(speed <= P.vmax || speed < P.eps_speed)) {
-                    v.x = __fmul_rn(__fdiv_rn(v.x, speed), P.vmax);
-                    v.y = __fmul_rn(__fdiv_rn(v.y, speed), P.vmax);
-                    v.z = __fmul_rn(__fdiv_rn(v.z, speed), P.vmax);
+                if (DR) {  // thrust noise: a <- a * (1 + sigma z), one normal per axis
+                    const uint4 r = philox4x32_10(genv, ekey, (unsigned)sc, (unsigned)i | (DR_STREAM_THRUST << 16),
+                                                  P.dr_key0, P.dr_key1);
+                    ax = __fmul_rn(ax, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, P.dr_qtable[r.x >> 20])));
+                    ay = __fmul_rn(ay, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, P.dr_qtable[r.y >> 20])));
+                    az = __fmul_rn(az, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, P.dr_qtable[r.z >> 20])));
                 }
-                p.x = __fadd_rn(p.x, __fmul_rn(v.x, P.dt));
-                p.y = __fadd_rn(p.y, __fmul_rn(v.y, P.dt));
-                p.z = __fadd_rn(p.z, __fmul_rn(v.z, P.dt));
+                v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(ax, c_amax), c_dt));
+                v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(ay, c_amax), c_dt));
+                v.z = __fadd_rn(v.z, __fmul_rn(__fmul_rn(az, c_amax), c_dt));
+                const float speed = norm1d<NORM>(v.x, v.y, v.z);  // _clip_speed (:179-183)
+                if (!(speed <= c_vmax || speed < P.eps_speed)) {
+                    v.x = __fmul_rn(__fdiv_rn(v.x, speed), c_vmax);
+                    v.y = __fmul_rn(__fdiv_rn(v.y, speed), c_vmax);
+                    v.z = __fmul_rn(__fdiv_rn(v.z, speed), c_vmax);
+                }
+                p.x = __fadd_rn(p.x, __fmul_rn(v.x, c_dt));
+                p.y = __fadd_rn(p.y, __fmul_rn(v.y, c_dt));
+                p.z = __fadd_rn(p.z, __fmul_rn(v.z, c_dt));
             }
             // wall clip for ALL drones (:113-117); velocity is not zeroed at the wall
-            p.x = clipf(p.x, -P.bound, P.bound);
-            p.y = clipf(p.y, -P.bound, P.bound);
-            p.z = clipf(p.z, -P.bound, P.bound);
+            p.x = clipf(p.x, -c_bound, c_bound);
+            p.y = clipf(p.y, -c_bound, c_bound);
+            p.z = clipf(p.z, -c_bound, c_bound);
         }
+        int sc_obs = MODE == kSmallStep ? sc + 1 : 0;  // step_count of the state the obs row describes (DR sensor stream)
+        if (DR && MODE == kSmallAux && lane_ok) sc_obs = P.step_count[env];
         if (lane_ok) tab_pos[lane] = make_float4(p.x, p.y, p.z, alive ? 1.0f : 0.0f);
         tab_vel[lane] = make_float4(v.x, v.y, v.z, prev_d);  // parked here while the scans need the registers
 
@@ -930,11 +971,46 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                 const int renv = env0 + el;
                 const unsigned long long sh = P.rng[(long long)renv * 4 + 0], sl = P.rng[(long long)renv * 4 + 1];
                 const unsigned long long ih = P.rng[(long long)renv * 4 + 2], il = P.rng[(long long)renv * 4 + 3];
+                double u_lo = P.rng_lo, u_range = P.rng_range;
+                if (DR) {
+                    // this episode's constants: 6 uniforms + an episode key from one counter per (env, reset)
+                    const unsigned ge = (unsigned)(P.env_index_base + renv);
+                    const uint4 ra = philox4x32_10(ge, (unsigned)sl, (unsigned)(sl >> 32), DR_CTR_EPISODE, P.dr_key0, P.dr_key1);
+                    const uint4 rb = philox4x32_10(ge, (unsigned)sl, (unsigned)(sl >> 32), DR_CTR_EPISODE + 1u, P.dr_key0, P.dr_key1);
+                    const double inv24 = 1.0 / 16777216.0;
+                    const double s_mass = __dadd_rn(P.dr_lo[0], __dmul_rn(P.dr_span[0], __dmul_rn((double)(ra.x >> 8), inv24)));
+                    const double s_acc = __dadd_rn(P.dr_lo[1], __dmul_rn(P.dr_span[1], __dmul_rn((double)(ra.y >> 8), inv24)));
+                    const double s_spd = __dadd_rn(P.dr_lo[2], __dmul_rn(P.dr_span[2], __dmul_rn((double)(ra.z >> 8), inv24)));
+                    const double s_dt = __dadd_rn(P.dr_lo[3], __dmul_rn(P.dr_span[3], __dmul_rn((double)(ra.w >> 8), inv24)));
+                    const double s_rad = __dadd_rn(P.dr_lo[4], __dmul_rn(P.dr_span[4], __dmul_rn((double)(rb.x >> 8), inv24)));
+                    const double s_wld = __dadd_rn(P.dr_lo[5], __dmul_rn(P.dr_span[5], __dmul_rn((double)(rb.y >> 8), inv24)));
+                    const double world = __dmul_rn(P.dr_world, s_wld);
+                    const double half_w = __dmul_rn(world, 0.5);
+                    u_lo = -half_w; u_range = __dsub_rn(half_w, -half_w);
+                    if (lane == 0) {
+                        const float4 d0 = make_float4(__double2float_rn(__ddiv_rn(__dmul_rn(P.dr_max_accel, s_acc), s_mass)),
+                                                      __double2float_rn(__dmul_rn(P.dr_max_speed, s_spd)),
+                                                      __double2float_rn(__dmul_rn(P.dr_dt, s_dt)), __double2float_rn(half_w));
+                        const float4 d1 = make_float4(__double2float_rn(__dadd_rn(P.dr_r_c, __dmul_rn(P.dr_r_o, s_rad))),
+                                                      __uint_as_float(rb.z), __double2float_rn(world), 0.0f);
+                        P.dr_params[(long long)renv * 2 + 0] = d0;
+                        P.dr_params[(long long)renv * 2 + 1] = d1;
+                    }
+                    if (lane_ok && e_l == el) {
+                        c_amax = __double2float_rn(__ddiv_rn(__dmul_rn(P.dr_max_accel, s_acc), s_mass));
+                        c_vmax = __double2float_rn(__dmul_rn(P.dr_max_speed, s_spd));
+                        c_dt = __double2float_rn(__dmul_rn(P.dr_dt, s_dt));
+                        c_bound = __double2float_rn(half_w);
+                        c_thr_obst = __double2float_rn(__dadd_rn(P.dr_r_c, __dmul_rn(P.dr_r_o, s_rad)));
+                        ekey = rb.z;
+                        sc_obs = 0;
+                    }
+                }
 #pragma unroll 1
                 for (int k = lane; k < P.n_draws; k += 32) {
                     unsigned long long oh, ol;
                     pcg_jump(P.jump[k + 1], sh, sl, ih, il, oh, ol);
-                    const float val = pcg_uniform_f32(oh, ol, P.rng_lo, P.rng_range);
+                    const float val = pcg_uniform_f32(oh, ol, u_lo, u_range);
                     // draw order: positions (N,3) -> goal (3,) -> obstacles (M,3)
                     if (k < 3 * N) {
                         reinterpret_cast<float*>(tab_pos + el * N + k / 3)[k % 3] = val;
@@ -1140,8 +1216,28 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
         // ============================ obs row -> staging tile ============================
         if ((out_lanes >> lane) & 1u) {
             float* row = region + lane * D;
-            row[0] = p.x; row[1] = p.y; row[2] = p.z;
-            row[3] = v.x; row[4] = v.y; row[5] = v.z;
+            // DR sensor noise: normal n of this row comes from Philox call n / 4 (n = 0-2 position,
+            // 3-5 velocity, 6 + q distance of sensed obstacle q), keyed by the observed state's step_count
+            uint4 rs0 = make_uint4(0, 0, 0, 0), rs1 = rs0, rs2 = rs0, rs3 = rs0;
+            if (DR) {
+                const unsigned c3 = (unsigned)i | (DR_STREAM_SENSOR << 16);
+                rs0 = philox4x32_10(genv, ekey, (unsigned)sc_obs, c3, P.dr_key0, P.dr_key1);
+                rs1 = philox4x32_10(genv, ekey, (unsigned)sc_obs, c3 + (1u << 16), P.dr_key0, P.dr_key1);
+                if (S > 2) rs2 = philox4x32_10(genv, ekey, (unsigned)sc_obs, c3 + (2u << 16), P.dr_key0, P.dr_key1);
+                if (S > 6) rs3 = philox4x32_10(genv, ekey, (unsigned)sc_obs, c3 + (3u << 16), P.dr_key0, P.dr_key1);
+            }
+            auto noisy = [&](float x, float sigma, unsigned bits) {
+                return DR ? __fadd_rn(x, __fmul_rn(sigma, P.dr_qtable[bits >> 20])) : x;
+            };
+            auto obst_bits = [&](int q) {  // normal 6 + q
+                const int n = 6 + q;
+                const uint4& r = n < 8 ? rs1 : (n < 12 ? rs2 : rs3);
+                return u4_get(r, n & 3);
+            };
+            row[0] = noisy(p.x, P.dr_std_pos, rs0.x); row[1] = noisy(p.y, P.dr_std_pos, rs0.y);
+            row[2] = noisy(p.z, P.dr_std_pos, rs0.z);
+            row[3] = noisy(v.x, P.dr_std_vel, rs0.w); row[4] = noisy(v.y, P.dr_std_vel, rs1.x);
+            row[5] = noisy(v.z, P.dr_std_vel, rs1.y);
             row[6] = __fsub_rn(gx, p.x); row[7] = __fsub_rn(gy, p.y); row[8] = __fsub_rn(gz, p.z);
             int off = 9;
             const bool all_slots = (KIND != SWARM_KIND_SWARM || n_others >= K) && M >= S;  // warp-uniform
@@ -1167,7 +1263,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                         row[off + 4 * q + 0] = __fsub_rn(t.x, p.x);
                         row[off + 4 * q + 1] = __fsub_rn(t.y, p.y);
                         row[off + 4 * q + 2] = __fsub_rn(t.z, p.z);
-                        row[off + 4 * q + 3] = od[q];
+                        row[off + 4 * q + 3] = noisy(od[q], P.dr_std_obst, obst_bits(q));
                     }
                 }
             } else {  // fewer candidates than slots: zero padding (:268-270, :288-290)
@@ -1195,7 +1291,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                         row[off + 4 * q + 0] = has ? __fsub_rn(t.x, p.x) : 0.f;
                         row[off + 4 * q + 1] = has ? __fsub_rn(t.y, p.y) : 0.f;
                         row[off + 4 * q + 2] = has ? __fsub_rn(t.z, p.z) : 0.f;
-                        row[off + 4 * q + 3] = has ? od[q] : 0.f;
+                        row[off + 4 * q + 3] = has ? noisy(od[q], P.dr_std_obst, obst_bits(q)) : 0.f;
                     }
                 }
             }
@@ -1211,7 +1307,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
 
         if (MODE == kSmallStep) {
             // ===================== rewards and flags (:120-172) =====================
-            const bool obst_hit = od[0] <= P.thr_obst;
+            const bool obst_hit = od[0] <= c_thr_obst;
             const bool reached = alive && curr_d <= P.thr_goal;       // :124-127 (double compare)
             const bool collided = alive && (obst_hit || pair_hit);     // :128
             double reward = 0.0;
@@ -1434,12 +1530,15 @@ __global__ void swarm_seed_kernel(const DevParams P) {
 typedef void (*EnvKernel)(const DevParams);
 
 template <int KT, int ST, bool EXACT, int KIND, int NT>
-static EnvKernel pick_small(int norm_mode, bool step) {
+static EnvKernel pick_small(int norm_mode, bool step, bool dr) {
+    if (dr)  // domain randomisation: norm_mode 0, runtime N
+        return step ? swarm_env_kernel_small<KT, ST, EXACT, 0, KIND, kSmallStep, 0, true>
+                    : swarm_env_kernel_small<KT, ST, EXACT, 0, KIND, kSmallAux, 0, true>;
     if (norm_mode == 0)
-        return step ? swarm_env_kernel_small<KT, ST, EXACT, 0, KIND, kSmallStep, NT>
-                    : swarm_env_kernel_small<KT, ST, EXACT, 0, KIND, kSmallAux, 0>;
-    return step ? swarm_env_kernel_small<KT, ST, EXACT, 1, KIND, kSmallStep, 0>
-                : swarm_env_kernel_small<KT, ST, EXACT, 1, KIND, kSmallAux, 0>;
+        return step ? swarm_env_kernel_small<KT, ST, EXACT, 0, KIND, kSmallStep, NT, false>
+                    : swarm_env_kernel_small<KT, ST, EXACT, 0, KIND, kSmallAux, 0, false>;
+    return step ? swarm_env_kernel_small<KT, ST, EXACT, 1, KIND, kSmallStep, 0, false>
+                : swarm_env_kernel_small<KT, ST, EXACT, 1, KIND, kSmallAux, 0, false>;
 }
 
 template <int KT, int ST, bool EXACT, int KIND>
@@ -1450,19 +1549,20 @@ static EnvKernel pick_large(int norm_mode) {
 static EnvKernel resolve(const DevParams& p, int norm_mode, int env_kind) {
     const bool small_n = p.N <= 32;
     const bool step = p.mode == kModeStep;
+    const bool dr = p.dr_enabled != 0;
     if (env_kind == SWARM_KIND_SWARM) {
         if (p.K == 3 && p.S == 4) {
             if (!small_n) return pick_large<3, 4, true, SWARM_KIND_SWARM>(norm_mode);
             // (N = 32 measured faster on the runtime-N instantiation: 9.6e9 vs 9.1e9 agent-steps/s)
-            if (p.N == 16) return pick_small<3, 4, true, SWARM_KIND_SWARM, 16>(norm_mode, step);
-            if (p.N == 8) return pick_small<3, 4, true, SWARM_KIND_SWARM, 8>(norm_mode, step);
-            return pick_small<3, 4, true, SWARM_KIND_SWARM, 0>(norm_mode, step);
+            if (p.N == 16) return pick_small<3, 4, true, SWARM_KIND_SWARM, 16>(norm_mode, step, dr);
+            if (p.N == 8) return pick_small<3, 4, true, SWARM_KIND_SWARM, 8>(norm_mode, step, dr);
+            return pick_small<3, 4, true, SWARM_KIND_SWARM, 0>(norm_mode, step, dr);
         }
         if (!small_n) return pick_large<SWARM_MAX_NEIGHBOR_K, SWARM_MAX_SENSED, false, SWARM_KIND_SWARM>(norm_mode);
-        return pick_small<SWARM_MAX_NEIGHBOR_K, SWARM_MAX_SENSED, false, SWARM_KIND_SWARM, 0>(norm_mode, step);
+        return pick_small<SWARM_MAX_NEIGHBOR_K, SWARM_MAX_SENSED, false, SWARM_KIND_SWARM, 0>(norm_mode, step, dr);
     }
-    if (p.S == 4) return pick_small<1, 4, true, SWARM_KIND_SINGLE, 1>(norm_mode, step);
-    return pick_small<1, SWARM_MAX_SENSED, false, SWARM_KIND_SINGLE, 0>(norm_mode, step);
+    if (p.S == 4) return pick_small<1, 4, true, SWARM_KIND_SINGLE, 1>(norm_mode, step, dr);
+    return pick_small<1, SWARM_MAX_SENSED, false, SWARM_KIND_SINGLE, 0>(norm_mode, step, dr);
 }
 
 cudaError_t launch_env_kernel(const DevParams& p, int norm_mode, int env_kind, int grid, size_t smem_bytes,

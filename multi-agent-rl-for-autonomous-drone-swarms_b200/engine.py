@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _abi
-from .config import DroneEnvConfig
+from .config import DroneEnvConfig, flatten_domain_randomization
 
 
 class SwarmEngine:
@@ -33,7 +33,14 @@ class SwarmEngine:
 
     def __init__(self, num_envs: int, config: dict[str, Any] | None = None, kind: str = "swarm",
                  device: str | torch.device = "cuda", global_state: bool = True, reward64: bool = False,
-                 norm_mode: int = 0):
+                 norm_mode: int = 0, domain_randomization: dict[str, Any] | None = None, dr_seed: int = 0,
+                 env_index_base: int = 0):
+        """domain_randomization: None / {} = off (bit-identical to the reference).  Otherwise either the
+        reference's `configs/domain_randomization_v1.yaml` document (as loaded: `randomization.dynamics.
+        mass_scale.{min,max}` ...; honoured even though its `enabled` flag is false there, pass None to
+        disable) or the flat form {"mass_scale": (lo, hi), ..., "thrust_noise_std": sigma, ...} -- see
+        `config.flatten_domain_randomization`.  `env_index_base`: global index of env 0 (sharded runs),
+        so the randomisation streams of an env do not depend on how the batch is split."""
         if kind not in ("swarm", "single"):
             raise ValueError(f"kind must be 'swarm' or 'single', got {kind!r}")
         self._lib = _abi.load()
@@ -60,6 +67,14 @@ class SwarmEngine:
         c.max_steps, c.norm_mode, c.device = int(self.cfg.max_steps), int(norm_mode), self.device.index
         for name in _abi._DOUBLES:
             setattr(c, name, float(getattr(self.cfg, name)))
+        self.dr = flatten_domain_randomization(domain_randomization)
+        if self.dr:
+            c.dr_enabled, c.dr_seed, c.env_index_base = 1, int(dr_seed) & (2**64 - 1), int(env_index_base)
+            for name in _abi.DR_RANGES:
+                lo, hi = self.dr.get(name[3:], (1.0, 1.0))
+                getattr(c, name)[0], getattr(c, name)[1] = float(lo), float(hi)
+            for name in _abi.DR_STDS:
+                setattr(c, name, float(self.dr.get(name[3:], 0.0)))
         self._c = c
         sz = _abi.SwarmSizes()
         _abi.check(self._lib.swarm_query_sizes(C.byref(c), C.byref(sz)), "swarm_query_sizes")
@@ -93,6 +108,8 @@ class SwarmEngine:
         self.episode_return = z((E,), torch.float32)
         self.episode_length = z((E,), torch.int32)
         self.stats_words = z((len(_abi.STAT_NAMES),), torch.int64)
+        # per-env per-episode dynamics constants of the domain randomisation (written by reset)
+        self.dr_params = z((E, 8), torch.float32) if self.dr else None
         self.pos4[..., 3] = 1.0
         self._actions_dev = None
         self._bufs = self._make_buffers()
@@ -223,6 +240,8 @@ class SwarmEngine:
         state; RLlib resumes only the policy).  CPU tensors, safe to `torch.save`."""
         torch.cuda.synchronize(self.device)
         out = {k: getattr(self, k).detach().cpu().clone() for k in self._STATE_KEYS}
+        if self.dr_params is not None:
+            out["dr_params"] = self.dr_params.detach().cpu().clone()
         out["meta"] = dict(kind=self.kind, E=self.E, N=self.N, M=self.M, K=self.K, S=self.S)
         return out
 
@@ -233,6 +252,8 @@ class SwarmEngine:
             raise ValueError(f"state_dict is for {meta}, this engine is {mine}")
         for k in self._STATE_KEYS:
             getattr(self, k).copy_(state[k].to(self.device))
+        if self.dr_params is not None:
+            self.dr_params.copy_(state["dr_params"].to(self.device))
         if observe:
             self.observe()
 

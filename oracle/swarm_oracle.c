@@ -60,6 +60,15 @@ typedef struct OracleConfig {
     int32_t env_kind;  /* 0 = SingleDroneEnv, 1 = DroneSwarmEnv */
     int32_t norm_mode; /* 0 = BLAS sdot (double accumulate), 1 = sequential f32 */
     int32_t reserved;
+    /* domain randomisation: NOT reference behaviour (configs/domain_randomization_v1.yaml is read by no
+     * reference code).  These semantics are the engine's; this restatement only
+     * pins the CUDA path to them.  dr_enabled == 0 -> everything below is ignored. */
+    int32_t dr_enabled;
+    int32_t dr_pad;
+    uint64_t dr_seed;
+    int64_t env_index_base;
+    double dr_lo[6], dr_span[6]; /* mass, max_accel, max_speed, dt, obstacle_radius, world_size scales */
+    double dr_std_thrust, dr_std_pos, dr_std_vel, dr_std_obst;
 } OracleConfig;
 
 /* One batch of E environments, arrays laid out exactly like the reference's
@@ -86,6 +95,7 @@ typedef struct OracleBatch {
     uint8_t *all_terminated; /* [E]    terminated["__all__"] */
     uint8_t *all_truncated;  /* [E]    truncated["__all__"] */
     float *global_state; /* [E][6N+3]  info["global_state"] (drone_swarm_env.py:293-302) */
+    float *dr_params;    /* [E][8]     DR only: {max_accel, max_speed, dt, bound, obst threshold, key, world, 0} */
 } OracleBatch;
 
 /* ------------------------------------------------------------------------- */
@@ -185,6 +195,68 @@ static float draw_uniform_f32(uint64_t rng[4], double lo, double range) {
     double v = lo + scaled;
     return (float)v;
 }
+
+/* ------------------------------------------------------------------------- */
+/* Domain randomisation streams (engine semantics, see OracleConfig)          */
+/* ------------------------------------------------------------------------- */
+static void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+static double inv_norm_cdf(double p) { /* Acklam's rational approximation */
+    static const double a[] = {-3.969683028665376e+01, 2.209460984245205e+02, -2.759285104469687e+02,
+                               1.383577518672690e+02, -3.066479806614716e+01, 2.506628277459239e+00};
+    static const double b[] = {-5.447609879822406e+01, 1.615858368580409e+02, -1.556989798598866e+02,
+                               6.680131188771972e+01, -1.328068155288572e+01};
+    static const double c[] = {-7.784894002430293e-03, -3.223964580411365e-01, -2.400758277161838e+00,
+                               -2.549732539343734e+00, 4.374664141464968e+00, 2.938163982698783e+00};
+    static const double d[] = {7.784695709041462e-03, 3.224671290700398e-01, 2.445134137142996e+00,
+                               3.754408661907416e+00};
+    const double plow = 0.02425;
+    if (p < plow) {
+        double q = sqrt(-2.0 * log(p));
+        return (((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) /
+               ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1.0);
+    }
+    if (p > 1.0 - plow) {
+        double q = sqrt(-2.0 * log(1.0 - p));
+        return -(((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) /
+               ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1.0);
+    }
+    double q = p - 0.5, r = q * q;
+    return (((((a[0] * r + a[1]) * r + a[2]) * r + a[3]) * r + a[4]) * r + a[5]) * q /
+           (((((b[0] * r + b[1]) * r + b[2]) * r + b[3]) * r + b[4]) * r + 1.0);
+}
+
+static float g_qtable[4096];
+static int g_qtable_ready = 0;
+static pthread_mutex_t g_qtable_lock = PTHREAD_MUTEX_INITIALIZER;
+static const float *qtable(void) {
+    pthread_mutex_lock(&g_qtable_lock);
+    if (!g_qtable_ready) {
+        for (int k = 0; k < 4096; ++k) g_qtable[k] = (float)inv_norm_cdf(((double)k + 0.5) / 4096.0);
+        g_qtable_ready = 1;
+    }
+    pthread_mutex_unlock(&g_qtable_lock);
+    return g_qtable;
+}
+void oracle_dr_quantile_table(float *out) { memcpy(out, qtable(), sizeof(float) * 4096); }
+
+/* per-env, per-episode view of the dynamics constants */
+typedef struct DynConst {
+    float amax, vmax, dt, bound, thr_obst;
+    int dr;             /* randomisation on */
+    uint32_t genv, ekey, k0, k1;
+    float std_thrust, std_pos, std_vel, std_obst;
+} DynConst;
+
+static float dr_normal(uint32_t bits) { return qtable()[bits >> 20]; }
 
 /* ------------------------------------------------------------------------- */
 /* np.linalg.norm restatements (T1, T2)                                       */
@@ -311,8 +383,8 @@ static void nearest_neighbor_features(const OracleConfig *c, const float *pos, i
 }
 
 /* _build_obs  drone_swarm_env.py:226-243 / single_drone_env.py:128-140 */
-static void build_obs(const OracleConfig *c, const float *pos, const float *vel, const float *goal,
-                      const float *obst, int index, float *out) {
+static void build_obs(const OracleConfig *c, const DynConst *kc, int step_obs, const float *pos, const float *vel,
+                      const float *goal, const float *obst, int index, float *out) {
     const float *p = pos + 3 * index, *v = vel + 3 * index;
     out[0] = p[0]; out[1] = p[1]; out[2] = p[2];
     out[3] = v[0]; out[4] = v[1]; out[5] = v[2];
@@ -323,6 +395,27 @@ static void build_obs(const OracleConfig *c, const float *pos, const float *vel,
         off += 4 * c->neighbor_k;
     }
     nearest_obstacle_features(c, p, obst, out + off);
+    if (kc->dr) {
+        /* DR sensor noise: normal n comes from Philox call n / 4 of stream (genv, ekey, step_count of the
+         * observed state, drone | (1 + n / 4) << 16); n = 0-2 position, 3-5 velocity, 6 + q obstacle q's distance */
+        uint32_t r[16];
+        for (int call = 0; call < 4; ++call) {
+            uint32_t ctr[4] = {kc->genv, kc->ekey, (uint32_t)step_obs, (uint32_t)index | ((uint32_t)(1 + call) << 16)};
+            philox4x32_10(ctr, kc->k0, kc->k1);
+            memcpy(r + 4 * call, ctr, sizeof(ctr));
+        }
+        for (int k = 0; k < 3; ++k) {
+            volatile float np_ = kc->std_pos * dr_normal(r[k]);
+            out[k] = out[k] + np_;
+            volatile float nv = kc->std_vel * dr_normal(r[3 + k]);
+            out[3 + k] = out[3 + k] + nv;
+        }
+        int filled = c->sensed_obstacles < c->num_obstacles ? c->sensed_obstacles : c->num_obstacles;
+        for (int q = 0; q < filled; ++q) {
+            volatile float nd = kc->std_obst * dr_normal(r[6 + q]);
+            out[off + 4 * q + 3] = out[off + 4 * q + 3] + nd;
+        }
+    }
 }
 
 /* _distance_to_goal  drone_swarm_env.py:176-177 / single_drone_env.py:113-114 */
@@ -340,9 +433,9 @@ static void global_state(const OracleConfig *c, const float *pos, const float *v
 }
 
 /* _clip_speed  drone_swarm_env.py:179-183 / single_drone_env.py:116-120 */
-static void clip_speed(const OracleConfig *c, float *v) {
+static void clip_speed(const OracleConfig *c, const DynConst *k, float *v) {
     float speed = norm1d(c, v[0], v[1], v[2]);
-    float vmax = (float)c->max_speed; /* np.float32 <= python float -> f32 compare (NEP 50) */
+    float vmax = k->vmax; /* (float)max_speed: np.float32 <= python float -> f32 compare (NEP 50) */
     if (speed <= vmax || speed < (float)1e-8) return;
     for (int k = 0; k < 3; ++k) {
         volatile float q = v[k] / speed;
@@ -357,16 +450,25 @@ static float clipf(float x, float lo, float hi) {
     return x;
 }
 
-/* integrate block  drone_swarm_env.py:103-111 / single_drone_env.py:74-84 */
-static void integrate(const OracleConfig *c, const float *action, float *p, float *v) {
-    float amax = (float)c->max_accel, dt = (float)c->dt;
+/* integrate block  drone_swarm_env.py:103-111 / single_drone_env.py:74-84
+ * (DR: thrust noise a <- a * (1 + sigma z), stream (genv, ekey, step_count before the step, drone)) */
+static void integrate(const OracleConfig *c, const DynConst *kc, int step_before, int drone, const float *action,
+                      float *p, float *v) {
+    float amax = kc->amax, dt = kc->dt;
+    uint32_t ctr[4] = {kc->genv, kc->ekey, (uint32_t)step_before, (uint32_t)drone};
+    if (kc->dr) philox4x32_10(ctr, kc->k0, kc->k1);
     for (int k = 0; k < 3; ++k) {
         float a = clipf(action[k], -1.0f, 1.0f);
+        if (kc->dr) {
+            volatile float sz = kc->std_thrust * dr_normal(ctr[k]);
+            volatile float one = 1.0f + sz;
+            a = a * one;
+        }
         volatile float accel = a * amax;
         volatile float dv = accel * dt;
         v[k] = v[k] + dv;
     }
-    clip_speed(c, v);
+    clip_speed(c, kc, v);
     for (int k = 0; k < 3; ++k) {
         volatile float dp = v[k] * dt;
         p[k] = p[k] + dp;
@@ -384,6 +486,8 @@ typedef struct EnvView {
     float *obs, *dist, *gs;
     double *reward;
     uint8_t *terminated, *truncated, *reached, *collision, *obs_valid, *all_term, *all_trunc;
+    float *dr;
+    int env_index;
 } EnvView;
 
 static EnvView view(const OracleConfig *c, const OracleBatch *b, int e) {
@@ -407,15 +511,42 @@ static EnvView view(const OracleConfig *c, const OracleBatch *b, int e) {
     v.obs_valid = b->obs_valid + (size_t)e * N;
     v.all_term = b->all_terminated + e;
     v.all_trunc = b->all_truncated + e;
+    v.dr = b->dr_params ? b->dr_params + (size_t)e * 8 : NULL;
+    v.env_index = e;
     return v;
+}
+
+/* the dynamics constants of one env: the config's, or (DR) this episode's */
+static DynConst dyn_const(const OracleConfig *c, const EnvView *v) {
+    DynConst k;
+    memset(&k, 0, sizeof(k));
+    k.amax = (float)c->max_accel;
+    k.vmax = (float)c->max_speed;
+    k.dt = (float)c->dt;
+    k.bound = (float)(c->world_size / 2.0);
+    k.thr_obst = (float)(c->collision_radius + c->obstacle_radius);
+    if (c->dr_enabled && v->dr) {
+        uint32_t key_bits;
+        memcpy(&key_bits, v->dr + 5, 4);
+        k.dr = 1;
+        k.amax = v->dr[0]; k.vmax = v->dr[1]; k.dt = v->dr[2]; k.bound = v->dr[3]; k.thr_obst = v->dr[4];
+        k.ekey = key_bits;
+        k.genv = (uint32_t)(c->env_index_base + v->env_index);
+        k.k0 = (uint32_t)(c->dr_seed & 0xffffffffu);
+        k.k1 = (uint32_t)(c->dr_seed >> 32);
+        k.std_thrust = (float)c->dr_std_thrust; k.std_pos = (float)c->dr_std_pos;
+        k.std_vel = (float)c->dr_std_vel; k.std_obst = (float)c->dr_std_obst;
+    }
+    return k;
 }
 
 /* obs + info for every drone of one env (what reset() returns, and what the
  * batched contract reports after set_state):  drone_swarm_env.py:82-89. */
 static void observe_env(const OracleConfig *c, EnvView *v) {
     int N = c->num_drones, D = obs_dim(c);
+    DynConst kc = dyn_const(c, v);
     for (int i = 0; i < N; ++i) {
-        build_obs(c, v->pos, v->vel, v->goal, v->obst, i, v->obs + (size_t)i * D);
+        build_obs(c, &kc, *v->step_count, v->pos, v->vel, v->goal, v->obst, i, v->obs + (size_t)i * D);
         v->dist[i] = distance_to_goal(c, v->goal, v->pos + 3 * i);
         v->obs_valid[i] = c->env_kind == 1 ? v->active[i] : 1;
         v->reward[i] = 0.0;
@@ -431,6 +562,39 @@ static void observe_env(const OracleConfig *c, EnvView *v) {
 static void reset_env(const OracleConfig *c, EnvView *v) {
     int N = c->num_drones, M = c->num_obstacles;
     double bound = c->world_size / 2.0;
+    if (c->dr_enabled && v->dr) {
+        /* this episode's constants: counter = (genv, PCG64 state_lo before the draws, 0xD5D5D5D5 [+1]) */
+        uint32_t genv = (uint32_t)(c->env_index_base + v->env_index);
+        uint32_t k0 = (uint32_t)(c->dr_seed & 0xffffffffu), k1 = (uint32_t)(c->dr_seed >> 32);
+        uint64_t sl = v->rng[1];
+        uint32_t ra[4] = {genv, (uint32_t)sl, (uint32_t)(sl >> 32), 0xD5D5D5D5u};
+        uint32_t rb[4] = {genv, (uint32_t)sl, (uint32_t)(sl >> 32), 0xD5D5D5D5u + 1u};
+        philox4x32_10(ra, k0, k1);
+        philox4x32_10(rb, k0, k1);
+        const double inv24 = 1.0 / 16777216.0;
+        uint32_t u[6] = {ra[0], ra[1], ra[2], ra[3], rb[0], rb[1]};
+        double sc[6];
+        for (int k = 0; k < 6; ++k) {
+            volatile double uu = (double)(u[k] >> 8) * inv24;
+            volatile double sp = c->dr_span[k] * uu;
+            sc[k] = c->dr_lo[k] + sp;
+        }
+        volatile double acc = c->max_accel * sc[1];
+        volatile double spd = c->max_speed * sc[2];
+        volatile double dtt = c->dt * sc[3];
+        volatile double rad = c->obstacle_radius * sc[4];
+        volatile double world = c->world_size * sc[5];
+        volatile double half_w = world * 0.5;
+        v->dr[0] = (float)(acc / sc[0]);
+        v->dr[1] = (float)spd;
+        v->dr[2] = (float)dtt;
+        v->dr[3] = (float)half_w;
+        v->dr[4] = (float)(c->collision_radius + rad);
+        memcpy(v->dr + 5, &rb[2], 4);
+        v->dr[6] = (float)world;
+        v->dr[7] = 0.0f;
+        bound = half_w;
+    }
     double lo = -bound, range = bound - (-bound);
     for (int i = 0; i < N; ++i) v->active[i] = 1;
     *v->step_count = 0;
@@ -442,9 +606,9 @@ static void reset_env(const OracleConfig *c, EnvView *v) {
 }
 
 /* _collision_mask  drone_swarm_env.py:185-208 (over active drones only) */
-static void collision_mask(const OracleConfig *c, const EnvView *v, uint8_t *collided) {
+static void collision_mask(const OracleConfig *c, const DynConst *kc, const EnvView *v, uint8_t *collided) {
     int N = c->num_drones, M = c->num_obstacles;
-    float thr_obst = (float)(c->collision_radius + c->obstacle_radius); /* array <= py float */
+    float thr_obst = kc->thr_obst; /* (float)(r_c + r_o): array <= py float */
     float thr_pair = (float)(2.0 * c->collision_radius);                /* np.float32 <= py float */
     for (int i = 0; i < N; ++i) collided[i] = 0;
     for (int i = 0; i < N; ++i) {
@@ -510,9 +674,10 @@ static void step_swarm_env(const OracleConfig *c, EnvView *v, const float *actio
 
     for (int i = 0; i < N; ++i) /* :98-101 */
         if (v->active[i]) prev[i] = (double)distance_to_goal(c, v->goal, v->pos + 3 * i);
+    DynConst kc = dyn_const(c, v);
     for (int i = 0; i < N; ++i) /* :103-111 */
-        if (v->active[i]) integrate(c, action + 3 * i, v->pos + 3 * i, v->vel + 3 * i);
-    float bound = (float)(c->world_size / 2.0); /* :113-117, all drones */
+        if (v->active[i]) integrate(c, &kc, *v->step_count, i, action + 3 * i, v->pos + 3 * i, v->vel + 3 * i);
+    float bound = kc.bound; /* (float)(world_size / 2): :113-117, all drones */
     for (int k = 0; k < 3 * N; ++k) v->pos[k] = clipf(v->pos[k], -bound, bound);
     *v->step_count += 1; /* :118 */
 
@@ -521,7 +686,7 @@ static void step_swarm_env(const OracleConfig *c, EnvView *v, const float *actio
             curr[i] = (double)distance_to_goal(c, v->goal, v->pos + 3 * i);
             v->reached[i] = curr[i] <= c->goal_radius; /* Python-float (double) compare, T3 */
         }
-    collision_mask(c, v, collided);
+    collision_mask(c, &kc, v, collided);
     formation_penalties(c, v, pen);
 
     int any_collision = 0;
@@ -543,7 +708,7 @@ static void step_swarm_env(const OracleConfig *c, EnvView *v, const float *actio
         v->collision[i] = collided[i];
         v->dist[i] = (float)curr[i];
         if (!done_agent && !time_limit && !any_collision) {
-            build_obs(c, v->pos, v->vel, v->goal, v->obst, i, v->obs + (size_t)i * D);
+            build_obs(c, &kc, *v->step_count, v->pos, v->vel, v->goal, v->obst, i, v->obs + (size_t)i * D);
             v->obs_valid[i] = 1;
             next_active[i] = 1;
             ++n_next;
@@ -564,15 +729,16 @@ static void step_swarm_env(const OracleConfig *c, EnvView *v, const float *actio
 static void step_single_env(const OracleConfig *c, EnvView *v, const float *action) {
     int M = c->num_obstacles;
     double prev = (double)distance_to_goal(c, v->goal, v->pos); /* :77 */
-    integrate(c, action, v->pos, v->vel);                        /* :74-75, 79-82 */
-    float bound = (float)(c->world_size / 2.0);
+    DynConst kc = dyn_const(c, v);
+    integrate(c, &kc, *v->step_count, 0, action, v->pos, v->vel); /* :74-75, 79-82 */
+    float bound = kc.bound;
     for (int k = 0; k < 3; ++k) v->pos[k] = clipf(v->pos[k], -bound, bound); /* :83-87 */
     *v->step_count += 1;                                                       /* :89 */
     double curr = (double)distance_to_goal(c, v->goal, v->pos);               /* :91 */
     double reward = (prev - curr) * c->reward_progress_scale;                  /* :92 */
     int reached = curr <= c->goal_radius;                                      /* :93 */
     int collision = 0;                                                         /* :122-126 */
-    float thr = (float)(c->obstacle_radius + c->collision_radius);
+    float thr = kc.thr_obst; /* (float)(obstacle_radius + collision_radius) */
     for (int m = 0; m < M; ++m) {
         float d = norm_axis(v->obst[3 * m] - v->pos[0], v->obst[3 * m + 1] - v->pos[1],
                             v->obst[3 * m + 2] - v->pos[2]);
@@ -587,7 +753,7 @@ static void step_single_env(const OracleConfig *c, EnvView *v, const float *acti
     v->collision[0] = (uint8_t)collision;
     v->dist[0] = (float)curr;
     v->obs_valid[0] = 1;
-    build_obs(c, v->pos, v->vel, v->goal, v->obst, 0, v->obs); /* :105 */
+    build_obs(c, &kc, *v->step_count, v->pos, v->vel, v->goal, v->obst, 0, v->obs); /* :105 */
     *v->all_term = v->terminated[0];
     *v->all_trunc = v->truncated[0];
     if (v->gs) global_state(c, v->pos, v->vel, v->goal, v->gs);

@@ -30,14 +30,20 @@ class OracleConfig(C.Structure):
         "obstacle_radius", "desired_spacing", "reward_progress_scale", "reward_goal",
         "reward_collision", "reward_formation_scale")] + [(n, C.c_int32) for n in (
         "max_steps", "num_obstacles", "sensed_obstacles", "neighbor_k", "num_drones", "env_kind",
-        "norm_mode", "reserved")]
+        "norm_mode", "reserved", "dr_enabled", "dr_pad")] + [("dr_seed", C.c_uint64), ("env_index_base", C.c_int64),
+                                                             ("dr_lo", C.c_double * 6), ("dr_span", C.c_double * 6)] + [
+        (n, C.c_double) for n in ("dr_std_thrust", "dr_std_pos", "dr_std_vel", "dr_std_obst")]
+
+DR_RANGE_KEYS = ("mass_scale", "max_accel_scale", "max_speed_scale", "dt_scale", "obstacle_radius_scale",
+                 "world_size_scale")
+DR_STD_KEYS = ("thrust_noise_std", "position_noise_std", "velocity_noise_std", "obstacle_distance_noise_std")
 
 
 class OracleBatch(C.Structure):
     _fields_ = [("num_envs", C.c_int32), ("pad", C.c_int32)] + [(n, C.c_void_p) for n in (
         "positions", "velocities", "goal", "obstacles", "step_count", "active", "rng", "obs", "reward",
         "dist", "terminated", "truncated", "reached", "collision", "obs_valid", "all_terminated",
-        "all_truncated", "global_state")]
+        "all_truncated", "global_state", "dr_params")]
 
 
 def build(force: bool = False) -> str:
@@ -74,7 +80,9 @@ class OracleSwarm:
     reference's constructor dict keys (unknown keys dropped, like DroneEnvConfig.from_dict).
     """
 
-    def __init__(self, num_envs: int, config: dict | None = None, kind: str = "swarm", norm_mode: int = 0):
+    def __init__(self, num_envs: int, config: dict | None = None, kind: str = "swarm", norm_mode: int = 0,
+                 dr: dict | None = None, dr_seed: int = 0, env_index_base: int = 0):
+        """dr: flat dict {<range key>: (min, max), <std key>: sigma} (engine semantics, not reference)."""
         cfg = dict(DEFAULTS)
         raw = dict(config or {})
         self.num_drones = int(raw.pop("num_drones", 3)) if kind == "swarm" else 1
@@ -88,6 +96,12 @@ class OracleSwarm:
         for k in DEFAULTS:
             setattr(c, k, cfg[k])
         c.num_drones, c.env_kind, c.norm_mode = self.N, (1 if kind == "swarm" else 0), norm_mode
+        if dr:
+            c.dr_enabled, c.dr_seed, c.env_index_base = 1, int(dr_seed), int(env_index_base)
+            for k, name in enumerate(DR_RANGE_KEYS):
+                lo, hi = dr.get(name, (1.0, 1.0))
+                c.dr_lo[k], c.dr_span[k] = float(lo), float(hi) - float(lo)
+            c.dr_std_thrust, c.dr_std_pos, c.dr_std_vel, c.dr_std_obst = (float(dr.get(n, 0.0)) for n in DR_STD_KEYS)
         self._c = c
         self.D = lib().oracle_obs_dim(C.byref(c))
         E, N, M, D = self.E, self.N, self.M, self.D
@@ -109,6 +123,7 @@ class OracleSwarm:
         self.all_terminated = np.zeros(E, np.uint8)
         self.all_truncated = np.zeros(E, np.uint8)
         self.global_state = np.zeros((E, 6 * N + 3), np.float32)
+        self.dr_params = np.zeros((E, 8), np.float32)
         b = OracleBatch()
         b.num_envs = E
         for name, _ in OracleBatch._fields_[2:]:

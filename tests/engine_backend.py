@@ -44,3 +44,4 @@ class EngineBackend:
     all_truncated = property(lambda s: s._np(s.eng.all_truncated))
     global_state = property(lambda s: s._np(s.eng.global_state))
     active = property(lambda s: s._np(s.eng.alive).astype(np.uint8))
+    dr_params = property(lambda s: s._np(s.eng.dr_params))
