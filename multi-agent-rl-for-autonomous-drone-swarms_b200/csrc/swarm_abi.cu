@@ -42,6 +42,8 @@ struct SwarmHandle {
     int num_sms;
     int blocks_per_sm;
     size_t smem_bytes;
+    bool rot_ok;             // the step launches run on swarm_step_rot_kernel (swarm_step_rot.cu)
+    int rot_blocks_per_sm;
     JumpEntry* jump_dev;
     uint8_t* reset_mask_dev;  // [E]
     unsigned* reset_count_dev;  // [(kHostChunks + 1) * 2] per launch slot, two parities
@@ -241,12 +243,29 @@ int bind_buffers(const SwarmHandle* h, const SwarmBuffers* b, DevParams& p) {
     return SWARM_OK;
 }
 
+// The rotation-pass step kernel covers the BASELINE swarm shapes; its float64 formation sum is
+// order-free only while every term is a multiple of 2^-37 and the sum stays below 2^16.
+bool rot_eligible(const SwarmConfig& c) {
+    if (c.env_kind != SWARM_KIND_SWARM || c.norm_mode != 0) return false;
+    if (c.num_drones != 8 && c.num_drones != 16 && c.num_drones != 32) return false;
+    if (c.neighbor_k != 3 || c.sensed_obstacles != 4) return false;
+    if (c.num_obstacles < 4 || c.num_obstacles > 32 || (c.num_obstacles & 3)) return false;
+    const double ds = c.desired_spacing;
+    if (!(ds >= 0.0) || !(ds < 1024.0) || std::ldexp(ds, 37) != std::floor(std::ldexp(ds, 37))) return false;
+    const double wscale = c.dr_enabled ? c.dr_world_size_scale[1] : 1.0;
+    if (!(c.world_size * wscale < 1024.0)) return false;   // every distance < 2048
+    const char* off = std::getenv("SWARM_B200_NO_ROT");
+    return !(off && off[0] == '1');
+}
+
 int launch(SwarmHandle* h, DevParams& p, int env_begin, int env_count, cudaStream_t stream, int slot = 0) {
     p.env_begin = env_begin;
     p.env_count = env_count;
     p.n_groups = (env_count + p.G - 1) / p.G;
     const int ctas_needed = (p.n_groups + kWarpsPerCta - 1) / kWarpsPerCta;
-    const int resident = h->num_sms * h->blocks_per_sm;
+    const bool rot = p.mode == kModeStep && h->rot_ok && (reinterpret_cast<uintptr_t>(p.actions) & 15u) == 0 &&
+                     env_begin % p.G == 0;
+    const int resident = h->num_sms * (rot ? h->rot_blocks_per_sm : h->blocks_per_sm);
     const int grid = ctas_needed < resident ? ctas_needed : resident;
     if (p.mode == kModeStep && p.auto_reset && p.N <= 32) {
         // the step kernel lists the groups that need a reset; counters alternate between steps so the
@@ -257,7 +276,8 @@ int launch(SwarmHandle* h, DevParams& p, int env_begin, int env_count, cudaStrea
         p.reset_list = h->reset_list_dev + env_begin / p.G;
         h->step_parity[slot] = par ^ 1u;
     }
-    CUDA_TRY(launch_env_kernel(p, h->cfg.norm_mode, h->cfg.env_kind, grid, h->smem_bytes, stream));
+    if (rot) CUDA_TRY(launch_rot_kernel(p, grid, stream));
+    else CUDA_TRY(launch_env_kernel(p, h->cfg.norm_mode, h->cfg.env_kind, grid, h->smem_bytes, stream));
     h->launches++;
     if (p.mode == kModeStep && p.auto_reset && p.N <= 32) {
         // N <= 32: the auto-reset runs as a second, tiny launch (kept out of the step kernel so each
@@ -346,6 +366,13 @@ int swarm_create(const SwarmConfig* cfg, SwarmHandle** out) {
     if (e != cudaSuccess || h->blocks_per_sm < 1) {
         delete h;
         return fail(SWARM_E_CUDA, "kernel occupancy query failed: %s", cudaGetErrorString(e));
+    }
+    h->rot_ok = false;
+    h->rot_blocks_per_sm = 0;
+    if (rot_eligible(*cfg) && rot_smem_bytes(h->base) <= (size_t)prop.sharedMemPerBlockOptin) {
+        e = rot_kernel_occupancy(h->base, &h->rot_blocks_per_sm);
+        if (e != cudaSuccess) { delete h; return fail(SWARM_E_CUDA, "kernel occupancy query failed: %s", cudaGetErrorString(e)); }
+        h->rot_ok = h->rot_blocks_per_sm >= 1;
     }
     std::vector<JumpEntry> table;
     build_jump_table(h->base.n_draws, table);

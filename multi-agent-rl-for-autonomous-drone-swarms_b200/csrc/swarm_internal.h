@@ -81,5 +81,9 @@ cudaError_t launch_env_kernel(const DevParams& p, int norm_mode, int env_kind, i
 cudaError_t env_kernel_occupancy(const DevParams& p, int norm_mode, int env_kind, size_t smem_bytes,
                                  int* blocks_per_sm);
 cudaError_t launch_seed_kernel(const DevParams& p, cudaStream_t stream);
+// rotation-pass step kernel (swarm_step_rot.cu)
+size_t rot_smem_bytes(const DevParams& p);
+cudaError_t launch_rot_kernel(const DevParams& p, int grid, cudaStream_t stream);
+cudaError_t rot_kernel_occupancy(const DevParams& p, int* blocks_per_sm);
 
 }  // namespace swarm

@@ -1,0 +1,629 @@
+// swarm_step_rot.cu -- the step kernel of the BASELINE swarm shapes: DroneSwarmEnv.step
+// (reference src/swarm_marl/envs/drone_swarm_env.py:92-174) for N in {8, 16, 32} drones, K = 3
+// neighbours, S = 4 sensed obstacles, M a multiple of 4, norm_mode 0.  Every other shape runs on
+// the general kernels of swarm_kernels.cu; the two produce bit-identical results (tests).
+//
+// Mapping: a warp owns 32 / N env instances, lane = env-local index * N + drone; no block barrier.
+//
+//   inputs    one lane issues TMA bulk copies (cp.async.bulk, SASS UBLKCP) of the next group's
+//             pos4 / vel4 / actions / goal / obstacles into one of two per-warp inboxes, completion
+//             on a per-warp mbarrier, while the current group is being processed.
+//   pairs     "rotation" pass: in round r (1 .. N/2) lane i evaluates d(i, i+r) once and hands it to
+//             lane i+r with one SHFL, so every unordered pair costs one distance evaluation and no
+//             shared-memory matrix.  The 3 nearest neighbours are kept as packed keys
+//             (distance bits with the low log2(N) bits replaced by the drone index) in a
+//             branch-free min/max merge network (VIMNMX3); the 4th key is tracked so that any pair
+//             of candidates that the truncation could have mis-ordered is DETECTED, and the warp
+//             then redoes the scan on the exact path (same code shape as the reference loop).
+//             Formation error sum |d - d*| (float64): every term is a multiple of 2^-37 and the sum
+//             stays below 2^16, so float64 addition is exact and the order of np.mean's pairwise
+//             summation does not matter (host checks d* and the world size, the kernel checks
+//             d >= 2^-14; otherwise the exact path runs).
+//   outputs   the 32 x 37 observation tile is staged in shared memory and leaves with ONE TMA bulk
+//             store per group; state / flags are float4 / byte stores straight from registers.
+#include "swarm_device.cuh"
+
+namespace swarm {
+
+namespace {
+
+constexpr int kD = 37;            // 9 + 4 * 3 + 4 * 4
+constexpr int kTileBytes = 32 * kD * 4;
+constexpr float kFormExactMinS = 3.725290298461914e-09f;  // 2^-28: d >= 2^-14
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (TMA engine), bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, unsigned src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// (a & mask) | c   and   (a & ~mask) | (b & mask)  as single LOP3s
+template <unsigned MASK>
+__device__ __forceinline__ unsigned and_or(unsigned a, unsigned c) {
+    unsigned r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(a), "n"(MASK), "r"(c));  // (a & b) | c
+    return r;
+}
+template <unsigned MASK>
+__device__ __forceinline__ unsigned merge_low(unsigned a, unsigned b) {
+    unsigned r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(r) : "r"(a), "r"(b), "n"(MASK));  // (a & ~c) | (b & c)
+    return r;
+}
+
+__device__ __forceinline__ unsigned umin3(unsigned a, unsigned b, unsigned c) { return min(min(a, b), c); }
+
+// sorted k0 <= k1 <= k2 <= k3 (4 smallest keys so far)  <-  two more keys
+__device__ __forceinline__ void merge2(unsigned x, unsigned y, unsigned& k0, unsigned& k1, unsigned& k2, unsigned& k3) {
+    const unsigned lo = min(x, y), hi = max(x, y);
+    const unsigned n0 = min(k0, lo);
+    const unsigned n1 = umin3(max(k0, lo), k1, hi);
+    const unsigned n2 = umin3(max(k0, hi), max(k1, lo), k2);
+    const unsigned n3 = umin3(max(k1, hi), max(k2, lo), k3);
+    k0 = n0; k1 = n1; k2 = n2; k3 = n3;
+}
+__device__ __forceinline__ void merge1(unsigned x, unsigned& k0, unsigned& k1, unsigned& k2, unsigned& k3) {
+    const unsigned n3 = min(k3, max(k2, x));
+    const unsigned n2 = min(k2, max(k1, x));
+    const unsigned n1 = min(k1, max(k0, x));
+    k0 = min(k0, x); k1 = n1; k2 = n2; k3 = n3;
+}
+__device__ __forceinline__ void merge1_5(unsigned x, unsigned& k0, unsigned& k1, unsigned& k2, unsigned& k3, unsigned& k4) {
+    const unsigned n4 = min(k4, max(k3, x));
+    const unsigned n3 = min(k3, max(k2, x));
+    const unsigned n2 = min(k2, max(k1, x));
+    const unsigned n1 = min(k1, max(k0, x));
+    k0 = min(k0, x); k1 = n1; k2 = n2; k3 = n3; k4 = n4;
+}
+
+__device__ __forceinline__ void cex(unsigned& a, unsigned& b) {
+    const unsigned lo = min(a, b), hi = max(a, b);
+    a = lo; b = hi;
+}
+// Batcher odd-even merge sort (19 / 5 compare-exchanges); unused outputs are dead-code eliminated
+__device__ __forceinline__ void sort8(unsigned (&k)[8]) {
+    cex(k[0], k[1]); cex(k[2], k[3]); cex(k[4], k[5]); cex(k[6], k[7]);
+    cex(k[0], k[2]); cex(k[1], k[3]); cex(k[4], k[6]); cex(k[5], k[7]);
+    cex(k[1], k[2]); cex(k[5], k[6]);
+    cex(k[0], k[4]); cex(k[1], k[5]); cex(k[2], k[6]); cex(k[3], k[7]);
+    cex(k[2], k[4]); cex(k[3], k[5]);
+    cex(k[1], k[2]); cex(k[3], k[4]); cex(k[5], k[6]);
+}
+__device__ __forceinline__ void sort4(unsigned (&k)[4]) {
+    cex(k[0], k[1]); cex(k[2], k[3]);
+    cex(k[0], k[2]); cex(k[1], k[3]);
+    cex(k[1], k[2]);
+}
+
+}  // namespace
+
+// smem per warp: mbarriers (16 B) | inbox x 2 | doubled position table (1 KB) | obs tile (4736 B)
+__host__ __device__ constexpr int rot_inbox_bytes(int G, int M, bool dr) { return 1408 + 16 * G * (1 + M) + (dr ? 32 * G : 0); }
+__host__ __device__ constexpr int rot_smem_per_warp(int G, int M, bool dr) {
+    return 16 + 2 * rot_inbox_bytes(G, M, dr) + 1024 + kTileBytes;
+}
+
+// MT: number of obstacles when known at compile time (4 / 8: sorting-network selection), 0 = P.M
+template <int NT, int MT, bool DR>
+__global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_step_rot_kernel(const DevParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int N = NT, G = 32 / NT, HALF = NT / 2;
+    constexpr unsigned IDX = NT - 1;  // index bits of a neighbour key
+    // (the shuffle makes the warp index provably warp-uniform: addresses and branches that derive from
+    //  it are then computed on the uniform datapath)
+    const int warp = __shfl_sync(FULL_MASK, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const int M = MT ? MT : P.M;
+    const int inbox_bytes = rot_inbox_bytes(G, M, DR);
+    const int per_warp = 16 + 2 * inbox_bytes + 1024 + kTileBytes;
+    unsigned char* wslice = smem_raw + (size_t)warp * per_warp;
+    const unsigned bar0 = smem_u32(wslice);
+    unsigned char* inbox0 = wslice + 16;
+    float4* tab2 = reinterpret_cast<float4*>(wslice + 16 + 2 * inbox_bytes);
+    float* tile = reinterpret_cast<float*>(wslice + 16 + 2 * inbox_bytes + 1024);
+    unsigned long long* wstats =
+        reinterpret_cast<unsigned long long*>(smem_raw + (size_t)kWarpsPerCta * per_warp) + warp * SWARM_STATS_WORDS;
+    if (lane < SWARM_STATS_WORDS) wstats[lane] = 0ull;
+
+    const int e_l = lane / N;
+    const int i = lane - e_l * N;
+    const int e_base = e_l * N;
+    const unsigned env_lanes = N == 32 ? FULL_MASK : (((1u << N) - 1u) << e_base);
+    float* srow = tile + lane * kD;  // this lane's tile row; before the obs is staged it stashes exact distances
+
+    const int warps_total = gridDim.x * kWarpsPerCta;
+    const int gwarp = blockIdx.x * kWarpsPerCta + warp;
+    const int n_iter = P.n_groups;
+    const int env_end = P.env_begin + P.env_count;
+
+    if (lane == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    // inbox: pos4[32] | vel4[32] | actions[96] | goal4[G] | obst4[G*M] | dr[2G]
+    const int goal_off = 1408, obst_off = 1408 + 16 * G, dr_off = 1408 + 16 * G * (1 + M);
+    int sc_pref = 0;
+    float ep_pref = 0.f;
+    auto issue = [&](int grp, int buf) {
+        const int env0 = P.env_begin + grp * G;
+        const int n_env = G == 1 ? 1 : min(G, env_end - env0);
+        if (lane == 0) {
+            const unsigned n_ag = (unsigned)(n_env * N);
+            const unsigned bar = bar0 + 8 * buf;
+            const unsigned dst = smem_u32(inbox0 + (size_t)buf * inbox_bytes);
+            const long long a0 = (long long)env0 * N;
+            mbar_expect_tx(bar, n_ag * 44u + (unsigned)n_env * (16u + 16u * M + (DR ? 32u : 0u)));
+            bulk_g2s(dst, P.pos4 + a0, n_ag * 16u, bar);
+            bulk_g2s(dst + 512, P.vel4 + a0, n_ag * 16u, bar);
+            bulk_g2s(dst + 1024, P.actions + a0 * 3, n_ag * 12u, bar);
+            bulk_g2s(dst + goal_off, P.goal4 + env0, (unsigned)n_env * 16u, bar);
+            bulk_g2s(dst + obst_off, P.obst4 + (long long)env0 * M, (unsigned)(n_env * M) * 16u, bar);
+            if (DR) bulk_g2s(dst + dr_off, P.dr_params + (long long)env0 * 2, (unsigned)n_env * 32u, bar);
+        }
+        if (lane < n_env) {  // 4 bytes per env: plain loads, consumed one iteration later
+            sc_pref = P.step_count[env0 + lane];
+            ep_pref = P.ep_return[env0 + lane];
+        }
+    };
+    if (gwarp < n_iter) issue(gwarp, 0);
+    unsigned phase = 0;  // bit b: parity the next wait on mbarrier b uses
+
+    int buf = 0;
+    for (int it = gwarp; it < n_iter; it += warps_total, buf ^= 1) {
+        const int env0 = P.env_begin + it * G;
+        const int n_env = G == 1 ? 1 : min(G, env_end - env0);
+        const bool lane_ok = G == 1 ? true : e_l < n_env;
+        const int env = env0 + (lane_ok ? e_l : 0);
+        const long long a0 = (long long)env0 * N;
+        const long long a = a0 + (lane_ok ? lane : 0);
+        const bool leader = lane_ok && i == 0;
+        const unsigned ok_lanes = __ballot_sync(FULL_MASK, lane_ok);
+        const unsigned char* ib = inbox0 + (size_t)buf * inbox_bytes;
+        const float4* in_pos = reinterpret_cast<const float4*>(ib);
+        const float4* tobs = reinterpret_cast<const float4*>(ib + obst_off) + e_l * M;
+
+        const int sc = __shfl_sync(FULL_MASK, sc_pref, e_l);
+        const float ep_ret = __shfl_sync(FULL_MASK, ep_pref, e_l);
+        mbar_wait(bar0 + 8 * buf, (phase >> buf) & 1u);
+        phase ^= 1u << buf;
+        if (it + warps_total < n_iter) issue(it + warps_total, buf ^ 1);  // the other inbox is free (see the syncs below)
+        // obstacle index -> .w of the inbox copy, so a key is one LOP3 (the table syncwarp below orders it)
+        for (int idx = lane; idx < G * M; idx += 32)
+            reinterpret_cast<unsigned*>(const_cast<unsigned char*>(ib) + obst_off)[idx * 4 + 3] = (unsigned)(idx % M);
+
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f), v = p, g4 = p;
+        float ax = 0.f, ay = 0.f, az = 0.f;
+        float c_amax = P.amax, c_vmax = P.vmax, c_dt = P.dt, c_bound = P.bound, c_thr_obst = P.thr_obst;
+        unsigned ekey = 0u;
+        if (lane_ok) {
+            p = in_pos[lane];
+            v = in_pos[32 + lane];
+            g4 = reinterpret_cast<const float4*>(ib + goal_off)[e_l];
+            const float* act = reinterpret_cast<const float*>(ib + 1024);
+            ax = act[lane * 3 + 0]; ay = act[lane * 3 + 1]; az = act[lane * 3 + 2];
+            if (DR) {
+                const float4* drp = reinterpret_cast<const float4*>(ib + dr_off) + 2 * e_l;
+                const float4 d0 = drp[0], d1 = drp[1];
+                c_amax = d0.x; c_vmax = d0.y; c_dt = d0.z; c_bound = d0.w;
+                c_thr_obst = d1.x; ekey = __float_as_uint(d1.y);
+            }
+        }
+        const float gx = g4.x, gy = g4.y, gz = g4.z;
+        const unsigned genv = DR ? (unsigned)(P.env_index_base + env) : 0u;
+        const bool alive = lane_ok && p.w != 0.0f;
+
+        // =========================== integrate (:98-118) ===========================
+        const float prev_d = norm1d<0>(__fsub_rn(gx, p.x), __fsub_rn(gy, p.y), __fsub_rn(gz, p.z));  // :98-101
+        if (alive) {
+            ax = clipf(ax, -1.0f, 1.0f); ay = clipf(ay, -1.0f, 1.0f); az = clipf(az, -1.0f, 1.0f);
+            if (DR) {  // thrust noise: a <- a * (1 + sigma z), one normal per axis
+                const uint4 r = philox4x32_10(genv, ekey, (unsigned)sc, (unsigned)i | (DR_STREAM_THRUST << 16), P.dr_key0,
+                                              P.dr_key1);
+                ax = __fmul_rn(ax, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, P.dr_qtable[r.x >> 20])));
+                ay = __fmul_rn(ay, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, P.dr_qtable[r.y >> 20])));
+                az = __fmul_rn(az, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, P.dr_qtable[r.z >> 20])));
+            }
+            v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(ax, c_amax), c_dt));
+            v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(ay, c_amax), c_dt));
+            v.z = __fadd_rn(v.z, __fmul_rn(__fmul_rn(az, c_amax), c_dt));
+            const float speed = norm1d<0>(v.x, v.y, v.z);  // _clip_speed (:179-183)
+            if (!(speed <= c_vmax || speed < P.eps_speed)) {
+                v.x = __fmul_rn(__fdiv_rn(v.x, speed), c_vmax);
+                v.y = __fmul_rn(__fdiv_rn(v.y, speed), c_vmax);
+                v.z = __fmul_rn(__fdiv_rn(v.z, speed), c_vmax);
+            }
+            p.x = __fadd_rn(p.x, __fmul_rn(v.x, c_dt));
+            p.y = __fadd_rn(p.y, __fmul_rn(v.y, c_dt));
+            p.z = __fadd_rn(p.z, __fmul_rn(v.z, c_dt));
+        }
+        // wall clip for ALL drones (:113-117); velocity is not zeroed at the wall
+        p.x = clipf(p.x, -c_bound, c_bound);
+        p.y = clipf(p.y, -c_bound, c_bound);
+        p.z = clipf(p.z, -c_bound, c_bound);
+
+        // doubled position table: entry [2N e_l + i + r] is drone (i + r) mod N for 0 <= r <= N; .w = drone index
+        {
+            const float4 t = make_float4(p.x, p.y, p.z, __int_as_float(i));
+            tab2[2 * e_base + i] = t;
+            tab2[2 * e_base + i + N] = t;
+        }
+        const unsigned alive_mask = __ballot_sync(FULL_MASK, alive);
+        const int n_alive_env = __popc(alive_mask & env_lanes);
+        if (lane == 0) bulk_wait_read0();  // the previous group's obs tile has left shared memory
+        __syncwarp();
+
+        float nd[3]; int nj[3];        // exact distances / drone indices of the 3 nearest neighbours
+        float od[4]; int om[4];        // same for the 4 nearest obstacles
+        bool pair_hit = false;
+        double form_sum = 0.0;
+        int form_n = 0;
+        const float4* tp = tab2 + 2 * e_base + i;  // tp[r] = drone (i + r) mod N
+        bool bad = false;
+        if (alive_mask == ok_lanes) {
+            // ================= rotation pass: every drone of the group is active =================
+            unsigned k0 = ~0u, k1 = ~0u, k2 = ~0u, k3 = ~0u;
+            double acc_f = 0.0, acc_b = 0.0;
+            float smin = F32_INF;
+            const double d_star = P.d_star;
+#pragma unroll
+            for (int r = 1; r < HALF; ++r) {
+                const float4 q = tp[r];
+                const float s = sumsq1d<0>(__fsub_rn(q.x, p.x), __fsub_rn(q.y, p.y), __fsub_rn(q.z, p.z));
+                smin = fminf(smin, s);
+                const float d = sqrt_rn_fast(s);
+                const float db = __shfl_sync(FULL_MASK, d, lane - r, N);  // d((i - r) mod N, i)
+                srow[r] = d;
+                srow[HALF + r] = db;
+                const unsigned kf = and_or<~IDX>(__float_as_uint(d), __float_as_uint(q.w));
+                const unsigned kb = merge_low<IDX>(__float_as_uint(db), (unsigned)(lane - r));
+                merge2(kf, kb, k0, k1, k2, k3);
+                acc_f = __dadd_rn(acc_f, fabs(__dsub_rn((double)d, d_star)));
+                acc_b = __dadd_rn(acc_b, fabs(__dsub_rn((double)db, d_star)));
+            }
+            {   // round N/2: the pair is visited from both ends, each end keeps its own copy
+                const float4 q = tp[HALF];
+                const float s = sumsq1d<0>(__fsub_rn(q.x, p.x), __fsub_rn(q.y, p.y), __fsub_rn(q.z, p.z));
+                smin = fminf(smin, s);
+                const float d = sqrt_rn_fast(s);
+                srow[HALF] = d;
+                merge1(and_or<~IDX>(__float_as_uint(d), __float_as_uint(q.w)), k0, k1, k2, k3);
+                acc_f = __dadd_rn(acc_f, fabs(__dsub_rn((double)d, d_star)));
+            }
+            // two candidates in one key bucket among the first four: truncation may have mis-ordered them
+            bad = !(smin >= kFormExactMinS) || ((k0 ^ k1) <= IDX) || ((k1 ^ k2) <= IDX) || ((k2 ^ k3) <= IDX);
+            const unsigned kk[3] = {k0, k1, k2};
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int j = (int)(kk[q] & IDX);
+                const int t = (j - i) & (int)IDX;           // forward distance i -> j
+                nj[q] = j;
+                nd[q] = srow[t <= HALF ? t : HALF + N - t];  // backward round N - t was stashed at HALF + (N - t)
+            }
+            pair_hit = nd[0] <= P.thr_pair;  // nearest drone decides (:202-207)
+            form_sum = __dadd_rn(acc_f, acc_b);
+            form_n = N - 1;
+
+            // ---- obstacles: _nearest_obstacle_features (:273-291) + obstacle part of _collision_mask
+            unsigned o0, o1, o2, o3, o4;
+            float smin_o = F32_INF;
+            if (MT == 8 || MT == 4) {
+                unsigned ok[MT ? MT : 1];
+#pragma unroll
+                for (int m = 0; m < MT; m += 2) {
+                    const float4 oa = tobs[m], ob = tobs[m + 1];
+                    const float sa = sumsq_axis(__fsub_rn(oa.x, p.x), __fsub_rn(oa.y, p.y), __fsub_rn(oa.z, p.z));
+                    const float sb = sumsq_axis(__fsub_rn(ob.x, p.x), __fsub_rn(ob.y, p.y), __fsub_rn(ob.z, p.z));
+                    smin_o = fminf(fminf(smin_o, sa), sb);
+                    const float da = sqrt_rn_fast(sa), db = sqrt_rn_fast(sb);
+                    srow[m] = da;
+                    srow[m + 1] = db;
+                    ok[m] = and_or<~31u>(__float_as_uint(da), __float_as_uint(oa.w));
+                    ok[m + 1] = and_or<~31u>(__float_as_uint(db), __float_as_uint(ob.w));
+                }
+                if (MT == 8) {
+                    sort8(reinterpret_cast<unsigned(&)[8]>(ok));
+                    o4 = ok[MT == 8 ? 4 : 0];
+                } else {
+                    sort4(reinterpret_cast<unsigned(&)[4]>(ok));
+                    o4 = ~0u;
+                }
+                o0 = ok[0]; o1 = ok[MT > 1 ? 1 : 0]; o2 = ok[MT > 2 ? 2 : 0]; o3 = ok[MT > 3 ? 3 : 0];
+            } else {
+                o0 = o1 = o2 = o3 = o4 = ~0u;
+#pragma unroll 1
+                for (int mb = 0; mb < M; mb += 4) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float4 o = tobs[mb + u];
+                        const float s = sumsq_axis(__fsub_rn(o.x, p.x), __fsub_rn(o.y, p.y), __fsub_rn(o.z, p.z));
+                        smin_o = fminf(smin_o, s);
+                        const float d = sqrt_rn_fast(s);
+                        srow[mb + u] = d;
+                        merge1_5(and_or<~31u>(__float_as_uint(d), __float_as_uint(o.w)), o0, o1, o2, o3, o4);
+                    }
+                }
+            }
+            bad = bad || !(smin_o >= SQRT_FAST_MIN) || ((o0 ^ o1) <= 31u) || ((o1 ^ o2) <= 31u) || ((o2 ^ o3) <= 31u) ||
+                  ((o3 ^ o4) <= 31u);
+            const unsigned oo[4] = {o0, o1, o2, o3};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                om[q] = (int)(oo[q] & 31u);
+                od[q] = srow[om[q]];
+            }
+            bad = bad && lane_ok;
+        }
+        if (alive_mask != ok_lanes || __any_sync(FULL_MASK, bad)) {
+            // ============ exact path: parked drones, coincident drones, or a detected near-tie ============
+            // the reference's loops as written: ascending j, strict '<' (lowest index wins ties),
+            // collision / formation over ACTIVE pairs only, np.mean's pairwise summation order
+#pragma unroll
+            for (int q = 0; q < 3; ++q) { nd[q] = F32_INF; nj[q] = 0; }
+            pair_hit = false;
+            const unsigned em = (alive_mask & env_lanes) >> e_base;  // bit j: drone j of this env active
+            const int n_f = alive ? n_alive_env - 1 : 0;
+            const int nf8 = n_f >= 8 ? (n_f & ~7) : 0;
+            double r8[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) r8[u] = 0.0;
+            double res = 0.0;
+            bool tree_done = false;
+            int cnt = 0;
+            const float4* te = tab2 + 2 * e_base;
+#pragma unroll 1
+            for (int j = 0; j < N; ++j) {
+                if (j == i) continue;
+                const float4 q = te[j];
+                const float d = norm1d<0>(__fsub_rn(q.x, p.x), __fsub_rn(q.y, p.y), __fsub_rn(q.z, p.z));
+                topk_insert<3>(d, j, nd, nj);
+                if (alive && ((em >> j) & 1u)) {
+                    pair_hit |= d <= P.thr_pair;
+                    const double err = fabs(__dsub_rn((double)d, P.d_star));
+                    if (cnt < nf8) {
+                        const int lane8 = cnt & 7;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) r8[u] = __dadd_rn(r8[u], lane8 == u ? err : 0.0);
+                    } else {
+                        if (!tree_done && nf8 > 0) res = tree8(r8);
+                        tree_done = true;
+                        res = __dadd_rn(res, err);
+                    }
+                    ++cnt;
+                }
+            }
+            if (!tree_done && nf8 > 0) res = tree8(r8);
+            form_sum = res;
+            form_n = n_f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { od[q] = F32_INF; om[q] = 0; }
+#pragma unroll 1
+            for (int m = 0; m < M; ++m) {
+                const float4 o = tobs[m];
+                const float d = __fsqrt_rn(sumsq_axis(__fsub_rn(o.x, p.x), __fsub_rn(o.y, p.y), __fsub_rn(o.z, p.z)));
+                topk_insert<4>(d, m, od, om);
+            }
+        }
+        const float curr_d = norm1d<0>(__fsub_rn(gx, p.x), __fsub_rn(gy, p.y), __fsub_rn(gz, p.z));
+
+        // ============================ obs row -> staging tile (:226-243) ============================
+        if (lane_ok) {
+            float* row = srow;
+            const float4 t0 = tab2[2 * e_base + nj[0]], t1 = tab2[2 * e_base + nj[1]], t2 = tab2[2 * e_base + nj[2]];
+            const float4 b0 = tobs[om[0]], b1 = tobs[om[1]], b2 = tobs[om[2]], b3 = tobs[om[3]];
+            uint4 rs0 = make_uint4(0, 0, 0, 0), rs1 = rs0, rs2 = rs0;
+            if (DR) {  // sensor noise: normal n of the row comes from Philox call n / 4 (see swarm_kernels.cu)
+                const unsigned c3 = (unsigned)i | (DR_STREAM_SENSOR << 16);
+                rs0 = philox4x32_10(genv, ekey, (unsigned)(sc + 1), c3, P.dr_key0, P.dr_key1);
+                rs1 = philox4x32_10(genv, ekey, (unsigned)(sc + 1), c3 + (1u << 16), P.dr_key0, P.dr_key1);
+                rs2 = philox4x32_10(genv, ekey, (unsigned)(sc + 1), c3 + (2u << 16), P.dr_key0, P.dr_key1);
+            }
+            auto noisy = [&](float x, float sigma, unsigned bits) {
+                return DR ? __fadd_rn(x, __fmul_rn(sigma, P.dr_qtable[bits >> 20])) : x;
+            };
+            row[0] = noisy(p.x, P.dr_std_pos, rs0.x); row[1] = noisy(p.y, P.dr_std_pos, rs0.y);
+            row[2] = noisy(p.z, P.dr_std_pos, rs0.z);
+            row[3] = noisy(v.x, P.dr_std_vel, rs0.w); row[4] = noisy(v.y, P.dr_std_vel, rs1.x);
+            row[5] = noisy(v.z, P.dr_std_vel, rs1.y);
+            row[6] = __fsub_rn(gx, p.x); row[7] = __fsub_rn(gy, p.y); row[8] = __fsub_rn(gz, p.z);
+            row[9] = __fsub_rn(t0.x, p.x); row[10] = __fsub_rn(t0.y, p.y); row[11] = __fsub_rn(t0.z, p.z); row[12] = nd[0];
+            row[13] = __fsub_rn(t1.x, p.x); row[14] = __fsub_rn(t1.y, p.y); row[15] = __fsub_rn(t1.z, p.z); row[16] = nd[1];
+            row[17] = __fsub_rn(t2.x, p.x); row[18] = __fsub_rn(t2.y, p.y); row[19] = __fsub_rn(t2.z, p.z); row[20] = nd[2];
+            row[21] = __fsub_rn(b0.x, p.x); row[22] = __fsub_rn(b0.y, p.y); row[23] = __fsub_rn(b0.z, p.z);
+            row[24] = noisy(od[0], P.dr_std_obst, rs1.z);
+            row[25] = __fsub_rn(b1.x, p.x); row[26] = __fsub_rn(b1.y, p.y); row[27] = __fsub_rn(b1.z, p.z);
+            row[28] = noisy(od[1], P.dr_std_obst, rs1.w);
+            row[29] = __fsub_rn(b2.x, p.x); row[30] = __fsub_rn(b2.y, p.y); row[31] = __fsub_rn(b2.z, p.z);
+            row[32] = noisy(od[2], P.dr_std_obst, rs2.x);
+            row[33] = __fsub_rn(b3.x, p.x); row[34] = __fsub_rn(b3.y, p.y); row[35] = __fsub_rn(b3.z, p.z);
+            row[36] = noisy(od[3], P.dr_std_obst, rs2.y);
+        }
+        fence_async_smem();  // generic-proxy tile writes -> visible to the bulk-copy engine
+        __syncwarp();        // (also: every lane is done with this inbox and the position table)
+        if (lane == 0) {
+            bulk_s2g(P.obs + a0 * kD, smem_u32(tile), (unsigned)(n_env * N * kD * 4));
+            bulk_commit();
+        }
+
+        // ===================== rewards and flags (:120-172) =====================
+        const bool obst_hit = od[0] <= c_thr_obst;
+        const bool reached = alive && curr_d <= P.thr_goal;    // :124-127 (double compare)
+        const bool collided = alive && (obst_hit || pair_hit);  // :128
+        double reward = 0.0;
+        if (alive) {
+            const double progress = __dmul_rn(__dsub_rn((double)prev_d, (double)curr_d), P.k_p);  // :142
+            double pen = 0.0;  // :210-224
+            if (form_n > 0) {
+                const double mean = form_n == N - 1 ? mean_markstein(form_sum, P.n_others, P.inv_n_others)
+                                                    : __ddiv_rn(form_sum, (double)form_n);
+                pen = __dmul_rn(P.neg_k_f, mean);
+            }
+            reward = __dadd_rn(progress, pen);                  // :143
+            if (reached) reward = __dadd_rn(reward, P.r_goal);  // :144-145
+            if (collided) reward = __dadd_rn(reward, P.r_col);  // :146-147
+        }
+        const float rew32 = __double2float_rn(reward);
+        const bool done_agent = reached || collided;
+        const bool any_col = (__ballot_sync(FULL_MASK, collided) & env_lanes) != 0;
+        const int n_cont = __popc(__ballot_sync(FULL_MASK, alive && !done_agent) & env_lanes);
+        float x = rew32;  // deterministic per-env reward sum (segmented tree over the env's lanes)
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const float t = __shfl_down_sync(FULL_MASK, x, off);
+            if (off < N && i + off < N) x = __fadd_rn(x, t);
+        }
+        const bool env_active = n_alive_env > 0;
+        const int sc_new = env_active ? sc + 1 : sc;
+        const bool time_limit = env_active && sc_new >= P.max_steps;
+        const bool all_reached = n_cont == 0 && !any_col && !time_limit;
+        const bool episode_done = all_reached || any_col;
+        const bool all_term = env_active ? episode_done : true;  // :94-95 when no agent is left
+        const bool all_trunc = env_active ? (time_limit && !episode_done) : false;
+        const bool ep_over = env_active && (all_term || all_trunc);
+        const bool need_reset = P.auto_reset && (ep_over || !env_active);
+        if (lane_ok) {
+            P.terminated[a] = (alive && done_agent) ? 1 : 0;                 // :150-151
+            P.truncated[a] = (alive && time_limit && !done_agent) ? 1 : 0;   // :152
+            const bool valid = alive && !done_agent && !time_limit && !any_col;  // :154
+            const bool alive_next = ep_over ? false : valid;                     // :169-172
+            P.reward[a] = rew32;
+            if (P.reward64) P.reward64[a] = reward;
+            P.reached[a] = reached ? 1 : 0;
+            P.collision[a] = collided ? 1 : 0;
+            if (!need_reset) {  // (a reset env gets these from the aux launch that follows)
+                P.dist[a] = curr_d;
+                P.obs_valid[a] = valid ? 1 : 0;
+                P.pos4[a] = make_float4(p.x, p.y, p.z, alive_next ? 1.0f : 0.0f);
+                P.vel4[a] = make_float4(v.x, v.y, v.z, 0.0f);
+                if (P.gs) {
+                    float* row = P.gs + (long long)env * P.R;
+                    __stcs(row + 3 * i + 0, p.x); __stcs(row + 3 * i + 1, p.y); __stcs(row + 3 * i + 2, p.z);
+                    __stcs(row + 3 * N + 3 * i + 0, v.x); __stcs(row + 3 * N + 3 * i + 1, v.y);
+                    __stcs(row + 3 * N + 3 * i + 2, v.z);
+                }
+            }
+        }
+        if (leader) {
+            P.all_term[env] = all_term ? 1 : 0;
+            P.all_trunc[env] = all_trunc ? 1 : 0;
+            if (P.reset_mask) P.reset_mask[env] = need_reset ? 1 : 0;
+            const float ret = __fadd_rn(ep_ret, x);
+            if (ep_over) {  // several env leaders per warp when G > 1: shared-memory atomics
+                atomicAdd(wstats + SWARM_STAT_EPISODES, 1ull);
+                atomicAdd(wstats + SWARM_STAT_LENGTH_SUM, (unsigned long long)sc_new);
+                atomicAdd(reinterpret_cast<double*>(wstats + SWARM_STAT_RETURN_SUM), (double)ret);
+                if (all_reached) atomicAdd(wstats + SWARM_STAT_SUCCESS, 1ull);
+                if (any_col) atomicAdd(wstats + SWARM_STAT_COLLISION, 1ull);
+                if (all_trunc) atomicAdd(wstats + SWARM_STAT_TIMEOUT, 1ull);
+            }
+            if (P.episode_return) P.episode_return[env] = ep_over ? ret : 0.0f;
+            if (P.episode_length) P.episode_length[env] = ep_over ? sc_new : 0;
+            if (!need_reset) {
+                P.step_count[env] = sc_new;
+                P.ep_return[env] = ep_over ? 0.0f : ret;
+                if (P.gs) {
+                    float* row = P.gs + (long long)env * P.R + 6 * N;
+                    __stcs(row + 0, gx); __stcs(row + 1, gy); __stcs(row + 2, gz);
+                }
+            }
+        }
+        if (P.auto_reset) {  // groups with an env to reset go on the list the aux launch walks
+            const unsigned rl = __ballot_sync(FULL_MASK, leader && need_reset);
+            if (rl != 0 && lane == 0) P.reset_list[atomicAdd(P.reset_count, 1u)] = env0;
+        }
+        {   // actions applied / envs stepped by this warp in this group
+            const unsigned act_envs = __ballot_sync(FULL_MASK, leader && env_active);
+            if (lane == 0) {
+                wstats[SWARM_STAT_AGENT_STEPS] += (unsigned long long)__popc(alive_mask);
+                wstats[SWARM_STAT_ENV_STEPS] += (unsigned long long)__popc(act_envs);
+            }
+        }
+    }
+
+    if (lane == 0) bulk_wait0();  // the last obs tile must have left shared memory before the CTA retires
+    __syncwarp();
+    if (P.stats && lane < SWARM_STATS_WORDS) {
+        const unsigned long long w = wstats[lane];
+        if (lane == SWARM_STAT_RETURN_SUM) {
+            const double dv = __longlong_as_double((long long)w);
+            if (dv != 0.0) atomicAdd(reinterpret_cast<double*>(P.stats + lane), dv);
+        } else if (w) {
+            atomicAdd(P.stats + lane, w);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: eligibility and launch
+// ------------------------------------------------------------------------------------------
+typedef void (*RotKernel)(const DevParams);
+
+template <int NT>
+static RotKernel pick_rot_m(const DevParams& p) {
+    const bool dr = p.dr_enabled != 0;
+    if (p.M == 8) return dr ? swarm_step_rot_kernel<NT, 8, true> : swarm_step_rot_kernel<NT, 8, false>;
+    if (p.M == 4) return dr ? swarm_step_rot_kernel<NT, 4, true> : swarm_step_rot_kernel<NT, 4, false>;
+    return dr ? swarm_step_rot_kernel<NT, 0, true> : swarm_step_rot_kernel<NT, 0, false>;
+}
+
+static RotKernel pick_rot(const DevParams& p) {
+    switch (p.N) {
+        case 8: return pick_rot_m<8>(p);
+        case 16: return pick_rot_m<16>(p);
+        case 32: return pick_rot_m<32>(p);
+    }
+    return nullptr;
+}
+
+size_t rot_smem_bytes(const DevParams& p) {
+    return (size_t)kWarpsPerCta * rot_smem_per_warp(32 / p.N, p.M, p.dr_enabled != 0) +
+           (size_t)kWarpsPerCta * SWARM_STATS_WORDS * sizeof(unsigned long long);
+}
+
+cudaError_t launch_rot_kernel(const DevParams& p, int grid, cudaStream_t stream) {
+    RotKernel k = pick_rot(p);
+    if (!k) return cudaErrorInvalidValue;
+    const size_t smem = rot_smem_bytes(p);
+    cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    k<<<grid, kThreadsPerCta, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t rot_kernel_occupancy(const DevParams& p, int* blocks_per_sm) {
+    RotKernel k = pick_rot(p);
+    if (!k) return cudaErrorInvalidValue;
+    const size_t smem = rot_smem_bytes(p);
+    cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, kThreadsPerCta, smem);
+}
+
+}  // namespace swarm
