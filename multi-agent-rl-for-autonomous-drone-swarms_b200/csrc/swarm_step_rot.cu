@@ -60,6 +60,11 @@ __device__ __forceinline__ void bulk_s2g(void* dst, unsigned src, unsigned bytes
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async4(unsigned saddr, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // (a & mask) | c   and   (a & ~mask) | (b & mask)  as single LOP3s
@@ -123,7 +128,9 @@ __device__ __forceinline__ void sort4(unsigned (&k)[4]) {
 }  // namespace
 
 // smem per warp: mbarriers (16 B) | inbox x 2 | doubled position table (1 KB) | obs tile (4736 B)
-__host__ __device__ constexpr int rot_inbox_bytes(int G, int M, bool dr) { return 1408 + 16 * G * (1 + M) + (dr ? 32 * G : 0); }
+__host__ __device__ constexpr int rot_inbox_bytes(int G, int M, bool dr) {
+    return 1408 + 16 * G * (1 + M) + (dr ? 32 * G : 0) + ((8 * G + 15) & ~15);
+}
 __host__ __device__ constexpr int rot_smem_per_warp(int G, int M, bool dr) {
     return 16 + 2 * rot_inbox_bytes(G, M, dr) + 1024 + kTileBytes;
 }
@@ -168,10 +175,9 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_step_ro
     }
     __syncwarp();
 
-    // inbox: pos4[32] | vel4[32] | actions[96] | goal4[G] | obst4[G*M] | dr[2G]
+    // inbox: pos4[32] | vel4[32] | actions[96] | goal4[G] | obst4[G*M] | dr[2G] | step_count[G] | ep_return[G]
     const int goal_off = 1408, obst_off = 1408 + 16 * G, dr_off = 1408 + 16 * G * (1 + M);
-    int sc_pref = 0;
-    float ep_pref = 0.f;
+    const int sc_off = dr_off + (DR ? 32 * G : 0);
     auto issue = [&](int grp, int buf) {
         const int env0 = P.env_begin + grp * G;
         const int n_env = G == 1 ? 1 : min(G, env_end - env0);
@@ -188,9 +194,11 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_step_ro
             bulk_g2s(dst + obst_off, P.obst4 + (long long)env0 * M, (unsigned)(n_env * M) * 16u, bar);
             if (DR) bulk_g2s(dst + dr_off, P.dr_params + (long long)env0 * 2, (unsigned)n_env * 32u, bar);
         }
-        if (lane < n_env) {  // 4 bytes per env: plain loads, consumed one iteration later
-            sc_pref = P.step_count[env0 + lane];
-            ep_pref = P.ep_return[env0 + lane];
+        if (lane < n_env) {  // 4 bytes per env: too small for the bulk-copy engine
+            const unsigned dst = smem_u32(inbox0 + (size_t)buf * inbox_bytes) + sc_off;
+            cp_async4(dst + 4 * lane, P.step_count + env0 + lane);
+            cp_async4(dst + 4 * (G + lane), P.ep_return + env0 + lane);
+            cp_async_commit();
         }
     };
     if (gwarp < n_iter) issue(gwarp, 0);
@@ -202,18 +210,18 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_step_ro
         const int n_env = G == 1 ? 1 : min(G, env_end - env0);
         const bool lane_ok = G == 1 ? true : e_l < n_env;
         const int env = env0 + (lane_ok ? e_l : 0);
-        const long long a0 = (long long)env0 * N;
-        const long long a = a0 + (lane_ok ? lane : 0);
+        const int a0 = env0 * N;                  // (num_envs * num_drones <= 2^30, checked at create)
+        const int a = a0 + (lane_ok ? lane : 0);
         const bool leader = lane_ok && i == 0;
         const unsigned ok_lanes = __ballot_sync(FULL_MASK, lane_ok);
         const unsigned char* ib = inbox0 + (size_t)buf * inbox_bytes;
         const float4* in_pos = reinterpret_cast<const float4*>(ib);
         const float4* tobs = reinterpret_cast<const float4*>(ib + obst_off) + e_l * M;
 
-        const int sc = __shfl_sync(FULL_MASK, sc_pref, e_l);
-        const float ep_ret = __shfl_sync(FULL_MASK, ep_pref, e_l);
+        cp_async_wait_all();
         mbar_wait(bar0 + 8 * buf, (phase >> buf) & 1u);
         phase ^= 1u << buf;
+        __syncwarp();  // the cp.async words of the other lanes
         if (it + warps_total < n_iter) issue(it + warps_total, buf ^ 1);  // the other inbox is free (see the syncs below)
         // obstacle index -> .w of the inbox copy, so a key is one LOP3 (the table syncwarp below orders it)
         for (int idx = lane; idx < G * M; idx += 32)
@@ -221,6 +229,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_step_ro
 
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f), v = p, g4 = p;
         float ax = 0.f, ay = 0.f, az = 0.f;
+        int sc = 0;
         float c_amax = P.amax, c_vmax = P.vmax, c_dt = P.dt, c_bound = P.bound, c_thr_obst = P.thr_obst;
         unsigned ekey = 0u;
         if (lane_ok) {
@@ -229,6 +238,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_step_ro
             g4 = reinterpret_cast<const float4*>(ib + goal_off)[e_l];
             const float* act = reinterpret_cast<const float*>(ib + 1024);
             ax = act[lane * 3 + 0]; ay = act[lane * 3 + 1]; az = act[lane * 3 + 2];
+            sc = reinterpret_cast<const int*>(ib + sc_off)[e_l];
             if (DR) {
                 const float4* drp = reinterpret_cast<const float4*>(ib + dr_off) + 2 * e_l;
                 const float4 d0 = drp[0], d1 = drp[1];
@@ -236,12 +246,12 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_step_ro
                 c_thr_obst = d1.x; ekey = __float_as_uint(d1.y);
             }
         }
-        const float gx = g4.x, gy = g4.y, gz = g4.z;
+        float gx = g4.x, gy = g4.y, gz = g4.z;
         const unsigned genv = DR ? (unsigned)(P.env_index_base + env) : 0u;
         const bool alive = lane_ok && p.w != 0.0f;
 
         // =========================== integrate (:98-118) ===========================
-        const float prev_d = norm1d<0>(__fsub_rn(gx, p.x), __fsub_rn(gy, p.y), __fsub_rn(gz, p.z));  // :98-101
+        float prev_d = norm1d<0>(__fsub_rn(gx, p.x), __fsub_rn(gy, p.y), __fsub_rn(gz, p.z));  // :98-101
         if (alive) {
             ax = clipf(ax, -1.0f, 1.0f); ay = clipf(ay, -1.0f, 1.0f); az = clipf(az, -1.0f, 1.0f);
             if (DR) {  // thrust noise: a <- a * (1 + sigma z), one normal per axis
@@ -274,6 +284,8 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_step_ro
             const float4 t = make_float4(p.x, p.y, p.z, __int_as_float(i));
             tab2[2 * e_base + i] = t;
             tab2[2 * e_base + i + N] = t;
+            // velocity / previous goal distance wait in the (consumed) inbox slot while the scans need the registers
+            const_cast<float4*>(in_pos)[32 + lane] = make_float4(v.x, v.y, v.z, prev_d);
         }
         const unsigned alive_mask = __ballot_sync(FULL_MASK, alive);
         const int n_alive_env = __popc(alive_mask & env_lanes);
@@ -293,9 +305,11 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_step_ro
             double acc_f = 0.0, acc_b = 0.0;
             float smin = F32_INF;
             const double d_star = P.d_star;
+            float4 qn = tp[1];
 #pragma unroll
             for (int r = 1; r < HALF; ++r) {
-                const float4 q = tp[r];
+                const float4 q = qn;
+                qn = tp[r + 1];
                 const float s = sumsq1d<0>(__fsub_rn(q.x, p.x), __fsub_rn(q.y, p.y), __fsub_rn(q.z, p.z));
                 smin = fminf(smin, s);
                 const float d = sqrt_rn_fast(s);
@@ -309,7 +323,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_step_ro
                 acc_b = __dadd_rn(acc_b, fabs(__dsub_rn((double)db, d_star)));
             }
             {   // round N/2: the pair is visited from both ends, each end keeps its own copy
-                const float4 q = tp[HALF];
+                const float4 q = qn;
                 const float s = sumsq1d<0>(__fsub_rn(q.x, p.x), __fsub_rn(q.y, p.y), __fsub_rn(q.z, p.z));
                 smin = fminf(smin, s);
                 const float d = sqrt_rn_fast(s);
@@ -431,6 +445,12 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_step_ro
                 topk_insert<4>(d, m, od, om);
             }
         }
+        {
+            const float4 t = in_pos[32 + lane];
+            v.x = t.x; v.y = t.y; v.z = t.z; prev_d = t.w;
+            const float4 gg = reinterpret_cast<const float4*>(ib + goal_off)[lane_ok ? e_l : 0];
+            gx = gg.x; gy = gg.y; gz = gg.z;
+        }
         const float curr_d = norm1d<0>(__fsub_rn(gx, p.x), __fsub_rn(gy, p.y), __fsub_rn(gz, p.z));
 
         // ============================ obs row -> staging tile (:226-243) ============================
@@ -468,7 +488,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_step_ro
         fence_async_smem();  // generic-proxy tile writes -> visible to the bulk-copy engine
         __syncwarp();        // (also: every lane is done with this inbox and the position table)
         if (lane == 0) {
-            bulk_s2g(P.obs + a0 * kD, smem_u32(tile), (unsigned)(n_env * N * kD * 4));
+            bulk_s2g(P.obs + (long long)a0 * kD, smem_u32(tile), (unsigned)(n_env * N * kD * 4));
             bulk_commit();
         }
 
@@ -534,7 +554,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_step_ro
             P.all_term[env] = all_term ? 1 : 0;
             P.all_trunc[env] = all_trunc ? 1 : 0;
             if (P.reset_mask) P.reset_mask[env] = need_reset ? 1 : 0;
-            const float ret = __fadd_rn(ep_ret, x);
+            const float ret = __fadd_rn(reinterpret_cast<const float*>(ib + sc_off)[G + e_l], x);
             if (ep_over) {  // several env leaders per warp when G > 1: shared-memory atomics
                 atomicAdd(wstats + SWARM_STAT_EPISODES, 1ull);
                 atomicAdd(wstats + SWARM_STAT_LENGTH_SUM, (unsigned long long)sc_new);
