@@ -48,6 +48,7 @@ struct SwarmHandle {
     uint8_t* reset_mask_dev;  // [E]
     unsigned* reset_count_dev;  // [(kHostChunks + 1) * 2] per launch slot, two parities
     int* reset_list_dev;        // [number of groups]
+    unsigned* work_counter_dev; // [(kHostChunks + 1) * 2] group queue of the rotation-pass step kernel, per launch slot
     float* qtable_dev;          // [4096] (domain randomisation only)
     unsigned step_parity[kHostChunks + 1];
     int64_t launches;
@@ -262,11 +263,14 @@ int launch(SwarmHandle* h, DevParams& p, int env_begin, int env_count, cudaStrea
     p.env_begin = env_begin;
     p.env_count = env_count;
     p.n_groups = (env_count + p.G - 1) / p.G;
-    const int ctas_needed = (p.n_groups + kWarpsPerCta - 1) / kWarpsPerCta;
     const bool rot = p.mode == kModeStep && h->rot_ok && (reinterpret_cast<uintptr_t>(p.actions) & 15u) == 0 &&
                      env_begin % p.G == 0;
-    const int resident = h->num_sms * (rot ? h->rot_blocks_per_sm : h->blocks_per_sm);
+    const int ctas_needed = (p.n_groups + kWarpsPerCta - 1) / kWarpsPerCta;
+    const int resident = h->num_sms * h->blocks_per_sm;
     const int grid = ctas_needed < resident ? ctas_needed : resident;
+    const int rot_needed = (p.n_groups + rot_warps_per_cta(p) - 1) / rot_warps_per_cta(p);
+    const int rot_resident = h->num_sms * h->rot_blocks_per_sm;
+    const int rot_grid = rot_needed < rot_resident ? rot_needed : rot_resident;
     if (p.mode == kModeStep && p.auto_reset && p.N <= 32) {
         // the step kernel lists the groups that need a reset; counters alternate between steps so the
         // aux launch can zero the next one while nobody uses it
@@ -276,7 +280,8 @@ int launch(SwarmHandle* h, DevParams& p, int env_begin, int env_count, cudaStrea
         p.reset_list = h->reset_list_dev + env_begin / p.G;
         h->step_parity[slot] = par ^ 1u;
     }
-    if (rot) CUDA_TRY(launch_rot_kernel(p, grid, stream));
+    p.work_counter = h->work_counter_dev + 2 * slot;
+    if (rot) CUDA_TRY(launch_rot_kernel(p, rot_grid, stream));
     else CUDA_TRY(launch_env_kernel(p, h->cfg.norm_mode, h->cfg.env_kind, grid, h->smem_bytes, stream));
     h->launches++;
     if (p.mode == kModeStep && p.auto_reset && p.N <= 32) {
@@ -345,6 +350,7 @@ int swarm_create(const SwarmConfig* cfg, SwarmHandle** out) {
     h->reset_mask_dev = nullptr;
     h->reset_count_dev = nullptr;
     h->reset_list_dev = nullptr;
+    h->work_counter_dev = nullptr;
     h->qtable_dev = nullptr;
     for (int c = 0; c <= kHostChunks; ++c) h->step_parity[c] = 0;
     h->actions_dev = nullptr;
@@ -385,6 +391,8 @@ int swarm_create(const SwarmConfig* cfg, SwarmHandle** out) {
     if (e == cudaSuccess) e = cudaMalloc(&h->reset_count_dev, sizeof(unsigned) * 2 * (kHostChunks + 1));
     if (e == cudaSuccess) e = cudaMemset(h->reset_count_dev, 0, sizeof(unsigned) * 2 * (kHostChunks + 1));
     if (e == cudaSuccess) e = cudaMalloc(&h->reset_list_dev, sizeof(int) * (n_groups_all + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&h->work_counter_dev, sizeof(unsigned) * 2 * (kHostChunks + 1));
+    if (e == cudaSuccess) e = cudaMemset(h->work_counter_dev, 0, sizeof(unsigned) * 2 * (kHostChunks + 1));
     if (e == cudaSuccess && cfg->dr_enabled) {
         std::vector<float> qt(4096);
         build_qtable(qt.data());
@@ -396,6 +404,7 @@ int swarm_create(const SwarmConfig* cfg, SwarmHandle** out) {
         if (h->reset_mask_dev) cudaFree(h->reset_mask_dev);
         if (h->reset_count_dev) cudaFree(h->reset_count_dev);
         if (h->reset_list_dev) cudaFree(h->reset_list_dev);
+        if (h->work_counter_dev) cudaFree(h->work_counter_dev);
         if (h->qtable_dev) cudaFree(h->qtable_dev);
         delete h;
         return fail(SWARM_E_CUDA, "jump table / reset mask allocation failed: %s", cudaGetErrorString(e));
@@ -418,6 +427,7 @@ int swarm_destroy(SwarmHandle* h) {
     if (h->reset_mask_dev) cudaFree(h->reset_mask_dev);
     if (h->reset_count_dev) cudaFree(h->reset_count_dev);
     if (h->reset_list_dev) cudaFree(h->reset_list_dev);
+    if (h->work_counter_dev) cudaFree(h->work_counter_dev);
     if (h->qtable_dev) cudaFree(h->qtable_dev);
     delete h;
     return SWARM_OK;

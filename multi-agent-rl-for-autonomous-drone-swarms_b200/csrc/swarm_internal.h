@@ -63,6 +63,7 @@ struct DevParams {
     unsigned* reset_count;        // number of groups on reset_list (this step's counter)
     unsigned* reset_count_other;  // the next step's counter (zeroed by the aux launch)
     int* reset_list;              // first env of every group with an env to reset
+    unsigned* work_counter;       // rotation-pass step kernel: {next group, warps done} of this launch slot
     const JumpEntry* jump;        // [n_draws + 1]
     // ---- domain randomisation (N <= 32 kernels, norm_mode 0)
     int dr_enabled;
@@ -85,5 +86,6 @@ cudaError_t launch_seed_kernel(const DevParams& p, cudaStream_t stream);
 size_t rot_smem_bytes(const DevParams& p);
 cudaError_t launch_rot_kernel(const DevParams& p, int grid, cudaStream_t stream);
 cudaError_t rot_kernel_occupancy(const DevParams& p, int* blocks_per_sm);
+int rot_warps_per_cta(const DevParams& p);
 
 }  // namespace swarm

@@ -60,6 +60,14 @@ __device__ __forceinline__ void bulk_s2g(void* dst, unsigned src, unsigned bytes
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// 1: the group inputs arrive by TMA bulk copies (one lane issues them, mbarrier completion);
+// 0: by per-lane 16-byte cp.async (LDGSTS), completion by cp.async.wait_group
+#ifndef SWARM_ROT_TMA_LOADS
+#define SWARM_ROT_TMA_LOADS 1
+#endif
+__device__ __forceinline__ void cp_async16(unsigned saddr, const void* g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
 __device__ __forceinline__ void cp_async4(unsigned saddr, const void* g) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(g) : "memory");
 }
@@ -79,6 +87,26 @@ __device__ __forceinline__ unsigned merge_low(unsigned a, unsigned b) {
     unsigned r;
     asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(r) : "r"(a), "r"(b), "n"(MASK));  // (a & ~c) | (b & c)
     return r;
+}
+
+// float32 -> float64 with two integer ops instead of the quarter-rate conversion unit.  Exact for
+// normal a >= 0; zero / denormal inputs come out as some value below 2^-125, which cannot change
+// the float64 sum of squares once that sum is >= 2^-28 (the rotation pass checks exactly that and
+// falls back to the exact path otherwise).
+#ifndef SWARM_ROT_INT_CVT
+#define SWARM_ROT_INT_CVT 0
+#endif
+__device__ __forceinline__ double f64_of_pos_f32(float a) {
+#if SWARM_ROT_INT_CVT
+    const unsigned b = __float_as_uint(a);
+    return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
+#else
+    return (double)a;
+#endif
+}
+__device__ __forceinline__ float sumsq1d_fast(float x, float y, float z) {
+    const float px = __fmul_rn(x, x), py = __fmul_rn(y, y), pz = __fmul_rn(z, z);
+    return __double2float_rn(__dadd_rn(__dadd_rn(f64_of_pos_f32(px), f64_of_pos_f32(py)), f64_of_pos_f32(pz)));
 }
 
 __device__ __forceinline__ unsigned umin3(unsigned a, unsigned b, unsigned c) { return min(min(a, b), c); }
@@ -127,34 +155,43 @@ __device__ __forceinline__ void sort4(unsigned (&k)[4]) {
 
 }  // namespace
 
-// smem per warp: mbarriers (16 B) | inbox x 2 | doubled position table (1 KB) | obs tile (4736 B)
-__host__ __device__ constexpr int rot_inbox_bytes(int G, int M, bool dr) {
-    return 1408 + 16 * G * (1 + M) + (dr ? 32 * G : 0) + ((8 * G + 15) & ~15);
+// CTA shape (measured): N = 32 runs best as 4 warps x 7 CTAs per SM (72 registers, 28 resident warps,
+// 7 per scheduler), N = 8 / 16 as 8 warps x 3 CTAs (80 registers)
+__host__ __device__ constexpr int rot_warps(int n) { return n == 32 ? 4 : 8; }
+__host__ __device__ constexpr int rot_min_blocks(int n) { return n == 32 ? 7 : 3; }
+
+// smem per warp: mbarriers (16 B) | agent inbox: pos4[32] vel4[32] actions[96] (single buffer, refilled as
+// soon as it has been read) | env inbox x 2: goal4[G] obst4[G*M] dr[2G] step_count[G] ep_return[G] |
+// doubled position table (1 KB) | obs tile (4736 B)
+__host__ __device__ constexpr int rot_envbox_bytes(int G, int M, bool dr) {
+    return 16 * G * (1 + M) + (dr ? 32 * G : 0) + ((8 * G + 15) & ~15);
 }
 __host__ __device__ constexpr int rot_smem_per_warp(int G, int M, bool dr) {
-    return 16 + 2 * rot_inbox_bytes(G, M, dr) + 1024 + kTileBytes;
+    return 16 + 1408 + 2 * rot_envbox_bytes(G, M, dr) + 1024 + kTileBytes;
 }
 
 // MT: number of obstacles when known at compile time (4 / 8: sorting-network selection), 0 = P.M
 template <int NT, int MT, bool DR>
-__global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_step_rot_kernel(const DevParams P) {
+__global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_step_rot_kernel(const DevParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int N = NT, G = 32 / NT, HALF = NT / 2;
     constexpr unsigned IDX = NT - 1;  // index bits of a neighbour key
+    constexpr int kRotWarps = rot_warps(NT);
     // (the shuffle makes the warp index provably warp-uniform: addresses and branches that derive from
     //  it are then computed on the uniform datapath)
     const int warp = __shfl_sync(FULL_MASK, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
     const int M = MT ? MT : P.M;
-    const int inbox_bytes = rot_inbox_bytes(G, M, DR);
-    const int per_warp = 16 + 2 * inbox_bytes + 1024 + kTileBytes;
+    const int envbox_bytes = rot_envbox_bytes(G, M, DR);
+    const int per_warp = 16 + 1408 + 2 * envbox_bytes + 1024 + kTileBytes;
     unsigned char* wslice = smem_raw + (size_t)warp * per_warp;
     const unsigned bar0 = smem_u32(wslice);
-    unsigned char* inbox0 = wslice + 16;
-    float4* tab2 = reinterpret_cast<float4*>(wslice + 16 + 2 * inbox_bytes);
-    float* tile = reinterpret_cast<float*>(wslice + 16 + 2 * inbox_bytes + 1024);
+    const float4* in_pos = reinterpret_cast<const float4*>(wslice + 16);  // agent inbox
+    unsigned char* envbox0 = wslice + 16 + 1408;
+    float4* tab2 = reinterpret_cast<float4*>(wslice + 16 + 1408 + 2 * envbox_bytes);
+    float* tile = reinterpret_cast<float*>(wslice + 16 + 1408 + 2 * envbox_bytes + 1024);
     unsigned long long* wstats =
-        reinterpret_cast<unsigned long long*>(smem_raw + (size_t)kWarpsPerCta * per_warp) + warp * SWARM_STATS_WORDS;
+        reinterpret_cast<unsigned long long*>(smem_raw + (size_t)kRotWarps * per_warp) + warp * SWARM_STATS_WORDS;
     if (lane < SWARM_STATS_WORDS) wstats[lane] = 0ull;
 
     const int e_l = lane / N;
@@ -163,8 +200,6 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_step_ro
     const unsigned env_lanes = N == 32 ? FULL_MASK : (((1u << N) - 1u) << e_base);
     float* srow = tile + lane * kD;  // this lane's tile row; before the obs is staged it stashes exact distances
 
-    const int warps_total = gridDim.x * kWarpsPerCta;
-    const int gwarp = blockIdx.x * kWarpsPerCta + warp;
     const int n_iter = P.n_groups;
     const int env_end = P.env_begin + P.env_count;
 
@@ -175,37 +210,63 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_step_ro
     }
     __syncwarp();
 
-    // inbox: pos4[32] | vel4[32] | actions[96] | goal4[G] | obst4[G*M] | dr[2G] | step_count[G] | ep_return[G]
-    const int goal_off = 1408, obst_off = 1408 + 16 * G, dr_off = 1408 + 16 * G * (1 + M);
+    // env inbox: goal4[G] | obst4[G*M] | dr[2G] | step_count[G] | ep_return[G]
+    const int goal_off = 0, obst_off = 16 * G, dr_off = 16 * G * (1 + M);
     const int sc_off = dr_off + (DR ? 32 * G : 0);
     auto issue = [&](int grp, int buf) {
         const int env0 = P.env_begin + grp * G;
         const int n_env = G == 1 ? 1 : min(G, env_end - env0);
+#if SWARM_ROT_TMA_LOADS
         if (lane == 0) {
             const unsigned n_ag = (unsigned)(n_env * N);
             const unsigned bar = bar0 + 8 * buf;
-            const unsigned dst = smem_u32(inbox0 + (size_t)buf * inbox_bytes);
+            const unsigned dsta = bar0 + 16;
+            const unsigned dst = smem_u32(envbox0 + (size_t)buf * envbox_bytes);
             const long long a0 = (long long)env0 * N;
             mbar_expect_tx(bar, n_ag * 44u + (unsigned)n_env * (16u + 16u * M + (DR ? 32u : 0u)));
-            bulk_g2s(dst, P.pos4 + a0, n_ag * 16u, bar);
-            bulk_g2s(dst + 512, P.vel4 + a0, n_ag * 16u, bar);
-            bulk_g2s(dst + 1024, P.actions + a0 * 3, n_ag * 12u, bar);
+            bulk_g2s(dsta, P.pos4 + a0, n_ag * 16u, bar);
+            bulk_g2s(dsta + 512, P.vel4 + a0, n_ag * 16u, bar);
+            bulk_g2s(dsta + 1024, P.actions + a0 * 3, n_ag * 12u, bar);
             bulk_g2s(dst + goal_off, P.goal4 + env0, (unsigned)n_env * 16u, bar);
             bulk_g2s(dst + obst_off, P.obst4 + (long long)env0 * M, (unsigned)(n_env * M) * 16u, bar);
             if (DR) bulk_g2s(dst + dr_off, P.dr_params + (long long)env0 * 2, (unsigned)n_env * 32u, bar);
         }
+#else
+        {
+            const int n_ag = n_env * N;
+            const unsigned dsta = bar0 + 16;
+            const unsigned dst = smem_u32(envbox0 + (size_t)buf * envbox_bytes);
+            const long long a0 = (long long)env0 * N;
+            if (G == 1 || lane < n_ag) {
+                cp_async16(dsta + lane * 16, P.pos4 + a0 + lane);
+                cp_async16(dsta + 512 + lane * 16, P.vel4 + a0 + lane);
+            }
+            if (lane * 4 < n_ag * 3) cp_async16(dsta + 1024 + lane * 16, P.actions + a0 * 3 + lane * 4);
+            if (lane < n_env) cp_async16(dst + goal_off + lane * 16, P.goal4 + env0 + lane);
+            for (int idx = lane; idx < n_env * M; idx += 32)
+                cp_async16(dst + obst_off + idx * 16, P.obst4 + (long long)env0 * M + idx);
+            if (DR && lane < 2 * n_env) cp_async16(dst + dr_off + lane * 16, P.dr_params + (long long)env0 * 2 + lane);
+        }
+#endif
         if (lane < n_env) {  // 4 bytes per env: too small for the bulk-copy engine
-            const unsigned dst = smem_u32(inbox0 + (size_t)buf * inbox_bytes) + sc_off;
+            const unsigned dst = smem_u32(envbox0 + (size_t)buf * envbox_bytes) + sc_off;
             cp_async4(dst + 4 * lane, P.step_count + env0 + lane);
             cp_async4(dst + 4 * (G + lane), P.ep_return + env0 + lane);
-            cp_async_commit();
         }
+        cp_async_commit();
     };
-    if (gwarp < n_iter) issue(gwarp, 0);
+    // dynamic group queue: lane 0 draws the next group index while the current group is processed, so
+    // every warp stays busy until the queue is empty (no static-stride tail)
+    int it = 0;
+    if (lane == 0) it = (int)atomicAdd(P.work_counter, 1u);
+    it = __shfl_sync(FULL_MASK, it, 0);
+    if (it < n_iter) issue(it, 0);
     unsigned phase = 0;  // bit b: parity the next wait on mbarrier b uses
 
     int buf = 0;
-    for (int it = gwarp; it < n_iter; it += warps_total, buf ^= 1) {
+    while (it < n_iter) {
+        int it_next = 0;
+        if (lane == 0) it_next = (int)atomicAdd(P.work_counter, 1u);
         const int env0 = P.env_begin + it * G;
         const int n_env = G == 1 ? 1 : min(G, env_end - env0);
         const bool lane_ok = G == 1 ? true : e_l < n_env;
@@ -214,15 +275,15 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_step_ro
         const int a = a0 + (lane_ok ? lane : 0);
         const bool leader = lane_ok && i == 0;
         const unsigned ok_lanes = __ballot_sync(FULL_MASK, lane_ok);
-        const unsigned char* ib = inbox0 + (size_t)buf * inbox_bytes;
-        const float4* in_pos = reinterpret_cast<const float4*>(ib);
+        const unsigned char* ib = envbox0 + (size_t)buf * envbox_bytes;
         const float4* tobs = reinterpret_cast<const float4*>(ib + obst_off) + e_l * M;
 
         cp_async_wait_all();
+#if SWARM_ROT_TMA_LOADS
         mbar_wait(bar0 + 8 * buf, (phase >> buf) & 1u);
         phase ^= 1u << buf;
+#endif
         __syncwarp();  // the cp.async words of the other lanes
-        if (it + warps_total < n_iter) issue(it + warps_total, buf ^ 1);  // the other inbox is free (see the syncs below)
         // obstacle index -> .w of the inbox copy, so a key is one LOP3 (the table syncwarp below orders it)
         for (int idx = lane; idx < G * M; idx += 32)
             reinterpret_cast<unsigned*>(const_cast<unsigned char*>(ib) + obst_off)[idx * 4 + 3] = (unsigned)(idx % M);
@@ -236,7 +297,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_step_ro
             p = in_pos[lane];
             v = in_pos[32 + lane];
             g4 = reinterpret_cast<const float4*>(ib + goal_off)[e_l];
-            const float* act = reinterpret_cast<const float*>(ib + 1024);
+            const float* act = reinterpret_cast<const float*>(in_pos + 64);
             ax = act[lane * 3 + 0]; ay = act[lane * 3 + 1]; az = act[lane * 3 + 2];
             sc = reinterpret_cast<const int*>(ib + sc_off)[e_l];
             if (DR) {
@@ -284,13 +345,17 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_step_ro
             const float4 t = make_float4(p.x, p.y, p.z, __int_as_float(i));
             tab2[2 * e_base + i] = t;
             tab2[2 * e_base + i + N] = t;
-            // velocity / previous goal distance wait in the (consumed) inbox slot while the scans need the registers
-            const_cast<float4*>(in_pos)[32 + lane] = make_float4(v.x, v.y, v.z, prev_d);
         }
         const unsigned alive_mask = __ballot_sync(FULL_MASK, alive);
         const int n_alive_env = __popc(alive_mask & env_lanes);
         if (lane == 0) bulk_wait_read0();  // the previous group's obs tile has left shared memory
         __syncwarp();
+        // every lane has consumed the agent inbox (its values went through the integrator): refill it, and
+        // the other env inbox, with the next group's inputs
+        it_next = __shfl_sync(FULL_MASK, it_next, 0);
+        if (it_next < n_iter) issue(it_next, buf ^ 1);
+        // velocity / previous goal distance wait in the tile row (slots 32-35) while the scans need the registers
+        srow[32] = v.x; srow[33] = v.y; srow[34] = v.z; srow[35] = prev_d;
 
         float nd[3]; int nj[3];        // exact distances / drone indices of the 3 nearest neighbours
         float od[4]; int om[4];        // same for the 4 nearest obstacles
@@ -303,15 +368,13 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_step_ro
             // ================= rotation pass: every drone of the group is active =================
             unsigned k0 = ~0u, k1 = ~0u, k2 = ~0u, k3 = ~0u;
             double acc_f = 0.0, acc_b = 0.0;
-            float smin = F32_INF;
             const double d_star = P.d_star;
             float4 qn = tp[1];
 #pragma unroll
             for (int r = 1; r < HALF; ++r) {
                 const float4 q = qn;
                 qn = tp[r + 1];
-                const float s = sumsq1d<0>(__fsub_rn(q.x, p.x), __fsub_rn(q.y, p.y), __fsub_rn(q.z, p.z));
-                smin = fminf(smin, s);
+                const float s = sumsq1d_fast(__fsub_rn(q.x, p.x), __fsub_rn(q.y, p.y), __fsub_rn(q.z, p.z));
                 const float d = sqrt_rn_fast(s);
                 const float db = __shfl_sync(FULL_MASK, d, lane - r, N);  // d((i - r) mod N, i)
                 srow[r] = d;
@@ -319,20 +382,23 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_step_ro
                 const unsigned kf = and_or<~IDX>(__float_as_uint(d), __float_as_uint(q.w));
                 const unsigned kb = merge_low<IDX>(__float_as_uint(db), (unsigned)(lane - r));
                 merge2(kf, kb, k0, k1, k2, k3);
-                acc_f = __dadd_rn(acc_f, fabs(__dsub_rn((double)d, d_star)));
-                acc_b = __dadd_rn(acc_b, fabs(__dsub_rn((double)db, d_star)));
+                acc_f = __dadd_rn(acc_f, fabs(__dsub_rn(f64_of_pos_f32(d), d_star)));
+                acc_b = __dadd_rn(acc_b, fabs(__dsub_rn(f64_of_pos_f32(db), d_star)));
             }
             {   // round N/2: the pair is visited from both ends, each end keeps its own copy
                 const float4 q = qn;
-                const float s = sumsq1d<0>(__fsub_rn(q.x, p.x), __fsub_rn(q.y, p.y), __fsub_rn(q.z, p.z));
-                smin = fminf(smin, s);
+                const float s = sumsq1d_fast(__fsub_rn(q.x, p.x), __fsub_rn(q.y, p.y), __fsub_rn(q.z, p.z));
                 const float d = sqrt_rn_fast(s);
                 srow[HALF] = d;
                 merge1(and_or<~IDX>(__float_as_uint(d), __float_as_uint(q.w)), k0, k1, k2, k3);
-                acc_f = __dadd_rn(acc_f, fabs(__dsub_rn((double)d, d_star)));
+                acc_f = __dadd_rn(acc_f, fabs(__dsub_rn(f64_of_pos_f32(d), d_star)));
             }
             // two candidates in one key bucket among the first four: truncation may have mis-ordered them
-            bad = !(smin >= kFormExactMinS) || ((k0 ^ k1) <= IDX) || ((k1 ^ k2) <= IDX) || ((k2 ^ k3) <= IDX);
+            form_sum = __dadd_rn(acc_f, acc_b);
+            // s < 2^-28 (a distance below 2^-14: fast sqrt / exact-sum preconditions) shows up either as the
+            // smallest key or, for s = 0 / denormal s (rsqrt -> inf -> NaN distance), as a NaN formation sum
+            bad = !(form_sum == form_sum) || k0 < 0x38800000u /* 2^-14 */ || ((k0 ^ k1) <= IDX) || ((k1 ^ k2) <= IDX) ||
+                  ((k2 ^ k3) <= IDX);
             const unsigned kk[3] = {k0, k1, k2};
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
@@ -342,7 +408,6 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_step_ro
                 nd[q] = srow[t <= HALF ? t : HALF + N - t];  // backward round N - t was stashed at HALF + (N - t)
             }
             pair_hit = nd[0] <= P.thr_pair;  // nearest drone decides (:202-207)
-            form_sum = __dadd_rn(acc_f, acc_b);
             form_n = N - 1;
 
             // ---- obstacles: _nearest_obstacle_features (:273-291) + obstacle part of _collision_mask
@@ -446,8 +511,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_step_ro
             }
         }
         {
-            const float4 t = in_pos[32 + lane];
-            v.x = t.x; v.y = t.y; v.z = t.z; prev_d = t.w;
+            v.x = srow[32]; v.y = srow[33]; v.z = srow[34]; prev_d = srow[35];
             const float4 gg = reinterpret_cast<const float4*>(ib + goal_off)[lane_ok ? e_l : 0];
             gx = gg.x; gy = gg.y; gz = gg.z;
         }
@@ -585,6 +649,13 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_step_ro
                 wstats[SWARM_STAT_ENV_STEPS] += (unsigned long long)__popc(act_envs);
             }
         }
+        it = it_next;
+        buf ^= 1;
+    }
+    // the last warp to leave re-arms the queue for the next launch
+    if (lane == 0 && atomicAdd(P.work_counter + 1, 1u) == (unsigned)(gridDim.x * kRotWarps) - 1u) {
+        P.work_counter[0] = 0u;
+        P.work_counter[1] = 0u;
     }
 
     if (lane == 0) bulk_wait0();  // the last obs tile must have left shared memory before the CTA retires
@@ -623,8 +694,8 @@ static RotKernel pick_rot(const DevParams& p) {
 }
 
 size_t rot_smem_bytes(const DevParams& p) {
-    return (size_t)kWarpsPerCta * rot_smem_per_warp(32 / p.N, p.M, p.dr_enabled != 0) +
-           (size_t)kWarpsPerCta * SWARM_STATS_WORDS * sizeof(unsigned long long);
+    return (size_t)rot_warps(p.N) * rot_smem_per_warp(32 / p.N, p.M, p.dr_enabled != 0) +
+           (size_t)rot_warps(p.N) * SWARM_STATS_WORDS * sizeof(unsigned long long);
 }
 
 cudaError_t launch_rot_kernel(const DevParams& p, int grid, cudaStream_t stream) {
@@ -633,7 +704,7 @@ cudaError_t launch_rot_kernel(const DevParams& p, int grid, cudaStream_t stream)
     const size_t smem = rot_smem_bytes(p);
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    k<<<grid, kThreadsPerCta, smem, stream>>>(p);
+    k<<<grid, rot_warps(p.N) * 32, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -643,7 +714,9 @@ cudaError_t rot_kernel_occupancy(const DevParams& p, int* blocks_per_sm) {
     const size_t smem = rot_smem_bytes(p);
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, kThreadsPerCta, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, rot_warps(p.N) * 32, smem);
 }
+
+int rot_warps_per_cta(const DevParams& p) { return rot_warps(p.N); }
 
 }  // namespace swarm
