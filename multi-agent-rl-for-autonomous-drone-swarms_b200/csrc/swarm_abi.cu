@@ -280,7 +280,7 @@ int launch(SwarmHandle* h, DevParams& p, int env_begin, int env_count, cudaStrea
         p.reset_list = h->reset_list_dev + env_begin / p.G;
         h->step_parity[slot] = par ^ 1u;
     }
-    p.work_counter = h->work_counter_dev + 2 * slot;
+    p.work_counter = h->work_counter_dev + 4 * slot;  // {step queue, warps done, reset queue, warps done}
     if (rot) CUDA_TRY(launch_rot_kernel(p, rot_grid, stream));
     else CUDA_TRY(launch_env_kernel(p, h->cfg.norm_mode, h->cfg.env_kind, grid, h->smem_bytes, stream));
     h->launches++;
@@ -290,7 +290,8 @@ int launch(SwarmHandle* h, DevParams& p, int env_begin, int env_count, cudaStrea
         DevParams q = p;
         q.mode = kModeAutoReset;
         q.env_mask = h->reset_mask_dev;
-        CUDA_TRY(launch_env_kernel(q, h->cfg.norm_mode, h->cfg.env_kind, grid, h->smem_bytes, stream));
+        if (rot) CUDA_TRY(launch_rot_kernel(q, rot_grid, stream));
+        else CUDA_TRY(launch_env_kernel(q, h->cfg.norm_mode, h->cfg.env_kind, grid, h->smem_bytes, stream));
         h->launches++;
     }
     return SWARM_OK;
@@ -391,8 +392,8 @@ int swarm_create(const SwarmConfig* cfg, SwarmHandle** out) {
     if (e == cudaSuccess) e = cudaMalloc(&h->reset_count_dev, sizeof(unsigned) * 2 * (kHostChunks + 1));
     if (e == cudaSuccess) e = cudaMemset(h->reset_count_dev, 0, sizeof(unsigned) * 2 * (kHostChunks + 1));
     if (e == cudaSuccess) e = cudaMalloc(&h->reset_list_dev, sizeof(int) * (n_groups_all + 1));
-    if (e == cudaSuccess) e = cudaMalloc(&h->work_counter_dev, sizeof(unsigned) * 2 * (kHostChunks + 1));
-    if (e == cudaSuccess) e = cudaMemset(h->work_counter_dev, 0, sizeof(unsigned) * 2 * (kHostChunks + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&h->work_counter_dev, sizeof(unsigned) * 4 * (kHostChunks + 1));
+    if (e == cudaSuccess) e = cudaMemset(h->work_counter_dev, 0, sizeof(unsigned) * 4 * (kHostChunks + 1));
     if (e == cudaSuccess && cfg->dr_enabled) {
         std::vector<float> qt(4096);
         build_qtable(qt.data());

@@ -27,36 +27,6 @@ namespace swarm {
 
 
 // ------------------------------------------------------------------------------------------
-// numpy PCG64 (XSL-RR 128/64) with jump-ahead, so the 3N+3+3M draws of a reset are generated
-// by 32 lanes in parallel:  state_{n+k} = A^k state_n + G_k inc.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mul128(unsigned long long ah, unsigned long long al, unsigned long long bh,
-                                       unsigned long long bl, unsigned long long& rh, unsigned long long& rl) {
-    rl = al * bl;
-    rh = __umul64hi(al, bl) + ah * bl + al * bh;
-}
-
-__device__ __forceinline__ void pcg_jump(const JumpEntry& j, unsigned long long sh, unsigned long long sl,
-                                         unsigned long long ih, unsigned long long il, unsigned long long& oh,
-                                         unsigned long long& ol) {
-    unsigned long long xh, xl, yh, yl;
-    mul128(j.a_hi, j.a_lo, sh, sl, xh, xl);
-    mul128(j.g_hi, j.g_lo, ih, il, yh, yl);
-    ol = xl + yl;
-    oh = xh + yh + (ol < xl ? 1ull : 0ull);
-}
-
-__device__ __forceinline__ float pcg_uniform_f32(unsigned long long hi, unsigned long long lo, double u_lo,
-                                                 double u_range) {
-    // Generator.uniform -> random_uniform: lo + range * ((next_uint64 >> 11) * 2^-53), then astype(f32)
-    const unsigned long long x = hi ^ lo;
-    const unsigned rot = (unsigned)(hi >> 58);
-    const unsigned long long out = (x >> rot) | (x << ((64u - rot) & 63u));
-    const double u = __dmul_rn(__ull2double_rn(out >> 11), 1.0 / 9007199254740992.0);
-    return __double2float_rn(__dadd_rn(u_lo, __dmul_rn(u_range, u)));
-}
-
-// ------------------------------------------------------------------------------------------
 // per-drone scan: obstacle distances + pairwise distances
 // ------------------------------------------------------------------------------------------
 struct ScanOut {

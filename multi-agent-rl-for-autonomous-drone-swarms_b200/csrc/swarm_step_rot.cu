@@ -171,7 +171,11 @@ __host__ __device__ constexpr int rot_smem_per_warp(int G, int M, bool dr) {
 }
 
 // MT: number of obstacles when known at compile time (4 / 8: sorting-network selection), 0 = P.M
-template <int NT, int MT, bool DR>
+// MODE: kRotStep = env.step() of every group (episode ends are put on the reset list);
+//       kRotReset = env.reset() + first observation of the listed envs (the auto-reset launch that follows)
+enum RotMode : int { kRotStep = 0, kRotReset = 1 };
+
+template <int NT, int MT, bool DR, int MODE>
 __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_step_rot_kernel(const DevParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int N = NT, G = 32 / NT, HALF = NT / 2;
@@ -200,8 +204,10 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
     const unsigned env_lanes = N == 32 ? FULL_MASK : (((1u << N) - 1u) << e_base);
     float* srow = tile + lane * kD;  // this lane's tile row; before the obs is staged it stashes exact distances
 
-    const int n_iter = P.n_groups;
+    // step: one item per env group; reset: one item per listed group
+    const int n_iter = MODE == kRotStep ? P.n_groups : (int)*reinterpret_cast<const volatile unsigned*>(P.reset_count);
     const int env_end = P.env_begin + P.env_count;
+    unsigned* const queue = P.work_counter + (MODE == kRotStep ? 0 : 2);
 
     if (lane == 0) {
         mbar_init(bar0, 1);
@@ -214,6 +220,7 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
     const int goal_off = 0, obst_off = 16 * G, dr_off = 16 * G * (1 + M);
     const int sc_off = dr_off + (DR ? 32 * G : 0);
     auto issue = [&](int grp, int buf) {
+        if (MODE != kRotStep) return;
         const int env0 = P.env_begin + grp * G;
         const int n_env = G == 1 ? 1 : min(G, env_end - env0);
 #if SWARM_ROT_TMA_LOADS
@@ -258,7 +265,7 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
     // dynamic group queue: lane 0 draws the next group index while the current group is processed, so
     // every warp stays busy until the queue is empty (no static-stride tail)
     int it = 0;
-    if (lane == 0) it = (int)atomicAdd(P.work_counter, 1u);
+    if (lane == 0) it = (int)atomicAdd(queue, 1u);
     it = __shfl_sync(FULL_MASK, it, 0);
     if (it < n_iter) issue(it, 0);
     unsigned phase = 0;  // bit b: parity the next wait on mbarrier b uses
@@ -266,8 +273,8 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
     int buf = 0;
     while (it < n_iter) {
         int it_next = 0;
-        if (lane == 0) it_next = (int)atomicAdd(P.work_counter, 1u);
-        const int env0 = P.env_begin + it * G;
+        if (lane == 0) it_next = (int)atomicAdd(queue, 1u);
+        const int env0 = MODE == kRotStep ? P.env_begin + it * G : P.reset_list[it];
         const int n_env = G == 1 ? 1 : min(G, env_end - env0);
         const bool lane_ok = G == 1 ? true : e_l < n_env;
         const int env = env0 + (lane_ok ? e_l : 0);
@@ -275,392 +282,517 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
         const int a = a0 + (lane_ok ? lane : 0);
         const bool leader = lane_ok && i == 0;
         const unsigned ok_lanes = __ballot_sync(FULL_MASK, lane_ok);
-        const unsigned char* ib = envbox0 + (size_t)buf * envbox_bytes;
-        const float4* tobs = reinterpret_cast<const float4*>(ib + obst_off) + e_l * M;
+        unsigned char* ib = envbox0 + (size_t)buf * envbox_bytes;
+        float4* tgoal = reinterpret_cast<float4*>(ib + goal_off);
+        float4* tobs_all = reinterpret_cast<float4*>(ib + obst_off);
+        const float4* tobs = tobs_all + e_l * M;
 
-        cp_async_wait_all();
-#if SWARM_ROT_TMA_LOADS
-        mbar_wait(bar0 + 8 * buf, (phase >> buf) & 1u);
-        phase ^= 1u << buf;
-#endif
-        __syncwarp();  // the cp.async words of the other lanes
-        // obstacle index -> .w of the inbox copy, so a key is one LOP3 (the table syncwarp below orders it)
-        for (int idx = lane; idx < G * M; idx += 32)
-            reinterpret_cast<unsigned*>(const_cast<unsigned char*>(ib) + obst_off)[idx * 4 + 3] = (unsigned)(idx % M);
-
-        float4 p = make_float4(0.f, 0.f, 0.f, 0.f), v = p, g4 = p;
-        float ax = 0.f, ay = 0.f, az = 0.f;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f), v = p;
+        float gx = 0.f, gy = 0.f, gz = 0.f, prev_d = 0.f;
         int sc = 0;
         float c_amax = P.amax, c_vmax = P.vmax, c_dt = P.dt, c_bound = P.bound, c_thr_obst = P.thr_obst;
         unsigned ekey = 0u;
-        if (lane_ok) {
-            p = in_pos[lane];
-            v = in_pos[32 + lane];
-            g4 = reinterpret_cast<const float4*>(ib + goal_off)[e_l];
-            const float* act = reinterpret_cast<const float*>(in_pos + 64);
-            ax = act[lane * 3 + 0]; ay = act[lane * 3 + 1]; az = act[lane * 3 + 2];
-            sc = reinterpret_cast<const int*>(ib + sc_off)[e_l];
-            if (DR) {
-                const float4* drp = reinterpret_cast<const float4*>(ib + dr_off) + 2 * e_l;
-                const float4 d0 = drp[0], d1 = drp[1];
-                c_amax = d0.x; c_vmax = d0.y; c_dt = d0.z; c_bound = d0.w;
-                c_thr_obst = d1.x; ekey = __float_as_uint(d1.y);
-            }
-        }
-        float gx = g4.x, gy = g4.y, gz = g4.z;
         const unsigned genv = DR ? (unsigned)(P.env_index_base + env) : 0u;
-        const bool alive = lane_ok && p.w != 0.0f;
+        bool alive = false;
+        unsigned reset_envs = 0u;  // reset launch: bit el = env el of the group is re-drawn
+        if (MODE == kRotReset) reset_envs = __ballot_sync(FULL_MASK, lane < n_env && P.env_mask[env0 + lane] != 0);
 
-        // =========================== integrate (:98-118) ===========================
-        float prev_d = norm1d<0>(__fsub_rn(gx, p.x), __fsub_rn(gy, p.y), __fsub_rn(gz, p.z));  // :98-101
-        if (alive) {
-            ax = clipf(ax, -1.0f, 1.0f); ay = clipf(ay, -1.0f, 1.0f); az = clipf(az, -1.0f, 1.0f);
-            if (DR) {  // thrust noise: a <- a * (1 + sigma z), one normal per axis
-                const uint4 r = philox4x32_10(genv, ekey, (unsigned)sc, (unsigned)i | (DR_STREAM_THRUST << 16), P.dr_key0,
-                                              P.dr_key1);
-                ax = __fmul_rn(ax, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, P.dr_qtable[r.x >> 20])));
-                ay = __fmul_rn(ay, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, P.dr_qtable[r.y >> 20])));
-                az = __fmul_rn(az, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, P.dr_qtable[r.z >> 20])));
-            }
-            v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(ax, c_amax), c_dt));
-            v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(ay, c_amax), c_dt));
-            v.z = __fadd_rn(v.z, __fmul_rn(__fmul_rn(az, c_amax), c_dt));
-            const float speed = norm1d<0>(v.x, v.y, v.z);  // _clip_speed (:179-183)
-            if (!(speed <= c_vmax || speed < P.eps_speed)) {
-                v.x = __fmul_rn(__fdiv_rn(v.x, speed), c_vmax);
-                v.y = __fmul_rn(__fdiv_rn(v.y, speed), c_vmax);
-                v.z = __fmul_rn(__fdiv_rn(v.z, speed), c_vmax);
-            }
-            p.x = __fadd_rn(p.x, __fmul_rn(v.x, c_dt));
-            p.y = __fadd_rn(p.y, __fmul_rn(v.y, c_dt));
-            p.z = __fadd_rn(p.z, __fmul_rn(v.z, c_dt));
-        }
-        // wall clip for ALL drones (:113-117); velocity is not zeroed at the wall
-        p.x = clipf(p.x, -c_bound, c_bound);
-        p.y = clipf(p.y, -c_bound, c_bound);
-        p.z = clipf(p.z, -c_bound, c_bound);
-
-        // doubled position table: entry [2N e_l + i + r] is drone (i + r) mod N for 0 <= r <= N; .w = drone index
+        constexpr auto step_pass = []() { return MODE == kRotStep; };
         {
-            const float4 t = make_float4(p.x, p.y, p.z, __int_as_float(i));
-            tab2[2 * e_base + i] = t;
-            tab2[2 * e_base + i + N] = t;
-        }
-        const unsigned alive_mask = __ballot_sync(FULL_MASK, alive);
-        const int n_alive_env = __popc(alive_mask & env_lanes);
-        if (lane == 0) bulk_wait_read0();  // the previous group's obs tile has left shared memory
-        __syncwarp();
-        // every lane has consumed the agent inbox (its values went through the integrator): refill it, and
-        // the other env inbox, with the next group's inputs
-        it_next = __shfl_sync(FULL_MASK, it_next, 0);
-        if (it_next < n_iter) issue(it_next, buf ^ 1);
-        // velocity / previous goal distance wait in the tile row (slots 32-35) while the scans need the registers
-        srow[32] = v.x; srow[33] = v.y; srow[34] = v.z; srow[35] = prev_d;
-
-        float nd[3]; int nj[3];        // exact distances / drone indices of the 3 nearest neighbours
-        float od[4]; int om[4];        // same for the 4 nearest obstacles
-        bool pair_hit = false;
-        double form_sum = 0.0;
-        int form_n = 0;
-        const float4* tp = tab2 + 2 * e_base + i;  // tp[r] = drone (i + r) mod N
-        bool bad = false;
-        if (alive_mask == ok_lanes) {
-            // ================= rotation pass: every drone of the group is active =================
-            unsigned k0 = ~0u, k1 = ~0u, k2 = ~0u, k3 = ~0u;
-            double acc_f = 0.0, acc_b = 0.0;
-            const double d_star = P.d_star;
-            float4 qn = tp[1];
-#pragma unroll
-            for (int r = 1; r < HALF; ++r) {
-                const float4 q = qn;
-                qn = tp[r + 1];
-                const float s = sumsq1d_fast(__fsub_rn(q.x, p.x), __fsub_rn(q.y, p.y), __fsub_rn(q.z, p.z));
-                const float d = sqrt_rn_fast(s);
-                const float db = __shfl_sync(FULL_MASK, d, lane - r, N);  // d((i - r) mod N, i)
-                srow[r] = d;
-                srow[HALF + r] = db;
-                const unsigned kf = and_or<~IDX>(__float_as_uint(d), __float_as_uint(q.w));
-                const unsigned kb = merge_low<IDX>(__float_as_uint(db), (unsigned)(lane - r));
-                merge2(kf, kb, k0, k1, k2, k3);
-                acc_f = __dadd_rn(acc_f, fabs(__dsub_rn(f64_of_pos_f32(d), d_star)));
-                acc_b = __dadd_rn(acc_b, fabs(__dsub_rn(f64_of_pos_f32(db), d_star)));
-            }
-            {   // round N/2: the pair is visited from both ends, each end keeps its own copy
-                const float4 q = qn;
-                const float s = sumsq1d_fast(__fsub_rn(q.x, p.x), __fsub_rn(q.y, p.y), __fsub_rn(q.z, p.z));
-                const float d = sqrt_rn_fast(s);
-                srow[HALF] = d;
-                merge1(and_or<~IDX>(__float_as_uint(d), __float_as_uint(q.w)), k0, k1, k2, k3);
-                acc_f = __dadd_rn(acc_f, fabs(__dsub_rn(f64_of_pos_f32(d), d_star)));
-            }
-            // two candidates in one key bucket among the first four: truncation may have mis-ordered them
-            form_sum = __dadd_rn(acc_f, acc_b);
-            // s < 2^-28 (a distance below 2^-14: fast sqrt / exact-sum preconditions) shows up either as the
-            // smallest key or, for s = 0 / denormal s (rsqrt -> inf -> NaN distance), as a NaN formation sum
-            bad = !(form_sum == form_sum) || k0 < 0x38800000u /* 2^-14 */ || ((k0 ^ k1) <= IDX) || ((k1 ^ k2) <= IDX) ||
-                  ((k2 ^ k3) <= IDX);
-            const unsigned kk[3] = {k0, k1, k2};
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                const int j = (int)(kk[q] & IDX);
-                const int t = (j - i) & (int)IDX;           // forward distance i -> j
-                nj[q] = j;
-                nd[q] = srow[t <= HALF ? t : HALF + N - t];  // backward round N - t was stashed at HALF + (N - t)
-            }
-            pair_hit = nd[0] <= P.thr_pair;  // nearest drone decides (:202-207)
-            form_n = N - 1;
-
-            // ---- obstacles: _nearest_obstacle_features (:273-291) + obstacle part of _collision_mask
-            unsigned o0, o1, o2, o3, o4;
-            float smin_o = F32_INF;
-            if (MT == 8 || MT == 4) {
-                unsigned ok[MT ? MT : 1];
-#pragma unroll
-                for (int m = 0; m < MT; m += 2) {
-                    const float4 oa = tobs[m], ob = tobs[m + 1];
-                    const float sa = sumsq_axis(__fsub_rn(oa.x, p.x), __fsub_rn(oa.y, p.y), __fsub_rn(oa.z, p.z));
-                    const float sb = sumsq_axis(__fsub_rn(ob.x, p.x), __fsub_rn(ob.y, p.y), __fsub_rn(ob.z, p.z));
-                    smin_o = fminf(fminf(smin_o, sa), sb);
-                    const float da = sqrt_rn_fast(sa), db = sqrt_rn_fast(sb);
-                    srow[m] = da;
-                    srow[m + 1] = db;
-                    ok[m] = and_or<~31u>(__float_as_uint(da), __float_as_uint(oa.w));
-                    ok[m + 1] = and_or<~31u>(__float_as_uint(db), __float_as_uint(ob.w));
+            if (step_pass()) {
+                cp_async_wait_all();
+#if SWARM_ROT_TMA_LOADS
+                mbar_wait(bar0 + 8 * buf, (phase >> buf) & 1u);
+                phase ^= 1u << buf;
+#endif
+                __syncwarp();  // the cp.async words of the other lanes
+                // obstacle index -> .w of the inbox copy, so a key is one LOP3 (the table syncwarp below orders it)
+                for (int idx = lane; idx < G * M; idx += 32)
+                    reinterpret_cast<unsigned*>(tobs_all)[idx * 4 + 3] = (unsigned)(idx % M);
+                float ax = 0.f, ay = 0.f, az = 0.f;
+                if (lane_ok) {
+                    p = in_pos[lane];
+                    v = in_pos[32 + lane];
+                    const float4 g4 = tgoal[e_l];
+                    gx = g4.x; gy = g4.y; gz = g4.z;
+                    const float* act = reinterpret_cast<const float*>(in_pos + 64);
+                    ax = act[lane * 3 + 0]; ay = act[lane * 3 + 1]; az = act[lane * 3 + 2];
+                    sc = reinterpret_cast<const int*>(ib + sc_off)[e_l];
+                    if (DR) {
+                        const float4* drp = reinterpret_cast<const float4*>(ib + dr_off) + 2 * e_l;
+                        const float4 d0 = drp[0], d1 = drp[1];
+                        c_amax = d0.x; c_vmax = d0.y; c_dt = d0.z; c_bound = d0.w;
+                        c_thr_obst = d1.x; ekey = __float_as_uint(d1.y);
+                    }
                 }
-                if (MT == 8) {
-                    sort8(reinterpret_cast<unsigned(&)[8]>(ok));
-                    o4 = ok[MT == 8 ? 4 : 0];
-                } else {
-                    sort4(reinterpret_cast<unsigned(&)[4]>(ok));
-                    o4 = ~0u;
+                alive = lane_ok && p.w != 0.0f;
+
+                // =========================== integrate (:98-118) ===========================
+                prev_d = norm1d<0>(__fsub_rn(gx, p.x), __fsub_rn(gy, p.y), __fsub_rn(gz, p.z));  // :98-101
+                if (alive) {
+                    ax = clipf(ax, -1.0f, 1.0f); ay = clipf(ay, -1.0f, 1.0f); az = clipf(az, -1.0f, 1.0f);
+                    if (DR) {  // thrust noise: a <- a * (1 + sigma z), one normal per axis
+                        const uint4 r = philox4x32_10(genv, ekey, (unsigned)sc, (unsigned)i | (DR_STREAM_THRUST << 16),
+                                                      P.dr_key0, P.dr_key1);
+                        ax = __fmul_rn(ax, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, P.dr_qtable[r.x >> 20])));
+                        ay = __fmul_rn(ay, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, P.dr_qtable[r.y >> 20])));
+                        az = __fmul_rn(az, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, P.dr_qtable[r.z >> 20])));
+                    }
+                    v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(ax, c_amax), c_dt));
+                    v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(ay, c_amax), c_dt));
+                    v.z = __fadd_rn(v.z, __fmul_rn(__fmul_rn(az, c_amax), c_dt));
+                    const float speed = norm1d<0>(v.x, v.y, v.z);  // _clip_speed (:179-183)
+                    if (!(speed <= c_vmax || speed < P.eps_speed)) {
+                        v.x = __fmul_rn(__fdiv_rn(v.x, speed), c_vmax);
+                        v.y = __fmul_rn(__fdiv_rn(v.y, speed), c_vmax);
+                        v.z = __fmul_rn(__fdiv_rn(v.z, speed), c_vmax);
+                    }
+                    p.x = __fadd_rn(p.x, __fmul_rn(v.x, c_dt));
+                    p.y = __fadd_rn(p.y, __fmul_rn(v.y, c_dt));
+                    p.z = __fadd_rn(p.z, __fmul_rn(v.z, c_dt));
                 }
-                o0 = ok[0]; o1 = ok[MT > 1 ? 1 : 0]; o2 = ok[MT > 2 ? 2 : 0]; o3 = ok[MT > 3 ? 3 : 0];
+                // wall clip for ALL drones (:113-117); velocity is not zeroed at the wall
+                p.x = clipf(p.x, -c_bound, c_bound);
+                p.y = clipf(p.y, -c_bound, c_bound);
+                p.z = clipf(p.z, -c_bound, c_bound);
             } else {
-                o0 = o1 = o2 = o3 = o4 = ~0u;
+                __syncwarp();  // every lane is done with the previous item's tables
+                // ================================ reset (:65-80) ================================
+                // draw order of env.reset(): positions (N,3) -> goal (3,) -> obstacles (M,3), each
+                // rng.uniform(-W/2, W/2) in float64 then float32; 32 lanes draw in parallel by PCG64 jump-ahead
 #pragma unroll 1
-                for (int mb = 0; mb < M; mb += 4) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float4 o = tobs[mb + u];
-                        const float s = sumsq_axis(__fsub_rn(o.x, p.x), __fsub_rn(o.y, p.y), __fsub_rn(o.z, p.z));
-                        smin_o = fminf(smin_o, s);
-                        const float d = sqrt_rn_fast(s);
-                        srow[mb + u] = d;
-                        merge1_5(and_or<~31u>(__float_as_uint(d), __float_as_uint(o.w)), o0, o1, o2, o3, o4);
+                for (int el = 0; el < n_env; ++el) {
+                    if (!((reset_envs >> el) & 1u)) continue;
+                    const int renv = env0 + el;
+                    const unsigned long long sh = P.rng[(long long)renv * 4 + 0], sl = P.rng[(long long)renv * 4 + 1];
+                    const unsigned long long ih = P.rng[(long long)renv * 4 + 2], il = P.rng[(long long)renv * 4 + 3];
+                    double u_lo = P.rng_lo, u_range = P.rng_range;
+                    if (DR) {
+                        // this episode's constants: 6 uniforms + an episode key from one counter per (env, reset)
+                        const unsigned ge = (unsigned)(P.env_index_base + renv);
+                        const uint4 ra = philox4x32_10(ge, (unsigned)sl, (unsigned)(sl >> 32), DR_CTR_EPISODE, P.dr_key0, P.dr_key1);
+                        const uint4 rb = philox4x32_10(ge, (unsigned)sl, (unsigned)(sl >> 32), DR_CTR_EPISODE + 1u, P.dr_key0, P.dr_key1);
+                        const double inv24 = 1.0 / 16777216.0;
+                        const double s_mass = __dadd_rn(P.dr_lo[0], __dmul_rn(P.dr_span[0], __dmul_rn((double)(ra.x >> 8), inv24)));
+                        const double s_acc = __dadd_rn(P.dr_lo[1], __dmul_rn(P.dr_span[1], __dmul_rn((double)(ra.y >> 8), inv24)));
+                        const double s_spd = __dadd_rn(P.dr_lo[2], __dmul_rn(P.dr_span[2], __dmul_rn((double)(ra.z >> 8), inv24)));
+                        const double s_dt = __dadd_rn(P.dr_lo[3], __dmul_rn(P.dr_span[3], __dmul_rn((double)(ra.w >> 8), inv24)));
+                        const double s_rad = __dadd_rn(P.dr_lo[4], __dmul_rn(P.dr_span[4], __dmul_rn((double)(rb.x >> 8), inv24)));
+                        const double s_wld = __dadd_rn(P.dr_lo[5], __dmul_rn(P.dr_span[5], __dmul_rn((double)(rb.y >> 8), inv24)));
+                        const double world = __dmul_rn(P.dr_world, s_wld);
+                        const double half_w = __dmul_rn(world, 0.5);
+                        u_lo = -half_w; u_range = __dsub_rn(half_w, -half_w);
+                        if (lane == 0) {
+                            P.dr_params[(long long)renv * 2 + 0] =
+                                make_float4(__double2float_rn(__ddiv_rn(__dmul_rn(P.dr_max_accel, s_acc), s_mass)),
+                                            __double2float_rn(__dmul_rn(P.dr_max_speed, s_spd)),
+                                            __double2float_rn(__dmul_rn(P.dr_dt, s_dt)), __double2float_rn(half_w));
+                            P.dr_params[(long long)renv * 2 + 1] =
+                                make_float4(__double2float_rn(__dadd_rn(P.dr_r_c, __dmul_rn(P.dr_r_o, s_rad))),
+                                            __uint_as_float(rb.z), __double2float_rn(world), 0.0f);
+                        }
+                        if (e_l == el) ekey = rb.z;  // (the dynamics constants are not needed to observe)
                     }
-                }
-            }
-            bad = bad || !(smin_o >= SQRT_FAST_MIN) || ((o0 ^ o1) <= 31u) || ((o1 ^ o2) <= 31u) || ((o2 ^ o3) <= 31u) ||
-                  ((o3 ^ o4) <= 31u);
-            const unsigned oo[4] = {o0, o1, o2, o3};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                om[q] = (int)(oo[q] & 31u);
-                od[q] = srow[om[q]];
-            }
-            bad = bad && lane_ok;
-        }
-        if (alive_mask != ok_lanes || __any_sync(FULL_MASK, bad)) {
-            // ============ exact path: parked drones, coincident drones, or a detected near-tie ============
-            // the reference's loops as written: ascending j, strict '<' (lowest index wins ties),
-            // collision / formation over ACTIVE pairs only, np.mean's pairwise summation order
-#pragma unroll
-            for (int q = 0; q < 3; ++q) { nd[q] = F32_INF; nj[q] = 0; }
-            pair_hit = false;
-            const unsigned em = (alive_mask & env_lanes) >> e_base;  // bit j: drone j of this env active
-            const int n_f = alive ? n_alive_env - 1 : 0;
-            const int nf8 = n_f >= 8 ? (n_f & ~7) : 0;
-            double r8[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) r8[u] = 0.0;
-            double res = 0.0;
-            bool tree_done = false;
-            int cnt = 0;
-            const float4* te = tab2 + 2 * e_base;
 #pragma unroll 1
-            for (int j = 0; j < N; ++j) {
-                if (j == i) continue;
-                const float4 q = te[j];
-                const float d = norm1d<0>(__fsub_rn(q.x, p.x), __fsub_rn(q.y, p.y), __fsub_rn(q.z, p.z));
-                topk_insert<3>(d, j, nd, nj);
-                if (alive && ((em >> j) & 1u)) {
-                    pair_hit |= d <= P.thr_pair;
-                    const double err = fabs(__dsub_rn((double)d, P.d_star));
-                    if (cnt < nf8) {
-                        const int lane8 = cnt & 7;
+                    for (int k = lane; k < P.n_draws; k += 32) {
+                        unsigned long long oh, ol;
+                        pcg_jump(P.jump[k + 1], sh, sl, ih, il, oh, ol);
+                        const float val = pcg_uniform_f32(oh, ol, u_lo, u_range);
+                        if (k < 3 * N) {
+                            reinterpret_cast<float*>(tab2 + 2 * el * N + k / 3)[k % 3] = val;
+                        } else if (k < 3 * N + 3) {
+                            reinterpret_cast<float*>(tgoal + el)[k - 3 * N] = val;
+                        } else {
+                            const int kk = k - 3 * N - 3;
+                            reinterpret_cast<float*>(tobs_all + el * M + kk / 3)[kk % 3] = val;
+                        }
+                    }
+                    if (lane == 0) {
+                        unsigned long long oh, ol;
+                        pcg_jump(P.jump[P.n_draws], sh, sl, ih, il, oh, ol);
+                        P.rng[(long long)renv * 4 + 0] = oh;
+                        P.rng[(long long)renv * 4 + 1] = ol;
+                        P.step_count[renv] = 0;
+                        P.ep_return[renv] = 0.0f;
+                        reinterpret_cast<float*>(tgoal + el)[3] = 0.0f;
+                    }
+                    for (int k = lane; k < M; k += 32)  // obstacle index in .w (one-LOP3 keys, as in the step launch)
+                        reinterpret_cast<unsigned*>(tobs_all + el * M + k)[3] = (unsigned)k;
+                }
+                __syncwarp();
+                if (lane < n_env && ((reset_envs >> lane) & 1u)) P.goal4[env0 + lane] = tgoal[lane];
+                for (int idx = lane; idx < n_env * M; idx += 32)
+                    if ((reset_envs >> (idx / M)) & 1u) {
+                        const float4 o = tobs_all[idx];
+                        P.obst4[(long long)env0 * M + idx] = make_float4(o.x, o.y, o.z, 0.0f);
+                    }
+                const bool fresh = lane_ok && ((reset_envs >> e_l) & 1u);
+                if (fresh) {
+                    p = tab2[2 * e_base + i];
+                    v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 g4 = tgoal[e_l];
+                    gx = g4.x; gy = g4.y; gz = g4.z;
+                    sc = -1;  // the observed state has step_count 0 (DR sensor stream is keyed by sc + 1)
+                }
+                alive = lane_ok;  // (only the re-drawn envs' results are used; every drone of theirs is active)
+                __syncwarp();     // the drawn positions have been read before the table is rewritten
+            }
+
+            // doubled position table: entry [2N e_l + i + r] is drone (i + r) mod N for 0 <= r <= N; .w = drone index
+            {
+                const float4 t = make_float4(p.x, p.y, p.z, __int_as_float(i));
+                tab2[2 * e_base + i] = t;
+                tab2[2 * e_base + i + N] = t;
+            }
+            const unsigned alive_mask = __ballot_sync(FULL_MASK, alive);
+            const int n_alive_env = __popc(alive_mask & env_lanes);
+            if (lane == 0) bulk_wait_read0();  // the previous obs tile has left shared memory
+            __syncwarp();
+            // every lane has consumed the agent inbox (its values went through the integrator): refill it,
+            // and the other env inbox, with the next group's inputs
+            it_next = __shfl_sync(FULL_MASK, it_next, 0);
+            if (step_pass() && it_next < n_iter) issue(it_next, buf ^ 1);
+            // velocity / previous goal distance wait in the tile row (slots 32-35) while the scans need the registers
+            srow[32] = v.x; srow[33] = v.y; srow[34] = v.z; srow[35] = prev_d;
+
+            float nd[3]; int nj[3];        // exact distances / drone indices of the 3 nearest neighbours
+            float od[4]; int om[4];        // same for the 4 nearest obstacles
+            bool pair_hit = false;
+            double form_sum = 0.0;
+            int form_n = 0;
+            const float4* tp = tab2 + 2 * e_base + i;  // tp[r] = drone (i + r) mod N
+            bool bad = false;
+            if (alive_mask == ok_lanes) {
+                // ================= rotation pass: every drone of the group is active =================
+                unsigned k0 = ~0u, k1 = ~0u, k2 = ~0u, k3 = ~0u;
+                double acc_f = 0.0, acc_b = 0.0;
+                const double d_star = P.d_star;
+                float4 qn = tp[1];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) r8[u] = __dadd_rn(r8[u], lane8 == u ? err : 0.0);
+                for (int r = 1; r < HALF; ++r) {
+                    const float4 q = qn;
+                    qn = tp[r + 1];
+                    const float s = sumsq1d_fast(__fsub_rn(q.x, p.x), __fsub_rn(q.y, p.y), __fsub_rn(q.z, p.z));
+                    const float d = sqrt_rn_fast(s);
+                    const float db = __shfl_sync(FULL_MASK, d, lane - r, N);  // d((i - r) mod N, i)
+                    srow[r] = d;
+                    srow[HALF + r] = db;
+                    const unsigned kf = and_or<~IDX>(__float_as_uint(d), __float_as_uint(q.w));
+                    const unsigned kb = merge_low<IDX>(__float_as_uint(db), (unsigned)(lane - r));
+                    merge2(kf, kb, k0, k1, k2, k3);
+                    acc_f = __dadd_rn(acc_f, fabs(__dsub_rn(f64_of_pos_f32(d), d_star)));
+                    acc_b = __dadd_rn(acc_b, fabs(__dsub_rn(f64_of_pos_f32(db), d_star)));
+                }
+                {   // round N/2: the pair is visited from both ends, each end keeps its own copy
+                    const float4 q = qn;
+                    const float s = sumsq1d_fast(__fsub_rn(q.x, p.x), __fsub_rn(q.y, p.y), __fsub_rn(q.z, p.z));
+                    const float d = sqrt_rn_fast(s);
+                    srow[HALF] = d;
+                    merge1(and_or<~IDX>(__float_as_uint(d), __float_as_uint(q.w)), k0, k1, k2, k3);
+                    acc_f = __dadd_rn(acc_f, fabs(__dsub_rn(f64_of_pos_f32(d), d_star)));
+                }
+                form_sum = __dadd_rn(acc_f, acc_b);
+                // s < 2^-28 (a distance below 2^-14: fast sqrt / exact-sum preconditions) shows up either as the
+                // smallest key or, for s = 0 / denormal s (rsqrt -> inf -> NaN distance), as a NaN formation sum;
+                // two candidates in one key bucket among the first four: truncation may have mis-ordered them
+                bad = !(form_sum == form_sum) || k0 < 0x38800000u /* 2^-14 */ || ((k0 ^ k1) <= IDX) || ((k1 ^ k2) <= IDX) ||
+                      ((k2 ^ k3) <= IDX);
+                const unsigned kk[3] = {k0, k1, k2};
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const int j = (int)(kk[q] & IDX);
+                    const int t = (j - i) & (int)IDX;           // forward distance i -> j
+                    nj[q] = j;
+                    nd[q] = srow[t <= HALF ? t : HALF + N - t];  // backward round N - t was stashed at HALF + (N - t)
+                }
+                pair_hit = nd[0] <= P.thr_pair;  // nearest drone decides (:202-207)
+                form_n = N - 1;
+
+                // ---- obstacles: _nearest_obstacle_features (:273-291) + obstacle part of _collision_mask
+                unsigned o0, o1, o2, o3, o4;
+                float smin_o = F32_INF;
+                if (MT == 8 || MT == 4) {
+                    unsigned ok[MT ? MT : 1];
+#pragma unroll
+                    for (int m = 0; m < MT; m += 2) {
+                        const float4 oa = tobs[m], ob = tobs[m + 1];
+                        const float sa = sumsq_axis(__fsub_rn(oa.x, p.x), __fsub_rn(oa.y, p.y), __fsub_rn(oa.z, p.z));
+                        const float sb = sumsq_axis(__fsub_rn(ob.x, p.x), __fsub_rn(ob.y, p.y), __fsub_rn(ob.z, p.z));
+                        smin_o = fminf(fminf(smin_o, sa), sb);
+                        const float da = sqrt_rn_fast(sa), db = sqrt_rn_fast(sb);
+                        srow[m] = da;
+                        srow[m + 1] = db;
+                        ok[m] = and_or<~31u>(__float_as_uint(da), __float_as_uint(oa.w));
+                        ok[m + 1] = and_or<~31u>(__float_as_uint(db), __float_as_uint(ob.w));
+                    }
+                    if (MT == 8) {
+                        sort8(reinterpret_cast<unsigned(&)[8]>(ok));
+                        o4 = ok[MT == 8 ? 4 : 0];
                     } else {
-                        if (!tree_done && nf8 > 0) res = tree8(r8);
-                        tree_done = true;
-                        res = __dadd_rn(res, err);
+                        sort4(reinterpret_cast<unsigned(&)[4]>(ok));
+                        o4 = ~0u;
                     }
-                    ++cnt;
-                }
-            }
-            if (!tree_done && nf8 > 0) res = tree8(r8);
-            form_sum = res;
-            form_n = n_f;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { od[q] = F32_INF; om[q] = 0; }
+                    o0 = ok[0]; o1 = ok[MT > 1 ? 1 : 0]; o2 = ok[MT > 2 ? 2 : 0]; o3 = ok[MT > 3 ? 3 : 0];
+                } else {
+                    o0 = o1 = o2 = o3 = o4 = ~0u;
 #pragma unroll 1
-            for (int m = 0; m < M; ++m) {
-                const float4 o = tobs[m];
-                const float d = __fsqrt_rn(sumsq_axis(__fsub_rn(o.x, p.x), __fsub_rn(o.y, p.y), __fsub_rn(o.z, p.z)));
-                topk_insert<4>(d, m, od, om);
-            }
-        }
-        {
-            v.x = srow[32]; v.y = srow[33]; v.z = srow[34]; prev_d = srow[35];
-            const float4 gg = reinterpret_cast<const float4*>(ib + goal_off)[lane_ok ? e_l : 0];
-            gx = gg.x; gy = gg.y; gz = gg.z;
-        }
-        const float curr_d = norm1d<0>(__fsub_rn(gx, p.x), __fsub_rn(gy, p.y), __fsub_rn(gz, p.z));
-
-        // ============================ obs row -> staging tile (:226-243) ============================
-        if (lane_ok) {
-            float* row = srow;
-            const float4 t0 = tab2[2 * e_base + nj[0]], t1 = tab2[2 * e_base + nj[1]], t2 = tab2[2 * e_base + nj[2]];
-            const float4 b0 = tobs[om[0]], b1 = tobs[om[1]], b2 = tobs[om[2]], b3 = tobs[om[3]];
-            uint4 rs0 = make_uint4(0, 0, 0, 0), rs1 = rs0, rs2 = rs0;
-            if (DR) {  // sensor noise: normal n of the row comes from Philox call n / 4 (see swarm_kernels.cu)
-                const unsigned c3 = (unsigned)i | (DR_STREAM_SENSOR << 16);
-                rs0 = philox4x32_10(genv, ekey, (unsigned)(sc + 1), c3, P.dr_key0, P.dr_key1);
-                rs1 = philox4x32_10(genv, ekey, (unsigned)(sc + 1), c3 + (1u << 16), P.dr_key0, P.dr_key1);
-                rs2 = philox4x32_10(genv, ekey, (unsigned)(sc + 1), c3 + (2u << 16), P.dr_key0, P.dr_key1);
-            }
-            auto noisy = [&](float x, float sigma, unsigned bits) {
-                return DR ? __fadd_rn(x, __fmul_rn(sigma, P.dr_qtable[bits >> 20])) : x;
-            };
-            row[0] = noisy(p.x, P.dr_std_pos, rs0.x); row[1] = noisy(p.y, P.dr_std_pos, rs0.y);
-            row[2] = noisy(p.z, P.dr_std_pos, rs0.z);
-            row[3] = noisy(v.x, P.dr_std_vel, rs0.w); row[4] = noisy(v.y, P.dr_std_vel, rs1.x);
-            row[5] = noisy(v.z, P.dr_std_vel, rs1.y);
-            row[6] = __fsub_rn(gx, p.x); row[7] = __fsub_rn(gy, p.y); row[8] = __fsub_rn(gz, p.z);
-            row[9] = __fsub_rn(t0.x, p.x); row[10] = __fsub_rn(t0.y, p.y); row[11] = __fsub_rn(t0.z, p.z); row[12] = nd[0];
-            row[13] = __fsub_rn(t1.x, p.x); row[14] = __fsub_rn(t1.y, p.y); row[15] = __fsub_rn(t1.z, p.z); row[16] = nd[1];
-            row[17] = __fsub_rn(t2.x, p.x); row[18] = __fsub_rn(t2.y, p.y); row[19] = __fsub_rn(t2.z, p.z); row[20] = nd[2];
-            row[21] = __fsub_rn(b0.x, p.x); row[22] = __fsub_rn(b0.y, p.y); row[23] = __fsub_rn(b0.z, p.z);
-            row[24] = noisy(od[0], P.dr_std_obst, rs1.z);
-            row[25] = __fsub_rn(b1.x, p.x); row[26] = __fsub_rn(b1.y, p.y); row[27] = __fsub_rn(b1.z, p.z);
-            row[28] = noisy(od[1], P.dr_std_obst, rs1.w);
-            row[29] = __fsub_rn(b2.x, p.x); row[30] = __fsub_rn(b2.y, p.y); row[31] = __fsub_rn(b2.z, p.z);
-            row[32] = noisy(od[2], P.dr_std_obst, rs2.x);
-            row[33] = __fsub_rn(b3.x, p.x); row[34] = __fsub_rn(b3.y, p.y); row[35] = __fsub_rn(b3.z, p.z);
-            row[36] = noisy(od[3], P.dr_std_obst, rs2.y);
-        }
-        fence_async_smem();  // generic-proxy tile writes -> visible to the bulk-copy engine
-        __syncwarp();        // (also: every lane is done with this inbox and the position table)
-        if (lane == 0) {
-            bulk_s2g(P.obs + (long long)a0 * kD, smem_u32(tile), (unsigned)(n_env * N * kD * 4));
-            bulk_commit();
-        }
-
-        // ===================== rewards and flags (:120-172) =====================
-        const bool obst_hit = od[0] <= c_thr_obst;
-        const bool reached = alive && curr_d <= P.thr_goal;    // :124-127 (double compare)
-        const bool collided = alive && (obst_hit || pair_hit);  // :128
-        double reward = 0.0;
-        if (alive) {
-            const double progress = __dmul_rn(__dsub_rn((double)prev_d, (double)curr_d), P.k_p);  // :142
-            double pen = 0.0;  // :210-224
-            if (form_n > 0) {
-                const double mean = form_n == N - 1 ? mean_markstein(form_sum, P.n_others, P.inv_n_others)
-                                                    : __ddiv_rn(form_sum, (double)form_n);
-                pen = __dmul_rn(P.neg_k_f, mean);
-            }
-            reward = __dadd_rn(progress, pen);                  // :143
-            if (reached) reward = __dadd_rn(reward, P.r_goal);  // :144-145
-            if (collided) reward = __dadd_rn(reward, P.r_col);  // :146-147
-        }
-        const float rew32 = __double2float_rn(reward);
-        const bool done_agent = reached || collided;
-        const bool any_col = (__ballot_sync(FULL_MASK, collided) & env_lanes) != 0;
-        const int n_cont = __popc(__ballot_sync(FULL_MASK, alive && !done_agent) & env_lanes);
-        float x = rew32;  // deterministic per-env reward sum (segmented tree over the env's lanes)
+                    for (int mb = 0; mb < M; mb += 4) {
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            const float t = __shfl_down_sync(FULL_MASK, x, off);
-            if (off < N && i + off < N) x = __fadd_rn(x, t);
-        }
-        const bool env_active = n_alive_env > 0;
-        const int sc_new = env_active ? sc + 1 : sc;
-        const bool time_limit = env_active && sc_new >= P.max_steps;
-        const bool all_reached = n_cont == 0 && !any_col && !time_limit;
-        const bool episode_done = all_reached || any_col;
-        const bool all_term = env_active ? episode_done : true;  // :94-95 when no agent is left
-        const bool all_trunc = env_active ? (time_limit && !episode_done) : false;
-        const bool ep_over = env_active && (all_term || all_trunc);
-        const bool need_reset = P.auto_reset && (ep_over || !env_active);
-        if (lane_ok) {
-            P.terminated[a] = (alive && done_agent) ? 1 : 0;                 // :150-151
-            P.truncated[a] = (alive && time_limit && !done_agent) ? 1 : 0;   // :152
-            const bool valid = alive && !done_agent && !time_limit && !any_col;  // :154
-            const bool alive_next = ep_over ? false : valid;                     // :169-172
-            P.reward[a] = rew32;
-            if (P.reward64) P.reward64[a] = reward;
-            P.reached[a] = reached ? 1 : 0;
-            P.collision[a] = collided ? 1 : 0;
-            if (!need_reset) {  // (a reset env gets these from the aux launch that follows)
-                P.dist[a] = curr_d;
-                P.obs_valid[a] = valid ? 1 : 0;
-                P.pos4[a] = make_float4(p.x, p.y, p.z, alive_next ? 1.0f : 0.0f);
-                P.vel4[a] = make_float4(v.x, v.y, v.z, 0.0f);
-                if (P.gs) {
-                    float* row = P.gs + (long long)env * P.R;
-                    __stcs(row + 3 * i + 0, p.x); __stcs(row + 3 * i + 1, p.y); __stcs(row + 3 * i + 2, p.z);
-                    __stcs(row + 3 * N + 3 * i + 0, v.x); __stcs(row + 3 * N + 3 * i + 1, v.y);
-                    __stcs(row + 3 * N + 3 * i + 2, v.z);
+                        for (int u = 0; u < 4; ++u) {
+                            const float4 o = tobs[mb + u];
+                            const float s = sumsq_axis(__fsub_rn(o.x, p.x), __fsub_rn(o.y, p.y), __fsub_rn(o.z, p.z));
+                            smin_o = fminf(smin_o, s);
+                            const float d = sqrt_rn_fast(s);
+                            srow[mb + u] = d;
+                            merge1_5(and_or<~31u>(__float_as_uint(d), __float_as_uint(o.w)), o0, o1, o2, o3, o4);
+                        }
+                    }
+                }
+                bad = bad || !(smin_o >= SQRT_FAST_MIN) || ((o0 ^ o1) <= 31u) || ((o1 ^ o2) <= 31u) || ((o2 ^ o3) <= 31u) ||
+                      ((o3 ^ o4) <= 31u);
+                const unsigned oo[4] = {o0, o1, o2, o3};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    om[q] = (int)(oo[q] & 31u);
+                    od[q] = srow[om[q]];
+                }
+                bad = bad && lane_ok && (step_pass() || ((reset_envs >> e_l) & 1u));
+            }
+            if (alive_mask != ok_lanes || __any_sync(FULL_MASK, bad)) {
+                // ============ exact path: parked drones, coincident drones, or a detected near-tie ============
+                // the reference's loops as written: ascending j, strict '<' (lowest index wins ties),
+                // collision / formation over ACTIVE pairs only, np.mean's pairwise summation order
+#pragma unroll
+                for (int q = 0; q < 3; ++q) { nd[q] = F32_INF; nj[q] = 0; }
+                pair_hit = false;
+                const unsigned em = (alive_mask & env_lanes) >> e_base;  // bit j: drone j of this env active
+                const int n_f = alive ? n_alive_env - 1 : 0;
+                const int nf8 = n_f >= 8 ? (n_f & ~7) : 0;
+                double r8[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) r8[u] = 0.0;
+                double res = 0.0;
+                bool tree_done = false;
+                int cnt = 0;
+                const float4* te = tab2 + 2 * e_base;
+#pragma unroll 1
+                for (int j = 0; j < N; ++j) {
+                    if (j == i) continue;
+                    const float4 q = te[j];
+                    const float d = norm1d<0>(__fsub_rn(q.x, p.x), __fsub_rn(q.y, p.y), __fsub_rn(q.z, p.z));
+                    topk_insert<3>(d, j, nd, nj);
+                    if (alive && ((em >> j) & 1u)) {
+                        pair_hit |= d <= P.thr_pair;
+                        const double err = fabs(__dsub_rn((double)d, P.d_star));
+                        if (cnt < nf8) {
+                            const int lane8 = cnt & 7;
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) r8[u] = __dadd_rn(r8[u], lane8 == u ? err : 0.0);
+                        } else {
+                            if (!tree_done && nf8 > 0) res = tree8(r8);
+                            tree_done = true;
+                            res = __dadd_rn(res, err);
+                        }
+                        ++cnt;
+                    }
+                }
+                if (!tree_done && nf8 > 0) res = tree8(r8);
+                form_sum = res;
+                form_n = n_f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { od[q] = F32_INF; om[q] = 0; }
+#pragma unroll 1
+                for (int m = 0; m < M; ++m) {
+                    const float4 o = tobs[m];
+                    const float d = __fsqrt_rn(sumsq_axis(__fsub_rn(o.x, p.x), __fsub_rn(o.y, p.y), __fsub_rn(o.z, p.z)));
+                    topk_insert<4>(d, m, od, om);
                 }
             }
-        }
-        if (leader) {
-            P.all_term[env] = all_term ? 1 : 0;
-            P.all_trunc[env] = all_trunc ? 1 : 0;
-            if (P.reset_mask) P.reset_mask[env] = need_reset ? 1 : 0;
-            const float ret = __fadd_rn(reinterpret_cast<const float*>(ib + sc_off)[G + e_l], x);
-            if (ep_over) {  // several env leaders per warp when G > 1: shared-memory atomics
-                atomicAdd(wstats + SWARM_STAT_EPISODES, 1ull);
-                atomicAdd(wstats + SWARM_STAT_LENGTH_SUM, (unsigned long long)sc_new);
-                atomicAdd(reinterpret_cast<double*>(wstats + SWARM_STAT_RETURN_SUM), (double)ret);
-                if (all_reached) atomicAdd(wstats + SWARM_STAT_SUCCESS, 1ull);
-                if (any_col) atomicAdd(wstats + SWARM_STAT_COLLISION, 1ull);
-                if (all_trunc) atomicAdd(wstats + SWARM_STAT_TIMEOUT, 1ull);
-            }
-            if (P.episode_return) P.episode_return[env] = ep_over ? ret : 0.0f;
-            if (P.episode_length) P.episode_length[env] = ep_over ? sc_new : 0;
-            if (!need_reset) {
-                P.step_count[env] = sc_new;
-                P.ep_return[env] = ep_over ? 0.0f : ret;
-                if (P.gs) {
-                    float* row = P.gs + (long long)env * P.R + 6 * N;
-                    __stcs(row + 0, gx); __stcs(row + 1, gy); __stcs(row + 2, gz);
+            v.x = srow[32]; v.y = srow[33]; v.z = srow[34]; prev_d = srow[35];
+            const float curr_d = norm1d<0>(__fsub_rn(gx, p.x), __fsub_rn(gy, p.y), __fsub_rn(gz, p.z));
+
+            // ============================ obs row -> staging tile (:226-243) ============================
+            // rows this launch delivers: step = every env, reset = the re-drawn ones
+            const unsigned out_envs = step_pass() ? ((1u << n_env) - 1u) : reset_envs;
+            if (out_envs != 0u) {
+                if (lane_ok) {
+                    float* row = srow;
+                    const float4 t0 = tab2[2 * e_base + nj[0]], t1 = tab2[2 * e_base + nj[1]], t2 = tab2[2 * e_base + nj[2]];
+                    const float4 b0 = tobs[om[0]], b1 = tobs[om[1]], b2 = tobs[om[2]], b3 = tobs[om[3]];
+                    uint4 rs0 = make_uint4(0, 0, 0, 0), rs1 = rs0, rs2 = rs0;
+                    if (DR) {  // sensor noise: normal n of the row comes from Philox call n / 4 (see swarm_kernels.cu)
+                        const unsigned c3 = (unsigned)i | (DR_STREAM_SENSOR << 16);
+                        rs0 = philox4x32_10(genv, ekey, (unsigned)(sc + 1), c3, P.dr_key0, P.dr_key1);
+                        rs1 = philox4x32_10(genv, ekey, (unsigned)(sc + 1), c3 + (1u << 16), P.dr_key0, P.dr_key1);
+                        rs2 = philox4x32_10(genv, ekey, (unsigned)(sc + 1), c3 + (2u << 16), P.dr_key0, P.dr_key1);
+                    }
+                    auto noisy = [&](float x, float sigma, unsigned bits) {
+                        return DR ? __fadd_rn(x, __fmul_rn(sigma, P.dr_qtable[bits >> 20])) : x;
+                    };
+                    row[0] = noisy(p.x, P.dr_std_pos, rs0.x); row[1] = noisy(p.y, P.dr_std_pos, rs0.y);
+                    row[2] = noisy(p.z, P.dr_std_pos, rs0.z);
+                    row[3] = noisy(v.x, P.dr_std_vel, rs0.w); row[4] = noisy(v.y, P.dr_std_vel, rs1.x);
+                    row[5] = noisy(v.z, P.dr_std_vel, rs1.y);
+                    row[6] = __fsub_rn(gx, p.x); row[7] = __fsub_rn(gy, p.y); row[8] = __fsub_rn(gz, p.z);
+                    row[9] = __fsub_rn(t0.x, p.x); row[10] = __fsub_rn(t0.y, p.y); row[11] = __fsub_rn(t0.z, p.z); row[12] = nd[0];
+                    row[13] = __fsub_rn(t1.x, p.x); row[14] = __fsub_rn(t1.y, p.y); row[15] = __fsub_rn(t1.z, p.z); row[16] = nd[1];
+                    row[17] = __fsub_rn(t2.x, p.x); row[18] = __fsub_rn(t2.y, p.y); row[19] = __fsub_rn(t2.z, p.z); row[20] = nd[2];
+                    row[21] = __fsub_rn(b0.x, p.x); row[22] = __fsub_rn(b0.y, p.y); row[23] = __fsub_rn(b0.z, p.z);
+                    row[24] = noisy(od[0], P.dr_std_obst, rs1.z);
+                    row[25] = __fsub_rn(b1.x, p.x); row[26] = __fsub_rn(b1.y, p.y); row[27] = __fsub_rn(b1.z, p.z);
+                    row[28] = noisy(od[1], P.dr_std_obst, rs1.w);
+                    row[29] = __fsub_rn(b2.x, p.x); row[30] = __fsub_rn(b2.y, p.y); row[31] = __fsub_rn(b2.z, p.z);
+                    row[32] = noisy(od[2], P.dr_std_obst, rs2.x);
+                    row[33] = __fsub_rn(b3.x, p.x); row[34] = __fsub_rn(b3.y, p.y); row[35] = __fsub_rn(b3.z, p.z);
+                    row[36] = noisy(od[3], P.dr_std_obst, rs2.y);
+                }
+                fence_async_smem();  // generic-proxy tile writes -> visible to the bulk-copy engine
+                __syncwarp();
+                if (lane == 0) {
+                    if (out_envs == (1u << n_env) - 1u) {  // whole tile, one TMA store
+                        bulk_s2g(P.obs + (long long)a0 * kD, smem_u32(tile), (unsigned)(n_env * N * kD * 4));
+                    } else {
+#pragma unroll 1
+                        for (int el = 0; el < n_env; ++el)
+                            if ((out_envs >> el) & 1u)
+                                bulk_s2g(P.obs + (long long)(a0 + el * N) * kD, smem_u32(tile + el * N * kD),
+                                         (unsigned)(N * kD * 4));
+                    }
+                    bulk_commit();
                 }
             }
-        }
-        if (P.auto_reset) {  // groups with an env to reset go on the list the aux launch walks
-            const unsigned rl = __ballot_sync(FULL_MASK, leader && need_reset);
-            if (rl != 0 && lane == 0) P.reset_list[atomicAdd(P.reset_count, 1u)] = env0;
-        }
-        {   // actions applied / envs stepped by this warp in this group
-            const unsigned act_envs = __ballot_sync(FULL_MASK, leader && env_active);
-            if (lane == 0) {
-                wstats[SWARM_STAT_AGENT_STEPS] += (unsigned long long)__popc(alive_mask);
-                wstats[SWARM_STAT_ENV_STEPS] += (unsigned long long)__popc(act_envs);
+
+            // ===================== rewards and flags (:120-172), pass 0 =====================
+            bool reached = false, collided = false, done_agent = false, any_col = false, time_limit = false;
+            bool all_reached = false, all_term = false, all_trunc = false, ep_over = false, need_reset = false;
+            bool env_active = false;
+            double reward = 0.0;
+            int sc_new = 0;
+            if (step_pass()) {
+                const bool obst_hit = od[0] <= c_thr_obst;
+                reached = alive && curr_d <= P.thr_goal;    // :124-127 (double compare)
+                collided = alive && (obst_hit || pair_hit);  // :128
+                if (alive) {
+                    const double progress = __dmul_rn(__dsub_rn((double)prev_d, (double)curr_d), P.k_p);  // :142
+                    double pen = 0.0;  // :210-224
+                    if (form_n > 0) {
+                        const double mean = form_n == N - 1 ? mean_markstein(form_sum, P.n_others, P.inv_n_others)
+                                                            : __ddiv_rn(form_sum, (double)form_n);
+                        pen = __dmul_rn(P.neg_k_f, mean);
+                    }
+                    reward = __dadd_rn(progress, pen);                  // :143
+                    if (reached) reward = __dadd_rn(reward, P.r_goal);  // :144-145
+                    if (collided) reward = __dadd_rn(reward, P.r_col);  // :146-147
+                }
+                done_agent = reached || collided;
+                any_col = (__ballot_sync(FULL_MASK, collided) & env_lanes) != 0;
+                const int n_cont = __popc(__ballot_sync(FULL_MASK, alive && !done_agent) & env_lanes);
+                env_active = n_alive_env > 0;
+                sc_new = env_active ? sc + 1 : sc;
+                time_limit = env_active && sc_new >= P.max_steps;
+                all_reached = n_cont == 0 && !any_col && !time_limit;
+                const bool episode_done = all_reached || any_col;
+                all_term = env_active ? episode_done : true;  // :94-95 when no agent is left
+                all_trunc = env_active ? (time_limit && !episode_done) : false;
+                ep_over = env_active && (all_term || all_trunc);
+                need_reset = P.auto_reset && (ep_over || !env_active);
+            }
+
+            if (step_pass()) {
+                const float rew32 = __double2float_rn(reward);
+                float x = rew32;  // deterministic per-env reward sum (segmented tree over the env's lanes)
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const float t = __shfl_down_sync(FULL_MASK, x, off);
+                    if (off < N && i + off < N) x = __fadd_rn(x, t);
+                }
+                if (lane_ok) {
+                    P.terminated[a] = (alive && done_agent) ? 1 : 0;                 // :150-151
+                    P.truncated[a] = (alive && time_limit && !done_agent) ? 1 : 0;   // :152
+                    const bool valid = alive && !done_agent && !time_limit && !any_col;  // :154
+                    const bool alive_next = ep_over ? false : valid;                     // :169-172
+                    P.reward[a] = rew32;
+                    if (P.reward64) P.reward64[a] = reward;
+                    P.reached[a] = reached ? 1 : 0;
+                    P.collision[a] = collided ? 1 : 0;
+                    if (!need_reset) {  // (a re-drawn env gets these from the reset launch that follows)
+                        P.dist[a] = curr_d;
+                        P.obs_valid[a] = valid ? 1 : 0;
+                        P.pos4[a] = make_float4(p.x, p.y, p.z, alive_next ? 1.0f : 0.0f);
+                        P.vel4[a] = make_float4(v.x, v.y, v.z, 0.0f);
+                        if (P.gs) {
+                            float* row = P.gs + (long long)env * P.R;
+                            __stcs(row + 3 * i + 0, p.x); __stcs(row + 3 * i + 1, p.y); __stcs(row + 3 * i + 2, p.z);
+                            __stcs(row + 3 * N + 3 * i + 0, v.x); __stcs(row + 3 * N + 3 * i + 1, v.y);
+                            __stcs(row + 3 * N + 3 * i + 2, v.z);
+                        }
+                    }
+                }
+                if (leader) {
+                    P.all_term[env] = all_term ? 1 : 0;
+                    P.all_trunc[env] = all_trunc ? 1 : 0;
+                    if (P.reset_mask) P.reset_mask[env] = need_reset ? 1 : 0;
+                    const float ret = __fadd_rn(reinterpret_cast<const float*>(ib + sc_off)[G + e_l], x);
+                    if (ep_over) {  // several env leaders per warp when G > 1: shared-memory atomics
+                        atomicAdd(wstats + SWARM_STAT_EPISODES, 1ull);
+                        atomicAdd(wstats + SWARM_STAT_LENGTH_SUM, (unsigned long long)sc_new);
+                        atomicAdd(reinterpret_cast<double*>(wstats + SWARM_STAT_RETURN_SUM), (double)ret);
+                        if (all_reached) atomicAdd(wstats + SWARM_STAT_SUCCESS, 1ull);
+                        if (any_col) atomicAdd(wstats + SWARM_STAT_COLLISION, 1ull);
+                        if (all_trunc) atomicAdd(wstats + SWARM_STAT_TIMEOUT, 1ull);
+                    }
+                    if (P.episode_return) P.episode_return[env] = ep_over ? ret : 0.0f;
+                    if (P.episode_length) P.episode_length[env] = ep_over ? sc_new : 0;
+                    if (!need_reset) {
+                        P.step_count[env] = sc_new;
+                        P.ep_return[env] = ep_over ? 0.0f : ret;
+                        if (P.gs) {
+                            float* row = P.gs + (long long)env * P.R + 6 * N;
+                            __stcs(row + 0, gx); __stcs(row + 1, gy); __stcs(row + 2, gz);
+                        }
+                    }
+                }
+                {   // actions applied / envs stepped by this warp in this group
+                    const unsigned act_envs = __ballot_sync(FULL_MASK, leader && env_active);
+                    if (lane == 0) {
+                        wstats[SWARM_STAT_AGENT_STEPS] += (unsigned long long)__popc(alive_mask);
+                        wstats[SWARM_STAT_ENV_STEPS] += (unsigned long long)__popc(act_envs);
+                    }
+                }
+                if (P.auto_reset) {  // groups with an env to reset go on the list the reset launch walks
+                    const unsigned rl = __ballot_sync(FULL_MASK, leader && need_reset);
+                    if (rl != 0 && lane == 0) P.reset_list[atomicAdd(P.reset_count, 1u)] = env0;
+                }
+            } else {
+                // =========== reset()'s obs / infos (:82-89) for the re-drawn envs; reward / flags stay ===========
+                if (lane_ok && ((reset_envs >> e_l) & 1u)) {
+                    P.dist[a] = curr_d;
+                    P.obs_valid[a] = 1;
+                    P.pos4[a] = make_float4(p.x, p.y, p.z, 1.0f);
+                    P.vel4[a] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (P.gs) {
+                        float* row = P.gs + (long long)env * P.R;
+                        __stcs(row + 3 * i + 0, p.x); __stcs(row + 3 * i + 1, p.y); __stcs(row + 3 * i + 2, p.z);
+                        __stcs(row + 3 * N + 3 * i + 0, 0.f); __stcs(row + 3 * N + 3 * i + 1, 0.f);
+                        __stcs(row + 3 * N + 3 * i + 2, 0.f);
+                        if (i == 0) { __stcs(row + 6 * N + 0, gx); __stcs(row + 6 * N + 1, gy); __stcs(row + 6 * N + 2, gz); }
+                    }
+                }
             }
         }
         it = it_next;
         buf ^= 1;
     }
     // the last warp to leave re-arms the queue for the next launch
-    if (lane == 0 && atomicAdd(P.work_counter + 1, 1u) == (unsigned)(gridDim.x * kRotWarps) - 1u) {
-        P.work_counter[0] = 0u;
-        P.work_counter[1] = 0u;
+    if (lane == 0 && atomicAdd(queue + 1, 1u) == (unsigned)(gridDim.x * kRotWarps) - 1u) {
+        queue[0] = 0u;
+        queue[1] = 0u;
+        if (MODE == kRotReset) *P.reset_count_other = 0u;  // the next step's list counter
     }
 
     if (lane == 0) bulk_wait0();  // the last obs tile must have left shared memory before the CTA retires
     __syncwarp();
-    if (P.stats && lane < SWARM_STATS_WORDS) {
+    if (MODE == kRotStep && P.stats && lane < SWARM_STATS_WORDS) {
         const unsigned long long w = wstats[lane];
         if (lane == SWARM_STAT_RETURN_SUM) {
             const double dv = __longlong_as_double((long long)w);
@@ -676,19 +808,20 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
 // ------------------------------------------------------------------------------------------
 typedef void (*RotKernel)(const DevParams);
 
-template <int NT>
+template <int NT, int MODE>
 static RotKernel pick_rot_m(const DevParams& p) {
     const bool dr = p.dr_enabled != 0;
-    if (p.M == 8) return dr ? swarm_step_rot_kernel<NT, 8, true> : swarm_step_rot_kernel<NT, 8, false>;
-    if (p.M == 4) return dr ? swarm_step_rot_kernel<NT, 4, true> : swarm_step_rot_kernel<NT, 4, false>;
-    return dr ? swarm_step_rot_kernel<NT, 0, true> : swarm_step_rot_kernel<NT, 0, false>;
+    if (p.M == 8) return dr ? swarm_step_rot_kernel<NT, 8, true, MODE> : swarm_step_rot_kernel<NT, 8, false, MODE>;
+    if (p.M == 4) return dr ? swarm_step_rot_kernel<NT, 4, true, MODE> : swarm_step_rot_kernel<NT, 4, false, MODE>;
+    return dr ? swarm_step_rot_kernel<NT, 0, true, MODE> : swarm_step_rot_kernel<NT, 0, false, MODE>;
 }
 
 static RotKernel pick_rot(const DevParams& p) {
+    const bool reset = p.mode == kModeAutoReset;
     switch (p.N) {
-        case 8: return pick_rot_m<8>(p);
-        case 16: return pick_rot_m<16>(p);
-        case 32: return pick_rot_m<32>(p);
+        case 8: return reset ? pick_rot_m<8, kRotReset>(p) : pick_rot_m<8, kRotStep>(p);
+        case 16: return reset ? pick_rot_m<16, kRotReset>(p) : pick_rot_m<16, kRotStep>(p);
+        case 32: return reset ? pick_rot_m<32, kRotReset>(p) : pick_rot_m<32, kRotStep>(p);
     }
     return nullptr;
 }
