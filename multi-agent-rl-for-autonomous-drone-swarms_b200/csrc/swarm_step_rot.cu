@@ -264,16 +264,21 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
     };
     // dynamic group queue: lane 0 draws the next group index while the current group is processed, so
     // every warp stays busy until the queue is empty (no static-stride tail)
-    int it = 0;
-    if (lane == 0) it = (int)atomicAdd(queue, 1u);
-    it = __shfl_sync(FULL_MASK, it, 0);
+    // (the first item of every warp is static, so the launch does not start with thousands of atomics on
+    //  one address; the reset launch has ~1-2 items per warp and keeps a static stride throughout)
+    const int warps_total = gridDim.x * kRotWarps;
+    int it = blockIdx.x * kRotWarps + warp;
     if (it < n_iter) issue(it, 0);
     unsigned phase = 0;  // bit b: parity the next wait on mbarrier b uses
 
     int buf = 0;
     while (it < n_iter) {
         int it_next = 0;
-        if (lane == 0) it_next = (int)atomicAdd(queue, 1u);
+        if (MODE == kRotStep) {
+            if (lane == 0) it_next = warps_total + (int)atomicAdd(queue, 1u);
+        } else {
+            it_next = it + warps_total;
+        }
         const int env0 = MODE == kRotStep ? P.env_begin + it * G : P.reset_list[it];
         const int n_env = G == 1 ? 1 : min(G, env_end - env0);
         const bool lane_ok = G == 1 ? true : e_l < n_env;
@@ -393,7 +398,7 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                         }
                         if (e_l == el) ekey = rb.z;  // (the dynamics constants are not needed to observe)
                     }
-#pragma unroll 1
+#pragma unroll 4
                     for (int k = lane; k < P.n_draws; k += 32) {
                         unsigned long long oh, ol;
                         pcg_jump(P.jump[k + 1], sh, sl, ih, il, oh, ol);
@@ -784,10 +789,13 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
         buf ^= 1;
     }
     // the last warp to leave re-arms the queue for the next launch
-    if (lane == 0 && atomicAdd(queue + 1, 1u) == (unsigned)(gridDim.x * kRotWarps) - 1u) {
-        queue[0] = 0u;
-        queue[1] = 0u;
-        if (MODE == kRotReset) *P.reset_count_other = 0u;  // the next step's list counter
+    if (MODE == kRotStep) {
+        if (lane == 0 && atomicAdd(queue + 1, 1u) == (unsigned)warps_total - 1u) {
+            queue[0] = 0u;
+            queue[1] = 0u;
+        }
+    } else if (blockIdx.x == 0 && warp == 0 && lane == 0) {
+        *P.reset_count_other = 0u;  // the next step's list counter (nobody reads it during this launch)
     }
 
     if (lane == 0) bulk_wait0();  // the last obs tile must have left shared memory before the CTA retires
