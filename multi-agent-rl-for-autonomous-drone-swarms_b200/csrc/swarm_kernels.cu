@@ -812,11 +812,11 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
             if (alive) {
                 ax = clipf(ax, -1.0f, 1.0f); ay = clipf(ay, -1.0f, 1.0f); az = clipf(az, -1.0f, 1.0f);
                 if (DR) {  // thrust noise: a <- a * (1 + sigma z), one normal per axis
-                    const uint4 r = philox4x32_10(genv, ekey, (unsigned)sc, (unsigned)i | (DR_STREAM_THRUST << 16),
-                                                  P.dr_key0, P.dr_key1);
-                    ax = __fmul_rn(ax, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, P.dr_qtable[r.x >> 20])));
-                    ay = __fmul_rn(ay, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, P.dr_qtable[r.y >> 20])));
-                    az = __fmul_rn(az, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, P.dr_qtable[r.z >> 20])));
+                    const uint4 r = philox4x32_10(genv, ekey, (unsigned)sc, (unsigned)i | (DR_STREAM_A << 16), P.dr_key0,
+                                                  P.dr_key1);
+                    ax = __fmul_rn(ax, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, P.dr_qtable[dr_field(r, 0)])));
+                    ay = __fmul_rn(ay, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, P.dr_qtable[dr_field(r, 1)])));
+                    az = __fmul_rn(az, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, P.dr_qtable[dr_field(r, 2)])));
                 }
                 v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(ax, c_amax), c_dt));
                 v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(ay, c_amax), c_dt));
@@ -1095,28 +1095,20 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
         // ============================ obs row -> staging tile ============================
         if ((out_lanes >> lane) & 1u) {
             float* row = region + lane * D;
-            // DR sensor noise: normal n of this row comes from Philox call n / 4 (n = 0-2 position,
-            // 3-5 velocity, 6 + q distance of sensed obstacle q), keyed by the observed state's step_count
-            uint4 rs0 = make_uint4(0, 0, 0, 0), rs1 = rs0, rs2 = rs0, rs3 = rs0;
+            // DR sensor noise of the observed state: blocks of counter (its step_count - 1), see swarm_device.cuh
+            uint4 rA = make_uint4(0, 0, 0, 0), rB = rA;
             if (DR) {
-                const unsigned c3 = (unsigned)i | (DR_STREAM_SENSOR << 16);
-                rs0 = philox4x32_10(genv, ekey, (unsigned)sc_obs, c3, P.dr_key0, P.dr_key1);
-                rs1 = philox4x32_10(genv, ekey, (unsigned)sc_obs, c3 + (1u << 16), P.dr_key0, P.dr_key1);
-                if (S > 2) rs2 = philox4x32_10(genv, ekey, (unsigned)sc_obs, c3 + (2u << 16), P.dr_key0, P.dr_key1);
-                if (S > 6) rs3 = philox4x32_10(genv, ekey, (unsigned)sc_obs, c3 + (3u << 16), P.dr_key0, P.dr_key1);
+                rA = philox4x32_10(genv, ekey, (unsigned)(sc_obs - 1), (unsigned)i | (DR_STREAM_A << 16), P.dr_key0, P.dr_key1);
+                rB = philox4x32_10(genv, ekey, (unsigned)(sc_obs - 1), (unsigned)i | (DR_STREAM_B << 16), P.dr_key0, P.dr_key1);
             }
-            auto noisy = [&](float x, float sigma, unsigned bits) {
-                return DR ? __fadd_rn(x, __fmul_rn(sigma, P.dr_qtable[bits >> 20])) : x;
+            auto noisy = [&](float x, float sigma, unsigned idx) {
+                return DR ? __fadd_rn(x, __fmul_rn(sigma, P.dr_qtable[idx])) : x;
             };
-            auto obst_bits = [&](int q) {  // normal 6 + q
-                const int n = 6 + q;
-                const uint4& r = n < 8 ? rs1 : (n < 12 ? rs2 : rs3);
-                return u4_get(r, n & 3);
-            };
-            row[0] = noisy(p.x, P.dr_std_pos, rs0.x); row[1] = noisy(p.y, P.dr_std_pos, rs0.y);
-            row[2] = noisy(p.z, P.dr_std_pos, rs0.z);
-            row[3] = noisy(v.x, P.dr_std_vel, rs0.w); row[4] = noisy(v.y, P.dr_std_vel, rs1.x);
-            row[5] = noisy(v.z, P.dr_std_vel, rs1.y);
+            auto obst_bits = [&](int q) { return dr_field(rB, q); };
+            row[0] = noisy(p.x, P.dr_std_pos, dr_field(rA, 3)); row[1] = noisy(p.y, P.dr_std_pos, dr_field(rA, 4));
+            row[2] = noisy(p.z, P.dr_std_pos, dr_field(rA, 5));
+            row[3] = noisy(v.x, P.dr_std_vel, dr_field(rA, 6)); row[4] = noisy(v.y, P.dr_std_vel, dr_field(rA, 7));
+            row[5] = noisy(v.z, P.dr_std_vel, dr_field(rA, 8));
             row[6] = __fsub_rn(gx, p.x); row[7] = __fsub_rn(gy, p.y); row[8] = __fsub_rn(gz, p.z);
             int off = 9;
             const bool all_slots = (KIND != SWARM_KIND_SWARM || n_others >= K) && M >= S;  // warp-uniform

@@ -299,6 +299,7 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
         unsigned ekey = 0u;
         const unsigned genv = DR ? (unsigned)(P.env_index_base + env) : 0u;
         bool alive = false;
+        uint4 rA = make_uint4(0, 0, 0, 0);  // DR: this step's stream-A block (thrust + observation noise)
         unsigned reset_envs = 0u;  // reset launch: bit el = env el of the group is re-drawn
         if (MODE == kRotReset) reset_envs = __ballot_sync(FULL_MASK, lane < n_env && P.env_mask[env0 + lane] != 0);
 
@@ -337,11 +338,10 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                 if (alive) {
                     ax = clipf(ax, -1.0f, 1.0f); ay = clipf(ay, -1.0f, 1.0f); az = clipf(az, -1.0f, 1.0f);
                     if (DR) {  // thrust noise: a <- a * (1 + sigma z), one normal per axis
-                        const uint4 r = philox4x32_10(genv, ekey, (unsigned)sc, (unsigned)i | (DR_STREAM_THRUST << 16),
-                                                      P.dr_key0, P.dr_key1);
-                        ax = __fmul_rn(ax, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, P.dr_qtable[r.x >> 20])));
-                        ay = __fmul_rn(ay, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, P.dr_qtable[r.y >> 20])));
-                        az = __fmul_rn(az, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, P.dr_qtable[r.z >> 20])));
+                        rA = philox4x32_10(genv, ekey, (unsigned)sc, (unsigned)i | (DR_STREAM_A << 16), P.dr_key0, P.dr_key1);
+                        ax = __fmul_rn(ax, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, P.dr_qtable[dr_field(rA, 0)])));
+                        ay = __fmul_rn(ay, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, P.dr_qtable[dr_field(rA, 1)])));
+                        az = __fmul_rn(az, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, P.dr_qtable[dr_field(rA, 2)])));
                     }
                     v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(ax, c_amax), c_dt));
                     v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(ay, c_amax), c_dt));
@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                     v = make_float4(0.f, 0.f, 0.f, 0.f);
                     const float4 g4 = tgoal[e_l];
                     gx = g4.x; gy = g4.y; gz = g4.z;
-                    sc = -1;  // the observed state has step_count 0 (DR sensor stream is keyed by sc + 1)
+                    sc = -1;  // the observed state has step_count 0: its sensor noise is keyed by 0 - 1
                 }
                 alive = lane_ok;  // (only the re-drawn envs' results are used; every drone of theirs is active)
                 __syncwarp();     // the drawn positions have been read before the table is rewritten
@@ -624,32 +624,31 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                     float* row = srow;
                     const float4 t0 = tab2[2 * e_base + nj[0]], t1 = tab2[2 * e_base + nj[1]], t2 = tab2[2 * e_base + nj[2]];
                     const float4 b0 = tobs[om[0]], b1 = tobs[om[1]], b2 = tobs[om[2]], b3 = tobs[om[3]];
-                    uint4 rs0 = make_uint4(0, 0, 0, 0), rs1 = rs0, rs2 = rs0;
-                    if (DR) {  // sensor noise: normal n of the row comes from Philox call n / 4 (see swarm_kernels.cu)
-                        const unsigned c3 = (unsigned)i | (DR_STREAM_SENSOR << 16);
-                        rs0 = philox4x32_10(genv, ekey, (unsigned)(sc + 1), c3, P.dr_key0, P.dr_key1);
-                        rs1 = philox4x32_10(genv, ekey, (unsigned)(sc + 1), c3 + (1u << 16), P.dr_key0, P.dr_key1);
-                        rs2 = philox4x32_10(genv, ekey, (unsigned)(sc + 1), c3 + (2u << 16), P.dr_key0, P.dr_key1);
+                    uint4 rB = make_uint4(0, 0, 0, 0);
+                    if (DR) {  // sensor noise of the observed state (step_count sc + 1): blocks of counter sc
+                        if (!step_pass() || !alive)  // (an active drone drew this block for its thrust already)
+                            rA = philox4x32_10(genv, ekey, (unsigned)sc, (unsigned)i | (DR_STREAM_A << 16), P.dr_key0, P.dr_key1);
+                        rB = philox4x32_10(genv, ekey, (unsigned)sc, (unsigned)i | (DR_STREAM_B << 16), P.dr_key0, P.dr_key1);
                     }
-                    auto noisy = [&](float x, float sigma, unsigned bits) {
-                        return DR ? __fadd_rn(x, __fmul_rn(sigma, P.dr_qtable[bits >> 20])) : x;
+                    auto noisy = [&](float x, float sigma, unsigned idx) {
+                        return DR ? __fadd_rn(x, __fmul_rn(sigma, P.dr_qtable[idx])) : x;
                     };
-                    row[0] = noisy(p.x, P.dr_std_pos, rs0.x); row[1] = noisy(p.y, P.dr_std_pos, rs0.y);
-                    row[2] = noisy(p.z, P.dr_std_pos, rs0.z);
-                    row[3] = noisy(v.x, P.dr_std_vel, rs0.w); row[4] = noisy(v.y, P.dr_std_vel, rs1.x);
-                    row[5] = noisy(v.z, P.dr_std_vel, rs1.y);
+                    row[0] = noisy(p.x, P.dr_std_pos, dr_field(rA, 3)); row[1] = noisy(p.y, P.dr_std_pos, dr_field(rA, 4));
+                    row[2] = noisy(p.z, P.dr_std_pos, dr_field(rA, 5));
+                    row[3] = noisy(v.x, P.dr_std_vel, dr_field(rA, 6)); row[4] = noisy(v.y, P.dr_std_vel, dr_field(rA, 7));
+                    row[5] = noisy(v.z, P.dr_std_vel, dr_field(rA, 8));
                     row[6] = __fsub_rn(gx, p.x); row[7] = __fsub_rn(gy, p.y); row[8] = __fsub_rn(gz, p.z);
                     row[9] = __fsub_rn(t0.x, p.x); row[10] = __fsub_rn(t0.y, p.y); row[11] = __fsub_rn(t0.z, p.z); row[12] = nd[0];
                     row[13] = __fsub_rn(t1.x, p.x); row[14] = __fsub_rn(t1.y, p.y); row[15] = __fsub_rn(t1.z, p.z); row[16] = nd[1];
                     row[17] = __fsub_rn(t2.x, p.x); row[18] = __fsub_rn(t2.y, p.y); row[19] = __fsub_rn(t2.z, p.z); row[20] = nd[2];
                     row[21] = __fsub_rn(b0.x, p.x); row[22] = __fsub_rn(b0.y, p.y); row[23] = __fsub_rn(b0.z, p.z);
-                    row[24] = noisy(od[0], P.dr_std_obst, rs1.z);
+                    row[24] = noisy(od[0], P.dr_std_obst, dr_field(rB, 0));
                     row[25] = __fsub_rn(b1.x, p.x); row[26] = __fsub_rn(b1.y, p.y); row[27] = __fsub_rn(b1.z, p.z);
-                    row[28] = noisy(od[1], P.dr_std_obst, rs1.w);
+                    row[28] = noisy(od[1], P.dr_std_obst, dr_field(rB, 1));
                     row[29] = __fsub_rn(b2.x, p.x); row[30] = __fsub_rn(b2.y, p.y); row[31] = __fsub_rn(b2.z, p.z);
-                    row[32] = noisy(od[2], P.dr_std_obst, rs2.x);
+                    row[32] = noisy(od[2], P.dr_std_obst, dr_field(rB, 2));
                     row[33] = __fsub_rn(b3.x, p.x); row[34] = __fsub_rn(b3.y, p.y); row[35] = __fsub_rn(b3.z, p.z);
-                    row[36] = noisy(od[3], P.dr_std_obst, rs2.y);
+                    row[36] = noisy(od[3], P.dr_std_obst, dr_field(rB, 3));
                 }
                 fence_async_smem();  // generic-proxy tile writes -> visible to the bulk-copy engine
                 __syncwarp();

@@ -256,7 +256,13 @@ typedef struct DynConst {
     float std_thrust, std_pos, std_vel, std_obst;
 } DynConst;
 
-static float dr_normal(uint32_t bits) { return qtable()[bits >> 20]; }
+/* 12-bit field f of a 128-bit Philox block (word 0 = bits 0-31) -> standard normal from the quantile table */
+static float dr_normal(const uint32_t r[4], int f) {
+    int b = 12 * f, k = b >> 5, sh = b & 31;
+    uint32_t v = r[k] >> sh;
+    if (sh > 20) v |= r[k + 1] << (32 - sh);
+    return qtable()[v & 0xFFFu];
+}
 
 /* ------------------------------------------------------------------------- */
 /* np.linalg.norm restatements (T1, T2)                                       */
@@ -396,23 +402,21 @@ static void build_obs(const OracleConfig *c, const DynConst *kc, int step_obs, c
     }
     nearest_obstacle_features(c, p, obst, out + off);
     if (kc->dr) {
-        /* DR sensor noise: normal n comes from Philox call n / 4 of stream (genv, ekey, step_count of the
-         * observed state, drone | (1 + n / 4) << 16); n = 0-2 position, 3-5 velocity, 6 + q obstacle q's distance */
-        uint32_t r[16];
-        for (int call = 0; call < 4; ++call) {
-            uint32_t ctr[4] = {kc->genv, kc->ekey, (uint32_t)step_obs, (uint32_t)index | ((uint32_t)(1 + call) << 16)};
-            philox4x32_10(ctr, kc->k0, kc->k1);
-            memcpy(r + 4 * call, ctr, sizeof(ctr));
-        }
+        /* DR sensor noise of the observed state: Philox blocks of counter (genv, ekey, step_count - 1,
+         * drone | stream << 16); stream A fields 3-5 position, 6-8 velocity; stream B field q = obstacle q */
+        uint32_t ra[4] = {kc->genv, kc->ekey, (uint32_t)(step_obs - 1), (uint32_t)index};
+        uint32_t rb[4] = {kc->genv, kc->ekey, (uint32_t)(step_obs - 1), (uint32_t)index | (1u << 16)};
+        philox4x32_10(ra, kc->k0, kc->k1);
+        philox4x32_10(rb, kc->k0, kc->k1);
         for (int k = 0; k < 3; ++k) {
-            volatile float np_ = kc->std_pos * dr_normal(r[k]);
+            volatile float np_ = kc->std_pos * dr_normal(ra, 3 + k);
             out[k] = out[k] + np_;
-            volatile float nv = kc->std_vel * dr_normal(r[3 + k]);
+            volatile float nv = kc->std_vel * dr_normal(ra, 6 + k);
             out[3 + k] = out[3 + k] + nv;
         }
         int filled = c->sensed_obstacles < c->num_obstacles ? c->sensed_obstacles : c->num_obstacles;
         for (int q = 0; q < filled; ++q) {
-            volatile float nd = kc->std_obst * dr_normal(r[6 + q]);
+            volatile float nd = kc->std_obst * dr_normal(rb, q);
             out[off + 4 * q + 3] = out[off + 4 * q + 3] + nd;
         }
     }
@@ -460,7 +464,7 @@ static void integrate(const OracleConfig *c, const DynConst *kc, int step_before
     for (int k = 0; k < 3; ++k) {
         float a = clipf(action[k], -1.0f, 1.0f);
         if (kc->dr) {
-            volatile float sz = kc->std_thrust * dr_normal(ctr[k]);
+            volatile float sz = kc->std_thrust * dr_normal(ctr, k);
             volatile float one = 1.0f + sz;
             a = a * one;
         }
