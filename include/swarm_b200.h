@@ -200,8 +200,9 @@ int swarm_step_host(SwarmHandle *h, const SwarmBuffers *bufs, const float *actio
 /* Number of kernel launches this handle has enqueued so far (bench bookkeeping). */
 int64_t swarm_launch_count(const SwarmHandle *h);
 
-/* The 4096-entry standard-normal quantile table the DR noise is drawn from (host, for tests). */
-int swarm_dr_quantile_table(float *out4096);
+/* The 256-entry half-normal quantile table q[m] = Phi^-1(0.5 + (m + 0.5) / 512) the DR noise is drawn from:
+ * a 9-bit field (sign bit 8, m = bits 0-7) of a Philox block maps to +-q[m] (host, for tests). */
+int swarm_dr_quantile_table(float *out256);
 
 #ifdef __cplusplus
 }

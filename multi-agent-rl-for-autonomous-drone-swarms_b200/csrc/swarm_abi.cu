@@ -49,7 +49,7 @@ struct SwarmHandle {
     unsigned* reset_count_dev;  // [(kHostChunks + 1) * 2] per launch slot, two parities
     int* reset_list_dev;        // [number of groups]
     unsigned* work_counter_dev; // [(kHostChunks + 1) * 2] group queue of the rotation-pass step kernel, per launch slot
-    float* qtable_dev;          // [4096] (domain randomisation only)
+    float* qtable_dev;          // [256] (domain randomisation only)
     unsigned step_parity[kHostChunks + 1];
     int64_t launches;
     // host-buffer path
@@ -109,8 +109,8 @@ float f32_floor_of(double x) {
     return f;
 }
 
-// Standard-normal quantiles z_k = Phi^-1((k + 0.5) / 4096): the DR noise is a 12-bit table lookup, so
-// the CUDA path and the C oracle produce identical noise without depending on libm / MUFU rounding.
+// Half-normal quantiles q[m] = Phi^-1(0.5 + (m + 0.5) / 512): the DR noise is a 9-bit table lookup (sign + m), so the
+// CUDA path and the C oracle produce identical noise without depending on libm / MUFU rounding.
 double inv_norm_cdf(double p) {  // Acklam's rational approximation
     static const double a[] = {-3.969683028665376e+01, 2.209460984245205e+02, -2.759285104469687e+02,
                                1.383577518672690e+02, -3.066479806614716e+01, 2.506628277459239e+00};
@@ -137,7 +137,7 @@ double inv_norm_cdf(double p) {  // Acklam's rational approximation
 }
 
 void build_qtable(float* out) {
-    for (int k = 0; k < 4096; ++k) out[k] = (float)inv_norm_cdf(((double)k + 0.5) / 4096.0);
+    for (int k = 0; k < 256; ++k) out[k] = (float)inv_norm_cdf(0.5 + ((double)k + 0.5) / 512.0);
 }
 
 void build_jump_table(int n_draws, std::vector<JumpEntry>& out) {
@@ -395,10 +395,10 @@ int swarm_create(const SwarmConfig* cfg, SwarmHandle** out) {
     if (e == cudaSuccess) e = cudaMalloc(&h->work_counter_dev, sizeof(unsigned) * 4 * (kHostChunks + 1));
     if (e == cudaSuccess) e = cudaMemset(h->work_counter_dev, 0, sizeof(unsigned) * 4 * (kHostChunks + 1));
     if (e == cudaSuccess && cfg->dr_enabled) {
-        std::vector<float> qt(4096);
+        std::vector<float> qt(256);
         build_qtable(qt.data());
-        e = cudaMalloc(&h->qtable_dev, 4096 * sizeof(float));
-        if (e == cudaSuccess) e = cudaMemcpy(h->qtable_dev, qt.data(), 4096 * sizeof(float), cudaMemcpyHostToDevice);
+        e = cudaMalloc(&h->qtable_dev, 256 * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpy(h->qtable_dev, qt.data(), 256 * sizeof(float), cudaMemcpyHostToDevice);
     }
     if (e != cudaSuccess) {
         if (h->jump_dev) cudaFree(h->jump_dev);
@@ -552,9 +552,9 @@ int swarm_step_host(SwarmHandle* h, const SwarmBuffers* bufs, const float* actio
 
 int64_t swarm_launch_count(const SwarmHandle* h) { return h ? h->launches : 0; }
 
-int swarm_dr_quantile_table(float* out4096) {
-    if (!out4096) return fail(SWARM_E_NULL, "out is NULL");
-    build_qtable(out4096);
+int swarm_dr_quantile_table(float* out256) {
+    if (!out256) return fail(SWARM_E_NULL, "out is NULL");
+    build_qtable(out256);
     return SWARM_OK;
 }
 

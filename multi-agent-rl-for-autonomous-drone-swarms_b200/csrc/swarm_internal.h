@@ -73,7 +73,7 @@ struct DevParams {
     double dr_max_accel, dr_max_speed, dr_dt, dr_world, dr_r_c, dr_r_o;
     float dr_std_thrust, dr_std_pos, dr_std_vel, dr_std_obst;
     float4* dr_params;            // [E][2] float4
-    const float* dr_qtable;       // [4096] standard-normal quantiles
+    const float* dr_qtable;       // [256] half-normal quantiles
 };
 
 // kernel selection (swarm_kernels.cu)

@@ -814,9 +814,9 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                 if (DR) {  // thrust noise: a <- a * (1 + sigma z), one normal per axis
                     const uint4 r = philox4x32_10(genv, ekey, (unsigned)sc, (unsigned)i | (DR_STREAM_A << 16), P.dr_key0,
                                                   P.dr_key1);
-                    ax = __fmul_rn(ax, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, P.dr_qtable[dr_field(r, 0)])));
-                    ay = __fmul_rn(ay, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, P.dr_qtable[dr_field(r, 1)])));
-                    az = __fmul_rn(az, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, P.dr_qtable[dr_field(r, 2)])));
+                    ax = __fmul_rn(ax, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, dr_normal(P.dr_qtable, dr_field(r, 0)))));
+                    ay = __fmul_rn(ay, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, dr_normal(P.dr_qtable, dr_field(r, 1)))));
+                    az = __fmul_rn(az, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, dr_normal(P.dr_qtable, dr_field(r, 2)))));
                 }
                 v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(ax, c_amax), c_dt));
                 v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(ay, c_amax), c_dt));
@@ -1099,12 +1099,12 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
             uint4 rA = make_uint4(0, 0, 0, 0), rB = rA;
             if (DR) {
                 rA = philox4x32_10(genv, ekey, (unsigned)(sc_obs - 1), (unsigned)i | (DR_STREAM_A << 16), P.dr_key0, P.dr_key1);
-                rB = philox4x32_10(genv, ekey, (unsigned)(sc_obs - 1), (unsigned)i | (DR_STREAM_B << 16), P.dr_key0, P.dr_key1);
+                if (S > 4) rB = philox4x32_10(genv, ekey, (unsigned)(sc_obs - 1), (unsigned)i | (DR_STREAM_B << 16), P.dr_key0, P.dr_key1);
             }
             auto noisy = [&](float x, float sigma, unsigned idx) {
-                return DR ? __fadd_rn(x, __fmul_rn(sigma, P.dr_qtable[idx])) : x;
+                return DR ? __fadd_rn(x, __fmul_rn(sigma, dr_normal(P.dr_qtable, idx))) : x;
             };
-            auto obst_bits = [&](int q) { return dr_field(rB, q); };
+            auto obst_bits = [&](int q) { return q < 4 ? dr_field(rA, 9 + q) : dr_field(rB, q - 4); };
             row[0] = noisy(p.x, P.dr_std_pos, dr_field(rA, 3)); row[1] = noisy(p.y, P.dr_std_pos, dr_field(rA, 4));
             row[2] = noisy(p.z, P.dr_std_pos, dr_field(rA, 5));
             row[3] = noisy(v.x, P.dr_std_vel, dr_field(rA, 6)); row[4] = noisy(v.y, P.dr_std_vel, dr_field(rA, 7));

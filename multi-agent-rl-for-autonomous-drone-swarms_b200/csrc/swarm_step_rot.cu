@@ -197,6 +197,14 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
     unsigned long long* wstats =
         reinterpret_cast<unsigned long long*>(smem_raw + (size_t)kRotWarps * per_warp) + warp * SWARM_STATS_WORDS;
     if (lane < SWARM_STATS_WORDS) wstats[lane] = 0ull;
+    // DR: the 256-entry half-normal quantile table lives in shared memory (13 lookups per agent-step)
+    const float* qtab = reinterpret_cast<const float*>(smem_raw + (size_t)kRotWarps * per_warp +
+                                                       (size_t)kRotWarps * SWARM_STATS_WORDS * sizeof(unsigned long long));
+    if (DR) {
+        float* qw = const_cast<float*>(qtab);
+        for (int k = threadIdx.x; k < 256; k += kRotWarps * 32) qw[k] = P.dr_qtable[k];
+        __syncthreads();
+    }
 
     const int e_l = lane / N;
     const int i = lane - e_l * N;
@@ -339,9 +347,9 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                     ax = clipf(ax, -1.0f, 1.0f); ay = clipf(ay, -1.0f, 1.0f); az = clipf(az, -1.0f, 1.0f);
                     if (DR) {  // thrust noise: a <- a * (1 + sigma z), one normal per axis
                         rA = philox4x32_10(genv, ekey, (unsigned)sc, (unsigned)i | (DR_STREAM_A << 16), P.dr_key0, P.dr_key1);
-                        ax = __fmul_rn(ax, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, P.dr_qtable[dr_field(rA, 0)])));
-                        ay = __fmul_rn(ay, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, P.dr_qtable[dr_field(rA, 1)])));
-                        az = __fmul_rn(az, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, P.dr_qtable[dr_field(rA, 2)])));
+                        ax = __fmul_rn(ax, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, dr_normal(qtab, dr_field(rA, 0)))));
+                        ay = __fmul_rn(ay, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, dr_normal(qtab, dr_field(rA, 1)))));
+                        az = __fmul_rn(az, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, dr_normal(qtab, dr_field(rA, 2)))));
                     }
                     v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(ax, c_amax), c_dt));
                     v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(ay, c_amax), c_dt));
@@ -624,14 +632,12 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                     float* row = srow;
                     const float4 t0 = tab2[2 * e_base + nj[0]], t1 = tab2[2 * e_base + nj[1]], t2 = tab2[2 * e_base + nj[2]];
                     const float4 b0 = tobs[om[0]], b1 = tobs[om[1]], b2 = tobs[om[2]], b3 = tobs[om[3]];
-                    uint4 rB = make_uint4(0, 0, 0, 0);
-                    if (DR) {  // sensor noise of the observed state (step_count sc + 1): blocks of counter sc
+                    if (DR) {  // sensor noise of the observed state (step_count sc + 1): the block of counter sc
                         if (!step_pass() || !alive)  // (an active drone drew this block for its thrust already)
                             rA = philox4x32_10(genv, ekey, (unsigned)sc, (unsigned)i | (DR_STREAM_A << 16), P.dr_key0, P.dr_key1);
-                        rB = philox4x32_10(genv, ekey, (unsigned)sc, (unsigned)i | (DR_STREAM_B << 16), P.dr_key0, P.dr_key1);
                     }
                     auto noisy = [&](float x, float sigma, unsigned idx) {
-                        return DR ? __fadd_rn(x, __fmul_rn(sigma, P.dr_qtable[idx])) : x;
+                        return DR ? __fadd_rn(x, __fmul_rn(sigma, dr_normal(qtab, idx))) : x;
                     };
                     row[0] = noisy(p.x, P.dr_std_pos, dr_field(rA, 3)); row[1] = noisy(p.y, P.dr_std_pos, dr_field(rA, 4));
                     row[2] = noisy(p.z, P.dr_std_pos, dr_field(rA, 5));
@@ -642,13 +648,13 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                     row[13] = __fsub_rn(t1.x, p.x); row[14] = __fsub_rn(t1.y, p.y); row[15] = __fsub_rn(t1.z, p.z); row[16] = nd[1];
                     row[17] = __fsub_rn(t2.x, p.x); row[18] = __fsub_rn(t2.y, p.y); row[19] = __fsub_rn(t2.z, p.z); row[20] = nd[2];
                     row[21] = __fsub_rn(b0.x, p.x); row[22] = __fsub_rn(b0.y, p.y); row[23] = __fsub_rn(b0.z, p.z);
-                    row[24] = noisy(od[0], P.dr_std_obst, dr_field(rB, 0));
+                    row[24] = noisy(od[0], P.dr_std_obst, dr_field(rA, 9));
                     row[25] = __fsub_rn(b1.x, p.x); row[26] = __fsub_rn(b1.y, p.y); row[27] = __fsub_rn(b1.z, p.z);
-                    row[28] = noisy(od[1], P.dr_std_obst, dr_field(rB, 1));
+                    row[28] = noisy(od[1], P.dr_std_obst, dr_field(rA, 10));
                     row[29] = __fsub_rn(b2.x, p.x); row[30] = __fsub_rn(b2.y, p.y); row[31] = __fsub_rn(b2.z, p.z);
-                    row[32] = noisy(od[2], P.dr_std_obst, dr_field(rB, 2));
+                    row[32] = noisy(od[2], P.dr_std_obst, dr_field(rA, 11));
                     row[33] = __fsub_rn(b3.x, p.x); row[34] = __fsub_rn(b3.y, p.y); row[35] = __fsub_rn(b3.z, p.z);
-                    row[36] = noisy(od[3], P.dr_std_obst, dr_field(rB, 3));
+                    row[36] = noisy(od[3], P.dr_std_obst, dr_field(rA, 12));
                 }
                 fence_async_smem();  // generic-proxy tile writes -> visible to the bulk-copy engine
                 __syncwarp();
@@ -835,7 +841,7 @@ static RotKernel pick_rot(const DevParams& p) {
 
 size_t rot_smem_bytes(const DevParams& p) {
     return (size_t)rot_warps(p.N) * rot_smem_per_warp(32 / p.N, p.M, p.dr_enabled != 0) +
-           (size_t)rot_warps(p.N) * SWARM_STATS_WORDS * sizeof(unsigned long long);
+           (size_t)rot_warps(p.N) * SWARM_STATS_WORDS * sizeof(unsigned long long) + (p.dr_enabled ? 1024 : 0);
 }
 
 cudaError_t launch_rot_kernel(const DevParams& p, int grid, cudaStream_t stream) {

@@ -234,19 +234,16 @@ static double inv_norm_cdf(double p) { /* Acklam's rational approximation */
            (((((b[0] * r + b[1]) * r + b[2]) * r + b[3]) * r + b[4]) * r + 1.0);
 }
 
-static float g_qtable[4096];
-static int g_qtable_ready = 0;
-static pthread_mutex_t g_qtable_lock = PTHREAD_MUTEX_INITIALIZER;
+static float g_qtable[256];
+static pthread_once_t g_qtable_once = PTHREAD_ONCE_INIT;
+static void qtable_init(void) {
+    for (int k = 0; k < 256; ++k) g_qtable[k] = (float)inv_norm_cdf(0.5 + ((double)k + 0.5) / 512.0);
+}
 static const float *qtable(void) {
-    pthread_mutex_lock(&g_qtable_lock);
-    if (!g_qtable_ready) {
-        for (int k = 0; k < 4096; ++k) g_qtable[k] = (float)inv_norm_cdf(((double)k + 0.5) / 4096.0);
-        g_qtable_ready = 1;
-    }
-    pthread_mutex_unlock(&g_qtable_lock);
+    pthread_once(&g_qtable_once, qtable_init);
     return g_qtable;
 }
-void oracle_dr_quantile_table(float *out) { memcpy(out, qtable(), sizeof(float) * 4096); }
+void oracle_dr_quantile_table(float *out) { memcpy(out, qtable(), sizeof(float) * 256); }
 
 /* per-env, per-episode view of the dynamics constants */
 typedef struct DynConst {
@@ -256,12 +253,14 @@ typedef struct DynConst {
     float std_thrust, std_pos, std_vel, std_obst;
 } DynConst;
 
-/* 12-bit field f of a 128-bit Philox block (word 0 = bits 0-31) -> standard normal from the quantile table */
+/* 9-bit field f of a 128-bit Philox block (word 0 = bits 0-31) -> standard normal: sign = bit 8,
+ * magnitude = half-normal quantile table[bits 0-7] */
 static float dr_normal(const uint32_t r[4], int f) {
-    int b = 12 * f, k = b >> 5, sh = b & 31;
+    int b = 9 * f, k = b >> 5, sh = b & 31;
     uint32_t v = r[k] >> sh;
-    if (sh > 20) v |= r[k + 1] << (32 - sh);
-    return qtable()[v & 0xFFFu];
+    if (sh > 23) v |= r[k + 1] << (32 - sh);
+    float q = qtable()[v & 0xFFu];
+    return (v & 0x100u) ? -q : q;
 }
 
 /* ------------------------------------------------------------------------- */
@@ -402,8 +401,9 @@ static void build_obs(const OracleConfig *c, const DynConst *kc, int step_obs, c
     }
     nearest_obstacle_features(c, p, obst, out + off);
     if (kc->dr) {
-        /* DR sensor noise of the observed state: Philox blocks of counter (genv, ekey, step_count - 1,
-         * drone | stream << 16); stream A fields 3-5 position, 6-8 velocity; stream B field q = obstacle q */
+        /* DR sensor noise of the observed state: Philox block of counter (genv, ekey, step_count - 1,
+         * drone | stream << 16); stream A fields 3-5 position, 6-8 velocity, 9-12 sensed obstacle 0-3;
+         * stream B field q - 4 = sensed obstacle q >= 4 */
         uint32_t ra[4] = {kc->genv, kc->ekey, (uint32_t)(step_obs - 1), (uint32_t)index};
         uint32_t rb[4] = {kc->genv, kc->ekey, (uint32_t)(step_obs - 1), (uint32_t)index | (1u << 16)};
         philox4x32_10(ra, kc->k0, kc->k1);
@@ -416,7 +416,7 @@ static void build_obs(const OracleConfig *c, const DynConst *kc, int step_obs, c
         }
         int filled = c->sensed_obstacles < c->num_obstacles ? c->sensed_obstacles : c->num_obstacles;
         for (int q = 0; q < filled; ++q) {
-            volatile float nd = kc->std_obst * dr_normal(rb, q);
+            volatile float nd = kc->std_obst * (q < 4 ? dr_normal(ra, 9 + q) : dr_normal(rb, q - 4));
             out[off + 4 * q + 3] = out[off + 4 * q + 3] + nd;
         }
     }

@@ -92,7 +92,7 @@ def test_oracle_randomised_constants_and_noise():
     assert np.all(np.abs(o.positions) <= bound[:, None, None])
     # same PCG64 stream, different world: the reset draws differ from the plain path only by the scale
     np.testing.assert_allclose(o.positions / bound[:, None, None], plain.positions / 10.0, rtol=2e-6, atol=1e-7)
-    # sensor noise: obs position = state position + N(0, 0.02) from the 12-bit quantile table
+    # sensor noise: obs position = state position + N(0, 0.02) from the 9-bit (sign + 256-entry) quantile table
     err = (o.obs[:, :, 0:3] - o.positions).ravel()
     assert abs(err.std() - 0.02) < 0.002 and abs(err.mean()) < 0.002
     assert np.all(o.obs[:, :, 6:9] == (o.goal[:, None, :] - o.positions))   # goal vector is not a sensed quantity
@@ -112,10 +112,11 @@ def test_oracle_randomised_constants_and_noise():
 def test_quantile_table_is_a_standard_normal():
     import ctypes as C
     import swarm_oracle as so
-    q = np.zeros(4096, np.float32)
+    q = np.zeros(256, np.float32)
     so.lib().oracle_dr_quantile_table(q.ctypes.data_as(C.c_void_p))
-    assert np.all(np.diff(q) > 0) and abs(q.mean()) < 1e-6 and abs(q.std() - 1.0) < 2e-3
-    assert np.array_equal(q, -q[::-1])
+    z = np.concatenate([-q[::-1], q])          # the 512 values a 9-bit field can take
+    assert np.all(np.diff(z) > 0) and abs(z.mean()) < 1e-6 and abs(z.std() - 1.0) < 6e-3
+    assert q[0] > 0 and q[-1] < 3.2
 
 
 # ------------------------------------------------------------------------------- CUDA path
@@ -173,7 +174,7 @@ def test_cuda_quantile_table_matches_oracle():
     import ctypes as C
     import swarm_b200
     import swarm_oracle as so
-    a, b = np.zeros(4096, np.float32), np.zeros(4096, np.float32)
+    a, b = np.zeros(256, np.float32), np.zeros(256, np.float32)
     so.lib().oracle_dr_quantile_table(a.ctypes.data_as(C.c_void_p))
     assert swarm_b200._abi.load().swarm_dr_quantile_table(b.ctypes.data_as(C.c_void_p)) == 0
     assert np.array_equal(a, b)
