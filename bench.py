@@ -5,10 +5,14 @@ Contract (driver):  python bench.py --gpus N --steps K --warmup W   (torchrun fo
 prints ONE JSON line on rank 0.
 
 Workload = BASELINE.json configs[3] ("C4", the config the metric is quoted on): 32-drone swarm,
-8 obstacles, reference-default DroneEnvConfig (world 20, K=3, S=4, max_steps 400), 65536 env
-instances PER GPU (weak scaling; the whole of C4 fits one GPU), i.i.d. U(-1,1) float32 actions
-read from device memory, auto-reset on, global_state emitted.  A "step" advances every env instance
-once (step launch + the tiny auto-reset launch enqueued behind it).  The per-step working set (~0.5 GB) exceeds the 126 MB L2.
+8 obstacles, reference-default DroneEnvConfig (world 20, K=3, S=4, max_steps 400), per-env domain
+randomisation with the ranges of the reference's configs/domain_randomization_v1.yaml (mass / accel /
+speed / dt / obstacle-radius / world scales, thrust and sensor noise; control delay not implemented),
+65536 env instances PER GPU (weak scaling; the whole of C4 fits one GPU), i.i.d. U(-1,1) float32
+actions read from device memory, auto-reset on, global_state emitted.  A "step" advances every env
+instance once (step launch + the small auto-reset launch enqueued behind it).  The per-step working
+set (~0.5 GB) exceeds the 126 MB L2.  The same run also times the path with randomisation off -- the
+one that is bit-identical to the reference -- and reports it under "dr_off".
 
   value     device-resident throughput: actions applied (device counter) / CUDA-event time, max over ranks
   e2e       same metric through the host-buffer C-ABI call (pinned H2D actions + D2H of every output)
@@ -54,7 +58,7 @@ DR_V1 = {"mass_scale": (0.85, 1.15), "max_accel_scale": (0.90, 1.10), "max_speed
 
 
 def dr_enabled(args):
-    return args.dr == "on"
+    return args.dr == "on" or (args.dr == "auto" and args.workload == "c4")
 
 
 def peaks():
@@ -115,11 +119,11 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-def cpu_port_rate(kind, cfg, n_envs, budget_s, threads):
+def cpu_port_rate(kind, cfg, n_envs, budget_s, threads, dr=False):
     """Times the C oracle (port of the reference algorithm) on the host cores: bounded sample."""
     import swarm_oracle as so
 
-    o = so.OracleSwarm(n_envs, cfg, kind=kind)
+    o = so.OracleSwarm(n_envs, cfg, kind=kind, dr=DR_V1 if dr else None, dr_seed=2026)
     o.seed(np.arange(n_envs, dtype=np.uint64))
     o.reset()
     rng = np.random.default_rng(1000)
@@ -146,7 +150,7 @@ def run_reference_arm(args, kind, cfg, wl_name, default_envs):
 
     threads = len(os.sched_getaffinity(0))
     n_envs = args.cpu_envs
-    o = so.OracleSwarm(n_envs, cfg, kind=kind)
+    o = so.OracleSwarm(n_envs, cfg, kind=kind, dr=DR_V1 if dr_enabled(args) else None, dr_seed=2026)
     o.seed(np.arange(n_envs, dtype=np.uint64))
     o.reset()
     rng = np.random.default_rng(1000)
@@ -202,6 +206,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-global-state", action="store_true")
+    ap.add_argument("--no-dr-off", action="store_true", help="skip the secondary DR-off measurement")
     ap.add_argument("--dr", default="auto", choices=["auto", "on", "off"],
                     help="domain randomisation (domain_randomization_v1 ranges); auto = on for c4 (BASELINE configs[3])")
     args = ap.parse_args()
@@ -226,50 +231,67 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    eng = swarm_b200.SwarmEngine(E, cfg, kind=kind, device=dev, global_state=not args.no_global_state,
-                                 domain_randomization=DR_V1 if dr_enabled(args) else None, dr_seed=2026,
-                                 env_index_base=rank * E)
+    def make_engine(dr):
+        e = swarm_b200.SwarmEngine(E, cfg, kind=kind, device=dev, global_state=not args.no_global_state,
+                                   domain_randomization=DR_V1 if dr else None, dr_seed=2026, env_index_base=rank * E)
+        # env e of rank r is global env r*E + e: seeds are a function of the GLOBAL env index
+        e.seed(np.arange(rank * E, (rank + 1) * E, dtype=np.uint64))
+        e.reset()
+        return e
+
+    eng = make_engine(dr_enabled(args))
     N = eng.N
-    # env e of rank r is global env r*E + e: seeds are a function of the GLOBAL env index
-    eng.seed(np.arange(rank * E, (rank + 1) * E, dtype=np.uint64))
-    eng.reset()
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
     n_act = 4
     actions = [torch.rand((E, N, 3), generator=gen, device=dev) * 2.0 - 1.0 for _ in range(n_act)]
 
-    for w in range(args.warmup):
-        eng.step(actions[w % n_act], auto_reset=True)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    eng.reset_stats()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    launches0 = eng.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    ev0.record()
-    for k in range(args.steps):
-        eng.step(actions[k % n_act], auto_reset=True)
-    ev1.record()
-    torch.cuda.synchronize()
-    launches = eng.launch_count - launches0
-    elapsed_ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop()
-    st = eng.stats()
-    agent_steps = st["agent_steps"]           # actions actually applied (device counter)
-    slot_steps = E * N * args.steps
+    def timed(e, steps, warmup, sample_clocks):
+        """W untimed + K timed steps, CUDA events on the launching stream, max over ranks."""
+        for w in range(warmup):
+            e.step(actions[w % n_act], auto_reset=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e.reset_stats()
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        l0 = e.launch_count
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ev0.record()
+        for k in range(steps):
+            e.step(actions[k % n_act], auto_reset=True)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        clk = sampler.stop() if sampler else None
+        st_ = e.stats()
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        tot = torch.tensor([st_["agent_steps"], E * N * steps, st_["episodes"], e.launch_count - l0], dtype=torch.float64,
+                           device=dev)
+        if world > 1:
+            # the one collective of the path: the episode-statistics reduction (NCCL, tiny)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        return float(t.item()), [float(x) for x in tot.tolist()], clk
 
-    # the one collective of the path: the episode-statistics reduction (NCCL, tiny)
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    tot = torch.tensor([agent_steps, slot_steps, st["episodes"], launches], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    elapsed_ms = float(t.item())
-    agent_steps_all, slot_steps_all, episodes_all, launches_all = (float(x) for x in tot.tolist())
+    timed(eng, 3, max(args.warmup, 3), False)   # (the first launches on a fresh box run cold: keep them out)
+    elapsed_ms, (agent_steps_all, slot_steps_all, episodes_all, launches_all), clocks = timed(eng, args.steps, args.warmup, True)
     value = agent_steps_all / (elapsed_ms * 1e-3)
+
+    dr_off = None
+    if dr_enabled(args) and not args.no_dr_off:
+        # the reference-identical path (no reference code implements the randomisation): same shape, DR off
+        eng0 = make_engine(False)
+        ms0, (as0, ss0, ep0, l0), _ = timed(eng0, max(args.steps // 4, 10), max(args.warmup, 3), False)
+        B0 = eng0.algorithmic_bytes_per_agent_step()
+        dr_off = {"value": as0 / (ms0 * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms0 / max(args.steps // 4, 10),
+                  "roofline_frac": B0 * ss0 / (ms0 * 1e-3) / 1e9 / peaks()[0],
+                  "note": "domain randomisation off: bit-identical to the reference's step (tests/)"}
+        eng0.close()
+        del eng0
 
     # ---- end-to-end through host buffers
     e2e = None
@@ -310,7 +332,7 @@ def main():
         peak, peak_src = peaks()
         B = eng.algorithmic_bytes_per_agent_step()
         kernel_ms = elapsed_ms / args.steps
-        bytes_per_launch = B * E * N
+        bytes_per_launch = B * E * N   # per GPU
         achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
         traffic = None
         prof = os.path.join(ROOT, "profiles", "traffic.json")
@@ -329,15 +351,16 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_agent_step": B, "bytes_per_launch": bytes_per_launch,
-                         "kernel": "swarm_env_kernel_small step launch + aux (auto-reset) launch; achieved uses the time of both",
+                         "kernel": "swarm_step_rot_kernel (step launch) + its auto-reset launch; achieved uses the time of both",
                          "kernel_ms": kernel_ms},
             "e2e": e2e,
+            "dr_off": dr_off,
             "gpu_launches": int(launches_all),
             "clocks": clocks,
         }
         if not args.no_cpu:
             threads = len(os.sched_getaffinity(0))
-            rate, csteps, cdt = cpu_port_rate(kind, cfg, args.cpu_envs, args.cpu_seconds, threads)
+            rate, csteps, cdt = cpu_port_rate(kind, cfg, args.cpu_envs, args.cpu_seconds, threads, dr_enabled(args))
             line["cpu_baseline"] = {
                 "value": rate, "unit": "agent-steps/s", "cores": threads, "kind": "port",
                 "sample": f"{args.cpu_envs} env instances x {csteps} steps of the same config in {cdt:.1f} s "

@@ -320,4 +320,6 @@ class SwarmEngine:
         if self.kind == "swarm" and self.global_state is not None:
             per_agent += 24
             per_env += 12
+        if self.dr_params is not None:
+            per_env += 32   # this episode's randomised constants
         return per_agent + per_env / N
