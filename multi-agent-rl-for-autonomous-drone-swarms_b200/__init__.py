@@ -8,6 +8,7 @@ hand-written sm_100a kernels behind the C ABI in include/swarm_b200.h.
     evaluate_batched reference evaluation protocol (SR / CFR / TTG / FE / PE) for E episodes at once
     DroneSwarmEnv    reference-compatible multi-agent env (dict API) backed by the engine
     SingleDroneEnv   reference-compatible single-agent env backed by the engine
+    DronePhysicsEnv  the PyBullet env's contract + force/drag/gravity model as point masses (parity unpinned)
     DroneEnvConfig   mirror of the reference's config dataclass
 
 The directory name contains hyphens, so import it as `swarm_b200` (alias module at the repo
@@ -22,7 +23,7 @@ def __getattr__(name):
     if name == "SwarmEngine":
         from .engine import SwarmEngine
         return SwarmEngine
-    if name in ("DroneSwarmEnv", "SingleDroneEnv", "make_env_creator", "VectorSwarmEnv"):
+    if name in ("DroneSwarmEnv", "SingleDroneEnv", "DronePhysicsEnv", "make_env_creator", "VectorSwarmEnv"):
         from . import envs
         return getattr(envs, name)
     if name == "evaluate_batched":

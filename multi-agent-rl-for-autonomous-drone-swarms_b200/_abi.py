@@ -12,7 +12,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SWARM_B200_LIB") or os.path.join(_PKG_DIR, "libswarm_b200.so")  # override: tuning builds
 
 ABI_VERSION = 2
-KIND_SINGLE, KIND_SWARM = 0, 1
+KIND_SINGLE, KIND_SWARM, KIND_PHYSICS = 0, 1, 2
 MAX_DRONES, MAX_NEIGHBOR_K, MAX_SENSED = 128, 8, 8
 
 STAT_NAMES = ("episodes", "success", "collision", "timeout", "length_sum", "return_sum", "agent_steps",

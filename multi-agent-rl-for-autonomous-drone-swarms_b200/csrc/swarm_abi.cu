@@ -62,7 +62,7 @@ struct SwarmHandle {
 namespace {
 
 int obs_dim_of(const SwarmConfig& c) {
-    return c.env_kind == SWARM_KIND_SWARM ? 9 + 4 * c.neighbor_k + 4 * c.sensed_obstacles
+    return c.env_kind != SWARM_KIND_SINGLE ? 9 + 4 * c.neighbor_k + 4 * c.sensed_obstacles
                                           : 9 + 4 * c.sensed_obstacles;
 }
 
@@ -70,8 +70,10 @@ int validate(const SwarmConfig* c) {
     if (!c) return fail(SWARM_E_NULL, "config is NULL");
     if (c->abi_version != SWARM_ABI_VERSION)
         return fail(SWARM_E_INVALID, "abi_version %d != %d", c->abi_version, SWARM_ABI_VERSION);
-    if (c->env_kind != SWARM_KIND_SINGLE && c->env_kind != SWARM_KIND_SWARM)
+    if (c->env_kind != SWARM_KIND_SINGLE && c->env_kind != SWARM_KIND_SWARM && c->env_kind != SWARM_KIND_PHYSICS)
         return fail(SWARM_E_INVALID, "env_kind %d unknown", c->env_kind);
+    if (c->env_kind == SWARM_KIND_PHYSICS && (c->num_drones > 32 || c->dr_enabled))
+        return fail(SWARM_E_UNSUPPORTED, "SWARM_KIND_PHYSICS needs num_drones <= 32 and no domain randomisation");
     if (c->num_envs < 1) return fail(SWARM_E_INVALID, "num_envs must be >= 1");
     if (c->num_drones < 1) return fail(SWARM_E_INVALID, "num_drones must be >= 1");
     if (c->env_kind == SWARM_KIND_SINGLE && c->num_drones != 1)
@@ -158,7 +160,7 @@ void build_jump_table(int n_draws, std::vector<JumpEntry>& out) {
 void fill_params(const SwarmConfig& c, DevParams& p) {
     memset(&p, 0, sizeof(p));
     p.E = c.num_envs; p.N = c.num_drones; p.M = c.num_obstacles;
-    p.K = c.env_kind == SWARM_KIND_SWARM ? c.neighbor_k : 0;
+    p.K = c.env_kind != SWARM_KIND_SINGLE ? c.neighbor_k : 0;
     p.S = c.sensed_obstacles;
     p.D = obs_dim_of(c);
     p.R = 6 * p.N + 3;
@@ -210,6 +212,19 @@ void fill_params(const SwarmConfig& c, DevParams& p) {
     p.neg_k_f = -c.reward_formation_scale; p.d_star = c.desired_spacing;
     const double bound = c.world_size / 2.0;           // :71
     p.rng_lo = -bound; p.rng_range = bound - (-bound); // Generator.uniform(low, high): high - low
+    if (c.env_kind == SWARM_KIND_PHYSICS) {
+        // drone_physics_env.py: 5 draws per drone (position, mass noise, damping noise), 3 per obstacle, 4 for
+        // the goal (:207-242); 24 sub-steps of 1/240 s (:323); g_comp 9.5 (:343) against gravity 9.81 (:197);
+        // contacts as a point mass: ground at the URDF box's half height, spheres of radius 0.15 for the drones
+        p.n_draws = 5 * p.N + 3 * p.M + 4;
+        p.phys_substeps = (int)(c.dt * 240.0);
+        p.phys_h = (float)(1.0 / 240.0);
+        p.phys_g_net = (float)(9.5 - 9.81);
+        p.phys_ground_z = 0.025f;
+        p.thr_obst = (float)(c.obstacle_radius + 0.15);
+        p.thr_pair = (float)(2.0 * 0.15);
+        p.goal_radius_d = c.goal_radius;
+    }
 }
 
 int bind_buffers(const SwarmHandle* h, const SwarmBuffers* b, DevParams& p) {

@@ -49,6 +49,10 @@ struct DevParams {
     double k_p, r_goal, r_col, neg_k_f, d_star;
     double rng_lo, rng_range;     // uniform(-W/2, W/2): lo, hi - lo
     double n_others, inv_n_others;  // N - 1 and RN(1 / (N - 1)) for the mean of the formation errors
+    // physics env (point-mass DronePhysicsEnv)
+    double goal_radius_d;         // reached = (double)dist < goal_radius
+    float phys_h, phys_g_net, phys_ground_z;  // 1/240 s, 9.5 - 9.81, drone half height
+    int phys_substeps;            // int(dt * 240)
     // state
     float4* pos4; float4* vel4; float4* goal4; float4* obst4;
     int* step_count; unsigned long long* rng; float* ep_return;

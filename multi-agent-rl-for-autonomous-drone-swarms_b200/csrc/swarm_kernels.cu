@@ -686,7 +686,9 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
     float* region = reinterpret_cast<float*>(wslice + 2 * (size_t)P.inbox_bytes);  // distance matrix / obs staging tile
     const int N = NT ? NT : P.N, M = P.M, G = NT ? 32 / NT : P.G, srow = NT ? small_srow(NT) : P.srow;
     const int K = EXACT ? KT : P.K, S = EXACT ? ST : P.S;
-    const int D = EXACT ? (KIND == SWARM_KIND_SWARM ? 9 + 4 * KT + 4 * ST : 9 + 4 * ST) : P.D;
+    constexpr bool HAS_NEIGH = KIND != SWARM_KIND_SINGLE;  // swarm and physics envs observe neighbours
+    constexpr bool PHYS = KIND == SWARM_KIND_PHYSICS;       // DronePhysicsEnv as a point mass (see oracle/swarm_oracle.c)
+    const int D = EXACT ? (HAS_NEIGH ? 9 + 4 * KT + 4 * ST : 9 + 4 * ST) : P.D;
     const int goal_off = 64, obst_off = 64 + G, dr_off4 = 64 + G + G * P.m_pad;     // inbox offsets, float4 units
     const int act_off4 = dr_off4 + (DR ? 2 * G : 0);
     const int e_l = lane / N;
@@ -809,7 +811,29 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
         if (MODE == kSmallStep) {
             // =========================== phase A: integrate (:98-118) ===========================
             prev_d = norm1d<NORM>(__fsub_rn(gx, p.x), __fsub_rn(gy, p.y), __fsub_rn(gz, p.z));  // :98-101
-            if (alive) {
+            if (PHYS) {
+                // drone_physics_env.py:323-360 as a point mass: per 1/240 s sub-step speed clamp, thrust
+                // (action neither clipped nor cast; the mass cancels) + 9.5 - 9.81 on z, Bullet's
+                // integrateVelocities -> applyDamping -> integrateTransforms; v.w = this drone's damping factor
+                if (alive) {
+                    const float h = P.phys_h, f = v.w, gnet = P.phys_g_net;
+#pragma unroll 1
+                    for (int sub = 0; sub < P.phys_substeps; ++sub) {
+                        const float speed = norm1d<NORM>(v.x, v.y, v.z);
+                        if (speed > c_vmax) {
+                            v.x = __fmul_rn(__fdiv_rn(v.x, speed), c_vmax);
+                            v.y = __fmul_rn(__fdiv_rn(v.y, speed), c_vmax);
+                            v.z = __fmul_rn(__fdiv_rn(v.z, speed), c_vmax);
+                        }
+                        v.x = __fmul_rn(__fadd_rn(v.x, __fmul_rn(__fmul_rn(ax, c_amax), h)), f);
+                        v.y = __fmul_rn(__fadd_rn(v.y, __fmul_rn(__fmul_rn(ay, c_amax), h)), f);
+                        v.z = __fmul_rn(__fadd_rn(v.z, __fmul_rn(__fadd_rn(__fmul_rn(az, c_amax), gnet), h)), f);
+                        p.x = __fadd_rn(p.x, __fmul_rn(v.x, h));
+                        p.y = __fadd_rn(p.y, __fmul_rn(v.y, h));
+                        p.z = __fadd_rn(p.z, __fmul_rn(v.z, h));
+                    }
+                }
+            } else if (alive) {
                 ax = clipf(ax, -1.0f, 1.0f); ay = clipf(ay, -1.0f, 1.0f); az = clipf(az, -1.0f, 1.0f);
                 if (DR) {  // thrust noise: a <- a * (1 + sigma z), one normal per axis
                     const uint4 r = philox4x32_10(genv, ekey, (unsigned)sc, (unsigned)i | (DR_STREAM_A << 16), P.dr_key0,
@@ -831,11 +855,14 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                 p.y = __fadd_rn(p.y, __fmul_rn(v.y, c_dt));
                 p.z = __fadd_rn(p.z, __fmul_rn(v.z, c_dt));
             }
-            // wall clip for ALL drones (:113-117); velocity is not zeroed at the wall
-            p.x = clipf(p.x, -c_bound, c_bound);
-            p.y = clipf(p.y, -c_bound, c_bound);
-            p.z = clipf(p.z, -c_bound, c_bound);
+            // wall clip for ALL drones (:113-117); velocity is not zeroed at the wall (the physics env has no walls)
+            if (!PHYS) {
+                p.x = clipf(p.x, -c_bound, c_bound);
+                p.y = clipf(p.y, -c_bound, c_bound);
+                p.z = clipf(p.z, -c_bound, c_bound);
+            }
         }
+        float damp = v.w;  // physics env: per-drone damping factor rides in vel4.w
         int sc_obs = MODE == kSmallStep ? sc + 1 : 0;  // step_count of the state the obs row describes (DR sensor stream)
         if (DR && MODE == kSmallAux && lane_ok) sc_obs = P.step_count[env];
         if (lane_ok) tab_pos[lane] = make_float4(p.x, p.y, p.z, alive ? 1.0f : 0.0f);
@@ -889,6 +916,31 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                 for (int k = lane; k < P.n_draws; k += 32) {
                     unsigned long long oh, ol;
                     pcg_jump(P.jump[k + 1], sh, sl, ih, il, oh, ol);
+                    if (PHYS) {
+                        // drone_physics_env.py:207-242: per drone position (z >= 1), mass noise (cancels), damping
+                        // noise; obstacles (z >= 0.5); goal xy, one discarded draw, goal z in [0.5, 2]
+                        if (k < 5 * N) {
+                            const int dr_ = k / 5, c5 = k - 5 * dr_;
+                            if (c5 < 3) {
+                                float val = pcg_uniform_f32(oh, ol, u_lo, u_range);
+                                if (c5 == 2) val = fmaxf(val, 1.0f);
+                                reinterpret_cast<float*>(tab_pos + el * N + dr_)[c5] = val;
+                            } else if (c5 == 4) {
+                                const double c_lin = __dmul_rn(0.5, pcg_uniform_f64(oh, ol, 0.8, 1.2 - 0.8));
+                                reinterpret_cast<float*>(tab_vel + el * N + dr_)[3] = __double2float_rn(phys_damp_factor(c_lin));
+                            }
+                        } else if (k < 5 * N + 3 * M) {
+                            const int kk = k - 5 * N, m_ = kk / 3, c3 = kk - 3 * m_;
+                            float val = pcg_uniform_f32(oh, ol, u_lo, u_range);
+                            if (c3 == 2) val = fmaxf(val, 0.5f);
+                            reinterpret_cast<float*>(tab_obst + el * P.m_pad + m_)[c3] = val;
+                        } else {
+                            const int g_ = k - 5 * N - 3 * M;
+                            if (g_ < 2) reinterpret_cast<float*>(tab_goal + el)[g_] = pcg_uniform_f32(oh, ol, u_lo, u_range);
+                            else if (g_ == 3) reinterpret_cast<float*>(tab_goal + el)[2] = pcg_uniform_f32(oh, ol, 0.5, 2.0 - 0.5);
+                        }
+                        continue;
+                    }
                     const float val = pcg_uniform_f32(oh, ol, u_lo, u_range);
                     // draw order: positions (N,3) -> goal (3,) -> obstacles (M,3)
                     if (k < 3 * N) {
@@ -902,7 +954,9 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                 }
                 if (lane < N) {
                     reinterpret_cast<float*>(tab_pos + el * N + lane)[3] = 1.0f;
-                    tab_vel[el * N + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float* tv = reinterpret_cast<float*>(tab_vel + el * N + lane);
+                    tv[0] = 0.f; tv[1] = 0.f; tv[2] = 0.f;
+                    if (!PHYS) tv[3] = 0.f;  // (physics: .w already holds this drone's damping factor)
                 }
                 if (lane == 0) {
                     unsigned long long oh, ol;
@@ -925,7 +979,8 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                 g4 = tab_goal[e_l]; gx = g4.x; gy = g4.y; gz = g4.z;
                 alive = true;
                 P.pos4[a] = p;
-                P.vel4[a] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (PHYS) damp = tab_vel[lane].w;
+                P.vel4[a] = make_float4(0.f, 0.f, 0.f, PHYS ? damp : 0.f);
             }
             out_lanes = __ballot_sync(FULL_MASK, fresh);
         }
@@ -934,7 +989,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
         __syncwarp();  // position / obstacle tables complete
 
         // ========================= B1: symmetric distance matrix =========================
-        if (KIND == SWARM_KIND_SWARM) {
+        if (HAS_NEIGH) {
             // Round r pairs drone i with j = i + r (wrapping inside the env).  Rounds 1 .. N/2 cover
             // every unordered pair; for even N the last round is visited from both ends, which only
             // stores the same value twice.  All addresses are (select of two lane constants) + r * stride.
@@ -1000,7 +1055,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
         bool pair_hit = false;
         double form_sum = 0.0;
         int form_n = 0;
-        if (KIND == SWARM_KIND_SWARM && lane_ok) {
+        if (HAS_NEIGH && lane_ok) {
             if (MODE == kSmallAux) {
 #pragma unroll 1
                 for (int cb = 0; cb < n_pad; cb += 8) {
@@ -1107,13 +1162,22 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
             auto obst_bits = [&](int q) { return q < 4 ? dr_field(rA, 9 + q) : dr_field(rB, q - 4); };
             row[0] = noisy(p.x, P.dr_std_pos, dr_field(rA, 3)); row[1] = noisy(p.y, P.dr_std_pos, dr_field(rA, 4));
             row[2] = noisy(p.z, P.dr_std_pos, dr_field(rA, 5));
-            row[3] = noisy(v.x, P.dr_std_vel, dr_field(rA, 6)); row[4] = noisy(v.y, P.dr_std_vel, dr_field(rA, 7));
-            row[5] = noisy(v.z, P.dr_std_vel, dr_field(rA, 8));
+            float ovx = v.x, ovy = v.y, ovz = v.z;
+            if (PHYS) {  // drone_physics_env.py:436-439: the observed velocity is clamped to max_speed
+                const float speed = norm1d<NORM>(v.x, v.y, v.z);
+                if (speed > c_vmax) {
+                    ovx = __fmul_rn(__fdiv_rn(v.x, speed), c_vmax);
+                    ovy = __fmul_rn(__fdiv_rn(v.y, speed), c_vmax);
+                    ovz = __fmul_rn(__fdiv_rn(v.z, speed), c_vmax);
+                }
+            }
+            row[3] = noisy(ovx, P.dr_std_vel, dr_field(rA, 6)); row[4] = noisy(ovy, P.dr_std_vel, dr_field(rA, 7));
+            row[5] = noisy(ovz, P.dr_std_vel, dr_field(rA, 8));
             row[6] = __fsub_rn(gx, p.x); row[7] = __fsub_rn(gy, p.y); row[8] = __fsub_rn(gz, p.z);
             int off = 9;
-            const bool all_slots = (KIND != SWARM_KIND_SWARM || n_others >= K) && M >= S;  // warp-uniform
+            const bool all_slots = (!HAS_NEIGH || n_others >= K) && M >= S;  // warp-uniform
             if (all_slots) {
-                if (KIND == SWARM_KIND_SWARM) {
+                if (HAS_NEIGH) {
 #pragma unroll
                     for (int q = 0; q < KT; ++q) {
                         if (q < K) {
@@ -1138,7 +1202,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                     }
                 }
             } else {  // fewer candidates than slots: zero padding (:268-270, :288-290)
-                if (KIND == SWARM_KIND_SWARM) {
+                if (HAS_NEIGH) {
 #pragma unroll
                     for (int q = 0; q < KT; ++q) {
                         if (q < K) {
@@ -1179,10 +1243,19 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
         if (MODE == kSmallStep) {
             // ===================== rewards and flags (:120-172) =====================
             const bool obst_hit = od[0] <= c_thr_obst;
-            const bool reached = alive && curr_d <= P.thr_goal;       // :124-127 (double compare)
-            const bool collided = alive && (obst_hit || pair_hit);     // :128
+            // physics env: reached = dist < goal_radius (strict, drone_physics_env.py:389); contact with the
+            // ground plane, an obstacle sphere or another drone (:368-372, point-mass radii set by the host)
+            const bool reached = PHYS ? (alive && (double)curr_d < P.goal_radius_d)
+                                      : (alive && curr_d <= P.thr_goal);  // :124-127 (double compare)
+            const bool collided = alive && (obst_hit || pair_hit || (PHYS && p.z <= P.phys_ground_z));  // :128
             double reward = 0.0;
-            if (alive) {
+            if (PHYS) {
+                if (alive) {  // drone_physics_env.py:378-392
+                    reward = __dmul_rn(-(double)curr_d, 0.1);
+                    if (collided) reward = __dsub_rn(reward, 10.0);
+                    else if (reached) reward = __dadd_rn(reward, 50.0);
+                }
+            } else if (alive) {
                 const double progress = __dmul_rn(__dsub_rn((double)prev_d, (double)curr_d), P.k_p);  // :142
                 if (KIND == SWARM_KIND_SWARM) {
                     double pen = 0.0;  // :210-224
@@ -1213,7 +1286,15 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
             const int sc_new = env_active ? sc + 1 : sc;
             const bool time_limit = env_active && sc_new >= P.max_steps;
             bool all_term, all_trunc, ep_over, all_reached = false;
-            if (KIND == SWARM_KIND_SWARM) {
+            if (PHYS) {  // drone_physics_env.py:397-417: one flag pair for every drone
+                const int n_open = __popc(__ballot_sync(FULL_MASK, alive && !collided && !reached) & env_lanes);
+                all_reached = n_open == 0;
+                const bool done = env_active && (any_col || all_reached || time_limit);
+                all_trunc = env_active && time_limit && !any_col && !all_reached;
+                all_term = env_active ? (any_col || all_reached) : true;
+                ep_over = done;
+                all_reached = all_reached && !any_col;
+            } else if (KIND == SWARM_KIND_SWARM) {
                 all_reached = n_cont == 0 && !any_col && !time_limit;
                 const bool episode_done = all_reached || any_col;
                 all_term = env_active ? episode_done : true;  // :94-95 when no agent is left
@@ -1227,7 +1308,12 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
             const bool need_reset = P.auto_reset && (ep_over || !env_active);
             if (lane_ok) {
                 bool valid, alive_next;
-                if (KIND == SWARM_KIND_SWARM) {
+                if (PHYS) {
+                    P.terminated[a] = (alive && ep_over && !all_trunc) ? 1 : 0;
+                    P.truncated[a] = (alive && ep_over && all_trunc) ? 1 : 0;
+                    valid = alive;              // every drone is observed on every step
+                    alive_next = alive && !ep_over;
+                } else if (KIND == SWARM_KIND_SWARM) {
                     P.terminated[a] = (alive && done_agent) ? 1 : 0;                 // :150-151
                     P.truncated[a] = (alive && time_limit && !done_agent) ? 1 : 0;   // :152
                     valid = alive && !done_agent && !time_limit && !any_col;         // :154
@@ -1246,7 +1332,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                     P.dist[a] = curr_d;
                     P.obs_valid[a] = valid ? 1 : 0;
                     P.pos4[a] = make_float4(p.x, p.y, p.z, alive_next ? 1.0f : 0.0f);
-                    P.vel4[a] = make_float4(v.x, v.y, v.z, 0.0f);
+                    P.vel4[a] = make_float4(v.x, v.y, v.z, PHYS ? damp : 0.0f);
                     if (P.gs) write_gs_drone(P.gs + (long long)env * P.R, N, i, p.x, p.y, p.z, v.x, v.y, v.z);
                 }
             }
@@ -1259,7 +1345,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                     atomicAdd(wstats + SWARM_STAT_EPISODES, 1ull);
                     atomicAdd(wstats + SWARM_STAT_LENGTH_SUM, (unsigned long long)sc_new);
                     atomicAdd(reinterpret_cast<double*>(wstats + SWARM_STAT_RETURN_SUM), (double)ret);
-                    if (KIND == SWARM_KIND_SWARM) {
+                    if (HAS_NEIGH) {
                         if (all_reached) atomicAdd(wstats + SWARM_STAT_SUCCESS, 1ull);
                         if (any_col) atomicAdd(wstats + SWARM_STAT_COLLISION, 1ull);
                         if (all_trunc) atomicAdd(wstats + SWARM_STAT_TIMEOUT, 1ull);
@@ -1431,6 +1517,10 @@ static EnvKernel resolve(const DevParams& p, int norm_mode, int env_kind) {
         }
         if (!small_n) return pick_large<SWARM_MAX_NEIGHBOR_K, SWARM_MAX_SENSED, false, SWARM_KIND_SWARM>(norm_mode);
         return pick_small<SWARM_MAX_NEIGHBOR_K, SWARM_MAX_SENSED, false, SWARM_KIND_SWARM, 0>(norm_mode, step, dr);
+    }
+    if (env_kind == SWARM_KIND_PHYSICS) {  // point-mass DronePhysicsEnv: N <= 32, no domain randomisation
+        if (p.K == 3 && p.S == 4) return pick_small<3, 4, true, SWARM_KIND_PHYSICS, 0>(norm_mode, step, false);
+        return pick_small<SWARM_MAX_NEIGHBOR_K, SWARM_MAX_SENSED, false, SWARM_KIND_PHYSICS, 0>(norm_mode, step, false);
     }
     if (p.S == 4) return pick_small<1, 4, true, SWARM_KIND_SINGLE, 1>(norm_mode, step, dr);
     return pick_small<1, SWARM_MAX_SENSED, false, SWARM_KIND_SINGLE, 0>(norm_mode, step, dr);

@@ -1,8 +1,9 @@
 """SwarmEngine -- batched, device-resident drone-swarm env step (host side of the C ABI).
 
 One engine = E independent instances of the reference's `DroneSwarmEnv` (kind="swarm",
-reference src/swarm_marl/envs/drone_swarm_env.py:17) or `SingleDroneEnv` (kind="single",
-src/swarm_marl/envs/single_drone_env.py:12) living on one GPU.  PyTorch is used only to own
+reference src/swarm_marl/envs/drone_swarm_env.py:17), `SingleDroneEnv` (kind="single",
+src/swarm_marl/envs/single_drone_env.py:12) or `DronePhysicsEnv` as a point mass (kind="physics",
+src/swarm_marl/envs/drone_physics_env.py:22; PyBullet is not vendored: parity unpinned) living on one GPU.  PyTorch is used only to own
 device memory and streams; every computation is a hand-written sm_100a kernel behind
 include/swarm_b200.h.  There is no fallback path: without the built library this module
 raises on import of the binding.
@@ -41,13 +42,13 @@ class SwarmEngine:
         disable) or the flat form {"mass_scale": (lo, hi), ..., "thrust_noise_std": sigma, ...} -- see
         `config.flatten_domain_randomization`.  `env_index_base`: global index of env 0 (sharded runs),
         so the randomisation streams of an env do not depend on how the batch is split."""
-        if kind not in ("swarm", "single"):
-            raise ValueError(f"kind must be 'swarm' or 'single', got {kind!r}")
+        if kind not in ("swarm", "single", "physics"):
+            raise ValueError(f"kind must be 'swarm', 'single' or 'physics', got {kind!r}")
         self._lib = _abi.load()
         raw = dict(config or {})
         self.kind = kind
         # drone_swarm_env.py:32-34: num_drones is popped, the rest goes through DroneEnvConfig.from_dict
-        self.num_drones = int(raw.pop("num_drones", 3)) if kind == "swarm" else 1
+        self.num_drones = int(raw.pop("num_drones", 3)) if kind in ("swarm", "physics") else 1
         raw.pop("num_drones", None)
         self.cfg = DroneEnvConfig.from_dict(raw)
         self.device = torch.device(device)
@@ -56,12 +57,12 @@ class SwarmEngine:
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.E, self.N, self.M = int(num_envs), self.num_drones, int(self.cfg.num_obstacles)
-        self.K = int(self.cfg.neighbor_k) if kind == "swarm" else 0
+        self.K = int(self.cfg.neighbor_k) if kind != "single" else 0
         self.S = int(self.cfg.sensed_obstacles)
 
         c = _abi.SwarmConfig()
         c.abi_version = _abi.ABI_VERSION
-        c.env_kind = _abi.KIND_SWARM if kind == "swarm" else _abi.KIND_SINGLE
+        c.env_kind = {"swarm": _abi.KIND_SWARM, "single": _abi.KIND_SINGLE, "physics": _abi.KIND_PHYSICS}[kind]
         c.num_envs, c.num_drones, c.num_obstacles = self.E, self.N, self.M
         c.sensed_obstacles, c.neighbor_k = self.S, int(self.cfg.neighbor_k)
         c.max_steps, c.norm_mode, c.device = int(self.cfg.max_steps), int(norm_mode), self.device.index
@@ -154,6 +155,10 @@ class SwarmEngine:
     @property
     def obstacles(self) -> torch.Tensor:   # .obstacles (:62)
         return self.obst4[..., :3]
+
+    @property
+    def damping(self) -> torch.Tensor:     # kind="physics": per-drone velocity factor of one 1/240 s sub-step
+        return self.vel4[..., 3]
 
     @property
     def alive(self) -> torch.Tensor:       # membership in .agents (:39, :169-172)
@@ -317,7 +322,7 @@ class SwarmEngine:
         N, M, D = self.N, self.M, self.D
         per_agent = 36 + 24 + 4 * D + 4 + 2 + 6
         per_env = 12 + 12 * M + 4 + 4 + 2
-        if self.kind == "swarm" and self.global_state is not None:
+        if self.kind != "single" and self.global_state is not None:
             per_agent += 24
             per_env += 12
         if self.dr_params is not None:

@@ -223,8 +223,88 @@ class SingleDroneEnv(_EngineBacked, _GymEnv):
                 bool(h["terminated"].numpy()[0, 0]), bool(h["truncated"].numpy()[0, 0]), info)
 
 
+class DronePhysicsEnv(_EngineBacked, _MultiAgentEnv):
+    """`DronePhysicsEnv` (reference drone_physics_env.py:22) with the drones as point masses.
+
+    Same constructor / reset / step contract: obs and infos for EVERY drone on every step
+    (:365-366), rewards for the drones of `self.agents`, one terminated / truncated pair shared by all
+    drones (:401-417), `self.agents = []` once the episode is over, `set_goal` (:265-277).  The force
+    / drag / gravity / speed-clamp model around PyBullet's solver is restated (24 sub-steps of 1/240 s,
+    thrust `a * max_accel + (0, 0, 9.5)`, gravity -9.81, per-episode linear damping 0.5 * U(0.8, 1.2));
+    the rigid-body solver itself is not (PyBullet is a third-party dependency that is neither vendored
+    nor installed): contacts are sphere / plane tests that end the episode, as any contact does in the
+    reference.  Parity unpinned."""
+
+    def __init__(self, config: dict[str, Any] | None = None, device=None):
+        super().__init__()
+        cfg_dict = dict(config or {})
+        self.num_drones = int(cfg_dict.get("num_drones", 3))                      # :115
+        env_cfg = {k: v for k, v in cfg_dict.items() if k not in ("num_drones", "gui")}
+        self.cfg = DroneEnvConfig.from_dict(env_cfg)                              # :118
+        self.gui = False                                                          # (no GUI: :119 is ignored)
+        self.agent_ids = [f"drone_{i}" for i in range(self.num_drones)]           # :164
+        self.agent_id_to_index = {a: i for i, a in enumerate(self.agent_ids)}
+        self.agents = list(self.agent_ids)
+        self._obs_dim = 9 + self.cfg.neighbor_k * 4 + self.cfg.sensed_obstacles * 4   # :152-156
+        self.observation_space = Box(low=-np.inf, high=np.inf, shape=(self._obs_dim,), dtype=np.float32)
+        self.action_space = Box(low=-1.0, high=1.0, shape=(3,), dtype=np.float32)
+        self._make_engine({**env_cfg, "num_drones": self.num_drones}, "physics", device)
+
+    @property
+    def positions(self) -> np.ndarray:
+        return self._engine.positions[0].cpu().numpy()
+
+    @property
+    def velocities(self) -> np.ndarray:
+        return self._engine.velocities[0].cpu().numpy()
+
+    def set_goal(self, new_pos):
+        """drone_physics_env.py:265-277 (interactive dashboard)."""
+        import torch
+
+        self._engine.goal4[0, :3] = torch.as_tensor(np.asarray(new_pos, dtype=np.float32), device=self._engine.device)
+
+    def reset(self, *, seed: int | None = None, options: dict[str, Any] | None = None):
+        """drone_physics_env.py:174-263.  With seed=None the reference re-seeds from OS entropy; so do we."""
+        self._engine.seed(np.asarray([seed if seed is not None else _entropy_seed()], dtype=np.uint64))
+        self.agents = list(self.agent_ids)
+        self._engine.reset()
+        obs, dist, _ = self._fetch_reset_outputs()
+        observations = {a: obs[i].copy() for i, a in enumerate(self.agent_ids)}
+        infos = {a: {"distance_to_goal": float(dist[i]), "reached_goal": False, "collision": False}   # :257-261
+                 for i, a in enumerate(self.agent_ids)}
+        return observations, infos
+
+    def step(self, action_dict: dict[str, np.ndarray]):
+        """drone_physics_env.py:279-419."""
+        active = list(self.agents)
+        act = self._host["actions"].numpy()
+        act[...] = 0.0
+        for a, raw in action_dict.items():                                        # :325 (no clip, :336)
+            act[0, self.agent_id_to_index[a]] = np.asarray(raw, dtype=np.float32).reshape(3)
+        if not active:
+            # the reference keeps integrating a finished episode and answers terminated["__all__"] = True with
+            # empty rewards (:374, :398-411); the batched contract parks the env instead
+            flags = {a: True for a in self.agent_ids}
+            return {}, {}, {**flags, "__all__": True}, {**{a: False for a in self.agent_ids}, "__all__": False}, {}
+        h = self._engine.step_host(None, auto_reset=False)
+        gs = h["global_state"].numpy()[0]
+        obs = {a: h["obs"].numpy()[0, i].copy() for i, a in enumerate(self.agent_ids)}
+        infos = {a: {"global_state": gs.copy(), "distance_to_goal": float(h["dist"].numpy()[0, i]),
+                     "reached_goal": bool(h["reached"].numpy()[0, i]), "collision": bool(h["collision"].numpy()[0, i])}
+                 for i, a in enumerate(self.agent_ids)}
+        rewards = {a: float(h["reward64"].numpy()[0, self.agent_id_to_index[a]]) for a in active}
+        terminated = {a: bool(h["terminated"].numpy()[0, i]) for i, a in enumerate(self.agent_ids)}
+        truncated = {a: bool(h["truncated"].numpy()[0, i]) for i, a in enumerate(self.agent_ids)}
+        terminated["__all__"] = bool(h["all_terminated"].numpy()[0])
+        truncated["__all__"] = bool(h["all_truncated"].numpy()[0])
+        if terminated["__all__"] or truncated["__all__"]:
+            self.agents = []                                                      # :411
+        return obs, rewards, terminated, truncated, infos
+
+
 def make_env_creator(kind: str = "swarm", device=None):
     """Env creator for `ray.tune.registry.register_env(name, creator)`:
     the drop-in for `lambda cfg: DroneSwarmEnv(cfg)` (reference scripts/train_multi_agent.py:96)."""
-    cls = {"swarm": DroneSwarmEnv, "single": SingleDroneEnv}[kind]
+    cls = {"swarm": DroneSwarmEnv, "single": SingleDroneEnv, "physics": DronePhysicsEnv}[kind]
     return lambda cfg: cls(dict(cfg) if cfg is not None else None, device=device)

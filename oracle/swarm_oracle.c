@@ -57,7 +57,7 @@ typedef struct OracleConfig {
     double reward_progress_scale, reward_goal, reward_collision, reward_formation_scale;
     int32_t max_steps, num_obstacles, sensed_obstacles, neighbor_k;
     int32_t num_drones;
-    int32_t env_kind;  /* 0 = SingleDroneEnv, 1 = DroneSwarmEnv */
+    int32_t env_kind;  /* 0 = SingleDroneEnv, 1 = DroneSwarmEnv, 2 = DronePhysicsEnv (point-mass restatement) */
     int32_t norm_mode; /* 0 = BLAS sdot (double accumulate), 1 = sequential f32 */
     int32_t reserved;
     /* domain randomisation: NOT reference behaviour (configs/domain_randomization_v1.yaml is read by no
@@ -96,6 +96,7 @@ typedef struct OracleBatch {
     uint8_t *all_truncated;  /* [E]    truncated["__all__"] */
     float *global_state; /* [E][6N+3]  info["global_state"] (drone_swarm_env.py:293-302) */
     float *dr_params;    /* [E][8]     DR only: {max_accel, max_speed, dt, bound, obst threshold, key, world, 0} */
+    float *damp;         /* [E][N]     physics env only: per-drone velocity factor of one 1/240 s sub-step */
 } OracleBatch;
 
 /* ------------------------------------------------------------------------- */
@@ -317,7 +318,7 @@ static double np_pairwise_sum(const double *a, int n) {
 
 static int obs_dim(const OracleConfig *c) {
     /* drone_swarm_env.py:41-45 ; single_drone_env.py:33 */
-    return c->env_kind == 1 ? 9 + 4 * c->neighbor_k + 4 * c->sensed_obstacles
+    return c->env_kind != 0 ? 9 + 4 * c->neighbor_k + 4 * c->sensed_obstacles
                             : 9 + 4 * c->sensed_obstacles;
 }
 
@@ -393,9 +394,18 @@ static void build_obs(const OracleConfig *c, const DynConst *kc, int step_obs, c
     const float *p = pos + 3 * index, *v = vel + 3 * index;
     out[0] = p[0]; out[1] = p[1]; out[2] = p[2];
     out[3] = v[0]; out[4] = v[1]; out[5] = v[2];
+    if (c->env_kind == 2) { /* drone_physics_env.py:436-439: the observed velocity is clamped to max_speed */
+        float speed = norm1d(c, v[0], v[1], v[2]);
+        float vmax = (float)c->max_speed;
+        if (speed > vmax)
+            for (int k = 0; k < 3; ++k) {
+                volatile float q = v[k] / speed;
+                out[3 + k] = q * vmax;
+            }
+    }
     out[6] = goal[0] - p[0]; out[7] = goal[1] - p[1]; out[8] = goal[2] - p[2];
     int off = 9;
-    if (c->env_kind == 1) {
+    if (c->env_kind != 0) {
         nearest_neighbor_features(c, pos, index, out + off);
         off += 4 * c->neighbor_k;
     }
@@ -491,6 +501,7 @@ typedef struct EnvView {
     double *reward;
     uint8_t *terminated, *truncated, *reached, *collision, *obs_valid, *all_term, *all_trunc;
     float *dr;
+    float *damp;
     int env_index;
 } EnvView;
 
@@ -516,6 +527,7 @@ static EnvView view(const OracleConfig *c, const OracleBatch *b, int e) {
     v.all_term = b->all_terminated + e;
     v.all_trunc = b->all_truncated + e;
     v.dr = b->dr_params ? b->dr_params + (size_t)e * 8 : NULL;
+    v.damp = b->damp ? b->damp + (size_t)e * N : NULL;
     v.env_index = e;
     return v;
 }
@@ -552,7 +564,7 @@ static void observe_env(const OracleConfig *c, EnvView *v) {
     for (int i = 0; i < N; ++i) {
         build_obs(c, &kc, *v->step_count, v->pos, v->vel, v->goal, v->obst, i, v->obs + (size_t)i * D);
         v->dist[i] = distance_to_goal(c, v->goal, v->pos + 3 * i);
-        v->obs_valid[i] = c->env_kind == 1 ? v->active[i] : 1;
+        v->obs_valid[i] = c->env_kind == 1 ? v->active[i] : 1;  /* the physics env observes every drone, always */
         v->reward[i] = 0.0;
         v->terminated[i] = v->truncated[i] = v->reached[i] = v->collision[i] = 0;
     }
@@ -563,9 +575,11 @@ static void observe_env(const OracleConfig *c, EnvView *v) {
 
 /* reset  drone_swarm_env.py:65-90 / single_drone_env.py:53-71.
  * Draw order: positions (N,3) -> goal (3,) -> obstacles (M,3). */
+static void reset_env_physics(const OracleConfig *c, EnvView *v);
 static void reset_env(const OracleConfig *c, EnvView *v) {
     int N = c->num_drones, M = c->num_obstacles;
     double bound = c->world_size / 2.0;
+    if (c->env_kind == 2) { reset_env_physics(c, v); return; }
     if (c->dr_enabled && v->dr) {
         /* this episode's constants: counter = (genv, PCG64 state_lo before the draws, 0xD5D5D5D5 [+1]) */
         uint32_t genv = (uint32_t)(c->env_index_base + v->env_index);
@@ -768,6 +782,183 @@ static void step_single_env(const OracleConfig *c, EnvView *v, const float *acti
 /* ------------------------------------------------------------------------- */
 int oracle_obs_dim(const OracleConfig *c) { return obs_dim(c); }
 
+/* ------------------------------------------------------------------------- */
+/* DronePhysicsEnv (drone_physics_env.py) as a POINT MASS.                     */
+/* The reference integrates rigid bodies with PyBullet (pybullet>=3.2.5, not    */
+/* vendored, not installed): PARITY UNPINNED.  What is restated here is the env */
+/* contract and the force / drag / gravity / clamp model around the solver:     */
+/*   per 1/240 s sub-step (:323-360, 24 per step at dt = 0.1):                  */
+/*     speed clamp |v| <= max_speed (:353-358), force = action * max_accel * m  */
+/*     + (0, 0, 9.5 m) (:336-343, action neither clipped nor cast), gravity     */
+/*     -9.81 (:197), Bullet's integrateVelocities -> applyDamping               */
+/*     (v *= (1 - c)^h) -> integrateTransforms order; the mass cancels.         */
+/*   contacts (:368-372) end the episode, so the contact RESPONSE is never      */
+/*   needed: ground z <= 0.025 (URDF box half height, assets/drone.urdf:12),    */
+/*   obstacle |p - o| <= r_o + 0.15, drone pair |p_i - p_j| <= 0.30.            */
+/* State is float32 (PyBullet's is double); distances use the swarm env's norms.*/
+/* ------------------------------------------------------------------------- */
+#define PHYS_SUBSTEP_HZ 240.0
+#define PHYS_G_COMP 9.5
+#define PHYS_GRAVITY 9.81
+#define PHYS_HALF_HEIGHT 0.025f
+#define PHYS_R_DRONE 0.15
+
+/* (1 - c)^(1/240) with + - * / only, so the CUDA path reproduces it bit for bit:
+ * ln x = 2 atanh((x - 1) / (x + 1)) (13 terms), exp by a 7-term Taylor series */
+static double phys_damp_factor(double c_lin) {
+    double x = 1.0 - c_lin;
+    double t = (x - 1.0) / (x + 1.0), t2 = t * t;
+    double term = t, acc = 0.0;
+    for (int k = 0; k < 13; ++k) {
+        volatile double q = term / (double)(2 * k + 1);
+        acc = acc + q;
+        volatile double nt = term * t2;
+        term = nt;
+    }
+    volatile double lnx = 2.0 * acc;
+    volatile double y = lnx / PHYS_SUBSTEP_HZ;
+    double e = 1.0, pw = 1.0;
+    for (int k = 1; k <= 7; ++k) {
+        volatile double npw = pw * y;
+        volatile double q = npw / (double)k;
+        pw = q;
+        e = e + pw;
+    }
+    return e;
+}
+
+static float draw_uniform_f64_to_f32_max(uint64_t rng[4], double lo, double range, double floor_) {
+    double u = (double)(oracle_pcg64_next(rng) >> 11) * (1.0 / 9007199254740992.0);
+    volatile double scaled = range * u;
+    double v = lo + scaled;
+    if (v < floor_) v = floor_;
+    return (float)v;
+}
+static double draw_uniform_f64(uint64_t rng[4], double lo, double range) {
+    double u = (double)(oracle_pcg64_next(rng) >> 11) * (1.0 / 9007199254740992.0);
+    volatile double scaled = range * u;
+    return lo + scaled;
+}
+
+/* reset  drone_physics_env.py:174-263.  Draw order per drone: position (3), mass noise, damping noise
+ * (:207-223); then obstacles (3 each, z >= 0.5, :229-232); then goal (3) and goal z in [0.5, 2] (:240-242).
+ * (The reference re-seeds from OS entropy when reset() gets no seed; here the env's stream continues.) */
+static void reset_env_physics(const OracleConfig *c, EnvView *v) {
+    int N = c->num_drones, M = c->num_obstacles;
+    double bound = c->world_size / 2.0;
+    double lo = -bound, range = bound - (-bound);
+    for (int i = 0; i < N; ++i) v->active[i] = 1;
+    *v->step_count = 0;
+    for (int i = 0; i < N; ++i) {
+        v->pos[3 * i + 0] = draw_uniform_f32(v->rng, lo, range);
+        v->pos[3 * i + 1] = draw_uniform_f32(v->rng, lo, range);
+        v->pos[3 * i + 2] = draw_uniform_f64_to_f32_max(v->rng, lo, range, 1.0);  /* pos[2] = max(1.0, pos[2]) */
+        (void)draw_uniform_f64(v->rng, 0.9, 1.1 - 0.9);                           /* mass noise: cancels for a point mass */
+        double damp_noise = draw_uniform_f64(v->rng, 0.8, 1.2 - 0.8);
+        volatile double c_lin = 0.5 * damp_noise;
+        v->damp[i] = (float)phys_damp_factor(c_lin);
+        v->vel[3 * i] = v->vel[3 * i + 1] = v->vel[3 * i + 2] = 0.0f;
+    }
+    for (int m = 0; m < M; ++m) {
+        v->obst[3 * m + 0] = draw_uniform_f32(v->rng, lo, range);
+        v->obst[3 * m + 1] = draw_uniform_f32(v->rng, lo, range);
+        v->obst[3 * m + 2] = draw_uniform_f64_to_f32_max(v->rng, lo, range, 0.5);
+    }
+    v->goal[0] = draw_uniform_f32(v->rng, lo, range);
+    v->goal[1] = draw_uniform_f32(v->rng, lo, range);
+    (void)draw_uniform_f32(v->rng, lo, range);
+    v->goal[2] = draw_uniform_f32(v->rng, 0.5, 2.0 - 0.5);
+    observe_env(c, v);
+}
+
+/* step  drone_physics_env.py:279-419 */
+static void step_physics_env(const OracleConfig *c, EnvView *v, const float *action) {
+    int N = c->num_drones, M = c->num_obstacles, D = obs_dim(c);
+    int n_active = 0;
+    for (int i = 0; i < N; ++i) n_active += v->active[i];
+    for (int i = 0; i < N; ++i) {
+        v->reward[i] = 0.0;
+        v->terminated[i] = v->truncated[i] = v->reached[i] = v->collision[i] = 0;
+    }
+    if (n_active == 0) { /* episode over and not reset: batched contract parks the env (swarm rule) */
+        *v->all_term = 1;
+        *v->all_trunc = 0;
+        for (int i = 0; i < N; ++i) v->obs_valid[i] = 0;
+        return;
+    }
+    const int substeps = (int)(c->dt * PHYS_SUBSTEP_HZ);                /* :323 */
+    const float h = (float)(1.0 / PHYS_SUBSTEP_HZ);
+    const float amax = (float)c->max_accel, vmax = (float)c->max_speed;
+    const float g_net = (float)(PHYS_G_COMP - PHYS_GRAVITY);            /* :343 minus :197 */
+    for (int i = 0; i < N; ++i) {
+        float *p = v->pos + 3 * i, *vel = v->vel + 3 * i;
+        const float *a = action + 3 * i;
+        const float f = v->damp[i];
+        for (int s = 0; s < substeps; ++s) {
+            float speed = norm1d(c, vel[0], vel[1], vel[2]);            /* :349-358 */
+            if (speed > vmax)
+                for (int k = 0; k < 3; ++k) {
+                    volatile float q = vel[k] / speed;
+                    vel[k] = q * vmax;
+                }
+            for (int k = 0; k < 3; ++k) {
+                volatile float acc = a[k] * amax;                       /* :336 (mass cancels) */
+                if (k == 2) { volatile float az = acc + g_net; acc = az; }
+                volatile float dv = acc * h;
+                volatile float vn = vel[k] + dv;
+                vel[k] = vn * f;                                        /* linear damping */
+            }
+            for (int k = 0; k < 3; ++k) {
+                volatile float dp = vel[k] * h;
+                p[k] = p[k] + dp;
+            }
+        }
+    }
+    *v->step_count += 1;                                                /* :363 */
+    const float thr_obst = (float)(c->obstacle_radius + PHYS_R_DRONE);
+    const float thr_pair = (float)(2.0 * PHYS_R_DRONE);
+    int any_collision = 0, all_goals = 1;
+    for (int i = 0; i < N; ++i) {
+        const float *p = v->pos + 3 * i;
+        int hit = p[2] <= PHYS_HALF_HEIGHT;
+        for (int m = 0; m < M; ++m) {
+            float d = norm_axis(v->obst[3 * m] - p[0], v->obst[3 * m + 1] - p[1], v->obst[3 * m + 2] - p[2]);
+            if (d <= thr_obst) hit = 1;
+        }
+        for (int j = 0; j < N; ++j) {
+            if (j == i) continue;
+            const float *q = v->pos + 3 * j;
+            float d = norm1d(c, q[0] - p[0], q[1] - p[1], q[2] - p[2]);
+            if (d <= thr_pair) hit = 1;
+        }
+        float dist = distance_to_goal(c, v->goal, p);
+        double reward = -(double)dist * 0.1;                            /* :381 */
+        int reached = (double)dist < c->goal_radius;                    /* :389, strict */
+        if (hit) { reward -= 10.0; any_collision = 1; }                 /* :385-387 */
+        else if (reached) reward += 50.0;                               /* :389-390 */
+        else all_goals = 0;
+        v->reward[i] = reward;
+        v->collision[i] = (uint8_t)hit;
+        v->reached[i] = (uint8_t)reached;                               /* infos reached_goal (:573) */
+        v->dist[i] = dist;
+        v->obs_valid[i] = 1;
+    }
+    int time_limit = *v->step_count >= c->max_steps;                    /* :397 */
+    int done = any_collision || all_goals || time_limit;
+    int trunc = time_limit && !any_collision && !all_goals;
+    for (int i = 0; i < N; ++i) {                                       /* :401-417 */
+        v->terminated[i] = (uint8_t)(done && !trunc);
+        v->truncated[i] = (uint8_t)(done && trunc);
+        if (done) v->active[i] = 0;
+    }
+    *v->all_term = (uint8_t)(any_collision || all_goals);
+    *v->all_trunc = (uint8_t)trunc;
+    DynConst kc = dyn_const(c, v);
+    for (int i = 0; i < N; ++i)
+        build_obs(c, &kc, *v->step_count, v->pos, v->vel, v->goal, v->obst, i, v->obs + (size_t)i * D);
+    if (v->gs) global_state(c, v->pos, v->vel, v->goal, v->gs);
+}
+
 void oracle_seed_batch(const OracleBatch *b, const uint64_t *seeds) {
     for (int e = 0; e < b->num_envs; ++e) oracle_seed(seeds[e], b->rng + (size_t)e * 4);
 }
@@ -798,6 +989,7 @@ static void step_range(const OracleConfig *c, const OracleBatch *b, const float 
         EnvView v = view(c, b, e);
         const float *act = actions + (size_t)e * N * 3;
         if (c->env_kind == 1) step_swarm_env(c, &v, act);
+        else if (c->env_kind == 2) step_physics_env(c, &v, act);
         else step_single_env(c, &v, act);
         if (auto_reset && (*v.all_term || *v.all_trunc)) {
             /* keep terminal reward / flags, replace obs + info with the reset ones */

@@ -43,7 +43,7 @@ class OracleBatch(C.Structure):
     _fields_ = [("num_envs", C.c_int32), ("pad", C.c_int32)] + [(n, C.c_void_p) for n in (
         "positions", "velocities", "goal", "obstacles", "step_count", "active", "rng", "obs", "reward",
         "dist", "terminated", "truncated", "reached", "collision", "obs_valid", "all_terminated",
-        "all_truncated", "global_state", "dr_params")]
+        "all_truncated", "global_state", "dr_params", "damp")]
 
 
 def build(force: bool = False) -> str:
@@ -85,7 +85,7 @@ class OracleSwarm:
         """dr: flat dict {<range key>: (min, max), <std key>: sigma} (engine semantics, not reference)."""
         cfg = dict(DEFAULTS)
         raw = dict(config or {})
-        self.num_drones = int(raw.pop("num_drones", 3)) if kind == "swarm" else 1
+        self.num_drones = int(raw.pop("num_drones", 3)) if kind in ("swarm", "physics") else 1
         raw.pop("seed", None)
         cfg.update({k: v for k, v in raw.items() if k in DEFAULTS})
         self.cfg = cfg
@@ -95,7 +95,7 @@ class OracleSwarm:
         c = OracleConfig()
         for k in DEFAULTS:
             setattr(c, k, cfg[k])
-        c.num_drones, c.env_kind, c.norm_mode = self.N, (1 if kind == "swarm" else 0), norm_mode
+        c.num_drones, c.env_kind, c.norm_mode = self.N, {"single": 0, "swarm": 1, "physics": 2}[kind], norm_mode
         if dr:
             c.dr_enabled, c.dr_seed, c.env_index_base = 1, int(dr_seed), int(env_index_base)
             for k, name in enumerate(DR_RANGE_KEYS):
@@ -124,6 +124,7 @@ class OracleSwarm:
         self.all_truncated = np.zeros(E, np.uint8)
         self.global_state = np.zeros((E, 6 * N + 3), np.float32)
         self.dr_params = np.zeros((E, 8), np.float32)
+        self.damp = np.ones((E, N), np.float32)   # physics env: per-drone sub-step velocity factor
         b = OracleBatch()
         b.num_envs = E
         for name, _ in OracleBatch._fields_[2:]:
