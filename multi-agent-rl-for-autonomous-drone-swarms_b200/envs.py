@@ -303,6 +303,128 @@ class DronePhysicsEnv(_EngineBacked, _MultiAgentEnv):
         return obs, rewards, terminated, truncated, infos
 
 
+class VectorSwarmEnv:
+    """E `DroneSwarmEnv` instances behind RLlib's `BaseEnv` polling interface
+    (`ray.rllib.env.base_env.BaseEnv`: `poll`, `send_actions`, `try_reset`, `get_sub_environments`),
+    stepped by ONE engine call per step instead of E Python envs (the reference runs
+    one env per rollout worker, `training/config_builders.py:19-23`).  ray is not required.
+
+    Dicts are keyed by env id then agent id and populated by the reference's rules
+    (drone_swarm_env.py:141-172); `infos[...]["global_state"]` is the row the `GlobalStateCallback`
+    (`training/callbacks.py:51-57`) stacks.  An env whose episode ended is reset inside the same engine
+    step (auto-reset); its first observation is handed out by `try_reset(env_id)`, as RLlib expects."""
+
+    def __init__(self, num_envs: int, config: dict[str, Any] | None = None, device=None, base_seed: int | None = None):
+        from .engine import SwarmEngine
+
+        cfg_dict = dict(config or {})
+        self.num_envs = int(num_envs)
+        self.num_drones = int(cfg_dict.get("num_drones", 3))
+        self.cfg = DroneEnvConfig.from_dict({k: v for k, v in cfg_dict.items() if k != "num_drones"})
+        self.agent_ids = [f"drone_{i}" for i in range(self.num_drones)]
+        self._obs_dim = 9 + self.cfg.neighbor_k * 4 + self.cfg.sensed_obstacles * 4
+        self.observation_space = Box(low=-np.inf, high=np.inf, shape=(self._obs_dim,), dtype=np.float32)
+        self.action_space = Box(low=-1.0, high=1.0, shape=(3,), dtype=np.float32)
+        self._engine = SwarmEngine(self.num_envs, cfg_dict, kind="swarm", device=device or "cuda", global_state=True,
+                                   reward64=True)
+        seed0 = base_seed if base_seed is not None else (self.cfg.seed if self.cfg.seed is not None else _entropy_seed())
+        self._engine.seed(np.uint64(seed0) + np.arange(self.num_envs, dtype=np.uint64))   # env e: seed0 + e
+        self._engine.reset()
+        self._active = np.ones((self.num_envs, self.num_drones), bool)   # membership in each env's .agents
+        self._pending = None       # outputs of the last step, not yet polled
+        self._fresh = set(range(self.num_envs))   # envs whose (reset) observation has not been handed out
+
+    def get_sub_environments(self):
+        return []
+
+    def _snapshot(self):
+        import torch
+
+        e = self._engine
+        torch.cuda.synchronize(e.device)
+        return {k: getattr(e, k).cpu().numpy() for k in ("obs", "dist", "global_state", "reward64", "terminated",
+                                                         "truncated", "reached", "collision", "obs_valid",
+                                                         "all_terminated", "all_truncated")}
+
+    def _reset_dicts(self, snap, e):
+        obs = {a: snap["obs"][e, i].copy() for i, a in enumerate(self.agent_ids)}
+        infos = {a: {"distance_to_goal": float(snap["dist"][e, i]), "global_state": snap["global_state"][e].copy()}
+                 for i, a in enumerate(self.agent_ids)}
+        return obs, infos
+
+    def poll(self):
+        """-> (obs, rewards, terminateds, truncateds, infos, off_policy_actions), each {env_id: {agent_id: ...}}."""
+        obs, rew, term, trunc, infos = {}, {}, {}, {}, {}
+        if self._pending is None:           # first poll: the reset observations
+            snap = self._snapshot()
+            for e in sorted(self._fresh):
+                obs[e], infos[e] = self._reset_dicts(snap, e)
+                rew[e], term[e], trunc[e] = {}, {"__all__": False}, {"__all__": False}
+            self._fresh.clear()
+            self._last = snap
+            return obs, rew, term, trunc, infos, {}
+        snap, was_active = self._pending
+        self._pending = None
+        self._last = snap
+        for e in range(self.num_envs):
+            done = bool(snap["all_terminated"][e] or snap["all_truncated"][e])
+            o, r, t, tr, inf = {}, {}, {}, {}, {}
+            for i, a in enumerate(self.agent_ids):
+                if not was_active[e, i]:
+                    continue
+                r[a] = float(snap["reward64"][e, i])
+                t[a] = bool(snap["terminated"][e, i])
+                tr[a] = bool(snap["truncated"][e, i])
+                keep = (not done) and bool(snap["obs_valid"][e, i])
+                if keep:   # drone_swarm_env.py:154-162 (after an auto-reset obs_valid describes the NEW episode)
+                    o[a] = snap["obs"][e, i].copy()
+                    inf[a] = {"distance_to_goal": float(snap["dist"][e, i]), "reached_goal": bool(snap["reached"][e, i]),
+                              "collision": bool(snap["collision"][e, i]), "global_state": snap["global_state"][e].copy()}
+                self._active[e, i] = keep
+            t["__all__"] = bool(snap["all_terminated"][e])
+            tr["__all__"] = bool(snap["all_truncated"][e])
+            if done:
+                self._active[e, :] = True      # the engine has already reset this env
+                self._fresh.add(e)
+            obs[e], rew[e], term[e], trunc[e], infos[e] = o, r, t, tr, inf
+        return obs, rew, term, trunc, infos, {}
+
+    def send_actions(self, action_dict):
+        """{env_id: {agent_id: action(3,)}}; agents without an action get zeros (drone_swarm_env.py:104)."""
+        import torch
+
+        act = np.zeros((self.num_envs, self.num_drones, 3), np.float32)
+        for e, per_agent in action_dict.items():
+            for a, v in per_agent.items():
+                act[e, int(a.rsplit("_", 1)[1])] = np.asarray(v, dtype=np.float32).reshape(3)
+        was_active = self._active.copy()
+        self._engine.step(torch.from_numpy(act).to(self._engine.device), auto_reset=True)
+        self._pending = (self._snapshot(), was_active)
+
+    def try_reset(self, env_id=None, *, seed=None, options=None):
+        """First observation of env `env_id`'s new episode -> ({env_id: obs}, {env_id: infos})."""
+        if env_id not in self._fresh:    # explicit reset of a running env
+            import torch
+
+            mask = torch.zeros(self.num_envs, dtype=torch.uint8)
+            mask[env_id] = 1
+            if seed is not None:
+                seeds = np.zeros(self.num_envs, np.uint64)
+                seeds[env_id] = seed
+                self._engine.seed(seeds, mask)
+            self._engine.reset(mask)
+            self._last = self._snapshot()
+            self._active[env_id, :] = True
+        self._fresh.discard(env_id)
+        obs, infos = self._reset_dicts(self._last, env_id)
+        return {env_id: obs}, {env_id: infos}
+
+    def stop(self):
+        self._engine.close()
+
+    close = stop
+
+
 def make_env_creator(kind: str = "swarm", device=None):
     """Env creator for `ray.tune.registry.register_env(name, creator)`:
     the drop-in for `lambda cfg: DroneSwarmEnv(cfg)` (reference scripts/train_multi_agent.py:96)."""

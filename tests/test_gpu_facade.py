@@ -139,3 +139,46 @@ def test_dead_env_step_and_reseed():
     env2 = DroneSwarmEnv({"num_drones": 3, "seed": 123, "max_steps": 2})
     o2, _ = env2.reset()
     assert all(np.array_equal(o1[a], o2[a]) for a in o1)
+
+
+@pytest.mark.gpu
+def test_vector_env_matches_per_env_facades():
+    """VectorSwarmEnv (RLlib BaseEnv-style poll / send_actions / try_reset over ONE engine) hands out
+    what E separate DroneSwarmEnv instances do, episode after episode."""
+    import swarm_b200
+
+    cfg = {"num_drones": 4, "num_obstacles": 6, "max_steps": 12, "world_size": 12.0}
+    E, base = 6, 4000
+    vec = swarm_b200.VectorSwarmEnv(E, cfg, base_seed=base)
+    refs = [swarm_b200.DroneSwarmEnv({**cfg, "seed": base + e}) for e in range(E)]
+    obs, rew, term, trunc, infos, _ = vec.poll()
+    cur = {}
+    for e, r in enumerate(refs):
+        o, i = r.reset()
+        cur[e] = o
+        assert set(obs[e]) == set(o) and all(np.array_equal(obs[e][a], o[a]) for a in o)
+        assert np.array_equal(infos[e]["drone_0"]["global_state"], i["drone_0"]["global_state"])
+    rng = np.random.default_rng(2)
+    episodes = 0
+    for t in range(60):
+        actions = {e: {a: rng.uniform(-1, 1, 3).astype(np.float32) for a in cur[e]} for e in range(E)}
+        vec.send_actions(actions)
+        obs, rew, term, trunc, infos, _ = vec.poll()
+        for e, r in enumerate(refs):
+            o, rw, te, tr, inf = r.step(actions[e])
+            assert rew[e] == rw and term[e] == te and trunc[e] == tr, (t, e)
+            assert set(obs[e]) == set(o) and all(np.array_equal(obs[e][a], o[a]) for a in o), (t, e)
+            assert all(infos[e][a]["collision"] == inf[a]["collision"] and
+                       np.array_equal(infos[e][a]["global_state"], inf[a]["global_state"]) for a in o)
+            cur[e] = o
+            if te["__all__"] or tr["__all__"]:
+                episodes += 1
+                ro, ri = vec.try_reset(e)
+                o2, i2 = r.reset()
+                assert all(np.array_equal(ro[e][a], o2[a]) for a in o2), (t, e)
+                assert ri[e]["drone_1"]["distance_to_goal"] == i2["drone_1"]["distance_to_goal"]
+                cur[e] = o2
+    assert episodes >= E
+    vec.stop()
+    for r in refs:
+        r.close()
