@@ -276,8 +276,13 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
     unsigned st_eps = 0, st_succ = 0, st_col = 0, st_to = 0, st_len = 0, st_asteps = 0, st_esteps = 0;
     double st_ret = 0.0;
 
+    // dynamic group queue (the first group of every warp is static): with only a few groups per warp a
+    // static grid stride leaves most SMs idle during the last round
     const int warps_total = gridDim.x * kWarpsPerCta;
-    for (int grp = blockIdx.x * kWarpsPerCta + warp; grp < P.n_groups; grp += warps_total) {
+    int grp = blockIdx.x * kWarpsPerCta + warp;
+    while (grp < P.n_groups) {
+        int grp_next = 0;
+        if (lane == 0) grp_next = warps_total + (int)atomicAdd(P.work_counter, 1u);
         const int env0 = P.env_begin + grp * G;
         const int n_env = min(G, P.env_begin + P.env_count - env0);
         const bool lane_env_ok = e_l < n_env;
@@ -607,6 +612,12 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                 if (P.episode_length) P.episode_length[env0 + lane] = 0;
             }
         }
+        grp = __shfl_sync(FULL_MASK, grp_next, 0);
+    }
+    // the last warp to leave re-arms the queue for the next launch
+    if (lane == 0 && atomicAdd(P.work_counter + 1, 1u) == (unsigned)warps_total - 1u) {
+        P.work_counter[0] = 0u;
+        P.work_counter[1] = 0u;
     }
 
     // ---- statistics: one atomic per warp per counter
