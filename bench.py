@@ -7,7 +7,8 @@ prints ONE JSON line on rank 0.
 Workload = BASELINE.json configs[3] ("C4", the config the metric is quoted on): 32-drone swarm,
 8 obstacles, reference-default DroneEnvConfig (world 20, K=3, S=4, max_steps 400), per-env domain
 randomisation with the ranges of the reference's configs/domain_randomization_v1.yaml (mass / accel /
-speed / dt / obstacle-radius / world scales, thrust and sensor noise; control delay not implemented),
+speed / dt / obstacle-radius / world scales, thrust and sensor noise; its control_delay_steps block
+is off by default because it routes the step to the slower general kernel: --dr-delay),
 65536 env instances PER GPU (weak scaling; the whole of C4 fits one GPU), i.i.d. U(-1,1) float32
 actions read from device memory, auto-reset on, global_state emitted.  A "step" advances every env
 instance once (step launch + the small auto-reset launch enqueued behind it).  The per-step working
@@ -50,7 +51,7 @@ WORKLOADS = {
 }
 
 
-# configs/domain_randomization_v1.yaml:9-60 of the reference (control_delay_steps excluded: not implemented)
+# configs/domain_randomization_v1.yaml:9-60 of the reference (control_delay_steps: see --dr-delay)
 DR_V1 = {"mass_scale": (0.85, 1.15), "max_accel_scale": (0.90, 1.10), "max_speed_scale": (0.90, 1.10),
          "dt_scale": (0.95, 1.05), "obstacle_radius_scale": (0.9, 1.1), "world_size_scale": (0.95, 1.05),
          "thrust_noise_std": 0.03, "position_noise_std": 0.02, "velocity_noise_std": 0.02,
@@ -207,6 +208,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-global-state", action="store_true")
     ap.add_argument("--no-dr-off", action="store_true", help="skip the secondary DR-off measurement")
+    ap.add_argument("--dr-delay", action="store_true",
+                    help="also randomise control_delay_steps ({0,1,2} with p {0.7,0.2,0.1}); runs on the general kernel")
     ap.add_argument("--dr", default="auto", choices=["auto", "on", "off"],
                     help="domain randomisation (domain_randomization_v1 ranges); auto = on for c4 (BASELINE configs[3])")
     args = ap.parse_args()
@@ -243,6 +246,8 @@ def main():
         e.reset()
         return e
 
+    if args.dr_delay:
+        DR_V1["control_delay_steps"] = ((0, 1, 2), (0.7, 0.2, 0.1))
     eng = make_engine(dr_enabled(args))
     N = eng.N
     gen = torch.Generator(device=dev)

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SWARM_ABI_VERSION 2
+#define SWARM_ABI_VERSION 3
 
 enum {
     SWARM_OK = 0,
@@ -81,6 +81,12 @@ typedef struct SwarmConfig {
     double dr_obstacle_radius_scale[2], dr_world_size_scale[2];   /* uniform [min, max], per env per episode */
     double dr_thrust_noise_std;             /* multiplicative Gaussian on the clipped action, per drone per step */
     double dr_position_noise_std, dr_velocity_noise_std, dr_obstacle_distance_noise_std;  /* additive, on the obs */
+    /* actuation.control_delay_steps: per episode a delay d is drawn from {values[k] with probability probs[k]};
+     * the command applied at step t is the one submitted at step t - d (zero while the episode is younger) */
+    int32_t dr_delay_count;       /* 0 = no control delay; <= 4 */
+    int32_t dr_delay_reserved;
+    int32_t dr_delay_values[4];   /* each in [0, 8] */
+    double dr_delay_probs[4];
 } SwarmConfig;
 
 /* Element counts of every buffer, as a function of the config (swarm_query_sizes). */
@@ -101,6 +107,7 @@ typedef struct SwarmSizes {
     int64_t global_state;  /* E*(6N+3) float32 */
     int64_t stats;         /* SWARM_STATS_WORDS uint64 */
     int64_t dr_params;     /* E*8 float32 */
+    int64_t act_hist;      /* E*H*N*3 float32, H = max(dr_delay_values) (0 when no control delay) */
 } SwarmSizes;
 
 /* Device pointers.  State is structure-of-arrays with one float4 per drone so every state
@@ -136,7 +143,8 @@ typedef struct SwarmBuffers {
     int32_t *episode_length; /* [E]    nullable: its length in steps (0 when no episode ended) */
     uint64_t *stats;     /* [SWARM_STATS_WORDS] nullable: running counters, see SWARM_STAT_* */
     float *dr_params;    /* [E][8] state, required when dr_enabled: per-env per-episode constants
-                            {max_accel, max_speed, dt, bound, obstacle threshold, episode key, world, 0} */
+                            {max_accel, max_speed, dt, bound, obstacle threshold, episode key, world, control delay} */
+    float *act_hist;     /* [E][H][N][3] state, required when a control delay is configured: command ring */
 } SwarmBuffers;
 
 /* stats block (uint64 words; SWARM_STAT_RETURN_SUM holds a double's bit pattern) */

@@ -11,7 +11,7 @@ import os
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SWARM_B200_LIB") or os.path.join(_PKG_DIR, "libswarm_b200.so")  # override: tuning builds
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 KIND_SINGLE, KIND_SWARM, KIND_PHYSICS = 0, 1, 2
 MAX_DRONES, MAX_NEIGHBOR_K, MAX_SENSED = 128, 8, 8
 
@@ -35,18 +35,20 @@ class SwarmConfig(C.Structure):
                [(n, C.c_double) for n in _DOUBLES] + \
                [("dr_enabled", C.c_int32), ("dr_reserved", C.c_int32), ("dr_seed", C.c_uint64),
                 ("env_index_base", C.c_int64)] + \
-               [(n, C.c_double * 2) for n in DR_RANGES] + [(n, C.c_double) for n in DR_STDS]
+               [(n, C.c_double * 2) for n in DR_RANGES] + [(n, C.c_double) for n in DR_STDS] + \
+               [("dr_delay_count", C.c_int32), ("dr_delay_reserved", C.c_int32), ("dr_delay_values", C.c_int32 * 4),
+                ("dr_delay_probs", C.c_double * 4)]
 
 
 class SwarmSizes(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("obs_dim", "state_dim", "pos4", "vel4", "goal4", "obst4", "step_count",
                                          "rng", "ep_return", "actions", "obs", "per_agent", "per_env",
-                                         "global_state", "stats", "dr_params")]
+                                         "global_state", "stats", "dr_params", "act_hist")]
 
 
 BUFFER_FIELDS = ("pos4", "vel4", "goal4", "obst4", "step_count", "rng", "ep_return", "obs", "reward", "reward64",
                  "dist", "terminated", "truncated", "reached", "collision", "obs_valid", "all_terminated",
-                 "all_truncated", "global_state", "episode_return", "episode_length", "stats", "dr_params")
+                 "all_truncated", "global_state", "episode_return", "episode_length", "stats", "dr_params", "act_hist")
 
 
 class SwarmBuffers(C.Structure):

@@ -49,8 +49,8 @@ def flatten_domain_randomization(spec: dict[str, Any] | None) -> dict[str, Any]:
     Accepts the flat form itself, or the document shape of the reference's
     `configs/domain_randomization_v1.yaml:9-60` (`randomization: {dynamics|actuation|sensing|
     environment: {<key>: {distribution, min, max | std}}}`).  No reference code reads that file, so
-    what each key DOES is defined by this engine.  `control_delay_steps` is not
-    implemented and is rejected rather than silently ignored unless it is the no-delay setting."""
+    what each key DOES is defined by this engine.  `control_delay_steps`
+    ({values, probs} or ((values...), (probs...))) is kept only when some value is non-zero."""
     if not spec:
         return {}
     flat: dict[str, Any] = {}
@@ -69,11 +69,13 @@ def flatten_domain_randomization(spec: dict[str, Any] | None) -> dict[str, Any]:
         elif k in DR_STD_KEYS:
             flat[k] = float(v["std"]) if isinstance(v, dict) else float(v)
         elif k == "control_delay_steps":
-            vals = v.get("values", [0]) if isinstance(v, dict) else v
-            probs = v.get("probs") if isinstance(v, dict) else None
-            live = [x for j, x in enumerate(vals) if probs is None or probs[j] > 0]
-            if any(int(x) != 0 for x in live):
-                raise NotImplementedError("control_delay_steps > 0 is not implemented by the engine")
+            vals, probs = (v.get("values", [0]), v.get("probs")) if isinstance(v, dict) else v
+            vals = [int(x) for x in vals]
+            probs = [1.0 / len(vals)] * len(vals) if probs is None else [float(x) for x in probs]
+            if len(vals) != len(probs) or not 1 <= len(vals) <= 4 or min(vals) < 0 or max(vals) > 8 or min(probs) < 0:
+                raise ValueError("control_delay_steps: 1-4 values in [0, 8] with matching non-negative probs")
+            if any(x for x, pr in zip(vals, probs) if pr > 0):
+                flat[k] = (tuple(vals), tuple(probs))
         elif groups is None:
             raise KeyError(f"unknown domain-randomisation key {k!r}")
     return flat

@@ -66,6 +66,14 @@ int obs_dim_of(const SwarmConfig& c) {
                                           : 9 + 4 * c.sensed_obstacles;
 }
 
+// ring size of the command history: the largest configured control delay (0 = no delay anywhere)
+int delay_hist_of(const SwarmConfig& c) {
+    int h = 0;
+    if (c.dr_enabled)
+        for (int k = 0; k < c.dr_delay_count && k < 4; ++k) h = c.dr_delay_values[k] > h ? c.dr_delay_values[k] : h;
+    return h;
+}
+
 int validate(const SwarmConfig* c) {
     if (!c) return fail(SWARM_E_NULL, "config is NULL");
     if (c->abi_version != SWARM_ABI_VERSION)
@@ -98,6 +106,11 @@ int validate(const SwarmConfig* c) {
         if (c->dr_thrust_noise_std < 0 || c->dr_position_noise_std < 0 || c->dr_velocity_noise_std < 0 ||
             c->dr_obstacle_distance_noise_std < 0)
             return fail(SWARM_E_INVALID, "domain randomisation noise std must be >= 0");
+        if (c->dr_delay_count < 0 || c->dr_delay_count > 4)
+            return fail(SWARM_E_INVALID, "dr_delay_count must be in [0, 4]");
+        for (int k = 0; k < c->dr_delay_count; ++k)
+            if (c->dr_delay_values[k] < 0 || c->dr_delay_values[k] > 8 || !(c->dr_delay_probs[k] >= 0.0))
+                return fail(SWARM_E_INVALID, "control delay %d: value must be in [0, 8] and its probability >= 0", k);
     }
     if ((int64_t)c->num_envs * c->num_drones > (int64_t)1 << 30)
         return fail(SWARM_E_UNSUPPORTED, "num_envs * num_drones too large");
@@ -195,6 +208,14 @@ void fill_params(const SwarmConfig& c, DevParams& p) {
         p.dr_r_c = c.collision_radius; p.dr_r_o = c.obstacle_radius;
         p.dr_std_thrust = (float)c.dr_thrust_noise_std; p.dr_std_pos = (float)c.dr_position_noise_std;
         p.dr_std_vel = (float)c.dr_velocity_noise_std; p.dr_std_obst = (float)c.dr_obstacle_distance_noise_std;
+        p.dr_delay_hist = delay_hist_of(c);
+        p.dr_delay_count = p.dr_delay_hist > 0 ? c.dr_delay_count : 0;
+        double cum = 0.0;
+        for (int k = 0; k < p.dr_delay_count; ++k) {
+            cum += c.dr_delay_probs[k];
+            p.dr_delay_values[k] = c.dr_delay_values[k];
+            p.dr_delay_cum[k] = cum;
+        }
     }
     p.n_others = (double)(p.N - 1);
     p.inv_n_others = p.N > 1 ? 1.0 / (double)(p.N - 1) : 0.0;
@@ -255,6 +276,10 @@ int bind_buffers(const SwarmHandle* h, const SwarmBuffers* b, DevParams& p) {
         if (reinterpret_cast<uintptr_t>(b->dr_params) & 15u) return fail(SWARM_E_INVALID, "dr_params must be 16-byte aligned");
         p.dr_params = reinterpret_cast<float4*>(b->dr_params);
         p.dr_qtable = h->qtable_dev;
+        if (p.dr_delay_hist > 0) {
+            if (!b->act_hist) return fail(SWARM_E_NULL, "act_hist is required when a control delay is configured");
+            p.act_hist = b->act_hist;
+        }
     }
     return SWARM_OK;
 }
@@ -268,6 +293,7 @@ bool rot_eligible(const SwarmConfig& c) {
     if (c.num_obstacles < 4 || c.num_obstacles > 32 || (c.num_obstacles & 3)) return false;
     const double ds = c.desired_spacing;
     if (!(ds >= 0.0) || !(ds < 1024.0) || std::ldexp(ds, 37) != std::floor(std::ldexp(ds, 37))) return false;
+    if (delay_hist_of(c) > 0) return false;   // the control-delay ring is handled by the general kernel
     const double wscale = c.dr_enabled ? c.dr_world_size_scale[1] : 1.0;
     if (!(c.world_size * wscale < 1024.0)) return false;   // every distance < 2048
     const char* off = std::getenv("SWARM_B200_NO_ROT");
@@ -346,6 +372,7 @@ int swarm_query_sizes(const SwarmConfig* cfg, SwarmSizes* out) {
     out->global_state = E * (6 * N + 3);
     out->stats = SWARM_STATS_WORDS;
     out->dr_params = E * 8;
+    out->act_hist = E * delay_hist_of(*cfg) * N * 3;
     return SWARM_OK;
 }
 

@@ -78,6 +78,10 @@ struct DevParams {
     float dr_std_thrust, dr_std_pos, dr_std_vel, dr_std_obst;
     float4* dr_params;            // [E][2] float4
     const float* dr_qtable;       // [256] half-normal quantiles
+    int dr_delay_count, dr_delay_hist;   // control delay: number of choices, ring size H (0 = off)
+    int dr_delay_values[4];
+    double dr_delay_cum[4];
+    float* act_hist;              // [E][H][N][3] ring of submitted commands
 };
 
 // kernel selection (swarm_kernels.cu)

@@ -76,6 +76,11 @@ class SwarmEngine:
                 getattr(c, name)[0], getattr(c, name)[1] = float(lo), float(hi)
             for name in _abi.DR_STDS:
                 setattr(c, name, float(self.dr.get(name[3:], 0.0)))
+            delay = self.dr.get("control_delay_steps")
+            if delay:
+                c.dr_delay_count = len(delay[0])
+                for k, (val, pr) in enumerate(zip(*delay)):
+                    c.dr_delay_values[k], c.dr_delay_probs[k] = int(val), float(pr)
         self._c = c
         sz = _abi.SwarmSizes()
         _abi.check(self._lib.swarm_query_sizes(C.byref(c), C.byref(sz)), "swarm_query_sizes")
@@ -111,6 +116,8 @@ class SwarmEngine:
         self.stats_words = z((len(_abi.STAT_NAMES),), torch.int64)
         # per-env per-episode dynamics constants of the domain randomisation (written by reset)
         self.dr_params = z((E, 8), torch.float32) if self.dr else None
+        # control delay: ring of the last H submitted commands per env
+        self.act_hist = z((E, int(sz.act_hist) // max(E * N * 3, 1), N, 3), torch.float32) if int(sz.act_hist) else None
         self.pos4[..., 3] = 1.0
         self._actions_dev = None
         self._bufs = self._make_buffers()
@@ -247,6 +254,8 @@ class SwarmEngine:
         out = {k: getattr(self, k).detach().cpu().clone() for k in self._STATE_KEYS}
         if self.dr_params is not None:
             out["dr_params"] = self.dr_params.detach().cpu().clone()
+        if self.act_hist is not None:
+            out["act_hist"] = self.act_hist.detach().cpu().clone()
         out["meta"] = dict(kind=self.kind, E=self.E, N=self.N, M=self.M, K=self.K, S=self.S)
         return out
 
@@ -259,6 +268,8 @@ class SwarmEngine:
             getattr(self, k).copy_(state[k].to(self.device))
         if self.dr_params is not None:
             self.dr_params.copy_(state["dr_params"].to(self.device))
+        if self.act_hist is not None:
+            self.act_hist.copy_(state["act_hist"].to(self.device))
         if observe:
             self.observe()
 

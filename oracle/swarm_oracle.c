@@ -69,6 +69,13 @@ typedef struct OracleConfig {
     int64_t env_index_base;
     double dr_lo[6], dr_span[6]; /* mass, max_accel, max_speed, dt, obstacle_radius, world_size scales */
     double dr_std_thrust, dr_std_pos, dr_std_vel, dr_std_obst;
+    /* control delay (yaml actuation.control_delay_steps): per episode a delay d is drawn from the discrete
+     * distribution {values[k] with probability probs[k]}; the command applied at step t is the one
+     * submitted at step t - d (zero while the episode is younger than d steps) */
+    int32_t dr_delay_count;      /* 0 = no control delay */
+    int32_t dr_delay_hist;       /* ring size of the command history = max(values), >= 1 when count > 0 */
+    int32_t dr_delay_values[4];
+    double dr_delay_cum[4];      /* cumulative probabilities */
 } OracleConfig;
 
 /* One batch of E environments, arrays laid out exactly like the reference's
@@ -97,6 +104,7 @@ typedef struct OracleBatch {
     float *global_state; /* [E][6N+3]  info["global_state"] (drone_swarm_env.py:293-302) */
     float *dr_params;    /* [E][8]     DR only: {max_accel, max_speed, dt, bound, obst threshold, key, world, 0} */
     float *damp;         /* [E][N]     physics env only: per-drone velocity factor of one 1/240 s sub-step */
+    float *act_hist;     /* [E][H][N][3] control delay only: ring of the last H submitted commands */
 } OracleBatch;
 
 /* ------------------------------------------------------------------------- */
@@ -502,6 +510,7 @@ typedef struct EnvView {
     uint8_t *terminated, *truncated, *reached, *collision, *obs_valid, *all_term, *all_trunc;
     float *dr;
     float *damp;
+    float *act_hist;
     int env_index;
 } EnvView;
 
@@ -528,8 +537,27 @@ static EnvView view(const OracleConfig *c, const OracleBatch *b, int e) {
     v.all_trunc = b->all_truncated + e;
     v.dr = b->dr_params ? b->dr_params + (size_t)e * 8 : NULL;
     v.damp = b->damp ? b->damp + (size_t)e * N : NULL;
+    v.act_hist = (b->act_hist && c->dr_delay_hist > 0) ? b->act_hist + (size_t)e * c->dr_delay_hist * N * 3 : NULL;
     v.env_index = e;
     return v;
+}
+
+/* control delay: the command applied at step t (= step_count before the step) is the one submitted at
+ * t - d; the ring slot t % H then takes the command submitted now.  out = 3 floats. */
+static void delayed_command(const OracleConfig *c, const EnvView *v, int drone, const float *submitted, float *out) {
+    int N = c->num_drones, H = c->dr_delay_hist;
+    int d = (c->dr_enabled && v->dr && v->act_hist) ? (int)v->dr[7] : 0;
+    int t = *v->step_count;
+    if (d == 0) { out[0] = submitted[0]; out[1] = submitted[1]; out[2] = submitted[2]; }
+    else if (t < d) { out[0] = out[1] = out[2] = 0.0f; }
+    else {
+        const float *h = v->act_hist + ((size_t)((t - d) % H) * N + drone) * 3;
+        out[0] = h[0]; out[1] = h[1]; out[2] = h[2];
+    }
+    if (v->act_hist) {
+        float *w = v->act_hist + ((size_t)(t % H) * N + drone) * 3;
+        w[0] = submitted[0]; w[1] = submitted[1]; w[2] = submitted[2];
+    }
 }
 
 /* the dynamics constants of one env: the config's, or (DR) this episode's */
@@ -611,6 +639,13 @@ static void reset_env(const OracleConfig *c, EnvView *v) {
         memcpy(v->dr + 5, &rb[2], 4);
         v->dr[6] = (float)world;
         v->dr[7] = 0.0f;
+        if (c->dr_delay_count > 0) { /* this episode's control delay from the 4th word of the second block */
+            double uu = (double)(rb[3] >> 8) * inv24;
+            int pick = c->dr_delay_count - 1;
+            for (int k = 0; k < c->dr_delay_count; ++k)
+                if (uu < c->dr_delay_cum[k]) { pick = k; break; }
+            v->dr[7] = (float)c->dr_delay_values[pick];
+        }
         bound = half_w;
     }
     double lo = -bound, range = bound - (-bound);
@@ -694,7 +729,11 @@ static void step_swarm_env(const OracleConfig *c, EnvView *v, const float *actio
         if (v->active[i]) prev[i] = (double)distance_to_goal(c, v->goal, v->pos + 3 * i);
     DynConst kc = dyn_const(c, v);
     for (int i = 0; i < N; ++i) /* :103-111 */
-        if (v->active[i]) integrate(c, &kc, *v->step_count, i, action + 3 * i, v->pos + 3 * i, v->vel + 3 * i);
+        if (v->active[i]) {
+            float cmd[3];
+            delayed_command(c, v, i, action + 3 * i, cmd);
+            integrate(c, &kc, *v->step_count, i, cmd, v->pos + 3 * i, v->vel + 3 * i);
+        }
     float bound = kc.bound; /* (float)(world_size / 2): :113-117, all drones */
     for (int k = 0; k < 3 * N; ++k) v->pos[k] = clipf(v->pos[k], -bound, bound);
     *v->step_count += 1; /* :118 */
@@ -748,7 +787,9 @@ static void step_single_env(const OracleConfig *c, EnvView *v, const float *acti
     int M = c->num_obstacles;
     double prev = (double)distance_to_goal(c, v->goal, v->pos); /* :77 */
     DynConst kc = dyn_const(c, v);
-    integrate(c, &kc, *v->step_count, 0, action, v->pos, v->vel); /* :74-75, 79-82 */
+    float cmd[3];
+    delayed_command(c, v, 0, action, cmd);
+    integrate(c, &kc, *v->step_count, 0, cmd, v->pos, v->vel); /* :74-75, 79-82 */
     float bound = kc.bound;
     for (int k = 0; k < 3; ++k) v->pos[k] = clipf(v->pos[k], -bound, bound); /* :83-87 */
     *v->step_count += 1;                                                       /* :89 */

@@ -32,7 +32,9 @@ class OracleConfig(C.Structure):
         "max_steps", "num_obstacles", "sensed_obstacles", "neighbor_k", "num_drones", "env_kind",
         "norm_mode", "reserved", "dr_enabled", "dr_pad")] + [("dr_seed", C.c_uint64), ("env_index_base", C.c_int64),
                                                              ("dr_lo", C.c_double * 6), ("dr_span", C.c_double * 6)] + [
-        (n, C.c_double) for n in ("dr_std_thrust", "dr_std_pos", "dr_std_vel", "dr_std_obst")]
+        (n, C.c_double) for n in ("dr_std_thrust", "dr_std_pos", "dr_std_vel", "dr_std_obst")] + [
+        ("dr_delay_count", C.c_int32), ("dr_delay_hist", C.c_int32), ("dr_delay_values", C.c_int32 * 4),
+        ("dr_delay_cum", C.c_double * 4)]
 
 DR_RANGE_KEYS = ("mass_scale", "max_accel_scale", "max_speed_scale", "dt_scale", "obstacle_radius_scale",
                  "world_size_scale")
@@ -43,7 +45,7 @@ class OracleBatch(C.Structure):
     _fields_ = [("num_envs", C.c_int32), ("pad", C.c_int32)] + [(n, C.c_void_p) for n in (
         "positions", "velocities", "goal", "obstacles", "step_count", "active", "rng", "obs", "reward",
         "dist", "terminated", "truncated", "reached", "collision", "obs_valid", "all_terminated",
-        "all_truncated", "global_state", "dr_params", "damp")]
+        "all_truncated", "global_state", "dr_params", "damp", "act_hist")]
 
 
 def build(force: bool = False) -> str:
@@ -102,6 +104,14 @@ class OracleSwarm:
                 lo, hi = dr.get(name, (1.0, 1.0))
                 c.dr_lo[k], c.dr_span[k] = float(lo), float(hi) - float(lo)
             c.dr_std_thrust, c.dr_std_pos, c.dr_std_vel, c.dr_std_obst = (float(dr.get(n, 0.0)) for n in DR_STD_KEYS)
+            delay = dr.get("control_delay_steps")   # ((values...), (probs...)), engine semantics
+            if delay and any(int(x) for x in delay[0]):
+                vals, probs = [int(x) for x in delay[0]], [float(x) for x in delay[1]]
+                c.dr_delay_count, c.dr_delay_hist = len(vals), max(vals)
+                cum = 0.0
+                for k, (x, pr) in enumerate(zip(vals, probs)):
+                    cum += pr
+                    c.dr_delay_values[k], c.dr_delay_cum[k] = x, cum
         self._c = c
         self.D = lib().oracle_obs_dim(C.byref(c))
         E, N, M, D = self.E, self.N, self.M, self.D
@@ -125,6 +135,7 @@ class OracleSwarm:
         self.global_state = np.zeros((E, 6 * N + 3), np.float32)
         self.dr_params = np.zeros((E, 8), np.float32)
         self.damp = np.ones((E, N), np.float32)   # physics env: per-drone sub-step velocity factor
+        self.act_hist = np.zeros((E, max(int(c.dr_delay_hist), 1), N, 3), np.float32)   # control delay: command ring
         b = OracleBatch()
         b.num_envs = E
         for name, _ in OracleBatch._fields_[2:]:

@@ -48,8 +48,8 @@ def test_flatten_yaml_document_shape():
     assert fl(doc) == {"mass_scale": (0.85, 1.15), "thrust_noise_std": 0.03, "position_noise_std": 0.02,
                        "world_size_scale": (0.95, 1.05)}
     assert fl(None) == {} and fl({}) == {}
-    with pytest.raises(NotImplementedError):
-        fl({"control_delay_steps": {"values": [0, 1, 2], "probs": [0.7, 0.2, 0.1]}})
+    with pytest.raises(ValueError):
+        fl({"control_delay_steps": {"values": [0, 1, 20], "probs": [0.7, 0.2, 0.1]}})
     with pytest.raises(KeyError):
         fl({"gravity_scale": (1, 2)})
 
@@ -178,3 +178,54 @@ def test_cuda_quantile_table_matches_oracle():
     so.lib().oracle_dr_quantile_table(a.ctypes.data_as(C.c_void_p))
     assert swarm_b200._abi.load().swarm_dr_quantile_table(b.ctypes.data_as(C.c_void_p)) == 0
     assert np.array_equal(a, b)
+
+
+DR_DELAY = {**DR_V1, "control_delay_steps": ((0, 1, 2), (0.7, 0.2, 0.1))}   # the yaml's actuation block
+
+
+def test_oracle_control_delay_shifts_the_command():
+    import swarm_oracle as so
+    cfg = {"num_drones": 3, "num_obstacles": 0, "max_steps": 50, "world_size": 100.0}
+    E = 4000
+    o = so.OracleSwarm(E, cfg, dr={"control_delay_steps": ((0, 1, 2), (0.7, 0.2, 0.1))}, dr_seed=4)
+    o.seed(np.arange(E, dtype=np.uint64))
+    o.reset()
+    d = o.dr_params[:, 7].astype(int)
+    np.testing.assert_allclose(np.bincount(d, minlength=3) / E, [0.7, 0.2, 0.1], atol=0.03)
+    impulse = np.zeros((E, 3, 3), np.float32)
+    impulse[..., 0] = 1.0
+    for t in range(4):
+        o.step(impulse if t == 0 else np.zeros_like(impulse), auto_reset=False)
+        arrived = o.velocities[:, 0, 0] != 0
+        assert np.array_equal(arrived, d <= t)      # the impulse of step 0 acts at step d
+
+
+def test_flatten_accepts_the_yaml_delay_block():
+    from swarm_b200.config import flatten_domain_randomization as fl
+    doc = {"randomization": {"actuation": {"control_delay_steps": {"distribution": "discrete", "values": [0, 1, 2],
+                                                                   "probs": [0.7, 0.2, 0.1]}}}}
+    assert fl(doc) == {"control_delay_steps": ((0, 1, 2), (0.7, 0.2, 0.1))}
+    assert fl({"control_delay_steps": ((0,), (1.0,))}) == {}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,cfg,E,T", [("swarm", {"num_drones": 32, "num_obstacles": 8}, 256, 40),
+                                          ("swarm", {"num_drones": 8, "num_obstacles": 4, "max_steps": 30}, 600, 70),
+                                          ("single", {"num_obstacles": 8, "max_steps": 40}, 1000, 90)])
+def test_cuda_control_delay_matches_oracle(kind, cfg, E, T):
+    import swarm_oracle as so
+    from engine_backend import EngineBackend
+    N = int(cfg.get("num_drones", 1)) if kind == "swarm" else 1
+
+    def make():
+        return [so.OracleSwarm(E, cfg, kind=kind, dr=DR_DELAY, dr_seed=77, env_index_base=10),
+                EngineBackend(E, cfg, kind=kind, domain_randomization=DR_DELAY, dr_seed=77, env_index_base=10)]
+
+    def check(envs, t):
+        o, b = envs
+        for name in FIELDS + ("dr_params",):
+            pu.assert_biteq(name, getattr(b, name), getattr(o, name), t)
+        valid = o.obs_valid.astype(bool)
+        assert not ((pu.bits(b.obs) != pu.bits(o.obs)).any(axis=2) & valid).any(), t
+
+    _roll(make, cfg, kind, E, T, N, check=check)
