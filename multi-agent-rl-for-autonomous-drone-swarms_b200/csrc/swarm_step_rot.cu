@@ -29,7 +29,6 @@ namespace {
 
 constexpr int kD = 37;            // 9 + 4 * 3 + 4 * 4
 constexpr int kTileBytes = 32 * kD * 4;
-constexpr float kFormExactMinS = 3.725290298461914e-09f;  // 2^-28: d >= 2^-14
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -65,9 +64,11 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 #ifndef SWARM_ROT_TMA_LOADS
 #define SWARM_ROT_TMA_LOADS 1
 #endif
+#if !SWARM_ROT_TMA_LOADS
 __device__ __forceinline__ void cp_async16(unsigned saddr, const void* g) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
 }
+#endif
 __device__ __forceinline__ void cp_async4(unsigned saddr, const void* g) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(g) : "memory");
 }
