@@ -362,3 +362,57 @@ def test_batched_evaluator_matches_reference_loop_on_facade():
     truth = swarm_b200.evaluate_batched(eng2, policy_t, faithful=False)
     assert 0.0 <= truth["aggregate"]["success_rate"] <= 1.0
     assert truth["per_episode"]["length"].tolist() == [r["length"] for r in ref]
+
+
+FULL_SIZE = [
+    # BASELINE.json configs at their FULL env counts (C2's 4096 envs is in CASES above)
+    ("c3", {"num_drones": 16, "num_obstacles": 8}, 16384, 40, None),
+    ("c4", {"num_drones": 32, "num_obstacles": 8}, 65536, 16, None),
+    ("c4_dr", {"num_drones": 32, "num_obstacles": 8}, 65536, 12, "v1"),
+    ("c5", {"num_drones": 128, "num_obstacles": 8, "world_size": 70.0}, 8192, 6, None),
+]
+
+
+@pytest.mark.parametrize("name,cfg,E,T,dr", FULL_SIZE)
+def test_cuda_matches_oracle_at_full_baseline_size(name, cfg, E, T, dr):
+    """The whole BASELINE batch (tens of thousands of env instances) against the C oracle, every array
+    bit for bit; the oracle needs a few seconds per config on the box's host threads."""
+    import os
+    import swarm_oracle as so
+    from parity_util import assert_biteq
+
+    dr_cfg = None
+    if dr:
+        from test_domain_randomization import DR_V1
+        dr_cfg = DR_V1
+    kw = dict(domain_randomization=dr_cfg, dr_seed=2026) if dr_cfg else {}
+    b = _backend(E, cfg, **kw)
+    o = so.OracleSwarm(E, cfg, dr=dr_cfg, dr_seed=2026)
+    seeds = np.arange(E, dtype=np.uint64)
+    for x in (b, o):
+        x.seed(seeds)
+        x.reset()
+    rng = np.random.default_rng(123)
+    N = o.N
+    threads = len(os.sched_getaffinity(0))
+    ties = 0
+    for t in range(-1, T):
+        if t >= 0:
+            act = rng.uniform(-1.0, 1.0, size=(E, N, 3)).astype(np.float32)
+            b.step(act, auto_reset=True)
+            o.step(act, auto_reset=True, num_threads=threads)
+        for fname in ("positions", "velocities", "goal", "obstacles", "step_count", "reward", "dist", "terminated",
+                      "truncated", "reached", "collision", "obs_valid", "all_terminated", "all_truncated",
+                      "global_state", "active"):
+            assert_biteq(fname, getattr(b, fname), getattr(o, fname), t)
+        valid = o.obs_valid.astype(bool)
+        bo, oo = b.obs, o.obs
+        diff = np.argwhere((pu.bits(bo) != pu.bits(oo)).any(axis=2) & valid)
+        for e, i in diff:
+            assert dr_cfg is None, "with sensor noise a tie-ordered row cannot be re-derived from the state"
+            assert pu.obs_row_ok_up_to_ties("swarm", {**so.DEFAULTS, **cfg}, o.positions[e], o.velocities[e], o.goal[e],
+                                            o.obstacles[e], i, bo[e, i]), f"obs row beyond ties at step {t} env {e} drone {i}"
+            ties += 1
+    st = b.eng.stats()
+    assert st["env_steps"] == E * T
+    print(f"{name}: {E} envs x {N} drones x {T} steps bit-exact; episodes {st['episodes']}, tie rows {ties}")
