@@ -76,6 +76,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+#ifndef SWARM_ROT_OBST_SQKEY
+#define SWARM_ROT_OBST_SQKEY 1
+#endif
 // (a & mask) | c   and   (a & ~mask) | (b & mask)  as single LOP3s
 template <unsigned MASK>
 __device__ __forceinline__ unsigned and_or(unsigned a, unsigned c) {
@@ -158,8 +161,12 @@ __device__ __forceinline__ void sort4(unsigned (&k)[4]) {
 
 // CTA shape (measured): N = 32 runs best as 4 warps x 7 CTAs per SM (72 registers, 28 resident warps,
 // 7 per scheduler), N = 8 / 16 as 8 warps x 3 CTAs (80 registers)
-__host__ __device__ constexpr int rot_warps(int n) { return n == 32 ? 4 : 8; }
-__host__ __device__ constexpr int rot_min_blocks(int n) { return n == 32 ? 7 : 3; }
+#ifndef SWARM_ROT_W32
+#define SWARM_ROT_W32 4
+#define SWARM_ROT_B32 7
+#endif
+__host__ __device__ constexpr int rot_warps(int n) { return n == 32 ? SWARM_ROT_W32 : 8; }
+__host__ __device__ constexpr int rot_min_blocks(int n) { return n == 32 ? SWARM_ROT_B32 : 3; }
 
 // smem per warp: mbarriers (16 B) | agent inbox: pos4[32] vel4[32] actions[96] (single buffer, refilled as
 // soon as it has been read) | env inbox x 2: goal4[G] obst4[G*M] dr[2G] step_count[G] ep_return[G] |
@@ -482,7 +489,13 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                 double acc_f = 0.0, acc_b = 0.0;
                 const double d_star = P.d_star;
                 float4 qn = tp[1];
-#pragma unroll
+#ifndef SWARM_ROT_DR_UNROLL
+#define SWARM_ROT_DR_UNROLL 5
+#endif
+                // (the DR variant's loop + noise code sits at the edge of the instruction cache: its unroll
+                //  factor is a tuning knob)
+                constexpr int kUnroll = DR ? (HALF > SWARM_ROT_DR_UNROLL ? SWARM_ROT_DR_UNROLL : HALF) : HALF;
+#pragma unroll kUnroll
                 for (int r = 1; r < HALF; ++r) {
                     const float4 q = qn;
                     qn = tp[r + 1];
@@ -532,12 +545,22 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                         const float4 oa = tobs[m], ob = tobs[m + 1];
                         const float sa = sumsq_axis(__fsub_rn(oa.x, p.x), __fsub_rn(oa.y, p.y), __fsub_rn(oa.z, p.z));
                         const float sb = sumsq_axis(__fsub_rn(ob.x, p.x), __fsub_rn(ob.y, p.y), __fsub_rn(ob.z, p.z));
+#if SWARM_ROT_OBST_SQKEY
+                        // keys from the SQUARED distance (sqrt is monotone; squares that a truncated key cannot
+                        // tell apart -- which includes every pair whose roots could coincide -- are flagged
+                        // below): the sqrt is then taken for the 4 selected obstacles only
+                        srow[m] = sa;
+                        srow[m + 1] = sb;
+                        ok[m] = and_or<~31u>(__float_as_uint(sa), __float_as_uint(oa.w));
+                        ok[m + 1] = and_or<~31u>(__float_as_uint(sb), __float_as_uint(ob.w));
+#else
                         smin_o = fminf(fminf(smin_o, sa), sb);
                         const float da = sqrt_rn_fast(sa), db = sqrt_rn_fast(sb);
                         srow[m] = da;
                         srow[m + 1] = db;
                         ok[m] = and_or<~31u>(__float_as_uint(da), __float_as_uint(oa.w));
                         ok[m + 1] = and_or<~31u>(__float_as_uint(db), __float_as_uint(ob.w));
+#endif
                     }
                     if (MT == 8) {
                         sort8(reinterpret_cast<unsigned(&)[8]>(ok));
@@ -570,6 +593,17 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                     om[q] = (int)(oo[q] & 31u);
                     od[q] = srow[om[q]];
                 }
+#if SWARM_ROT_OBST_SQKEY
+                if (MT == 8 || MT == 4) {
+                    bad = bad || !(od[0] >= SQRT_FAST_MIN);   // od[] still holds squares here; od[0] is the smallest
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) od[q] = sqrt_rn_fast(od[q]);
+                    // different squares can round to the SAME distance (then the reference orders by index, the
+                    // keys by square): any exact tie among the first five distances goes to the exact path
+                    const float d4 = MT == 8 ? sqrt_rn_fast(srow[o4 & 31u]) : F32_INF;
+                    bad = bad || od[0] == od[1] || od[1] == od[2] || od[2] == od[3] || od[3] == d4;
+                }
+#endif
                 bad = bad && lane_ok && (step_pass() || ((reset_envs >> e_l) & 1u));
             }
             if (alive_mask != ok_lanes || __any_sync(FULL_MASK, bad)) {
