@@ -755,7 +755,14 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
     int buf = 0;
     if (MODE == kSmallStep && gwarp < n_iter) prefetch(gwarp, 0);
 
-    for (int it = gwarp; it < n_iter; it += warps_total, buf ^= 1) {
+    // step launches: dynamic group queue (first group static, then an atomic counter drawn at the top of a
+    // group and consumed after the integrator); aux launches keep the static stride
+    // (short groups -- the single-drone env, tiny swarms -- are cheaper than the atomic: static stride there)
+    const bool dyn_queue = MODE == kSmallStep && N >= 8;
+    int it = gwarp;
+    while (it < n_iter) {
+        int it_next = it + warps_total;
+        if (dyn_queue && lane == 0) it_next = warps_total + (int)atomicAdd(P.work_counter, 1u);
         const int env0 = listed ? P.reset_list[it] : P.env_begin + it * G;
         const int n_env = min(G, P.env_begin + P.env_count - env0);
         const bool lane_ok = e_l < n_env;
@@ -775,7 +782,11 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
         if (MODE == kSmallAux && P.mode != kModeObserve) {
             const bool want = lane < n_env && (P.env_mask == nullptr || P.env_mask[env0 + lane] != 0);
             reset_envs = __ballot_sync(FULL_MASK, want);
-            if (reset_envs == 0) continue;  // nothing to reset in this group
+            if (reset_envs == 0) {  // nothing to reset in this group
+                it = it_next;
+                buf ^= 1;
+                continue;
+            }
         }
 
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f), v = p, g4 = p;
@@ -784,7 +795,6 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
         if (MODE == kSmallStep) {
             cp_async_wait_all();
             __syncwarp();  // this group's inbox is complete; the other inbox is free again
-            if (it + warps_total < n_iter) prefetch(it + warps_total, buf ^ 1);
             if (lane_ok) {
                 p = tab_pos[lane];
                 v = tab_vel[lane];
@@ -891,6 +901,10 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                 p.y = clipf(p.y, -c_bound, c_bound);
                 p.z = clipf(p.z, -c_bound, c_bound);
             }
+        }
+        if (MODE == kSmallStep) {  // next group's inputs -> the other inbox
+            if (dyn_queue) it_next = __shfl_sync(FULL_MASK, it_next, 0);
+            if (it_next < n_iter) prefetch(it_next, buf ^ 1);
         }
         float damp = v.w;  // physics env: per-drone damping factor rides in vel4.w
         int sc_obs = MODE == kSmallStep ? sc + 1 : 0;  // step_count of the state the obs row describes (DR sensor stream)
@@ -1435,6 +1449,14 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                     if (P.episode_length) P.episode_length[env] = 0;
                 }
             }
+        }
+        it = it_next;
+        buf ^= 1;
+    }
+    if (dyn_queue) {  // the last warp to leave re-arms the queue for the next launch
+        if (lane == 0 && atomicAdd(P.work_counter + 1, 1u) == (unsigned)warps_total - 1u) {
+            P.work_counter[0] = 0u;
+            P.work_counter[1] = 0u;
         }
     }
 
