@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -44,6 +45,9 @@ struct SwarmHandle {
     size_t smem_bytes;
     bool rot_ok;             // the step launches run on swarm_step_rot_kernel (swarm_step_rot.cu)
     int rot_blocks_per_sm;
+    bool rotx_ok;            // N = 64 / 128: swarm_step_rotx_kernel (swarm_step_rotx.cu)
+    int rotx_blocks_per_sm;
+    int rotx_min_envs;       // launches with fewer envs stay on the general kernel (SWARM_B200_ROTX_MIN_ENVS)
     JumpEntry* jump_dev;
     uint8_t* reset_mask_dev;  // [E]
     unsigned* reset_count_dev;  // [(kHostChunks + 1) * 2] per launch slot, two parities
@@ -300,6 +304,19 @@ bool rot_eligible(const SwarmConfig& c) {
     return !(off && off[0] == '1');
 }
 
+// The wide rotation-pass kernels (several drones per lane) cover the dense swarms of BASELINE config 5.
+bool rotx_eligible(const SwarmConfig& c) {
+    if (c.env_kind != SWARM_KIND_SWARM || c.norm_mode != 0 || c.dr_enabled) return false;
+    if (c.num_drones != 64 && c.num_drones != 128) return false;
+    if (c.neighbor_k != 3 || c.sensed_obstacles != 4) return false;
+    if (c.num_obstacles < 4 || c.num_obstacles > 32 || (c.num_obstacles & 3)) return false;
+    const double ds = c.desired_spacing;
+    if (!(ds >= 0.0) || !(ds < 512.0) || std::ldexp(ds, 37) != std::floor(std::ldexp(ds, 37))) return false;
+    if (!(c.world_size < 256.0)) return false;   // 127 terms, each < 512: the float64 formation sum stays exact
+    const char* off = std::getenv("SWARM_B200_NO_ROT");
+    return !(off && off[0] == '1');
+}
+
 int launch(SwarmHandle* h, DevParams& p, int env_begin, int env_count, cudaStream_t stream, int slot = 0) {
     p.env_begin = env_begin;
     p.env_count = env_count;
@@ -312,7 +329,15 @@ int launch(SwarmHandle* h, DevParams& p, int env_begin, int env_count, cudaStrea
     const int rot_needed = (p.n_groups + rot_warps_per_cta(p) - 1) / rot_warps_per_cta(p);
     const int rot_resident = h->num_sms * h->rot_blocks_per_sm;
     const int rot_grid = rot_needed < rot_resident ? rot_needed : rot_resident;
-    if (p.mode == kModeStep && p.auto_reset && p.N <= 32) {
+    // the wide kernel runs one env per warp with ~15 k instructions per item: it wins once every warp gets
+    // enough items to amortise its tail (measured at N = 128: parity at 8 192 envs, +15 % at 16 384, +27 % at 32 768)
+    const bool rotx = p.mode == kModeStep && h->rotx_ok && (reinterpret_cast<uintptr_t>(p.actions) & 15u) == 0 &&
+                      env_count >= h->rotx_min_envs;
+    const int rotx_needed = (p.n_groups + rotx_warps_per_cta() - 1) / rotx_warps_per_cta();
+    const int rotx_resident = h->num_sms * h->rotx_blocks_per_sm;
+    const int rotx_grid = rotx_needed < rotx_resident ? rotx_needed : rotx_resident;
+    const bool two_launch = p.mode == kModeStep && p.auto_reset && (p.N <= 32 || rotx);
+    if (two_launch) {
         // the step kernel lists the groups that need a reset; counters alternate between steps so the
         // aux launch can zero the next one while nobody uses it
         const unsigned par = h->step_parity[slot];
@@ -323,15 +348,17 @@ int launch(SwarmHandle* h, DevParams& p, int env_begin, int env_count, cudaStrea
     }
     p.work_counter = h->work_counter_dev + 4 * slot;  // {step queue, warps done, reset queue, warps done}
     if (rot) CUDA_TRY(launch_rot_kernel(p, rot_grid, stream));
+    else if (rotx) CUDA_TRY(launch_rotx_kernel(p, rotx_grid, stream));
     else CUDA_TRY(launch_env_kernel(p, h->cfg.norm_mode, h->cfg.env_kind, grid, h->smem_bytes, stream));
     h->launches++;
-    if (p.mode == kModeStep && p.auto_reset && p.N <= 32) {
+    if (two_launch) {
         // N <= 32: the auto-reset runs as a second, tiny launch (kept out of the step kernel so each
         // launch's instruction working set fits the SM instruction cache)
         DevParams q = p;
         q.mode = kModeAutoReset;
         q.env_mask = h->reset_mask_dev;
         if (rot) CUDA_TRY(launch_rot_kernel(q, rot_grid, stream));
+        else if (rotx) CUDA_TRY(launch_rotx_kernel(q, rotx_grid, stream));
         else CUDA_TRY(launch_env_kernel(q, h->cfg.norm_mode, h->cfg.env_kind, grid, h->smem_bytes, stream));
         h->launches++;
     }
@@ -422,6 +449,15 @@ int swarm_create(const SwarmConfig* cfg, SwarmHandle** out) {
         e = rot_kernel_occupancy(h->base, &h->rot_blocks_per_sm);
         if (e != cudaSuccess) { delete h; return fail(SWARM_E_CUDA, "kernel occupancy query failed: %s", cudaGetErrorString(e)); }
         h->rot_ok = h->rot_blocks_per_sm >= 1;
+    }
+    h->rotx_ok = false;
+    h->rotx_blocks_per_sm = 0;
+    h->rotx_min_envs = 12288;
+    if (const char* me = std::getenv("SWARM_B200_ROTX_MIN_ENVS")) h->rotx_min_envs = std::atoi(me);
+    if (rotx_eligible(*cfg) && rotx_smem_bytes(h->base) <= (size_t)prop.sharedMemPerBlockOptin) {
+        e = rotx_kernel_occupancy(h->base, &h->rotx_blocks_per_sm);
+        if (e != cudaSuccess) { delete h; return fail(SWARM_E_CUDA, "kernel occupancy query failed: %s", cudaGetErrorString(e)); }
+        h->rotx_ok = h->rotx_blocks_per_sm >= 1;
     }
     std::vector<JumpEntry> table;
     build_jump_table(h->base.n_draws, table);

@@ -95,5 +95,10 @@ size_t rot_smem_bytes(const DevParams& p);
 cudaError_t launch_rot_kernel(const DevParams& p, int grid, cudaStream_t stream);
 cudaError_t rot_kernel_occupancy(const DevParams& p, int* blocks_per_sm);
 int rot_warps_per_cta(const DevParams& p);
+// rotation-pass kernels for N = 64 / 128 (swarm_step_rotx.cu)
+size_t rotx_smem_bytes(const DevParams& p);
+cudaError_t launch_rotx_kernel(const DevParams& p, int grid, cudaStream_t stream);
+cudaError_t rotx_kernel_occupancy(const DevParams& p, int* blocks_per_sm);
+int rotx_warps_per_cta();
 
 }  // namespace swarm

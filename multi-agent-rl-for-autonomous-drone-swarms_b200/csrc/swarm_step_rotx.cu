@@ -1,0 +1,649 @@
+// swarm_step_rotx.cu -- rotation-pass step / auto-reset kernels for the dense swarms: N = 64 / 128 drones
+// (BASELINE config 5), K = 3, S = 4, M a multiple of 4, norm_mode 0, no domain randomisation.
+// Reference: DroneSwarmEnv.step / reset, src/swarm_marl/envs/drone_swarm_env.py:92-174, 65-90.
+//
+// Same scheme as swarm_step_rot.cu (read its header first), with NS = N / 32 drones per lane:
+// a warp owns ONE env, lane l holds drones s * 32 + l (slot s).  In round r = 1 .. 16 lane l meets lane
+// l + r: it evaluates the NS x NS distances between its drones and that lane's once and hands each to the
+// partner with one SHFL; round 0 covers the pairs inside a lane.  Keys carry log2(N) index bits; the 4
+// smallest per drone are kept by the min/max merge network.  The rounds are a rolled loop (the body alone
+// is ~10 KB of SASS) and the per-drone tail (neighbour picks, obstacles, observation row, reward) is ONE
+// copy of code executed NS times over register arrays that are rotated between the passes, so the
+// kernel stays inside the instruction cache.
+#include <type_traits>
+
+#include "swarm_rot_common.cuh"
+
+namespace swarm {
+
+#ifndef SWARM_ROTX_MINB
+#define SWARM_ROTX_MINB 3
+#endif
+// 0 (default): pos4 / vel4 / actions are prefetched by TMA into a per-warp inbox (14.8 KB of shared memory per
+// warp at N = 128: 3 CTAs of 161 registers per SM);  1: they are read straight from global memory at the top
+// of an item (9.2 KB, 4 CTAs of 128 registers) -- measured 6-8 % slower (spills, exposed load latency)
+#ifndef SWARM_ROTX_DIRECT
+#define SWARM_ROTX_DIRECT 0
+#endif
+constexpr int kXWarps = 4;  // warps per CTA
+
+__host__ __device__ constexpr int rotx_envbox_bytes(int M) { return 16 * (1 + M) + 16; }
+// per warp: mbarriers (16) | agent inbox pos4[N] vel4[N] actions[3N] | env inbox x 2 | doubled position
+// table per slot (NS x 64 float4) | obs tile (one slot at a time)
+__host__ __device__ constexpr int rotx_smem_per_warp(int N, int M) {
+    return 16 + (SWARM_ROTX_DIRECT ? 0 : 44 * N) + 2 * rotx_envbox_bytes(M) + (N / 32) * 64 * 16 + kTileBytes;
+}
+
+namespace {
+
+template <int NS, typename T>
+__device__ __forceinline__ void rotate(T (&a)[NS]) {
+    const T t = a[0];
+#pragma unroll
+    for (int s = 0; s + 1 < NS; ++s) a[s] = a[s + 1];
+    a[NS - 1] = t;
+}
+
+}  // namespace
+
+template <int NS, int MT, int MODE>
+__global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx_kernel(const DevParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int N = 32 * NS;
+    constexpr unsigned IDX = N - 1;  // index bits of a neighbour key
+    constexpr bool STEP = MODE == 0;
+    const int warp = __shfl_sync(FULL_MASK, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const int M = MT ? MT : P.M;
+    const int envbox_bytes = rotx_envbox_bytes(M);
+    constexpr int kAgentBox = SWARM_ROTX_DIRECT ? 0 : 44 * N;
+    const int per_warp = 16 + kAgentBox + 2 * envbox_bytes + NS * 1024 + kTileBytes;
+    unsigned char* wslice = smem_raw + (size_t)warp * per_warp;
+    const unsigned bar0 = smem_u32(wslice);
+    const float4* in_pos = reinterpret_cast<const float4*>(wslice + 16);       // pos4[N] | vel4[N] | actions[3N]
+    unsigned char* envbox0 = wslice + 16 + kAgentBox;
+    float4* tab2 = reinterpret_cast<float4*>(wslice + 16 + kAgentBox + 2 * envbox_bytes);   // [NS][64]
+    float* tile = reinterpret_cast<float*>(wslice + 16 + kAgentBox + 2 * envbox_bytes + NS * 1024);
+    unsigned long long* wstats =
+        reinterpret_cast<unsigned long long*>(smem_raw + (size_t)kXWarps * per_warp) + warp * SWARM_STATS_WORDS;
+    if (lane < SWARM_STATS_WORDS) wstats[lane] = 0ull;
+    float* srow = tile + lane * kD;
+
+    const int n_iter = STEP ? P.n_groups : (int)*reinterpret_cast<const volatile unsigned*>(P.reset_count);
+    unsigned* const queue = P.work_counter + (STEP ? 0 : 2);
+    if (lane == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    // env inbox: goal4 | obst4[M] | step_count | ep_return
+    const int obst_off = 16, sc_off = 16 * (1 + M);
+    auto issue = [&](int item, int buf) {
+        if (!STEP) return;
+        const int env0 = P.env_begin + item;
+        if (lane == 0) {
+            const unsigned bar = bar0 + 8 * buf;
+            const unsigned dsta = bar0 + 16;
+            const unsigned dst = smem_u32(envbox0 + (size_t)buf * envbox_bytes);
+            const long long a0 = (long long)env0 * N;
+            mbar_expect_tx(bar, (SWARM_ROTX_DIRECT ? 0u : (unsigned)N * 44u) + 16u + 16u * M);
+            if (!SWARM_ROTX_DIRECT) {
+                bulk_g2s(dsta, P.pos4 + a0, N * 16u, bar);
+                bulk_g2s(dsta + N * 16, P.vel4 + a0, N * 16u, bar);
+                bulk_g2s(dsta + N * 32, P.actions + a0 * 3, N * 12u, bar);
+            }
+            bulk_g2s(dst, P.goal4 + env0, 16u, bar);
+            bulk_g2s(dst + obst_off, P.obst4 + (long long)env0 * M, (unsigned)M * 16u, bar);
+            cp_async4(dst + sc_off, P.step_count + env0);
+            cp_async4(dst + sc_off + 4, P.ep_return + env0);
+        }
+        cp_async_commit();
+    };
+    const int warps_total = gridDim.x * kXWarps;
+    int it = blockIdx.x * kXWarps + warp;
+    if (it < n_iter) issue(it, 0);
+    unsigned phase = 0;
+    int buf = 0;
+
+    while (it < n_iter) {
+        int it_next = it + warps_total;
+        if (STEP && lane == 0) it_next = warps_total + (int)atomicAdd(queue, 1u);
+        const int env = STEP ? P.env_begin + it : P.reset_list[it];
+        const int a0 = env * N;
+        unsigned char* ib = envbox0 + (size_t)buf * envbox_bytes;
+        float4* tgoal = reinterpret_cast<float4*>(ib);
+        float4* tobs = reinterpret_cast<float4*>(ib + obst_off);
+
+        float px[NS], py[NS], pz[NS], vx[NS], vy[NS], vz[NS], prev_d[NS];
+        bool alive[NS];
+        float gx, gy, gz;
+        int sc = 0;
+        if (STEP) {
+            float4 lp[NS], lv[NS];
+            float la[NS][3];
+            if (SWARM_ROTX_DIRECT) {  // coalesced loads, issued together before the inbox wait
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    lp[s] = P.pos4[a0 + s * 32 + lane];
+                    lv[s] = P.vel4[a0 + s * 32 + lane];
+                    const float* ga = P.actions + (long long)(a0 + s * 32 + lane) * 3;
+                    la[s][0] = ga[0]; la[s][1] = ga[1]; la[s][2] = ga[2];
+                }
+            }
+            cp_async_wait_all();
+            mbar_wait(bar0 + 8 * buf, (phase >> buf) & 1u);
+            phase ^= 1u << buf;
+            __syncwarp();
+            for (int idx = lane; idx < M; idx += 32) reinterpret_cast<unsigned*>(tobs)[idx * 4 + 3] = (unsigned)idx;
+            const float4 g4 = tgoal[0];
+            gx = g4.x; gy = g4.y; gz = g4.z;
+            sc = reinterpret_cast<const int*>(ib + sc_off)[0];
+            const float* act = reinterpret_cast<const float*>(in_pos + 2 * N);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const float4 p = SWARM_ROTX_DIRECT ? lp[s] : in_pos[s * 32 + lane];
+                float4 v = SWARM_ROTX_DIRECT ? lv[s] : in_pos[N + s * 32 + lane];
+                float ax = SWARM_ROTX_DIRECT ? la[s][0] : act[(s * 32 + lane) * 3 + 0];
+                float ay = SWARM_ROTX_DIRECT ? la[s][1] : act[(s * 32 + lane) * 3 + 1];
+                float az = SWARM_ROTX_DIRECT ? la[s][2] : act[(s * 32 + lane) * 3 + 2];
+                alive[s] = p.w != 0.0f;
+                px[s] = p.x; py[s] = p.y; pz[s] = p.z;
+                prev_d[s] = norm1d<0>(__fsub_rn(gx, p.x), __fsub_rn(gy, p.y), __fsub_rn(gz, p.z));  // :98-101
+                if (alive[s]) {  // integrate (:103-111)
+                    ax = clipf(ax, -1.0f, 1.0f); ay = clipf(ay, -1.0f, 1.0f); az = clipf(az, -1.0f, 1.0f);
+                    v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(ax, P.amax), P.dt));
+                    v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(ay, P.amax), P.dt));
+                    v.z = __fadd_rn(v.z, __fmul_rn(__fmul_rn(az, P.amax), P.dt));
+                    const float speed = norm1d<0>(v.x, v.y, v.z);  // _clip_speed (:179-183)
+                    if (!(speed <= P.vmax || speed < P.eps_speed)) {
+                        v.x = __fmul_rn(__fdiv_rn(v.x, speed), P.vmax);
+                        v.y = __fmul_rn(__fdiv_rn(v.y, speed), P.vmax);
+                        v.z = __fmul_rn(__fdiv_rn(v.z, speed), P.vmax);
+                    }
+                    px[s] = __fadd_rn(px[s], __fmul_rn(v.x, P.dt));
+                    py[s] = __fadd_rn(py[s], __fmul_rn(v.y, P.dt));
+                    pz[s] = __fadd_rn(pz[s], __fmul_rn(v.z, P.dt));
+                }
+                px[s] = clipf(px[s], -P.bound, P.bound);  // wall clip for ALL drones (:113-117)
+                py[s] = clipf(py[s], -P.bound, P.bound);
+                pz[s] = clipf(pz[s], -P.bound, P.bound);
+                vx[s] = v.x; vy[s] = v.y; vz[s] = v.z;
+            }
+        } else {
+            // ================================ reset (:65-80) ================================
+            __syncwarp();
+            const unsigned long long sh = P.rng[(long long)env * 4 + 0], sl = P.rng[(long long)env * 4 + 1];
+            const unsigned long long ih = P.rng[(long long)env * 4 + 2], il = P.rng[(long long)env * 4 + 3];
+#pragma unroll 4
+            for (int k = lane; k < P.n_draws; k += 32) {
+                unsigned long long oh, ol;
+                pcg_jump(P.jump[k + 1], sh, sl, ih, il, oh, ol);
+                const float val = pcg_uniform_f32(oh, ol, P.rng_lo, P.rng_range);
+                if (k < 3 * N) {  // drone j = k / 3 lives at [slot j / 32][lane j % 32]
+                    const int j = k / 3;
+                    reinterpret_cast<float*>(tab2 + (j >> 5) * 64 + (j & 31))[k - 3 * j] = val;
+                } else if (k < 3 * N + 3) {
+                    reinterpret_cast<float*>(tgoal)[k - 3 * N] = val;
+                } else {
+                    const int kk = k - 3 * N - 3;
+                    reinterpret_cast<float*>(tobs + kk / 3)[kk % 3] = val;
+                }
+            }
+            if (lane == 0) {
+                unsigned long long oh, ol;
+                pcg_jump(P.jump[P.n_draws], sh, sl, ih, il, oh, ol);
+                P.rng[(long long)env * 4 + 0] = oh;
+                P.rng[(long long)env * 4 + 1] = ol;
+                P.step_count[env] = 0;
+                P.ep_return[env] = 0.0f;
+                reinterpret_cast<float*>(tgoal)[3] = 0.0f;
+            }
+            for (int k = lane; k < M; k += 32) reinterpret_cast<unsigned*>(tobs + k)[3] = (unsigned)k;
+            __syncwarp();
+            if (lane == 0) P.goal4[env] = tgoal[0];
+            for (int idx = lane; idx < M; idx += 32) {
+                const float4 o = tobs[idx];
+                P.obst4[(long long)env * M + idx] = make_float4(o.x, o.y, o.z, 0.0f);
+            }
+            const float4 g4 = tgoal[0];
+            gx = g4.x; gy = g4.y; gz = g4.z;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const float4 p = tab2[s * 64 + lane];
+                px[s] = p.x; py[s] = p.y; pz[s] = p.z;
+                vx[s] = vy[s] = vz[s] = 0.0f;
+                prev_d[s] = 0.0f;
+                alive[s] = true;
+            }
+            __syncwarp();
+        }
+
+        // doubled position tables: tab2[s][l + r] is drone s * 32 + (l + r) % 32; .w = drone index
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const float4 t = make_float4(px[s], py[s], pz[s], __int_as_float(s * 32 + lane));
+            tab2[s * 64 + lane] = t;
+            tab2[s * 64 + lane + 32] = t;
+        }
+        bool all_alive_l = true;
+        int n_alive_l = 0;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) { all_alive_l = all_alive_l && alive[s]; n_alive_l += alive[s] ? 1 : 0; }
+        const bool all_alive = __all_sync(FULL_MASK, all_alive_l);
+        unsigned amask[NS];  // bit l of amask[s]: drone s * 32 + l is active
+#pragma unroll
+        for (int s = 0; s < NS; ++s) amask[s] = __ballot_sync(FULL_MASK, alive[s]);
+        int n_alive_env = n_alive_l;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) n_alive_env += __shfl_xor_sync(FULL_MASK, n_alive_env, off);
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+        it_next = __shfl_sync(FULL_MASK, it_next, 0);
+        if (STEP && it_next < n_iter) issue(it_next, buf ^ 1);
+
+        // ================= rotation pass (every drone active) =================
+        unsigned k0[NS], k1[NS], k2[NS], k3[NS];
+        double acc[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) { k0[s] = k1[s] = k2[s] = k3[s] = ~0u; acc[s] = 0.0; }
+        bool bad = false;
+        if (all_alive) {
+            const double d_star = P.d_star;
+            // round 0: the pairs inside a lane
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+#pragma unroll
+                for (int s2 = s + 1; s2 < NS; ++s2) {
+                    const float d = sqrt_rn_fast(sumsq1d_fast(__fsub_rn(px[s2], px[s]), __fsub_rn(py[s2], py[s]),
+                                                              __fsub_rn(pz[s2], pz[s])));
+                    const double t = fabs(__dsub_rn(f64_of_pos_f32(d), d_star));
+                    merge1((__float_as_uint(d) & ~IDX) | (unsigned)(s2 * 32 + lane), k0[s], k1[s], k2[s], k3[s]);
+                    merge1((__float_as_uint(d) & ~IDX) | (unsigned)(s * 32 + lane), k0[s2], k1[s2], k2[s2], k3[s2]);
+                    acc[s] = __dadd_rn(acc[s], t);
+                    acc[s2] = __dadd_rn(acc[s2], t);
+                }
+            // one round: my NS drones against the NS drones of lane l + r; LAST = round 16, where lanes l and
+            // l + 16 both evaluate their pairs and nothing is handed over
+            auto round = [&](int r, auto last_tag) {
+                constexpr bool LAST = decltype(last_tag)::value;
+                const int lb = (lane - r) & 31;
+                const float4* tq = tab2 + lane + r;
+                unsigned kf[NS][NS], kb[NS][NS];
+#pragma unroll
+                for (int s2 = 0; s2 < NS; ++s2) {
+                    const float4 q = tq[s2 * 64];
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) {
+                        const float d = sqrt_rn_fast(sumsq1d_fast(__fsub_rn(q.x, px[s]), __fsub_rn(q.y, py[s]), __fsub_rn(q.z, pz[s])));
+                        kf[s][s2] = and_or<~IDX>(__float_as_uint(d), __float_as_uint(q.w));
+                        acc[s] = __dadd_rn(acc[s], fabs(__dsub_rn(f64_of_pos_f32(d), d_star)));
+                        if (!LAST) {
+                            const float db = __shfl_sync(FULL_MASK, d, lb);  // d(drone s of lane l - r, my drone s2)
+                            kb[s][s2] = and_or<~IDX>(__float_as_uint(db), (unsigned)(s * 32 + lb));
+                            acc[s2] = __dadd_rn(acc[s2], fabs(__dsub_rn(f64_of_pos_f32(db), d_star)));
+                        }
+                    }
+                }
+                // my drone s: forward keys kf[s][*]; my drone s2: backward keys kb[*][s2]
+#pragma unroll
+                for (int s = 0; s < NS; ++s)
+#pragma unroll
+                    for (int u = 0; u < NS; u += 2) {
+                        merge2(kf[s][u], kf[s][u + 1], k0[s], k1[s], k2[s], k3[s]);
+                        if (!LAST) merge2(kb[u][s], kb[u + 1][s], k0[s], k1[s], k2[s], k3[s]);
+                    }
+            };
+#pragma unroll 1
+            for (int r = 1; r < 16; ++r) round(r, std::false_type{});
+            round(16, std::true_type{});
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+                // (keys 0-2 sharing a bucket only leave their ORDER open: settled below with the exact distances;
+                //  the 3rd and 4th key in one bucket leave the SET open -> exact path)
+                bad = bad || !(acc[s] == acc[s]) || k0[s] < 0x38800000u || ((k2[s] ^ k3[s]) <= IDX);
+        }
+        const bool exact = !all_alive || __any_sync(FULL_MASK, bad);
+
+        // ================= per-drone tail: one copy of code, NS passes over rotated register arrays =================
+        double rew[NS];
+        float cd[NS];
+        unsigned fl[NS];  // bit 0 reached, bit 1 collided
+#pragma unroll 1
+        for (int s = 0; s < NS; ++s) {
+            if (s > 0) {  // the previous slot's tile must have left shared memory before this pass scribbles on it
+                if (lane == 0) bulk_wait_read0();
+                __syncwarp();
+            }
+            const float p_x = px[0], p_y = py[0], p_z = pz[0];
+            const int me = s * 32 + lane;
+            float nd[3]; int nj[3];
+            bool pair_hit = false;
+            double form_sum = 0.0;
+            int form_n = 0;
+            if (!exact) {
+                const unsigned kk[3] = {k0[0], k1[0], k2[0]};
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    nj[q] = (int)(kk[q] & IDX);
+                    const float4 t = tab2[(nj[q] >> 5) * 64 + (nj[q] & 31)];
+                    nd[q] = norm1d<0>(__fsub_rn(t.x, p_x), __fsub_rn(t.y, p_y), __fsub_rn(t.z, p_z));
+                }
+                // exact (distance, index) order of the three picks -- the reference's argsort order
+                auto cex3 = [&](int a, int b) {
+                    const bool sw = nd[a] > nd[b] || (nd[a] == nd[b] && nj[a] > nj[b]);
+                    const float td = sw ? nd[b] : nd[a], tD = sw ? nd[a] : nd[b];
+                    const int tj = sw ? nj[b] : nj[a], tJ = sw ? nj[a] : nj[b];
+                    nd[a] = td; nd[b] = tD; nj[a] = tj; nj[b] = tJ;
+                };
+                cex3(0, 1); cex3(1, 2); cex3(0, 1);
+                pair_hit = nd[0] <= P.thr_pair;
+                form_sum = acc[0];
+                form_n = N - 1;
+            } else {
+                // exact path: the reference's loops as written (ascending j, strict '<', active pairs, numpy's
+                // pairwise summation order)
+#pragma unroll
+                for (int q = 0; q < 3; ++q) { nd[q] = F32_INF; nj[q] = 0; }
+                const int n_f = alive[0] ? n_alive_env - 1 : 0;
+                const int nf8 = n_f >= 8 ? (n_f & ~7) : 0;
+                double r8[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) r8[u] = 0.0;
+                double res = 0.0;
+                bool tree_done = false;
+                int cnt = 0;
+#pragma unroll 1
+                for (int j = 0; j < N; ++j) {
+                    if (j == me) continue;
+                    unsigned am = 0u;
+#pragma unroll
+                    for (int u = 0; u < NS; ++u) am = (j >> 5) == u ? amask[u] : am;
+                    const bool aj = (am >> (j & 31)) & 1u;
+                    const float4 q = tab2[(j >> 5) * 64 + (j & 31)];
+                    const float d = norm1d<0>(__fsub_rn(q.x, p_x), __fsub_rn(q.y, p_y), __fsub_rn(q.z, p_z));
+                    topk_insert<3>(d, j, nd, nj);
+                    if (alive[0] && aj) {
+                        pair_hit |= d <= P.thr_pair;
+                        const double err = fabs(__dsub_rn((double)d, P.d_star));
+                        if (cnt < nf8) {
+                            const int lane8 = cnt & 7;
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) r8[u] = __dadd_rn(r8[u], lane8 == u ? err : 0.0);
+                        } else {
+                            if (!tree_done && nf8 > 0) res = tree8(r8);
+                            tree_done = true;
+                            res = __dadd_rn(res, err);
+                        }
+                        ++cnt;
+                    }
+                }
+                if (!tree_done && nf8 > 0) res = tree8(r8);
+                form_sum = res;
+                form_n = n_f;
+            }
+
+            // ---- obstacles (:273-291, :190-200)
+            float od[4]; int om[4];
+            bool bad_o = false;
+            {
+                unsigned o0, o1, o2, o3, o4;
+                if (MT == 8 || MT == 4) {
+                    unsigned ok[MT ? MT : 1];
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) {
+                        const float4 o = tobs[m];
+                        const float sq = sumsq_axis(__fsub_rn(o.x, p_x), __fsub_rn(o.y, p_y), __fsub_rn(o.z, p_z));
+                        srow[m] = sq;
+                        ok[m] = and_or<~31u>(__float_as_uint(sq), __float_as_uint(o.w));
+                    }
+                    if (MT == 8) { sort8(reinterpret_cast<unsigned(&)[8]>(ok)); o4 = ok[MT == 8 ? 4 : 0]; }
+                    else { sort4(reinterpret_cast<unsigned(&)[4]>(ok)); o4 = ~0u; }
+                    o0 = ok[0]; o1 = ok[MT > 1 ? 1 : 0]; o2 = ok[MT > 2 ? 2 : 0]; o3 = ok[MT > 3 ? 3 : 0];
+                } else {
+                    o0 = o1 = o2 = o3 = o4 = ~0u;
+#pragma unroll 1
+                    for (int m = 0; m < M; ++m) {
+                        const float4 o = tobs[m];
+                        const float sq = sumsq_axis(__fsub_rn(o.x, p_x), __fsub_rn(o.y, p_y), __fsub_rn(o.z, p_z));
+                        srow[m] = sq;
+                        merge1_5(and_or<~31u>(__float_as_uint(sq), __float_as_uint(o.w)), o0, o1, o2, o3, o4);
+                    }
+                }
+                bad_o = ((o0 ^ o1) <= 31u) || ((o1 ^ o2) <= 31u) || ((o2 ^ o3) <= 31u) || ((o3 ^ o4) <= 31u);
+                const unsigned oo[4] = {o0, o1, o2, o3};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { om[q] = (int)(oo[q] & 31u); od[q] = srow[om[q]]; }
+                bad_o = bad_o || !(od[0] >= SQRT_FAST_MIN);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) od[q] = sqrt_rn_fast(od[q]);
+                const float d4 = o4 != ~0u ? sqrt_rn_fast(srow[o4 & 31u]) : F32_INF;
+                bad_o = bad_o || od[0] == od[1] || od[1] == od[2] || od[2] == od[3] || od[3] == d4;
+            }
+            if (__any_sync(FULL_MASK, bad_o)) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { od[q] = F32_INF; om[q] = 0; }
+#pragma unroll 1
+                for (int m = 0; m < M; ++m) {
+                    const float4 o = tobs[m];
+                    const float d = __fsqrt_rn(sumsq_axis(__fsub_rn(o.x, p_x), __fsub_rn(o.y, p_y), __fsub_rn(o.z, p_z)));
+                    topk_insert<4>(d, m, od, om);
+                }
+            }
+            const float curr_d = norm1d<0>(__fsub_rn(gx, p_x), __fsub_rn(gy, p_y), __fsub_rn(gz, p_z));
+
+            // ---- obs row -> tile -> one TMA store per slot (:226-243)
+            {
+                float* row = srow;
+                const float4 t0 = tab2[(nj[0] >> 5) * 64 + (nj[0] & 31)], t1 = tab2[(nj[1] >> 5) * 64 + (nj[1] & 31)];
+                const float4 t2 = tab2[(nj[2] >> 5) * 64 + (nj[2] & 31)];
+                const float4 b0 = tobs[om[0]], b1 = tobs[om[1]], b2 = tobs[om[2]], b3 = tobs[om[3]];
+                row[0] = p_x; row[1] = p_y; row[2] = p_z;
+                row[3] = vx[0]; row[4] = vy[0]; row[5] = vz[0];
+                row[6] = __fsub_rn(gx, p_x); row[7] = __fsub_rn(gy, p_y); row[8] = __fsub_rn(gz, p_z);
+                row[9] = __fsub_rn(t0.x, p_x); row[10] = __fsub_rn(t0.y, p_y); row[11] = __fsub_rn(t0.z, p_z); row[12] = nd[0];
+                row[13] = __fsub_rn(t1.x, p_x); row[14] = __fsub_rn(t1.y, p_y); row[15] = __fsub_rn(t1.z, p_z); row[16] = nd[1];
+                row[17] = __fsub_rn(t2.x, p_x); row[18] = __fsub_rn(t2.y, p_y); row[19] = __fsub_rn(t2.z, p_z); row[20] = nd[2];
+                row[21] = __fsub_rn(b0.x, p_x); row[22] = __fsub_rn(b0.y, p_y); row[23] = __fsub_rn(b0.z, p_z); row[24] = od[0];
+                row[25] = __fsub_rn(b1.x, p_x); row[26] = __fsub_rn(b1.y, p_y); row[27] = __fsub_rn(b1.z, p_z); row[28] = od[1];
+                row[29] = __fsub_rn(b2.x, p_x); row[30] = __fsub_rn(b2.y, p_y); row[31] = __fsub_rn(b2.z, p_z); row[32] = od[2];
+                row[33] = __fsub_rn(b3.x, p_x); row[34] = __fsub_rn(b3.y, p_y); row[35] = __fsub_rn(b3.z, p_z); row[36] = od[3];
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                bulk_s2g(P.obs + (long long)(a0 + s * 32) * kD, smem_u32(tile), (unsigned)kTileBytes);
+                bulk_commit();
+            }
+
+            // ---- per-drone reward pieces (:141-148); env-level flags need every slot: finished below
+            double reward = 0.0;
+            unsigned f = 0u;
+            if (STEP) {
+                const bool obst_hit = od[0] <= P.thr_obst;
+                const bool reached = alive[0] && curr_d <= P.thr_goal;
+                const bool collided = alive[0] && (obst_hit || pair_hit);
+                if (alive[0]) {
+                    const double progress = __dmul_rn(__dsub_rn((double)prev_d[0], (double)curr_d), P.k_p);
+                    double pen = 0.0;
+                    if (form_n > 0) {
+                        const double mean = form_n == N - 1 ? mean_markstein(form_sum, P.n_others, P.inv_n_others)
+                                                            : __ddiv_rn(form_sum, (double)form_n);
+                        pen = __dmul_rn(P.neg_k_f, mean);
+                    }
+                    reward = __dadd_rn(progress, pen);
+                    if (reached) reward = __dadd_rn(reward, P.r_goal);
+                    if (collided) reward = __dadd_rn(reward, P.r_col);
+                }
+                f = (reached ? 1u : 0u) | (collided ? 2u : 0u);
+            }
+            rew[0] = reward; cd[0] = curr_d; fl[0] = f;
+            rotate<NS>(px); rotate<NS>(py); rotate<NS>(pz); rotate<NS>(vx); rotate<NS>(vy); rotate<NS>(vz);
+            rotate<NS>(prev_d); rotate<NS>(alive); rotate<NS>(k0); rotate<NS>(k1); rotate<NS>(k2); rotate<NS>(acc);
+            rotate<NS>(rew); rotate<NS>(cd); rotate<NS>(fl);
+        }
+
+        // ================= env-level flags and outputs (:149-172) =================
+        if (STEP) {
+            bool col_l = false;
+            int cont_l = 0;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                col_l = col_l || (fl[s] & 2u);
+                cont_l += (alive[s] && fl[s] == 0u) ? 1 : 0;
+            }
+            const bool any_col = __any_sync(FULL_MASK, col_l);
+            int n_cont = cont_l;
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) n_cont += __shfl_xor_sync(FULL_MASK, n_cont, off);
+            const bool env_active = n_alive_env > 0;
+            const int sc_new = env_active ? sc + 1 : sc;
+            const bool time_limit = env_active && sc_new >= P.max_steps;
+            const bool all_reached = n_cont == 0 && !any_col && !time_limit;
+            const bool episode_done = all_reached || any_col;
+            const bool all_term = env_active ? episode_done : true;
+            const bool all_trunc = env_active ? (time_limit && !episode_done) : false;
+            const bool ep_over = env_active && (all_term || all_trunc);
+            const bool need_reset = P.auto_reset && (ep_over || !env_active);
+            float x = 0.0f;  // per-env reward sum: slots in order inside a lane, then a tree over the lanes
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const int a = a0 + s * 32 + lane;
+                const bool reached = fl[s] & 1u, collided = fl[s] & 2u, done_agent = fl[s] != 0u;
+                const float rew32 = __double2float_rn(rew[s]);
+                x = __fadd_rn(x, rew32);
+                P.terminated[a] = (alive[s] && done_agent) ? 1 : 0;
+                P.truncated[a] = (alive[s] && time_limit && !done_agent) ? 1 : 0;
+                const bool valid = alive[s] && !done_agent && !time_limit && !any_col;
+                const bool alive_next = ep_over ? false : valid;
+                P.reward[a] = rew32;
+                if (P.reward64) P.reward64[a] = rew[s];
+                P.reached[a] = reached ? 1 : 0;
+                P.collision[a] = collided ? 1 : 0;
+                if (!need_reset) {
+                    P.dist[a] = cd[s];
+                    P.obs_valid[a] = valid ? 1 : 0;
+                    P.pos4[a] = make_float4(px[s], py[s], pz[s], alive_next ? 1.0f : 0.0f);
+                    P.vel4[a] = make_float4(vx[s], vy[s], vz[s], 0.0f);
+                    if (P.gs) {
+                        float* row = P.gs + (long long)env * P.R;
+                        const int i = s * 32 + lane;
+                        __stcs(row + 3 * i + 0, px[s]); __stcs(row + 3 * i + 1, py[s]); __stcs(row + 3 * i + 2, pz[s]);
+                        __stcs(row + 3 * N + 3 * i + 0, vx[s]); __stcs(row + 3 * N + 3 * i + 1, vy[s]);
+                        __stcs(row + 3 * N + 3 * i + 2, vz[s]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) x = __fadd_rn(x, __shfl_down_sync(FULL_MASK, x, off));
+            if (lane == 0) {
+                P.all_term[env] = all_term ? 1 : 0;
+                P.all_trunc[env] = all_trunc ? 1 : 0;
+                if (P.reset_mask) P.reset_mask[env] = need_reset ? 1 : 0;
+                const float ret = __fadd_rn(reinterpret_cast<const float*>(ib + sc_off)[1], x);
+                if (ep_over) {
+                    wstats[SWARM_STAT_EPISODES] += 1ull;
+                    wstats[SWARM_STAT_LENGTH_SUM] += (unsigned long long)sc_new;
+                    reinterpret_cast<double*>(wstats)[SWARM_STAT_RETURN_SUM] += (double)ret;
+                    if (all_reached) wstats[SWARM_STAT_SUCCESS] += 1ull;
+                    if (any_col) wstats[SWARM_STAT_COLLISION] += 1ull;
+                    if (all_trunc) wstats[SWARM_STAT_TIMEOUT] += 1ull;
+                }
+                if (P.episode_return) P.episode_return[env] = ep_over ? ret : 0.0f;
+                if (P.episode_length) P.episode_length[env] = ep_over ? sc_new : 0;
+                if (!need_reset) {
+                    P.step_count[env] = sc_new;
+                    P.ep_return[env] = ep_over ? 0.0f : ret;
+                    if (P.gs) {
+                        float* row = P.gs + (long long)env * P.R + 6 * N;
+                        __stcs(row + 0, gx); __stcs(row + 1, gy); __stcs(row + 2, gz);
+                    }
+                }
+                wstats[SWARM_STAT_AGENT_STEPS] += (unsigned long long)n_alive_env;
+                wstats[SWARM_STAT_ENV_STEPS] += env_active ? 1ull : 0ull;
+                if (P.auto_reset && need_reset) P.reset_list[atomicAdd(P.reset_count, 1u)] = env;
+            }
+        } else {
+            // reset()'s obs / infos (:82-89); reward / flags of the terminal step stay
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const int a = a0 + s * 32 + lane;
+                P.dist[a] = cd[s];
+                P.obs_valid[a] = 1;
+                P.pos4[a] = make_float4(px[s], py[s], pz[s], 1.0f);
+                P.vel4[a] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (P.gs) {
+                    float* row = P.gs + (long long)env * P.R;
+                    const int i = s * 32 + lane;
+                    __stcs(row + 3 * i + 0, px[s]); __stcs(row + 3 * i + 1, py[s]); __stcs(row + 3 * i + 2, pz[s]);
+                    __stcs(row + 3 * N + 3 * i + 0, 0.f); __stcs(row + 3 * N + 3 * i + 1, 0.f); __stcs(row + 3 * N + 3 * i + 2, 0.f);
+                    if (i == 0) { __stcs(row + 6 * N + 0, gx); __stcs(row + 6 * N + 1, gy); __stcs(row + 6 * N + 2, gz); }
+                }
+            }
+        }
+        it = it_next;
+        buf ^= 1;
+    }
+    if (STEP) {
+        if (lane == 0 && atomicAdd(queue + 1, 1u) == (unsigned)warps_total - 1u) {
+            queue[0] = 0u;
+            queue[1] = 0u;
+        }
+    } else if (blockIdx.x == 0 && warp == 0 && lane == 0) {
+        *P.reset_count_other = 0u;
+    }
+    if (lane == 0) bulk_wait0();
+    __syncwarp();
+    if (STEP && P.stats && lane < SWARM_STATS_WORDS) {
+        const unsigned long long w = wstats[lane];
+        if (lane == SWARM_STAT_RETURN_SUM) {
+            const double dv = __longlong_as_double((long long)w);
+            if (dv != 0.0) atomicAdd(reinterpret_cast<double*>(P.stats + lane), dv);
+        } else if (w) {
+            atomicAdd(P.stats + lane, w);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+typedef void (*RotxKernel)(const DevParams);
+
+template <int NS>
+static RotxKernel pick_rotx_m(const DevParams& p) {
+    const bool reset = p.mode == kModeAutoReset;
+    if (p.M == 8) return reset ? swarm_step_rotx_kernel<NS, 8, 1> : swarm_step_rotx_kernel<NS, 8, 0>;
+    if (p.M == 4) return reset ? swarm_step_rotx_kernel<NS, 4, 1> : swarm_step_rotx_kernel<NS, 4, 0>;
+    return reset ? swarm_step_rotx_kernel<NS, 0, 1> : swarm_step_rotx_kernel<NS, 0, 0>;
+}
+static RotxKernel pick_rotx(const DevParams& p) {
+    if (p.N == 128) return pick_rotx_m<4>(p);
+    if (p.N == 64) return pick_rotx_m<2>(p);
+    return nullptr;
+}
+
+size_t rotx_smem_bytes(const DevParams& p) {
+    return (size_t)kXWarps * rotx_smem_per_warp(p.N, p.M) + (size_t)kXWarps * SWARM_STATS_WORDS * sizeof(unsigned long long);
+}
+int rotx_warps_per_cta() { return kXWarps; }
+
+cudaError_t launch_rotx_kernel(const DevParams& p, int grid, cudaStream_t stream) {
+    RotxKernel k = pick_rotx(p);
+    if (!k) return cudaErrorInvalidValue;
+    const size_t smem = rotx_smem_bytes(p);
+    cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    k<<<grid, kXWarps * 32, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t rotx_kernel_occupancy(const DevParams& p, int* blocks_per_sm) {
+    RotxKernel k = pick_rotx(p);
+    if (!k) return cudaErrorInvalidValue;
+    const size_t smem = rotx_smem_bytes(p);
+    cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, kXWarps * 32, smem);
+}
+
+}  // namespace swarm

@@ -45,10 +45,46 @@ CASES = [
     ("swarm", {"num_drones": 12, "num_obstacles": 3, "neighbor_k": 5, "sensed_obstacles": 2}, 333, 40, 1.2),
     ("swarm", {"num_drones": 20, "num_obstacles": 6, "neighbor_k": 8, "sensed_obstacles": 8}, 100, 40, 1.2),
     ("swarm", {"num_drones": 40, "num_obstacles": 5, "world_size": 50.0}, 50, 30, 1.2),   # two slots, ragged
+    ("swarm", {"num_drones": 64, "num_obstacles": 4, "world_size": 40.0, "max_steps": 25}, 200, 40, 1.2),  # wide rotation kernel, 2 slots
+    ("swarm", {"num_drones": 128, "num_obstacles": 8, "world_size": 20.0}, 100, 10, 1.0),  # C5 as BASELINE names it: resets every step
+    ("swarm", {"num_drones": 128, "num_obstacles": 12, "world_size": 120.0, "max_steps": 15}, 60, 40, 1.5),
     ("swarm", {"num_drones": 1, "num_obstacles": 2, "max_steps": 20}, 500, 50, 1.0),
     ("single", {"num_obstacles": 8, "max_steps": 50}, 5000, 120, 1.5),                    # C1 batched
     ("single", {"num_obstacles": 0, "max_steps": 10}, 33, 30, 1.0),
 ]
+
+
+@pytest.fixture(autouse=True)
+def _wide_kernel_everywhere(monkeypatch):
+    """N = 64 / 128 launches below 12 288 envs normally stay on the general kernel; the tests of this file want
+    the wide rotation-pass kernel (csrc/swarm_step_rotx.cu) exercised at their small sizes too."""
+    monkeypatch.setenv("SWARM_B200_ROTX_MIN_ENVS", "0")
+
+
+def test_wide_and_general_kernels_agree(monkeypatch):
+    """N = 128: the wide rotation-pass kernel and the general kernel step the same batch to the same bits."""
+    import torch
+    import swarm_b200
+    cfg = {"num_drones": 128, "num_obstacles": 8, "world_size": 60.0, "max_steps": 20}
+    E, T = 300, 30
+    engines = []
+    for min_envs in ("0", "1000000000"):
+        monkeypatch.setenv("SWARM_B200_ROTX_MIN_ENVS", min_envs)
+        e = swarm_b200.SwarmEngine(E, cfg, device="cuda:0", reward64=True)
+        e.seed(np.arange(E, dtype=np.uint64))
+        e.reset()
+        engines.append(e)
+    gen = torch.Generator(device="cuda:0")
+    gen.manual_seed(11)
+    for t in range(T):
+        act = torch.rand((E, 128, 3), generator=gen, device="cuda:0") * 2.4 - 1.2
+        for e in engines:
+            e.step(act)
+        a, b = engines
+        for name in ("pos4", "vel4", "goal4", "obs", "reward64", "dist", "terminated", "truncated", "reached", "collision",
+                     "obs_valid", "all_terminated", "all_truncated", "global_state", "rng", "step_count"):
+            assert torch.equal(getattr(a, name), getattr(b, name)), (name, t)
+    assert engines[0].launch_count != engines[1].launch_count   # two launches per step vs one
 
 
 @pytest.mark.parametrize("kind,cfg,E,T,scale", CASES)
