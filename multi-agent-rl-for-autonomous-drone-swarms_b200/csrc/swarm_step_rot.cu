@@ -23,6 +23,11 @@
 //             store per group; state / flags are float4 / byte stores straight from registers.
 #include "swarm_rot_common.cuh"
 
+// programmatic dependent launch of the step / reset kernels (hides the launch latency between them)
+#ifndef SWARM_ROT_PDL
+#define SWARM_ROT_PDL 1
+#endif
+
 namespace swarm {
 
 
@@ -87,6 +92,11 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
     const unsigned env_lanes = N == 32 ? FULL_MASK : (((1u << N) - 1u) << e_base);
     float* srow = tile + lane * kD;  // this lane's tile row; before the obs is staged it stashes exact distances
 
+#if SWARM_ROT_PDL
+    // programmatic dependent launch: this grid may have been started while the previous launch of the
+    // stream (the reset launch of the last step / the step launch of this one) was still draining
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
     // step: one item per env group; reset: one item per listed group
     const int n_iter = MODE == kRotStep ? P.n_groups : (int)*reinterpret_cast<const volatile unsigned*>(P.reset_count);
     const int env_end = P.env_begin + P.env_count;
@@ -696,6 +706,9 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
         buf ^= 1;
     }
     // the last warp to leave re-arms the queue for the next launch
+#if SWARM_ROT_PDL
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
     if (MODE == kRotStep) {
         if (lane == 0 && atomicAdd(queue + 1, 1u) == (unsigned)warps_total - 1u) {
             queue[0] = 0u;
@@ -752,8 +765,22 @@ cudaError_t launch_rot_kernel(const DevParams& p, int grid, cudaStream_t stream)
     const size_t smem = rot_smem_bytes(p);
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
+#if SWARM_ROT_PDL
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)grid);
+    lc.blockDim = dim3((unsigned)(rot_warps(p.N) * 32));
+    lc.dynamicSmemBytes = smem;
+    lc.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    return cudaLaunchKernelEx(&lc, k, p);
+#else
     k<<<grid, rot_warps(p.N) * 32, smem, stream>>>(p);
     return cudaGetLastError();
+#endif
 }
 
 cudaError_t rot_kernel_occupancy(const DevParams& p, int* blocks_per_sm) {
