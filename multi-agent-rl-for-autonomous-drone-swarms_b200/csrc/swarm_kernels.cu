@@ -276,6 +276,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
     unsigned st_eps = 0, st_succ = 0, st_col = 0, st_to = 0, st_len = 0, st_asteps = 0, st_esteps = 0;
     double st_ret = 0.0;
 
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // programmatic dependent launch: the previous launch is done
     // dynamic group queue (the first group of every warp is static): with only a few groups per warp a
     // static grid stride leaves most SMs idle during the last round
     const int warps_total = gridDim.x * kWarpsPerCta;
@@ -715,6 +716,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
         reinterpret_cast<unsigned long long*>(smem_raw + (size_t)kWarpsPerCta * P.smem_per_warp) + warp * SWARM_STATS_WORDS;
     if (MODE == kSmallStep && lane < SWARM_STATS_WORDS) wstats[lane] = 0ull;
 
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // programmatic dependent launch: the previous launch is done
     const int warps_total = gridDim.x * kWarpsPerCta;
     const int gwarp = blockIdx.x * kWarpsPerCta + warp;
     // aux launches behind a step (auto-reset) walk the compacted list of groups that asked for a reset
@@ -1591,8 +1593,17 @@ cudaError_t launch_env_kernel(const DevParams& p, int norm_mode, int env_kind, i
     EnvKernel k = resolve(p, norm_mode, env_kind);
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (err != cudaSuccess) return err;
-    k<<<grid, kThreadsPerCta, smem_bytes, stream>>>(p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)grid);
+    lc.blockDim = dim3((unsigned)kThreadsPerCta);
+    lc.dynamicSmemBytes = smem_bytes;
+    lc.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    return cudaLaunchKernelEx(&lc, k, p);
 }
 
 cudaError_t env_kernel_occupancy(const DevParams& p, int norm_mode, int env_kind, size_t smem_bytes,

@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
     if (lane < SWARM_STATS_WORDS) wstats[lane] = 0ull;
     float* srow = tile + lane * kD;
 
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // programmatic dependent launch (see swarm_step_rot.cu)
     const int n_iter = STEP ? P.n_groups : (int)*reinterpret_cast<const volatile unsigned*>(P.reset_count);
     unsigned* const queue = P.work_counter + (STEP ? 0 : 2);
     if (lane == 0) {
@@ -585,6 +586,7 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
         it = it_next;
         buf ^= 1;
     }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (STEP) {
         if (lane == 0 && atomicAdd(queue + 1, 1u) == (unsigned)warps_total - 1u) {
             queue[0] = 0u;
@@ -633,8 +635,17 @@ cudaError_t launch_rotx_kernel(const DevParams& p, int grid, cudaStream_t stream
     const size_t smem = rotx_smem_bytes(p);
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    k<<<grid, kXWarps * 32, smem, stream>>>(p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)grid);
+    lc.blockDim = dim3((unsigned)(kXWarps * 32));
+    lc.dynamicSmemBytes = smem;
+    lc.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    return cudaLaunchKernelEx(&lc, k, p);
 }
 
 cudaError_t rotx_kernel_occupancy(const DevParams& p, int* blocks_per_sm) {
