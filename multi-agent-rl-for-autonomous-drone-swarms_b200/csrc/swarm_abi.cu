@@ -452,7 +452,7 @@ int swarm_create(const SwarmConfig* cfg, SwarmHandle** out) {
     }
     h->rotx_ok = false;
     h->rotx_blocks_per_sm = 0;
-    h->rotx_min_envs = 12288;
+    h->rotx_min_envs = 4096;
     if (const char* me = std::getenv("SWARM_B200_ROTX_MIN_ENVS")) h->rotx_min_envs = std::atoi(me);
     if (rotx_eligible(*cfg) && rotx_smem_bytes(h->base) <= (size_t)prop.sharedMemPerBlockOptin) {
         e = rotx_kernel_occupancy(h->base, &h->rotx_blocks_per_sm);

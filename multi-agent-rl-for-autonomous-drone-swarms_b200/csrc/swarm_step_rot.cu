@@ -398,9 +398,12 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                 form_sum = __dadd_rn(acc_f, acc_b);
                 // s < 2^-28 (a distance below 2^-14: fast sqrt / exact-sum preconditions) shows up either as the
                 // smallest key or, for s = 0 / denormal s (rsqrt -> inf -> NaN distance), as a NaN formation sum;
-                // two candidates in one key bucket among the first four: truncation may have mis-ordered them
-                bad = !(form_sum == form_sum) || k0 < 0x38800000u /* 2^-14 */ || ((k0 ^ k1) <= IDX) || ((k1 ^ k2) <= IDX) ||
-                      ((k2 ^ k3) <= IDX);
+                // either sends the whole group to the exact path.  Candidates sharing a key bucket (truncation may
+                // have mis-ordered them) are settled per drone: among keys 0-2 only the ORDER is open -> the
+                // picks are sorted by their exact (distance, index) below; a 3rd/4th-key collision leaves the
+                // SET open -> exact neighbour rescan
+                bad = !(form_sum == form_sum) || k0 < 0x38800000u /* 2^-14 */;
+                const bool mine = lane_ok && (step_pass() || ((reset_envs >> e_l) & 1u));
                 const unsigned kk[3] = {k0, k1, k2};
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
@@ -408,6 +411,26 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                     const int t = (j - i) & (int)IDX;           // forward distance i -> j
                     nj[q] = j;
                     nd[q] = srow[t <= HALF ? t : HALF + N - t];  // backward round N - t was stashed at HALF + (N - t)
+                }
+                {
+                    auto cex3 = [&](int a, int b) {
+                        const bool sw = nd[a] > nd[b] || (nd[a] == nd[b] && nj[a] > nj[b]);
+                        const float td = sw ? nd[b] : nd[a], tD = sw ? nd[a] : nd[b];
+                        const int tj = sw ? nj[b] : nj[a], tJ = sw ? nj[a] : nj[b];
+                        nd[a] = td; nd[b] = tD; nj[a] = tj; nj[b] = tJ;
+                    };
+                    cex3(0, 1); cex3(1, 2); cex3(0, 1);
+                }
+                if (__any_sync(FULL_MASK, mine && (k2 ^ k3) <= IDX)) {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) { nd[q] = F32_INF; nj[q] = 0; }
+                    const float4* te = tab2 + 2 * e_base;
+#pragma unroll 1
+                    for (int j = 0; j < N; ++j) {
+                        if (j == i) continue;
+                        const float4 q = te[j];
+                        topk_insert<3>(norm1d<0>(__fsub_rn(q.x, p.x), __fsub_rn(q.y, p.y), __fsub_rn(q.z, p.z)), j, nd, nj);
+                    }
                 }
                 pair_hit = nd[0] <= P.thr_pair;  // nearest drone decides (:202-207)
                 form_n = N - 1;
@@ -462,8 +485,8 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                         }
                     }
                 }
-                bad = bad || !(smin_o >= SQRT_FAST_MIN) || ((o0 ^ o1) <= 31u) || ((o1 ^ o2) <= 31u) || ((o2 ^ o3) <= 31u) ||
-                      ((o3 ^ o4) <= 31u);
+                bool bad_o = !(smin_o >= SQRT_FAST_MIN) || ((o0 ^ o1) <= 31u) || ((o1 ^ o2) <= 31u) || ((o2 ^ o3) <= 31u) ||
+                             ((o3 ^ o4) <= 31u);
                 const unsigned oo[4] = {o0, o1, o2, o3};
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -472,16 +495,25 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                 }
 #if SWARM_ROT_OBST_SQKEY
                 if (MT == 8 || MT == 4) {
-                    bad = bad || !(od[0] >= SQRT_FAST_MIN);   // od[] still holds squares here; od[0] is the smallest
+                    bad_o = bad_o || !(od[0] >= SQRT_FAST_MIN);   // od[] still holds squares here; od[0] is the smallest
 #pragma unroll
                     for (int q = 0; q < 4; ++q) od[q] = sqrt_rn_fast(od[q]);
                     // different squares can round to the SAME distance (then the reference orders by index, the
                     // keys by square): any exact tie among the first five distances goes to the exact path
                     const float d4 = MT == 8 ? sqrt_rn_fast(srow[o4 & 31u]) : F32_INF;
-                    bad = bad || od[0] == od[1] || od[1] == od[2] || od[2] == od[3] || od[3] == d4;
+                    bad_o = bad_o || od[0] == od[1] || od[1] == od[2] || od[2] == od[3] || od[3] == d4;
                 }
 #endif
-                bad = bad && lane_ok && (step_pass() || ((reset_envs >> e_l) & 1u));
+                if (__any_sync(FULL_MASK, mine && bad_o)) {  // an undecided obstacle order: the reference's loop as written
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { od[q] = F32_INF; om[q] = 0; }
+#pragma unroll 1
+                    for (int m = 0; m < M; ++m) {
+                        const float4 o = tobs[m];
+                        topk_insert<4>(__fsqrt_rn(sumsq_axis(__fsub_rn(o.x, p.x), __fsub_rn(o.y, p.y), __fsub_rn(o.z, p.z))), m, od, om);
+                    }
+                }
+                bad = bad && mine;
             }
             if (alive_mask != ok_lanes || __any_sync(FULL_MASK, bad)) {
                 // ============ exact path: parked drones, coincident drones, or a detected near-tie ============

@@ -301,9 +301,10 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
             round(16, std::true_type{});
 #pragma unroll
             for (int s = 0; s < NS; ++s)
-                // (keys 0-2 sharing a bucket only leave their ORDER open: settled below with the exact distances;
-                //  the 3rd and 4th key in one bucket leave the SET open -> exact path)
-                bad = bad || !(acc[s] == acc[s]) || k0[s] < 0x38800000u || ((k2[s] ^ k3[s]) <= IDX);
+                // (keys sharing a bucket are settled per drone in the tail: among keys 0-2 only the ORDER is open,
+                //  a 3rd/4th-key collision triggers an exact neighbour rescan of that slot pass; only a distance
+                //  below 2^-14 -- fast sqrt / exact-sum preconditions -- sends the whole item to the exact path)
+                bad = bad || !(acc[s] == acc[s]) || k0[s] < 0x38800000u;
         }
         const bool exact = !all_alive || __any_sync(FULL_MASK, bad);
 
@@ -339,6 +340,19 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
                     nd[a] = td; nd[b] = tD; nj[a] = tj; nj[b] = tJ;
                 };
                 cex3(0, 1); cex3(1, 2); cex3(0, 1);
+                if (__any_sync(FULL_MASK, (k2[0] ^ k3[0]) <= IDX)) {
+                    // some drone's 3rd and 4th key share a bucket: which candidates make its first three is open.
+                    // Redo the neighbour selection of this slot pass exactly (ascending j, strict '<'); the
+                    // formation sum is exact regardless.
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) { nd[q] = F32_INF; nj[q] = 0; }
+#pragma unroll 1
+                    for (int j = 0; j < N; ++j) {
+                        if (j == me) continue;
+                        const float4 q = tab2[(j >> 5) * 64 + (j & 31)];
+                        topk_insert<3>(norm1d<0>(__fsub_rn(q.x, p_x), __fsub_rn(q.y, p_y), __fsub_rn(q.z, p_z)), j, nd, nj);
+                    }
+                }
                 pair_hit = nd[0] <= P.thr_pair;
                 form_sum = acc[0];
                 form_n = N - 1;
@@ -481,7 +495,7 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
             }
             rew[0] = reward; cd[0] = curr_d; fl[0] = f;
             rotate<NS>(px); rotate<NS>(py); rotate<NS>(pz); rotate<NS>(vx); rotate<NS>(vy); rotate<NS>(vz);
-            rotate<NS>(prev_d); rotate<NS>(alive); rotate<NS>(k0); rotate<NS>(k1); rotate<NS>(k2); rotate<NS>(acc);
+            rotate<NS>(prev_d); rotate<NS>(alive); rotate<NS>(k0); rotate<NS>(k1); rotate<NS>(k2); rotate<NS>(k3); rotate<NS>(acc);
             rotate<NS>(rew); rotate<NS>(cd); rotate<NS>(fl);
         }
 
