@@ -240,7 +240,8 @@ def main():
 
     def make_engine(dr):
         e = swarm_b200.SwarmEngine(E, cfg, kind=kind, device=dev, global_state=not args.no_global_state,
-                                   domain_randomization=DR_V1 if dr else None, dr_seed=2026, env_index_base=rank * E)
+                                   domain_randomization=(dr if isinstance(dr, dict) else DR_V1) if dr else None,
+                                   dr_seed=2026, env_index_base=rank * E)
         # env e of rank r is global env r*E + e: seeds are a function of the GLOBAL env index
         e.seed(np.arange(rank * E, (rank + 1) * E, dtype=np.uint64))
         e.reset()
@@ -301,6 +302,18 @@ def main():
                   "note": "domain randomisation off: bit-identical to the reference's step (tests/)"}
         eng0.close()
         del eng0
+
+    dr_delay = None
+    if dr_enabled(args) and not args.no_dr_off and not args.dr_delay:
+        # the yaml's whole actuation block: control_delay_steps {0, 1, 2} on top (command ring in HBM, same kernel)
+        eng1 = make_engine({**DR_V1, "control_delay_steps": ((0, 1, 2), (0.7, 0.2, 0.1))})
+        ms1, (as1, ss1, ep1, l1), _ = timed(eng1, max(args.steps // 4, 10), max(args.warmup, 3), False)
+        B1 = eng1.algorithmic_bytes_per_agent_step()
+        dr_delay = {"value": as1 / (ms1 * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms1 / max(args.steps // 4, 10),
+                    "roofline_frac": B1 * ss1 / (ms1 * 1e-3) / 1e9 / peaks()[0],
+                    "note": "domain randomisation + control_delay_steps (0,1,2)/(0.7,0.2,0.1): command ring read + written"}
+        eng1.close()
+        del eng1
 
     # ---- end-to-end through host buffers
     e2e = None
@@ -364,6 +377,7 @@ def main():
                          "kernel_ms": kernel_ms},
             "e2e": e2e,
             "dr_off": dr_off,
+            "dr_delay": dr_delay,
             "gpu_launches": int(launches_all),
             "clocks": clocks,
         }

@@ -297,7 +297,6 @@ bool rot_eligible(const SwarmConfig& c) {
     if (c.num_obstacles < 4 || c.num_obstacles > 32 || (c.num_obstacles & 3)) return false;
     const double ds = c.desired_spacing;
     if (!(ds >= 0.0) || !(ds < 1024.0) || std::ldexp(ds, 37) != std::floor(std::ldexp(ds, 37))) return false;
-    if (delay_hist_of(c) > 0) return false;   // the control-delay ring is handled by the general kernel
     const double wscale = c.dr_enabled ? c.dr_world_size_scale[1] : 1.0;
     if (!(c.world_size * wscale < 1024.0)) return false;   // every distance < 2048
     const char* off = std::getenv("SWARM_B200_NO_ROT");

@@ -190,6 +190,7 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
         int sc = 0;
         float c_amax = P.amax, c_vmax = P.vmax, c_dt = P.dt, c_bound = P.bound, c_thr_obst = P.thr_obst;
         unsigned ekey = 0u;
+        int ctrl_delay = 0;
         const unsigned genv = DR ? (unsigned)(P.env_index_base + env) : 0u;
         bool alive = false;
         uint4 rA = make_uint4(0, 0, 0, 0);  // DR: this step's stream-A block (thrust + observation noise)
@@ -222,6 +223,7 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                         const float4 d0 = drp[0], d1 = drp[1];
                         c_amax = d0.x; c_vmax = d0.y; c_dt = d0.z; c_bound = d0.w;
                         c_thr_obst = d1.x; ekey = __float_as_uint(d1.y);
+                        ctrl_delay = (int)d1.w;
                     }
                 }
                 alive = lane_ok && p.w != 0.0f;
@@ -229,6 +231,25 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                 // =========================== integrate (:98-118) ===========================
                 prev_d = norm1d<0>(__fsub_rn(gx, p.x), __fsub_rn(gy, p.y), __fsub_rn(gz, p.z));  // :98-101
                 if (alive) {
+                    if (DR && P.dr_delay_hist > 0) {
+                        // control delay: apply the command submitted ctrl_delay steps ago (zero while the episode
+                        // is younger), then file the one submitted now in ring slot step_count % H
+                        const int H = P.dr_delay_hist;
+                        float* ring = P.act_hist + ((long long)env * H * N + i) * 3;
+                        const float sx = ax, sy = ay, sz = az;
+                        const int slot_w = (int)((unsigned)sc % (unsigned)H);
+                        if (ctrl_delay > 0) {
+                            if (sc < ctrl_delay) {
+                                ax = 0.f; ay = 0.f; az = 0.f;
+                            } else {  // (sc - ctrl_delay) % H without a second division: ctrl_delay <= H
+                                const int slot_r = slot_w - ctrl_delay + (slot_w < ctrl_delay ? H : 0);
+                                const float* hp = ring + slot_r * (N * 3);
+                                ax = hp[0]; ay = hp[1]; az = hp[2];
+                            }
+                        }
+                        float* wp = ring + slot_w * (N * 3);
+                        wp[0] = sx; wp[1] = sy; wp[2] = sz;
+                    }
                     ax = clipf(ax, -1.0f, 1.0f); ay = clipf(ay, -1.0f, 1.0f); az = clipf(az, -1.0f, 1.0f);
                     if (DR) {  // thrust noise: a <- a * (1 + sigma z), one normal per axis
                         rA = philox4x32_10(genv, ekey, (unsigned)sc, (unsigned)i | (DR_STREAM_A << 16), P.dr_key0, P.dr_key1);
@@ -281,13 +302,22 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                         const double half_w = __dmul_rn(world, 0.5);
                         u_lo = -half_w; u_range = __dsub_rn(half_w, -half_w);
                         if (lane == 0) {
+                            float delay = 0.0f;  // this episode's control delay: 4th word of the second block
+                            if (P.dr_delay_count > 0) {
+                                const double uu = __dmul_rn((double)(rb.w >> 8), inv24);
+                                int pick = P.dr_delay_count - 1;
+#pragma unroll 1
+                                for (int k = P.dr_delay_count - 1; k >= 0; --k)
+                                    if (uu < P.dr_delay_cum[k]) pick = k;
+                                delay = (float)P.dr_delay_values[pick];
+                            }
                             P.dr_params[(long long)renv * 2 + 0] =
                                 make_float4(__double2float_rn(__ddiv_rn(__dmul_rn(P.dr_max_accel, s_acc), s_mass)),
                                             __double2float_rn(__dmul_rn(P.dr_max_speed, s_spd)),
                                             __double2float_rn(__dmul_rn(P.dr_dt, s_dt)), __double2float_rn(half_w));
                             P.dr_params[(long long)renv * 2 + 1] =
                                 make_float4(__double2float_rn(__dadd_rn(P.dr_r_c, __dmul_rn(P.dr_r_o, s_rad))),
-                                            __uint_as_float(rb.z), __double2float_rn(world), 0.0f);
+                                            __uint_as_float(rb.z), __double2float_rn(world), delay);
                         }
                         if (e_l == el) ekey = rb.z;  // (the dynamics constants are not needed to observe)
                     }
