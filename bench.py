@@ -48,6 +48,9 @@ WORKLOADS = {
     "c5": ("swarm", {"num_drones": 128, "num_obstacles": 8}, 8192),
     "c5_w70": ("swarm", {"num_drones": 128, "num_obstacles": 8, "world_size": 70.0}, 8192),
     "c1": ("single", {"num_obstacles": 8}, 1048576),
+    # DronePhysicsEnv as a point mass: 24 sub-steps of 1/240 s per step, reference default 3 drones
+    "phys": ("physics", {"num_drones": 3, "num_obstacles": 8}, 524288),
+    "phys8": ("physics", {"num_drones": 8, "num_obstacles": 8}, 262144),
 }
 
 
@@ -133,7 +136,7 @@ def cpu_port_rate(kind, cfg, n_envs, budget_s, threads, dr=False):
     steps, agent_steps = 0, 0
     t0 = time.perf_counter()
     while True:
-        agent_steps += int(o.active.sum()) if kind == "swarm" else n_envs
+        agent_steps += int(o.active.sum()) if kind == "swarm" else n_envs * o.N
         o.step(acts[steps % 4], auto_reset=True, num_threads=threads)
         steps += 1
         if time.perf_counter() - t0 >= budget_s:
@@ -161,7 +164,7 @@ def run_reference_arm(args, kind, cfg, wl_name, default_envs):
     agent_steps = 0
     t0 = time.perf_counter()
     for k in range(args.steps):
-        agent_steps += int(o.active.sum()) if kind == "swarm" else n_envs
+        agent_steps += int(o.active.sum()) if kind == "swarm" else n_envs * o.N
         o.step(acts[k % 4], auto_reset=True, num_threads=threads)
     dt = time.perf_counter() - t0
     val = agent_steps / dt
@@ -179,6 +182,15 @@ def run_reference_arm(args, kind, cfg, wl_name, default_envs):
                 "port of its algorithm pinned bit-exact to fixtures recorded from it",
     }
     print(json.dumps(line), flush=True)
+
+
+def kernel_name(kind, n, envs):
+    """The kernel `swarm_step` selects for this shape (swarm_abi.cu: rot_eligible / rotx_eligible / launch)."""
+    if kind == "swarm" and n in (8, 16, 32):
+        return "swarm_step_rot_kernel"
+    if kind == "swarm" and n in (64, 128) and envs >= 4096:
+        return "swarm_step_rotx_kernel"
+    return "swarm_env_kernel_small" if n <= 32 else "swarm_env_kernel"
 
 
 def workload_config(name, kind, cfg, envs_per_gpu, n_gpus, dr=False):
@@ -373,7 +385,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_agent_step": B, "bytes_per_launch": bytes_per_launch,
-                         "kernel": "swarm_step_rot_kernel (step launch) + its auto-reset launch; achieved uses the time of both",
+                         "kernel": kernel_name(kind, N, E) + " (step launch) + its auto-reset launch; achieved uses the time of both",
                          "kernel_ms": kernel_ms},
             "e2e": e2e,
             "dr_off": dr_off,

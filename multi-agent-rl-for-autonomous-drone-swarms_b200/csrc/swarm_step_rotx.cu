@@ -244,13 +244,18 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
         it_next = __shfl_sync(FULL_MASK, it_next, 0);
         if (STEP && it_next < n_iter) issue(it_next, buf ^ 1);
 
-        // ================= rotation pass (every drone active) =================
+        // ================= rotation pass =================
+        // MASKED = some drone of the env is parked (it reached the goal earlier): neighbour keys still cover every
+        // drone, but the formation sum runs over ACTIVE partners only -- each term is multiplied by the partner's
+        // 0.0 / 1.0 flag (the float64 sum is order-free, DESIGN.md 4.1, so the masked pass gives the reference's
+        // value too); collisions among active drones are read off the three picks in the tail
         unsigned k0[NS], k1[NS], k2[NS], k3[NS];
         double acc[NS];
 #pragma unroll
         for (int s = 0; s < NS; ++s) { k0[s] = k1[s] = k2[s] = k3[s] = ~0u; acc[s] = 0.0; }
         bool bad = false;
-        if (all_alive) {
+        auto rotation_pass = [&](auto masked_tag) {
+            constexpr bool MASKED = decltype(masked_tag)::value;
             const double d_star = P.d_star;
             // round 0: the pairs inside a lane
 #pragma unroll
@@ -262,8 +267,8 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
                     const double t = fabs(__dsub_rn(f64_of_pos_f32(d), d_star));
                     merge1((__float_as_uint(d) & ~IDX) | (unsigned)(s2 * 32 + lane), k0[s], k1[s], k2[s], k3[s]);
                     merge1((__float_as_uint(d) & ~IDX) | (unsigned)(s * 32 + lane), k0[s2], k1[s2], k2[s2], k3[s2]);
-                    acc[s] = __dadd_rn(acc[s], t);
-                    acc[s2] = __dadd_rn(acc[s2], t);
+                    acc[s] = __dadd_rn(acc[s], MASKED ? __dmul_rn(t, alive[s2] ? 1.0 : 0.0) : t);
+                    acc[s2] = __dadd_rn(acc[s2], MASKED ? __dmul_rn(t, alive[s] ? 1.0 : 0.0) : t);
                 }
             // one round: my NS drones against the NS drones of lane l + r; LAST = round 16, where lanes l and
             // l + 16 both evaluate their pairs and nothing is handed over
@@ -272,6 +277,14 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
                 const int lb = (lane - r) & 31;
                 const float4* tq = tab2 + lane + r;
                 unsigned kf[NS][NS], kb[NS][NS];
+                double mf[NS], mb[NS];  // MASKED: 1.0 / 0.0 = partner (s2, lane + r) / (s, lane - r) is active
+                if (MASKED) {
+#pragma unroll
+                    for (int u = 0; u < NS; ++u) {
+                        mf[u] = ((amask[u] >> ((lane + r) & 31)) & 1u) ? 1.0 : 0.0;
+                        mb[u] = ((amask[u] >> lb) & 1u) ? 1.0 : 0.0;
+                    }
+                }
 #pragma unroll
                 for (int s2 = 0; s2 < NS; ++s2) {
                     const float4 q = tq[s2 * 64];
@@ -279,11 +292,13 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
                     for (int s = 0; s < NS; ++s) {
                         const float d = sqrt_rn_fast(sumsq1d_fast(__fsub_rn(q.x, px[s]), __fsub_rn(q.y, py[s]), __fsub_rn(q.z, pz[s])));
                         kf[s][s2] = and_or<~IDX>(__float_as_uint(d), __float_as_uint(q.w));
-                        acc[s] = __dadd_rn(acc[s], fabs(__dsub_rn(f64_of_pos_f32(d), d_star)));
+                        const double t = fabs(__dsub_rn(f64_of_pos_f32(d), d_star));
+                        acc[s] = __dadd_rn(acc[s], MASKED ? __dmul_rn(t, mf[s2]) : t);
                         if (!LAST) {
                             const float db = __shfl_sync(FULL_MASK, d, lb);  // d(drone s of lane l - r, my drone s2)
                             kb[s][s2] = and_or<~IDX>(__float_as_uint(db), (unsigned)(s * 32 + lb));
-                            acc[s2] = __dadd_rn(acc[s2], fabs(__dsub_rn(f64_of_pos_f32(db), d_star)));
+                            const double tb = fabs(__dsub_rn(f64_of_pos_f32(db), d_star));
+                            acc[s2] = __dadd_rn(acc[s2], MASKED ? __dmul_rn(tb, mb[s]) : tb);
                         }
                     }
                 }
@@ -305,8 +320,10 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
                 //  a 3rd/4th-key collision triggers an exact neighbour rescan of that slot pass; only a distance
                 //  below 2^-14 -- fast sqrt / exact-sum preconditions -- sends the whole item to the exact path)
                 bad = bad || !(acc[s] == acc[s]) || k0[s] < 0x38800000u;
-        }
-        const bool exact = !all_alive || __any_sync(FULL_MASK, bad);
+        };
+        if (all_alive) rotation_pass(std::false_type{});
+        else rotation_pass(std::true_type{});
+        const bool exact = __any_sync(FULL_MASK, bad);
 
         // ================= per-drone tail: one copy of code, NS passes over rotated register arrays =================
         double rew[NS];
@@ -353,9 +370,38 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
                         topk_insert<3>(norm1d<0>(__fsub_rn(q.x, p_x), __fsub_rn(q.y, p_y), __fsub_rn(q.z, p_z)), j, nd, nj);
                     }
                 }
-                pair_hit = nd[0] <= P.thr_pair;
                 form_sum = acc[0];
-                form_n = N - 1;
+                if (all_alive) {
+                    pair_hit = nd[0] <= P.thr_pair;
+                    form_n = N - 1;
+                } else {
+                    // collisions count among ACTIVE drones only (:202-207): an active pick within the threshold
+                    // settles it; three parked picks within the threshold leave it open -> scan the active drones
+                    auto active = [&](int j) {
+                        unsigned am = 0u;
+#pragma unroll
+                        for (int u = 0; u < NS; ++u) am = (j >> 5) == u ? amask[u] : am;
+                        return ((am >> (j & 31)) & 1u) != 0u;
+                    };
+                    bool open = alive[0];
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        const bool within = nd[q] <= P.thr_pair;
+                        pair_hit = pair_hit || (within && active(nj[q]));
+                        open = open && within;
+                    }
+                    open = open && !pair_hit;
+                    if (__any_sync(FULL_MASK, open)) {
+#pragma unroll 1
+                        for (int j = 0; j < N; ++j) {
+                            if (j == me || !active(j)) continue;
+                            const float4 q = tab2[(j >> 5) * 64 + (j & 31)];
+                            pair_hit = pair_hit || norm1d<0>(__fsub_rn(q.x, p_x), __fsub_rn(q.y, p_y), __fsub_rn(q.z, p_z)) <= P.thr_pair;
+                        }
+                    }
+                    pair_hit = pair_hit && alive[0];
+                    form_n = alive[0] ? n_alive_env - 1 : 0;
+                }
             } else {
                 // exact path: the reference's loops as written (ascending j, strict '<', active pairs, numpy's
                 // pairwise summation order)

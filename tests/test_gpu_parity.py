@@ -87,6 +87,67 @@ def test_wide_and_general_kernels_agree(monkeypatch):
     assert engines[0].launch_count != engines[1].launch_count   # two launches per step vs one
 
 
+@pytest.mark.parametrize("N,world", [(64, 60.0), (128, 90.0), (32, 40.0)])
+def test_parked_drones_masked_rotation_pass(N, world):
+    """Envs with parked drones (they reached the goal earlier) stay on the rotation-pass kernels: neighbour blocks
+    see every drone, formation error and collisions only the ACTIVE ones (drone_swarm_env.py:185-224).  Injected
+    states: random subsets parked, parked drones sitting inside an active drone's collision sphere, and an active
+    drone whose three nearest are all parked-and-touching with / without an active one just behind them."""
+    import swarm_oracle as so
+    from parity_util import assert_biteq, obs_row_ok_up_to_ties
+
+    cfg = {"num_drones": N, "num_obstacles": 8, "world_size": world, "max_steps": 50}
+    E, T = 96, 10
+    b = _backend(E, cfg)
+    o = so.OracleSwarm(E, cfg)
+    seeds = np.arange(50, 50 + E, dtype=np.uint64)
+    b.seed(seeds); o.seed(seeds)
+    b.reset(); o.reset()
+    rng = np.random.default_rng(5)
+    active = (rng.random((E, N)) > rng.uniform(0.0, 0.4, (E, 1))).astype(np.uint8)
+    active[0] = 1                      # nobody parked
+    active[1] = 0; active[1, 7] = 1    # a single active drone
+    active[:, 0] = 1
+    pos = o.positions.copy()
+    behind, touching = [], []
+    for e in range(2, E):
+        parked = np.flatnonzero(active[e] == 0)
+        if e % 3 == 0 and len(parked) >= 3:   # three parked drones touching active drone 0 ...
+            (behind if e % 6 == 0 else touching).append(e)
+            for q, j in enumerate(parked[:3]):
+                pos[e, j] = pos[e, 0] + np.float32(0.2 + 0.1 * q) * np.eye(3, dtype=np.float32)[q]
+            if e % 6 == 0:                    # ... and an active one just behind them (the 4th nearest)
+                j = 1 + int(np.flatnonzero(active[e, 1:])[0])
+                pos[e, j] = pos[e, 0] - np.float32([0.0, 0.0, 0.7])
+        elif e % 3 == 1 and len(parked) >= 1:  # one parked drone inside an active drone's collision sphere
+            pos[e, parked[0]] = pos[e, 0] + np.float32([0.3, 0.0, 0.0])
+    o.positions[:] = pos
+    o.active[:] = active
+    o.observe()
+    b.eng.set_state(pos, o.velocities, o.goal, o.obstacles, alive=active)
+    ties = 0
+    for t in range(-1, T):
+        if t >= 0:
+            act = rng.uniform(-0.3, 0.3, size=(E, N, 3)).astype(np.float32)
+            b.step(act, auto_reset=True)
+            o.step(act, auto_reset=True, num_threads=8)
+        for name in ("positions", "velocities", "goal", "obstacles", "step_count", "dist", "obs_valid", "global_state",
+                     "active") + (() if t < 0 else ("reward", "terminated", "truncated", "reached", "collision",
+                                                    "all_terminated", "all_truncated")):
+            assert_biteq(name, getattr(b, name), getattr(o, name), t)
+        valid = o.obs_valid.astype(bool)
+        bo, oo = b.obs, o.obs
+        for e, i in np.argwhere((pu.bits(bo) != pu.bits(oo)).any(axis=2) & valid):
+            assert obs_row_ok_up_to_ties("swarm", {**so.DEFAULTS, **cfg}, o.positions[e], o.velocities[e], o.goal[e],
+                                         o.obstacles[e], i, bo[e, i]), f"obs row beyond ties at step {t} env {e} drone {i}"
+            ties += 1
+        if t == 0:   # the injected layouts did what they were built for
+            assert len(behind) > 3 and len(touching) > 3
+            assert (o.collision[behind, 0] == 1).all()       # the active 4th-nearest behind three parked ones counts
+            assert (o.collision[touching, 0] == 0).sum() > 3  # parked neighbours alone never collide
+    assert int(o.active.sum()) < E * N and ties < 10
+
+
 @pytest.mark.parametrize("kind,cfg,E,T,scale", CASES)
 def test_cuda_matches_oracle_seeded(kind, cfg, E, T, scale):
     import swarm_oracle as so
