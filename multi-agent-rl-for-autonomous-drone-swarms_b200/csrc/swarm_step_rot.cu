@@ -394,6 +394,7 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                 // ================= rotation pass: every drone of the group is active =================
                 unsigned k0 = ~0u, k1 = ~0u, k2 = ~0u, k3 = ~0u;
                 double acc_f = 0.0, acc_b = 0.0;
+                float smin = F32_INF;
                 const double d_star = P.d_star;
                 float4 qn = tp[1];
 #ifndef SWARM_ROT_DR_UNROLL
@@ -414,8 +415,12 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                     const unsigned kf = and_or<~IDX>(__float_as_uint(d), __float_as_uint(q.w));
                     const unsigned kb = merge_low<IDX>(__float_as_uint(db), (unsigned)(lane - r));
                     merge2(kf, kb, k0, k1, k2, k3);
-                    acc_f = __dadd_rn(acc_f, fabs(__dsub_rn(f64_of_pos_f32(d), d_star)));
-                    acc_b = __dadd_rn(acc_b, fabs(__dsub_rn(f64_of_pos_f32(db), d_star)));
+                    if (step_pass()) {
+                        acc_f = __dadd_rn(acc_f, fabs(__dsub_rn(f64_of_pos_f32(d), d_star)));
+                        acc_b = __dadd_rn(acc_b, fabs(__dsub_rn(f64_of_pos_f32(db), d_star)));
+                    } else {
+                        smin = fminf(smin, s);  // reset(): no reward, so no formation sum -- only its range check
+                    }
                 }
                 {   // round N/2: the pair is visited from both ends, each end keeps its own copy
                     const float4 q = qn;
@@ -423,7 +428,8 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                     const float d = sqrt_rn_fast(s);
                     srow[HALF] = d;
                     merge1(and_or<~IDX>(__float_as_uint(d), __float_as_uint(q.w)), k0, k1, k2, k3);
-                    acc_f = __dadd_rn(acc_f, fabs(__dsub_rn(f64_of_pos_f32(d), d_star)));
+                    if (step_pass()) acc_f = __dadd_rn(acc_f, fabs(__dsub_rn(f64_of_pos_f32(d), d_star)));
+                    else smin = fminf(smin, s);
                 }
                 form_sum = __dadd_rn(acc_f, acc_b);
                 // s < 2^-28 (a distance below 2^-14: fast sqrt / exact-sum preconditions) shows up either as the
@@ -432,7 +438,8 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                 // have mis-ordered them) are settled per drone: among keys 0-2 only the ORDER is open -> the
                 // picks are sorted by their exact (distance, index) below; a 3rd/4th-key collision leaves the
                 // SET open -> exact neighbour rescan
-                bad = !(form_sum == form_sum) || k0 < 0x38800000u /* 2^-14 */;
+                // (the reset launch, which needs no formation sum, tracks the smallest squared distance instead)
+                bad = !(form_sum == form_sum) || k0 < 0x38800000u /* 2^-14 */ || !(smin >= 0x1p-28f);
                 const bool mine = lane_ok && (step_pass() || ((reset_envs >> e_l) & 1u));
                 const unsigned kk[3] = {k0, k1, k2};
 #pragma unroll

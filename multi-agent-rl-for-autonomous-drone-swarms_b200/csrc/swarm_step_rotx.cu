@@ -109,8 +109,10 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
     int buf = 0;
 
     while (it < n_iter) {
-        int it_next = it + warps_total;
-        if (STEP && lane == 0) it_next = warps_total + (int)atomicAdd(queue, 1u);
+        // dynamic item queue in both launches (an item is >= 10k warp instructions and a warp sees only ~5 of them,
+        // so a static stride would leave a fifth of the warps one item short)
+        int it_next = 0;
+        if (lane == 0) it_next = warps_total + (int)atomicAdd(queue, 1u);
         const int env = STEP ? P.env_begin + it : P.reset_list[it];
         const int a0 = env * N;
         unsigned char* ib = envbox0 + (size_t)buf * envbox_bytes;
@@ -254,6 +256,7 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
 #pragma unroll
         for (int s = 0; s < NS; ++s) { k0[s] = k1[s] = k2[s] = k3[s] = ~0u; acc[s] = 0.0; }
         bool bad = false;
+        float smin = F32_INF;
         auto rotation_pass = [&](auto masked_tag) {
             constexpr bool MASKED = decltype(masked_tag)::value;
             const double d_star = P.d_star;
@@ -262,13 +265,16 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
             for (int s = 0; s < NS; ++s)
 #pragma unroll
                 for (int s2 = s + 1; s2 < NS; ++s2) {
-                    const float d = sqrt_rn_fast(sumsq1d_fast(__fsub_rn(px[s2], px[s]), __fsub_rn(py[s2], py[s]),
-                                                              __fsub_rn(pz[s2], pz[s])));
+                    const float sq = sumsq1d_fast(__fsub_rn(px[s2], px[s]), __fsub_rn(py[s2], py[s]), __fsub_rn(pz[s2], pz[s]));
+                    const float d = sqrt_rn_fast(sq);
+                    if (!STEP) smin = fminf(smin, sq);
                     const double t = fabs(__dsub_rn(f64_of_pos_f32(d), d_star));
                     merge1((__float_as_uint(d) & ~IDX) | (unsigned)(s2 * 32 + lane), k0[s], k1[s], k2[s], k3[s]);
                     merge1((__float_as_uint(d) & ~IDX) | (unsigned)(s * 32 + lane), k0[s2], k1[s2], k2[s2], k3[s2]);
-                    acc[s] = __dadd_rn(acc[s], MASKED ? __dmul_rn(t, alive[s2] ? 1.0 : 0.0) : t);
-                    acc[s2] = __dadd_rn(acc[s2], MASKED ? __dmul_rn(t, alive[s] ? 1.0 : 0.0) : t);
+                    if (STEP) {
+                        acc[s] = __dadd_rn(acc[s], MASKED ? __dmul_rn(t, alive[s2] ? 1.0 : 0.0) : t);
+                        acc[s2] = __dadd_rn(acc[s2], MASKED ? __dmul_rn(t, alive[s] ? 1.0 : 0.0) : t);
+                    }
                 }
             // one round: my NS drones against the NS drones of lane l + r; LAST = round 16, where lanes l and
             // l + 16 both evaluate their pairs and nothing is handed over
@@ -290,15 +296,22 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
                     const float4 q = tq[s2 * 64];
 #pragma unroll
                     for (int s = 0; s < NS; ++s) {
-                        const float d = sqrt_rn_fast(sumsq1d_fast(__fsub_rn(q.x, px[s]), __fsub_rn(q.y, py[s]), __fsub_rn(q.z, pz[s])));
+                        const float sq = sumsq1d_fast(__fsub_rn(q.x, px[s]), __fsub_rn(q.y, py[s]), __fsub_rn(q.z, pz[s]));
+                        const float d = sqrt_rn_fast(sq);
                         kf[s][s2] = and_or<~IDX>(__float_as_uint(d), __float_as_uint(q.w));
-                        const double t = fabs(__dsub_rn(f64_of_pos_f32(d), d_star));
-                        acc[s] = __dadd_rn(acc[s], MASKED ? __dmul_rn(t, mf[s2]) : t);
+                        if (STEP) {
+                            const double t = fabs(__dsub_rn(f64_of_pos_f32(d), d_star));
+                            acc[s] = __dadd_rn(acc[s], MASKED ? __dmul_rn(t, mf[s2]) : t);
+                        } else {
+                            smin = fminf(smin, sq);  // reset(): no reward, so no formation sum -- only its range check
+                        }
                         if (!LAST) {
                             const float db = __shfl_sync(FULL_MASK, d, lb);  // d(drone s of lane l - r, my drone s2)
                             kb[s][s2] = and_or<~IDX>(__float_as_uint(db), (unsigned)(s * 32 + lb));
-                            const double tb = fabs(__dsub_rn(f64_of_pos_f32(db), d_star));
-                            acc[s2] = __dadd_rn(acc[s2], MASKED ? __dmul_rn(tb, mb[s]) : tb);
+                            if (STEP) {
+                                const double tb = fabs(__dsub_rn(f64_of_pos_f32(db), d_star));
+                                acc[s2] = __dadd_rn(acc[s2], MASKED ? __dmul_rn(tb, mb[s]) : tb);
+                            }
                         }
                     }
                 }
@@ -320,6 +333,7 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
                 //  a 3rd/4th-key collision triggers an exact neighbour rescan of that slot pass; only a distance
                 //  below 2^-14 -- fast sqrt / exact-sum preconditions -- sends the whole item to the exact path)
                 bad = bad || !(acc[s] == acc[s]) || k0[s] < 0x38800000u;
+            bad = bad || !(smin >= 0x1p-28f);  // (the reset launch tracks the smallest squared distance instead of the sum)
         };
         if (all_alive) rotation_pass(std::false_type{});
         else rotation_pass(std::true_type{});
@@ -647,14 +661,11 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
         buf ^= 1;
     }
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (STEP) {
-        if (lane == 0 && atomicAdd(queue + 1, 1u) == (unsigned)warps_total - 1u) {
-            queue[0] = 0u;
-            queue[1] = 0u;
-        }
-    } else if (blockIdx.x == 0 && warp == 0 && lane == 0) {
-        *P.reset_count_other = 0u;
+    if (lane == 0 && atomicAdd(queue + 1, 1u) == (unsigned)warps_total - 1u) {  // last warp out re-arms the queue
+        queue[0] = 0u;
+        queue[1] = 0u;
     }
+    if (!STEP && blockIdx.x == 0 && warp == 0 && lane == 0) *P.reset_count_other = 0u;
     if (lane == 0) bulk_wait0();
     __syncwarp();
     if (STEP && P.stats && lane < SWARM_STATS_WORDS) {
