@@ -98,6 +98,10 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
     asm volatile("griddepcontrol.wait;" ::: "memory");
 #endif
     // step: one item per env group; reset: one item per listed group
+    // (reset launch: the first list entry is fetched together with the list length -- the entry is only used if
+    //  it turns out to be inside the list -- so a warp's first item starts one memory round trip earlier)
+    int env0_pref = 0;
+    if (MODE == kRotReset) env0_pref = P.reset_list[min((int)(blockIdx.x * kRotWarps + warp), P.n_groups - 1)];
     const int n_iter = MODE == kRotStep ? P.n_groups : (int)*reinterpret_cast<const volatile unsigned*>(P.reset_count);
     const int env_end = P.env_begin + P.env_count;
     unsigned* const queue = P.work_counter + (MODE == kRotStep ? 0 : 2);
@@ -172,7 +176,8 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
         } else {
             it_next = it + warps_total;
         }
-        const int env0 = MODE == kRotStep ? P.env_begin + it * G : P.reset_list[it];
+        const int env0 = MODE == kRotStep ? P.env_begin + it * G : env0_pref;
+        if (MODE == kRotReset) env0_pref = P.reset_list[min(it_next, P.n_groups - 1)];  // the next item's entry, early
         const int n_env = G == 1 ? 1 : min(G, env_end - env0);
         const bool lane_ok = G == 1 ? true : e_l < n_env;
         const int env = env0 + (lane_ok ? e_l : 0);
@@ -195,7 +200,11 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
         bool alive = false;
         uint4 rA = make_uint4(0, 0, 0, 0);  // DR: this step's stream-A block (thrust + observation noise)
         unsigned reset_envs = 0u;  // reset launch: bit el = env el of the group is re-drawn
-        if (MODE == kRotReset) reset_envs = __ballot_sync(FULL_MASK, lane < n_env && P.env_mask[env0 + lane] != 0);
+        if (MODE == kRotReset) {
+            // one env per group: being on the list means it is re-drawn (no mask load in the dependency chain)
+            if (G == 1) reset_envs = 1u;
+            else reset_envs = __ballot_sync(FULL_MASK, lane < n_env && P.env_mask[env0 + lane] != 0);
+        }
 
         constexpr auto step_pass = []() { return MODE == kRotStep; };
         {
