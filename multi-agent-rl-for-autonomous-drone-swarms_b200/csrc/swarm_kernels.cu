@@ -842,13 +842,20 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                 // integrateVelocities -> applyDamping -> integrateTransforms; v.w = this drone's damping factor
                 if (alive) {
                     const float h = P.phys_h, f = v.w, gnet = P.phys_g_net;
+                    // |v| can exceed max_speed only if the plain float32 sum of squares (within 2^-22 of the exact
+                    // one, like the reference's norm) comes within 2^-19 of max_speed^2: the exact norm -- float64
+                    // accumulate + IEEE sqrt, 24 times per step -- is evaluated only then (NaN compares false on
+                    // both sides)
+                    const float clamp_gate = __fmul_rn(__fmul_rn(c_vmax, c_vmax), 0.99999809265136719f /* 1 - 2^-19 */);
 #pragma unroll 1
                     for (int sub = 0; sub < P.phys_substeps; ++sub) {
-                        const float speed = norm1d<NORM>(v.x, v.y, v.z);
-                        if (speed > c_vmax) {
-                            v.x = __fmul_rn(__fdiv_rn(v.x, speed), c_vmax);
-                            v.y = __fmul_rn(__fdiv_rn(v.y, speed), c_vmax);
-                            v.z = __fmul_rn(__fdiv_rn(v.z, speed), c_vmax);
+                        if (sumsq_axis(v.x, v.y, v.z) > clamp_gate) {
+                            const float speed = norm1d<NORM>(v.x, v.y, v.z);
+                            if (speed > c_vmax) {
+                                v.x = __fmul_rn(__fdiv_rn(v.x, speed), c_vmax);
+                                v.y = __fmul_rn(__fdiv_rn(v.y, speed), c_vmax);
+                                v.z = __fmul_rn(__fdiv_rn(v.z, speed), c_vmax);
+                            }
                         }
                         v.x = __fmul_rn(__fadd_rn(v.x, __fmul_rn(__fmul_rn(ax, c_amax), h)), f);
                         v.y = __fmul_rn(__fadd_rn(v.y, __fmul_rn(__fmul_rn(ay, c_amax), h)), f);
