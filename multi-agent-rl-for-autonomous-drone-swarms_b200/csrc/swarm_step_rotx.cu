@@ -17,7 +17,7 @@
 namespace swarm {
 
 #ifndef SWARM_ROTX_MINB
-#define SWARM_ROTX_MINB 3
+#define SWARM_ROTX_MINB 4
 #endif
 // 0 (default): pos4 / vel4 / actions are prefetched by TMA into a per-warp inbox (14.8 KB of shared memory per
 // warp at N = 128: 3 CTAs of 161 registers per SM);  1: they are read straight from global memory at the top
@@ -28,10 +28,11 @@ namespace swarm {
 constexpr int kXWarps = 4;  // warps per CTA
 
 __host__ __device__ constexpr int rotx_envbox_bytes(int M) { return 16 * (1 + M) + 16; }
-// per warp: mbarriers (16) | agent inbox pos4[N] vel4[N] actions[3N] | env inbox x 2 | doubled position
-// table per slot (NS x 64 float4) | obs tile (one slot at a time)
+// per warp: mbarriers (16) | agent inbox pos4[N] vel4[N] actions[3N] | env inbox x 2 | position table
+// (N float4; not doubled: the partner lane index is masked instead, which lets 4 CTAs = 16 warps fit an SM) |
+// obs tile (one slot at a time)
 __host__ __device__ constexpr int rotx_smem_per_warp(int N, int M) {
-    return 16 + (SWARM_ROTX_DIRECT ? 0 : 44 * N) + 2 * rotx_envbox_bytes(M) + (N / 32) * 64 * 16 + kTileBytes;
+    return 16 + (SWARM_ROTX_DIRECT ? 0 : 44 * N) + 2 * rotx_envbox_bytes(M) + (N / 32) * 32 * 16 + kTileBytes;
 }
 
 namespace {
@@ -57,13 +58,13 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
     const int M = MT ? MT : P.M;
     const int envbox_bytes = rotx_envbox_bytes(M);
     constexpr int kAgentBox = SWARM_ROTX_DIRECT ? 0 : 44 * N;
-    const int per_warp = 16 + kAgentBox + 2 * envbox_bytes + NS * 1024 + kTileBytes;
+    const int per_warp = 16 + kAgentBox + 2 * envbox_bytes + NS * 512 + kTileBytes;
     unsigned char* wslice = smem_raw + (size_t)warp * per_warp;
     const unsigned bar0 = smem_u32(wslice);
     const float4* in_pos = reinterpret_cast<const float4*>(wslice + 16);       // pos4[N] | vel4[N] | actions[3N]
     unsigned char* envbox0 = wslice + 16 + kAgentBox;
-    float4* tab2 = reinterpret_cast<float4*>(wslice + 16 + kAgentBox + 2 * envbox_bytes);   // [NS][64]
-    float* tile = reinterpret_cast<float*>(wslice + 16 + kAgentBox + 2 * envbox_bytes + NS * 1024);
+    float4* tab2 = reinterpret_cast<float4*>(wslice + 16 + kAgentBox + 2 * envbox_bytes);   // [NS][32]: drone j at tab2[j]; .w = drone index
+    float* tile = reinterpret_cast<float*>(wslice + 16 + kAgentBox + 2 * envbox_bytes + NS * 512);
     unsigned long long* wstats =
         reinterpret_cast<unsigned long long*>(smem_raw + (size_t)kXWarps * per_warp) + warp * SWARM_STATS_WORDS;
     if (lane < SWARM_STATS_WORDS) wstats[lane] = 0ull;
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
                 const float val = pcg_uniform_f32(oh, ol, P.rng_lo, P.rng_range);
                 if (k < 3 * N) {  // drone j = k / 3 lives at [slot j / 32][lane j % 32]
                     const int j = k / 3;
-                    reinterpret_cast<float*>(tab2 + (j >> 5) * 64 + (j & 31))[k - 3 * j] = val;
+                    reinterpret_cast<float*>(tab2 + j)[k - 3 * j] = val;
                 } else if (k < 3 * N + 3) {
                     reinterpret_cast<float*>(tgoal)[k - 3 * N] = val;
                 } else {
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
             gx = g4.x; gy = g4.y; gz = g4.z;
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
-                const float4 p = tab2[s * 64 + lane];
+                const float4 p = tab2[s * 32 + lane];
                 px[s] = p.x; py[s] = p.y; pz[s] = p.z;
                 vx[s] = vy[s] = vz[s] = 0.0f;
                 prev_d[s] = 0.0f;
@@ -223,12 +224,11 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
             __syncwarp();
         }
 
-        // doubled position tables: tab2[s][l + r] is drone s * 32 + (l + r) % 32; .w = drone index
+        // position table: tab2[j] is drone j (slot j / 32, lane j % 32); .w = drone index
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
             const float4 t = make_float4(px[s], py[s], pz[s], __int_as_float(s * 32 + lane));
-            tab2[s * 64 + lane] = t;
-            tab2[s * 64 + lane + 32] = t;
+            tab2[s * 32 + lane] = t;
         }
         bool all_alive_l = true;
         int n_alive_l = 0;
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
             auto round = [&](int r, auto last_tag) {
                 constexpr bool LAST = decltype(last_tag)::value;
                 const int lb = (lane - r) & 31;
-                const float4* tq = tab2 + lane + r;
+                const float4* tq = tab2 + ((lane + r) & 31);
                 unsigned kf[NS][NS], kb[NS][NS];
                 double mf[NS], mb[NS];  // MASKED: 1.0 / 0.0 = partner (s2, lane + r) / (s, lane - r) is active
                 if (MASKED) {
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
                 }
 #pragma unroll
                 for (int s2 = 0; s2 < NS; ++s2) {
-                    const float4 q = tq[s2 * 64];
+                    const float4 q = tq[s2 * 32];
 #pragma unroll
                     for (int s = 0; s < NS; ++s) {
                         const float sq = sumsq1d_fast(__fsub_rn(q.x, px[s]), __fsub_rn(q.y, py[s]), __fsub_rn(q.z, pz[s]));
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
                     nj[q] = (int)(kk[q] & IDX);
-                    const float4 t = tab2[(nj[q] >> 5) * 64 + (nj[q] & 31)];
+                    const float4 t = tab2[nj[q]];
                     nd[q] = norm1d<0>(__fsub_rn(t.x, p_x), __fsub_rn(t.y, p_y), __fsub_rn(t.z, p_z));
                 }
                 // exact (distance, index) order of the three picks -- the reference's argsort order
@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
 #pragma unroll 1
                     for (int j = 0; j < N; ++j) {
                         if (j == me) continue;
-                        const float4 q = tab2[(j >> 5) * 64 + (j & 31)];
+                        const float4 q = tab2[j];
                         topk_insert<3>(norm1d<0>(__fsub_rn(q.x, p_x), __fsub_rn(q.y, p_y), __fsub_rn(q.z, p_z)), j, nd, nj);
                     }
                 }
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
 #pragma unroll 1
                         for (int j = 0; j < N; ++j) {
                             if (j == me || !active(j)) continue;
-                            const float4 q = tab2[(j >> 5) * 64 + (j & 31)];
+                            const float4 q = tab2[j];
                             pair_hit = pair_hit || norm1d<0>(__fsub_rn(q.x, p_x), __fsub_rn(q.y, p_y), __fsub_rn(q.z, p_z)) <= P.thr_pair;
                         }
                     }
@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
 #pragma unroll
                     for (int u = 0; u < NS; ++u) am = (j >> 5) == u ? amask[u] : am;
                     const bool aj = (am >> (j & 31)) & 1u;
-                    const float4 q = tab2[(j >> 5) * 64 + (j & 31)];
+                    const float4 q = tab2[j];
                     const float d = norm1d<0>(__fsub_rn(q.x, p_x), __fsub_rn(q.y, p_y), __fsub_rn(q.z, p_z));
                     topk_insert<3>(d, j, nd, nj);
                     if (alive[0] && aj) {
@@ -511,8 +511,8 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
             // ---- obs row -> tile -> one TMA store per slot (:226-243)
             {
                 float* row = srow;
-                const float4 t0 = tab2[(nj[0] >> 5) * 64 + (nj[0] & 31)], t1 = tab2[(nj[1] >> 5) * 64 + (nj[1] & 31)];
-                const float4 t2 = tab2[(nj[2] >> 5) * 64 + (nj[2] & 31)];
+                const float4 t0 = tab2[nj[0]], t1 = tab2[nj[1]];
+                const float4 t2 = tab2[nj[2]];
                 const float4 b0 = tobs[om[0]], b1 = tobs[om[1]], b2 = tobs[om[2]], b3 = tobs[om[3]];
                 row[0] = p_x; row[1] = p_y; row[2] = p_z;
                 row[3] = vx[0]; row[4] = vy[0]; row[5] = vz[0];
