@@ -256,7 +256,6 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
 #pragma unroll
         for (int s = 0; s < NS; ++s) { k0[s] = k1[s] = k2[s] = k3[s] = ~0u; acc[s] = 0.0; }
         bool bad = false;
-        float smin = F32_INF;
         auto rotation_pass = [&](auto masked_tag) {
             constexpr bool MASKED = decltype(masked_tag)::value;
             const double d_star = P.d_star;
@@ -265,10 +264,13 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
             for (int s = 0; s < NS; ++s)
 #pragma unroll
                 for (int s2 = s + 1; s2 < NS; ++s2) {
-                    const float sq = sumsq1d_fast(__fsub_rn(px[s2], px[s]), __fsub_rn(py[s2], py[s]), __fsub_rn(pz[s2], pz[s]));
-                    const float d = sqrt_rn_fast(sq);
-                    if (!STEP) smin = fminf(smin, sq);
-                    const double t = fabs(__dsub_rn(f64_of_pos_f32(d), d_star));
+                    // reset launch (no reward, so no formation sum and no exact distance per pair): the keys are built
+                    // from a plain float32 sum of squares -- monotone in the distance up to 2 ulp, which the widened
+                    // 3rd/4th-key check of the tail covers; the picks' distances are recomputed exactly there
+                    const float sq = STEP ? sumsq1d_fast(__fsub_rn(px[s2], px[s]), __fsub_rn(py[s2], py[s]), __fsub_rn(pz[s2], pz[s]))
+                                          : sumsq_axis(__fsub_rn(px[s2], px[s]), __fsub_rn(py[s2], py[s]), __fsub_rn(pz[s2], pz[s]));
+                    const float d = STEP ? sqrt_rn_fast(sq) : sq;
+                    const double t = STEP ? fabs(__dsub_rn(f64_of_pos_f32(d), d_star)) : 0.0;
                     merge1((__float_as_uint(d) & ~IDX) | (unsigned)(s2 * 32 + lane), k0[s], k1[s], k2[s], k3[s]);
                     merge1((__float_as_uint(d) & ~IDX) | (unsigned)(s * 32 + lane), k0[s2], k1[s2], k2[s2], k3[s2]);
                     if (STEP) {
@@ -296,14 +298,13 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
                     const float4 q = tq[s2 * 32];
 #pragma unroll
                     for (int s = 0; s < NS; ++s) {
-                        const float sq = sumsq1d_fast(__fsub_rn(q.x, px[s]), __fsub_rn(q.y, py[s]), __fsub_rn(q.z, pz[s]));
-                        const float d = sqrt_rn_fast(sq);
+                        const float sq = STEP ? sumsq1d_fast(__fsub_rn(q.x, px[s]), __fsub_rn(q.y, py[s]), __fsub_rn(q.z, pz[s]))
+                                              : sumsq_axis(__fsub_rn(q.x, px[s]), __fsub_rn(q.y, py[s]), __fsub_rn(q.z, pz[s]));
+                        const float d = STEP ? sqrt_rn_fast(sq) : sq;  // (reset launch: key = squared distance, see round 0)
                         kf[s][s2] = and_or<~IDX>(__float_as_uint(d), __float_as_uint(q.w));
                         if (STEP) {
                             const double t = fabs(__dsub_rn(f64_of_pos_f32(d), d_star));
                             acc[s] = __dadd_rn(acc[s], MASKED ? __dmul_rn(t, mf[s2]) : t);
-                        } else {
-                            smin = fminf(smin, sq);  // reset(): no reward, so no formation sum -- only its range check
                         }
                         if (!LAST) {
                             const float db = __shfl_sync(FULL_MASK, d, lb);  // d(drone s of lane l - r, my drone s2)
@@ -332,8 +333,7 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
                 // (keys sharing a bucket are settled per drone in the tail: among keys 0-2 only the ORDER is open,
                 //  a 3rd/4th-key collision triggers an exact neighbour rescan of that slot pass; only a distance
                 //  below 2^-14 -- fast sqrt / exact-sum preconditions -- sends the whole item to the exact path)
-                bad = bad || !(acc[s] == acc[s]) || k0[s] < 0x38800000u;
-            bad = bad || !(smin >= 0x1p-28f);  // (the reset launch tracks the smallest squared distance instead of the sum)
+                bad = bad || (STEP && (!(acc[s] == acc[s]) || k0[s] < 0x38800000u));
         };
         if (all_alive) rotation_pass(std::false_type{});
         else rotation_pass(std::true_type{});
@@ -371,7 +371,9 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
                     nd[a] = td; nd[b] = tD; nj[a] = tj; nj[b] = tJ;
                 };
                 cex3(0, 1); cex3(1, 2); cex3(0, 1);
-                if (__any_sync(FULL_MASK, (k2[0] ^ k3[0]) <= IDX)) {
+                // (reset launch: approximate squared-distance keys -> anything within one bucket of the 3rd key is open)
+                constexpr int SH = NS == 4 ? 7 : 6;
+                if (__any_sync(FULL_MASK, STEP ? (k2[0] ^ k3[0]) <= IDX : ((k3[0] >> SH) - (k2[0] >> SH)) <= 1u)) {
                     // some drone's 3rd and 4th key share a bucket: which candidates make its first three is open.
                     // Redo the neighbour selection of this slot pass exactly (ascending j, strict '<'); the
                     // formation sum is exact regardless.
