@@ -94,14 +94,6 @@ __device__ __forceinline__ float sumsq1d_fast(float x, float y, float z) {
     return __double2float_rn(__dadd_rn(__dadd_rn(f64_of_pos_f32(px), f64_of_pos_f32(py)), f64_of_pos_f32(pz)));
 }
 
-// atomicAdd() inside `if (lane == 0)` still gets the compiler's warp-aggregation wrapper (vote, leader election, popc,
-// shuffle: ~12 instructions around one ATOMG); the queue draw is once per item, so it is issued directly
-__device__ __forceinline__ unsigned atom_add_u32(unsigned* p, unsigned v) {
-    unsigned old;
-    asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
-    return old;
-}
-
 __device__ __forceinline__ unsigned umin3(unsigned a, unsigned b, unsigned c) { return min(min(a, b), c); }
 
 // sorted k0 <= k1 <= k2 <= k3 (4 smallest keys so far)  <-  two more keys

@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
     while (it < n_iter) {
         int it_next = 0;
         if (MODE == kRotStep) {
-            if (lane == 0) it_next = warps_total + (int)atom_add_u32(queue, 1u);
+            if (lane == 0) it_next = warps_total + (int)atomicAdd(queue, 1u);
         } else {
             it_next = it + warps_total;
         }
@@ -761,7 +761,7 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                 }
                 if (P.auto_reset) {  // groups with an env to reset go on the list the reset launch walks
                     const unsigned rl = __ballot_sync(FULL_MASK, leader && need_reset);
-                    if (rl != 0 && lane == 0) P.reset_list[atom_add_u32(P.reset_count, 1u)] = env0;
+                    if (rl != 0 && lane == 0) P.reset_list[atomicAdd(P.reset_count, 1u)] = env0;
                 }
             } else {
                 // =========== reset()'s obs / infos (:82-89) for the re-drawn envs; reward / flags stay ===========

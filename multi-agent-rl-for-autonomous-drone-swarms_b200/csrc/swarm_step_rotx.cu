@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
         // dynamic item queue in both launches (an item is >= 10k warp instructions and a warp sees only ~5 of them,
         // so a static stride would leave a fifth of the warps one item short)
         int it_next = 0;
-        if (lane == 0) it_next = warps_total + (int)atom_add_u32(queue, 1u);
+        if (lane == 0) it_next = warps_total + (int)atomicAdd(queue, 1u);
         const int env = STEP ? P.env_begin + it : P.reset_list[it];
         const int a0 = env * N;
         unsigned char* ib = envbox0 + (size_t)buf * envbox_bytes;
@@ -639,7 +639,7 @@ __global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx
                 }
                 wstats[SWARM_STAT_AGENT_STEPS] += (unsigned long long)n_alive_env;
                 wstats[SWARM_STAT_ENV_STEPS] += env_active ? 1ull : 0ull;
-                if (P.auto_reset && need_reset) P.reset_list[atom_add_u32(P.reset_count, 1u)] = env;
+                if (P.auto_reset && need_reset) P.reset_list[atomicAdd(P.reset_count, 1u)] = env;
             }
         } else {
             // reset()'s obs / infos (:82-89); reward / flags of the terminal step stay
