@@ -127,6 +127,8 @@ GPU_CASES = [
     ("swarm", {"num_drones": 20, "num_obstacles": 6, "neighbor_k": 8, "sensed_obstacles": 8}, 100, 40),
     ("swarm", {"num_drones": 12, "num_obstacles": 3, "neighbor_k": 5, "sensed_obstacles": 2}, 200, 40),
     ("single", {"num_obstacles": 8, "max_steps": 40}, 2000, 90),
+    # curriculum_v1 stage 4 (configs/curriculum_v1.yaml:47-55) under domain_randomization_v1: BASELINE config 4's recipe
+    ("swarm", {"num_drones": 8, "num_obstacles": 12, "max_steps": 450, "world_size": 28.0}, 512, 60),
 ]
 
 

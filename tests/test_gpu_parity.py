@@ -49,6 +49,11 @@ CASES = [
     ("swarm", {"num_drones": 128, "num_obstacles": 8, "world_size": 20.0}, 100, 10, 1.0),  # C5 as BASELINE names it: resets every step
     ("swarm", {"num_drones": 128, "num_obstacles": 12, "world_size": 120.0, "max_steps": 15}, 60, 40, 1.5),
     ("swarm", {"num_drones": 1, "num_obstacles": 2, "max_steps": 20}, 500, 50, 1.0),
+    # the four stage env_configs of the reference's configs/curriculum_v1.yaml:12-55
+    ("swarm", {"num_drones": 3, "num_obstacles": 0, "max_steps": 300, "world_size": 20.0}, 512, 50, 1.0),
+    ("swarm", {"num_drones": 3, "num_obstacles": 4, "max_steps": 350, "world_size": 20.0}, 512, 50, 1.0),
+    ("swarm", {"num_drones": 5, "num_obstacles": 8, "max_steps": 400, "world_size": 24.0}, 512, 50, 1.0),
+    ("swarm", {"num_drones": 8, "num_obstacles": 12, "max_steps": 450, "world_size": 28.0}, 512, 50, 1.0),
     ("single", {"num_obstacles": 8, "max_steps": 50}, 5000, 120, 1.5),                    # C1 batched
     ("single", {"num_obstacles": 0, "max_steps": 10}, 33, 30, 1.0),
 ]

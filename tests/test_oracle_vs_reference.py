@@ -25,6 +25,11 @@ CASES = [
                "desired_spacing": 1.75, "reward_formation_scale": 0.3}, 4, 120),
     ("swarm", {"num_drones": 16, "num_obstacles": 8}, 3, 60),
     ("single", {"num_obstacles": 5, "max_steps": 35, "world_size": 12.0, "goal_radius": 1.1}, 8, 200),
+    # the stage env_configs of configs/curriculum_v1.yaml:12-55 (BASELINE config 4 trains through them)
+    ("swarm", {"num_drones": 3, "num_obstacles": 0, "max_steps": 300, "world_size": 20.0}, 4, 120),
+    ("swarm", {"num_drones": 3, "num_obstacles": 4, "max_steps": 350, "world_size": 20.0}, 4, 120),
+    ("swarm", {"num_drones": 5, "num_obstacles": 8, "max_steps": 400, "world_size": 24.0}, 4, 120),
+    ("swarm", {"num_drones": 8, "num_obstacles": 12, "max_steps": 450, "world_size": 28.0}, 3, 100),
 ]
 
 
