@@ -12,6 +12,9 @@
 // kernel stays inside the instruction cache.
 #include <type_traits>
 
+// float32 -> float64 by two integer ops instead of F2F (swarm_rot_common.cuh): with 6 conversions per pair the quarter-rate
+// conversion unit is ~60 % busy at N = 128 and stalls the issue (MIO throttle 17 %); measured +3.5 % here, neutral at N <= 32
+#define SWARM_ROT_INT_CVT 1
 #include "swarm_rot_common.cuh"
 
 namespace swarm {
