@@ -31,14 +31,14 @@
 namespace swarm {
 
 
-// CTA shape (measured): N = 32 runs best as 4 warps x 7 CTAs per SM (72 registers, 28 resident warps,
-// 7 per scheduler), N = 8 / 16 as 8 warps x 3 CTAs (80 registers)
+// CTA shape (measured): N = 32 and N = 16 run best as 4 warps x 7 CTAs per SM (72 registers, 28 resident warps,
+// 7 per scheduler; N = 16: +4 % over 8 x 3), N = 8 as 8 warps x 3 CTAs (80 registers; 4 x 7 is 5 % slower there)
 #ifndef SWARM_ROT_W32
 #define SWARM_ROT_W32 4
 #define SWARM_ROT_B32 7
 #endif
-__host__ __device__ constexpr int rot_warps(int n) { return n == 32 ? SWARM_ROT_W32 : 8; }
-__host__ __device__ constexpr int rot_min_blocks(int n) { return n == 32 ? SWARM_ROT_B32 : 3; }
+__host__ __device__ constexpr int rot_warps(int n) { return n >= 16 ? SWARM_ROT_W32 : 8; }
+__host__ __device__ constexpr int rot_min_blocks(int n) { return n >= 16 ? SWARM_ROT_B32 : 3; }
 
 // smem per warp: mbarriers (16 B) | agent inbox: pos4[32] vel4[32] actions[96] (single buffer, refilled as
 // soon as it has been read) | env inbox x 2: goal4[G] obst4[G*M] dr[2G] step_count[G] ep_return[G] |
