@@ -356,9 +356,20 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
             dist.all_reduce(se, op=dist.ReduceOp.SUM)
         h2d, d2h = eng.host_bytes_per_step()
+        # what the link gives a bare pinned device->host copy of the largest output (explains the e2e number)
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h["obs"].copy_(eng.obs, non_blocking=True)
+        torch.cuda.synchronize()
+        pe0.record()
+        for _ in range(4):
+            h["obs"].copy_(eng.obs, non_blocking=True)
+        pe1.record()
+        torch.cuda.synchronize()
+        link_gbs = 4 * eng.obs.numel() * 4 / (pe0.elapsed_time(pe1) * 1e-3) / 1e9
         e2e = {"value": float(se.item()) / (float(te.item()) * 1e-3), "unit": "agent-steps/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
                "ms_per_step": float(te.item()) / args.e2e_steps,
+               "d2h_gbs": d2h / (float(te.item()) / args.e2e_steps * 1e-3) / 1e9, "link_d2h_gbs_measured": link_gbs,
                "path": "swarm_step_host: pinned host actions -> H2D -> fused step -> D2H of obs, reward, dist, "
                        "5 flag arrays, __all__ flags, global_state (4 env-axis chunks on side streams)"}
 
