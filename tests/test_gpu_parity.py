@@ -471,6 +471,8 @@ FULL_SIZE = [
     ("c3", {"num_drones": 16, "num_obstacles": 8}, 16384, 40, None),
     ("c4", {"num_drones": 32, "num_obstacles": 8}, 65536, 16, None),
     ("c4_dr", {"num_drones": 32, "num_obstacles": 8}, 65536, 12, "v1"),
+    ("c4_dr_delay", {"num_drones": 32, "num_obstacles": 8}, 65536, 12, "v1+delay"),   # the yaml's whole actuation block
+    ("c5_w20", {"num_drones": 128, "num_obstacles": 8}, 8192, 5, None),              # C5 as named: every env resets every step
     ("c5", {"num_drones": 128, "num_obstacles": 8, "world_size": 70.0}, 8192, 6, None),
 ]
 
@@ -485,8 +487,8 @@ def test_cuda_matches_oracle_at_full_baseline_size(name, cfg, E, T, dr):
 
     dr_cfg = None
     if dr:
-        from test_domain_randomization import DR_V1
-        dr_cfg = DR_V1
+        from test_domain_randomization import DR_V1, DR_DELAY
+        dr_cfg = DR_DELAY if dr.endswith("delay") else DR_V1
     kw = dict(domain_randomization=dr_cfg, dr_seed=2026) if dr_cfg else {}
     b = _backend(E, cfg, **kw)
     o = so.OracleSwarm(E, cfg, dr=dr_cfg, dr_seed=2026)
