@@ -92,6 +92,36 @@ def test_wide_and_general_kernels_agree(monkeypatch):
     assert engines[0].launch_count != engines[1].launch_count   # two launches per step vs one
 
 
+@pytest.mark.parametrize("N,M", [(8, 4), (16, 8), (32, 12)])
+def test_rotation_and_general_kernels_agree_under_randomisation(monkeypatch, N, M):
+    """Same batch, same actions, domain randomisation incl. the control-delay ring: the rotation-pass kernels and the
+    general kernel (SWARM_B200_NO_ROT=1) write the same bits, ring and per-episode constants included."""
+    import torch
+    import swarm_b200
+    from test_domain_randomization import DR_DELAY
+    cfg = {"num_drones": N, "num_obstacles": M, "max_steps": 30}
+    E, T = 700, 45
+    engines = []
+    for no_rot in ("0", "1"):
+        monkeypatch.setenv("SWARM_B200_NO_ROT", no_rot)
+        e = swarm_b200.SwarmEngine(E, cfg, device="cuda:0", reward64=True, domain_randomization=DR_DELAY, dr_seed=9)
+        e.seed(np.arange(E, dtype=np.uint64))
+        e.reset()
+        engines.append(e)
+    gen = torch.Generator(device="cuda:0")
+    gen.manual_seed(3)
+    for t in range(T):
+        act = torch.rand((E, N, 3), generator=gen, device="cuda:0") * 2.4 - 1.2
+        for e in engines:
+            e.step(act)
+        a, b = engines
+        for name in ("pos4", "vel4", "goal4", "obst4", "obs", "reward64", "dist", "terminated", "truncated", "reached",
+                     "collision", "obs_valid", "all_terminated", "all_truncated", "global_state", "rng", "step_count",
+                     "dr_params", "act_hist"):
+            assert torch.equal(getattr(a, name).view(torch.uint8), getattr(b, name).view(torch.uint8)), (name, t)
+    assert engines[0].launch_count == engines[1].launch_count   # both: step + auto-reset launch
+
+
 @pytest.mark.parametrize("N,world", [(64, 60.0), (128, 90.0), (32, 40.0)])
 def test_parked_drones_masked_rotation_pass(N, world):
     """Envs with parked drones (they reached the goal earlier) stay on the rotation-pass kernels: neighbour blocks
