@@ -46,7 +46,8 @@ struct SwarmHandle {
     bool rot_ok;             // the step launches run on swarm_step_rot_kernel (swarm_step_rot.cu)
     int rot_blocks_per_sm;
     bool rotx_ok;            // N = 64 / 128: swarm_step_rotx_kernel (swarm_step_rotx.cu)
-    int rotx_blocks_per_sm;
+    int rotx_blocks_per_sm;        // step launch
+    int rotx_reset_blocks_per_sm;  // auto-reset launch (lighter kernel, more CTAs per SM)
     int rotx_min_envs;       // launches with fewer envs stay on the general kernel (SWARM_B200_ROTX_MIN_ENVS)
     JumpEntry* jump_dev;
     uint8_t* reset_mask_dev;  // [E]
@@ -357,7 +358,10 @@ int launch(SwarmHandle* h, DevParams& p, int env_begin, int env_count, cudaStrea
         q.mode = kModeAutoReset;
         q.env_mask = h->reset_mask_dev;
         if (rot) CUDA_TRY(launch_rot_kernel(q, rot_grid, stream));
-        else if (rotx) CUDA_TRY(launch_rotx_kernel(q, rotx_grid, stream));
+        else if (rotx) {
+            const int rr = h->num_sms * h->rotx_reset_blocks_per_sm;
+            CUDA_TRY(launch_rotx_kernel(q, rotx_needed < rr ? rotx_needed : rr, stream));
+        }
         else CUDA_TRY(launch_env_kernel(q, h->cfg.norm_mode, h->cfg.env_kind, grid, h->smem_bytes, stream));
         h->launches++;
     }
@@ -451,12 +455,18 @@ int swarm_create(const SwarmConfig* cfg, SwarmHandle** out) {
     }
     h->rotx_ok = false;
     h->rotx_blocks_per_sm = 0;
+    h->rotx_reset_blocks_per_sm = 0;
     h->rotx_min_envs = 4096;
     if (const char* me = std::getenv("SWARM_B200_ROTX_MIN_ENVS")) h->rotx_min_envs = std::atoi(me);
     if (rotx_eligible(*cfg) && rotx_smem_bytes(h->base) <= (size_t)prop.sharedMemPerBlockOptin) {
         e = rotx_kernel_occupancy(h->base, &h->rotx_blocks_per_sm);
+        if (e == cudaSuccess) {
+            DevParams q = h->base;
+            q.mode = kModeAutoReset;
+            e = rotx_kernel_occupancy(q, &h->rotx_reset_blocks_per_sm);
+        }
         if (e != cudaSuccess) { delete h; return fail(SWARM_E_CUDA, "kernel occupancy query failed: %s", cudaGetErrorString(e)); }
-        h->rotx_ok = h->rotx_blocks_per_sm >= 1;
+        h->rotx_ok = h->rotx_blocks_per_sm >= 1 && h->rotx_reset_blocks_per_sm >= 1;
     }
     std::vector<JumpEntry> table;
     build_jump_table(h->base.n_draws, table);

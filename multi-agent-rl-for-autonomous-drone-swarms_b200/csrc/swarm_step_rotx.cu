@@ -19,8 +19,13 @@
 
 namespace swarm {
 
-#ifndef SWARM_ROTX_MINB
-#define SWARM_ROTX_MINB 4
+// CTAs per SM (4 warps each): the step launch runs best with 3 (157 registers, no spills: +6 % at world 70 over
+// 4 CTAs of 128 registers with ~20 spilled), the lighter reset launch with 4 (124 registers; +3 % at world 20)
+#ifndef SWARM_ROTX_MINB_STEP
+#define SWARM_ROTX_MINB_STEP 3
+#endif
+#ifndef SWARM_ROTX_MINB_RESET
+#define SWARM_ROTX_MINB_RESET 4
 #endif
 // 0 (default): pos4 / vel4 / actions are prefetched by TMA into a per-warp inbox (14.8 KB of shared memory per
 // warp at N = 128: 3 CTAs of 161 registers per SM);  1: they are read straight from global memory at the top
@@ -51,7 +56,8 @@ __device__ __forceinline__ void rotate(T (&a)[NS]) {
 }  // namespace
 
 template <int NS, int MT, int MODE>
-__global__ void __launch_bounds__(kXWarps * 32, SWARM_ROTX_MINB) swarm_step_rotx_kernel(const DevParams P) {
+__global__ void __launch_bounds__(kXWarps * 32, MODE == 0 ? SWARM_ROTX_MINB_STEP : SWARM_ROTX_MINB_RESET)
+swarm_step_rotx_kernel(const DevParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int N = 32 * NS;
     constexpr unsigned IDX = N - 1;  // index bits of a neighbour key
