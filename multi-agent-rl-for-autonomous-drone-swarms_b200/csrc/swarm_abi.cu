@@ -329,8 +329,9 @@ int launch(SwarmHandle* h, DevParams& p, int env_begin, int env_count, cudaStrea
     const int rot_needed = (p.n_groups + rot_warps_per_cta(p) - 1) / rot_warps_per_cta(p);
     const int rot_resident = h->num_sms * h->rot_blocks_per_sm;
     const int rot_grid = rot_needed < rot_resident ? rot_needed : rot_resident;
-    // the wide kernel runs one env per warp with ~15 k instructions per item: it wins once every warp gets
-    // enough items to amortise its tail (measured at N = 128: parity at 8 192 envs, +15 % at 16 384, +27 % at 32 768)
+    // the wide kernel runs one env per warp with ~14 k instructions per item; SWARM_B200_ROTX_MIN_ENVS keeps launches
+    // below that many envs on the general kernel (default 0: since the masked pass removed its serial exact-path
+    // items the wide kernel is 2-3 x faster at small batches too)
     const bool rotx = p.mode == kModeStep && h->rotx_ok && (reinterpret_cast<uintptr_t>(p.actions) & 15u) == 0 &&
                       env_count >= h->rotx_min_envs;
     const int rotx_needed = (p.n_groups + rotx_warps_per_cta() - 1) / rotx_warps_per_cta();
@@ -456,7 +457,7 @@ int swarm_create(const SwarmConfig* cfg, SwarmHandle** out) {
     h->rotx_ok = false;
     h->rotx_blocks_per_sm = 0;
     h->rotx_reset_blocks_per_sm = 0;
-    h->rotx_min_envs = 4096;
+    h->rotx_min_envs = 0;   // the wide kernel wins at every batch size now (128 envs: 46 vs 111 us per step at N = 128)
     if (const char* me = std::getenv("SWARM_B200_ROTX_MIN_ENVS")) h->rotx_min_envs = std::atoi(me);
     if (rotx_eligible(*cfg) && rotx_smem_bytes(h->base) <= (size_t)prop.sharedMemPerBlockOptin) {
         e = rotx_kernel_occupancy(h->base, &h->rotx_blocks_per_sm);

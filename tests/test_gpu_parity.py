@@ -61,8 +61,8 @@ CASES = [
 
 @pytest.fixture(autouse=True)
 def _wide_kernel_everywhere(monkeypatch):
-    """N = 64 / 128 launches below 12 288 envs normally stay on the general kernel; the tests of this file want
-    the wide rotation-pass kernel (csrc/swarm_step_rotx.cu) exercised at their small sizes too."""
+    """N = 64 / 128 run on the wide rotation-pass kernel (csrc/swarm_step_rotx.cu) at every batch size; pin the
+    threshold knob to its default so an inherited environment variable cannot move these tests to the general kernel."""
     monkeypatch.setenv("SWARM_B200_ROTX_MIN_ENVS", "0")
 
 
