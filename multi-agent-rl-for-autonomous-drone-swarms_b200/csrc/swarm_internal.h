@@ -101,4 +101,25 @@ cudaError_t launch_rotx_kernel(const DevParams& p, int grid, cudaStream_t stream
 cudaError_t rotx_kernel_occupancy(const DevParams& p, int* blocks_per_sm);
 int rotx_warps_per_cta();
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) costs ~1 us: do it once per (device, kernel), not per launch
+// (small batches are launch-bound: 10-14 us of host time per step)
+inline cudaError_t ensure_dynamic_smem(const void* kernel, size_t smem) {
+    constexpr int kSlots = 128;
+    static thread_local const void* done_kernel[kSlots];
+    static thread_local size_t done_smem[kSlots];
+    static thread_local int done_dev[kSlots];
+    static thread_local int n_done = 0;
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    for (int k = 0; k < n_done; ++k)
+        if (done_kernel[k] == kernel && done_dev[k] == dev && done_smem[k] >= smem) return cudaSuccess;
+    err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err == cudaSuccess && n_done < kSlots) {
+        done_kernel[n_done] = kernel; done_smem[n_done] = smem; done_dev[n_done] = dev;
+        ++n_done;
+    }
+    return err;
+}
+
 }  // namespace swarm

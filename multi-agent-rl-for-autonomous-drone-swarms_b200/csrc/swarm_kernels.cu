@@ -1598,7 +1598,7 @@ static EnvKernel resolve(const DevParams& p, int norm_mode, int env_kind) {
 cudaError_t launch_env_kernel(const DevParams& p, int norm_mode, int env_kind, int grid, size_t smem_bytes,
                               cudaStream_t stream) {
     EnvKernel k = resolve(p, norm_mode, env_kind);
-    cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    cudaError_t err = ensure_dynamic_smem(reinterpret_cast<const void*>(k), smem_bytes);
     if (err != cudaSuccess) return err;
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3((unsigned)grid);

@@ -841,7 +841,7 @@ cudaError_t launch_rot_kernel(const DevParams& p, int grid, cudaStream_t stream)
     RotKernel k = pick_rot(p);
     if (!k) return cudaErrorInvalidValue;
     const size_t smem = rot_smem_bytes(p);
-    cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = ensure_dynamic_smem(reinterpret_cast<const void*>(k), smem);
     if (err != cudaSuccess) return err;
 #if SWARM_ROT_PDL
     cudaLaunchConfig_t lc = {};

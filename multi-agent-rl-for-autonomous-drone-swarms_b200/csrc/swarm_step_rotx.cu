@@ -715,7 +715,7 @@ cudaError_t launch_rotx_kernel(const DevParams& p, int grid, cudaStream_t stream
     RotxKernel k = pick_rotx(p);
     if (!k) return cudaErrorInvalidValue;
     const size_t smem = rotx_smem_bytes(p);
-    cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = ensure_dynamic_smem(reinterpret_cast<const void*>(k), smem);
     if (err != cudaSuccess) return err;
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3((unsigned)grid);
