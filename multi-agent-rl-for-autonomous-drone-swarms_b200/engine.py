@@ -121,6 +121,9 @@ class SwarmEngine:
         self.pos4[..., 3] = 1.0
         self._actions_dev = None
         self._bufs = self._make_buffers()
+        self._bufs_ref = C.byref(self._bufs)
+        self._n_actions = E * N * 3
+        self._step_result = (self.obs, self.reward, self.terminated, self.truncated)
         self._host = None
 
     # ------------------------------------------------------------------ plumbing
@@ -217,13 +220,16 @@ class SwarmEngine:
         actions: [E,N,3] float32 CUDA tensor (a drone without an action gets a zero row)."""
         if not (torch.is_tensor(actions) and actions.is_cuda):
             raise TypeError("actions must be a CUDA tensor (use step_host for host buffers)")
-        a = actions.to(dtype=torch.float32).contiguous()
-        if a.numel() != self.E * self.N * 3:
+        a = actions
+        if a.dtype is not torch.float32 or not a.is_contiguous():   # (small batches are host-bound: keep the fast path lean)
+            a = a.to(dtype=torch.float32).contiguous()
+        if a.numel() != self._n_actions:
             raise ValueError(f"actions must have shape [{self.E},{self.N},3]")
-        _abi.check(self._lib.swarm_step(self._handle, C.byref(self._bufs), a.data_ptr(), int(auto_reset),
-                                        self._stream()), "swarm_step")
+        rc = self._lib.swarm_step(self._handle, self._bufs_ref, a.data_ptr(), 1 if auto_reset else 0, self._stream())
+        if rc != 0:
+            _abi.check(rc, "swarm_step")
         self._keep = a
-        return self.obs, self.reward, self.terminated, self.truncated
+        return self._step_result
 
     def set_state(self, positions=None, velocities=None, goal=None, obstacles=None, alive=None, step_count=None,
                   observe: bool = True):
