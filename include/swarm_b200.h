@@ -196,8 +196,9 @@ int swarm_observe(SwarmHandle *h, const SwarmBuffers *bufs, void *stream);
 
 /* env.step(action_dict) (drone_swarm_env.py:92-174 / single_drone_env.py:73-111) for every env.
  * actions: device [E][N][3] float32 (a missing dict key is a zero row, :104).  auto_reset != 0:
- * an env whose episode ends is reset inside the same launch (stream continues like
- * `env.reset()` without a seed); reward / flags keep the terminal step's values while
+ * an env whose episode ends is reset inside the same call -- by a second launch enqueued right
+ * behind the step launch on the same stream -- from its own PCG64 stream, like `env.reset()`
+ * without a seed; reward / flags keep the terminal step's values while
  * obs / dist / obs_valid / global_state describe the new episode. */
 int swarm_step(SwarmHandle *h, const SwarmBuffers *bufs, const float *actions, int auto_reset, void *stream);
 
