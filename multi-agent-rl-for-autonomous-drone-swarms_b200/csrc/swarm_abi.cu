@@ -44,6 +44,7 @@ struct SwarmHandle {
     int blocks_per_sm;
     size_t smem_bytes;
     bool rot_ok;             // the step launches run on swarm_step_rot_kernel (swarm_step_rot.cu)
+    bool rot_fused;          // ... with the auto-reset inside the step launch (SWARM_B200_FUSED_RESET=0: second launch)
     int rot_blocks_per_sm;
     bool rotx_ok;            // N = 64 / 128: swarm_step_rotx_kernel (swarm_step_rotx.cu)
     int rotx_blocks_per_sm;        // step launch
@@ -54,7 +55,7 @@ struct SwarmHandle {
     unsigned* reset_count_dev;  // [(kHostChunks + 1) * 2] per launch slot, two parities
     int* reset_list_dev;        // [number of groups]
     unsigned* work_counter_dev; // [(kHostChunks + 1) * 2] group queue of the rotation-pass step kernel, per launch slot
-    float* qtable_dev;          // [256] (domain randomisation only)
+    float* qtable_dev;          // [512] signed quantile table (domain randomisation only)
     unsigned step_parity[kHostChunks + 1];
     int64_t launches;
     // host-buffer path
@@ -205,6 +206,10 @@ void fill_params(const SwarmConfig& c, DevParams& p) {
     if (p.dr_enabled) {
         p.dr_key0 = (unsigned)(c.dr_seed & 0xffffffffu);
         p.dr_key1 = (unsigned)(c.dr_seed >> 32);
+        for (int r = 0; r < 10; ++r) {
+            p.dr_rk0[r] = p.dr_key0 + (unsigned)r * 0x9E3779B9u;
+            p.dr_rk1[r] = p.dr_key1 + (unsigned)r * 0xBB67AE85u;
+        }
         p.env_index_base = c.env_index_base;
         const double* rng[6] = {c.dr_mass_scale, c.dr_max_accel_scale, c.dr_max_speed_scale, c.dr_dt_scale,
                                 c.dr_obstacle_radius_scale, c.dr_world_size_scale};
@@ -337,7 +342,8 @@ int launch(SwarmHandle* h, DevParams& p, int env_begin, int env_count, cudaStrea
     const int rotx_needed = (p.n_groups + rotx_warps_per_cta() - 1) / rotx_warps_per_cta();
     const int rotx_resident = h->num_sms * h->rotx_blocks_per_sm;
     const int rotx_grid = rotx_needed < rotx_resident ? rotx_needed : rotx_resident;
-    const bool two_launch = p.mode == kModeStep && p.auto_reset && (p.N <= 32 || rotx);
+    p.fused_reset = rot && p.auto_reset && h->rot_fused ? 1 : 0;
+    const bool two_launch = p.mode == kModeStep && p.auto_reset && (p.N <= 32 || rotx) && !p.fused_reset;
     if (two_launch) {
         // the step kernel lists the groups that need a reset; counters alternate between steps so the
         // aux launch can zero the next one while nobody uses it
@@ -454,6 +460,8 @@ int swarm_create(const SwarmConfig* cfg, SwarmHandle** out) {
         if (e != cudaSuccess) { delete h; return fail(SWARM_E_CUDA, "kernel occupancy query failed: %s", cudaGetErrorString(e)); }
         h->rot_ok = h->rot_blocks_per_sm >= 1;
     }
+    h->rot_fused = false;   // (measured slower than the second launch so far: see DESIGN.md)
+    if (const char* fr = std::getenv("SWARM_B200_FUSED_RESET")) h->rot_fused = fr[0] != '0';
     h->rotx_ok = false;
     h->rotx_blocks_per_sm = 0;
     h->rotx_reset_blocks_per_sm = 0;
@@ -483,10 +491,11 @@ int swarm_create(const SwarmConfig* cfg, SwarmHandle** out) {
     if (e == cudaSuccess) e = cudaMalloc(&h->work_counter_dev, sizeof(unsigned) * 4 * (kHostChunks + 1));
     if (e == cudaSuccess) e = cudaMemset(h->work_counter_dev, 0, sizeof(unsigned) * 4 * (kHostChunks + 1));
     if (e == cudaSuccess && cfg->dr_enabled) {
-        std::vector<float> qt(256);
+        std::vector<float> qt(256), qs(512);
         build_qtable(qt.data());
-        e = cudaMalloc(&h->qtable_dev, 256 * sizeof(float));
-        if (e == cudaSuccess) e = cudaMemcpy(h->qtable_dev, qt.data(), 256 * sizeof(float), cudaMemcpyHostToDevice);
+        for (int f = 0; f < 512; ++f) qs[f] = (f & 0x100) ? -qt[f & 0xFF] : qt[f & 0xFF];   // sign = bit 8 of the field
+        e = cudaMalloc(&h->qtable_dev, 512 * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpy(h->qtable_dev, qs.data(), 512 * sizeof(float), cudaMemcpyHostToDevice);
     }
     if (e != cudaSuccess) {
         if (h->jump_dev) cudaFree(h->jump_dev);

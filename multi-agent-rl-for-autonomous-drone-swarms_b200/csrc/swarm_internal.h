@@ -40,6 +40,7 @@ struct DevParams {
     int inbox_bytes;              // N <= 32 kernel: bytes of one input inbox (two per warp, then the staging region)
     int mode;                     // Mode
     int auto_reset;
+    int fused_reset;              // rotation-pass step launch: the auto-reset runs inside it (one launch per step)
     int max_steps;
     // float32 constants the reference's numpy expressions effectively use
     float amax, dt, vmax, eps_speed, bound;
@@ -72,12 +73,13 @@ struct DevParams {
     // ---- domain randomisation (N <= 32 kernels, norm_mode 0)
     int dr_enabled;
     unsigned dr_key0, dr_key1;    // Philox key = dr_seed
+    unsigned dr_rk0[10], dr_rk1[10];  // its round keys: key + r * Weyl constant
     long long env_index_base;
     double dr_lo[6], dr_span[6];  // mass, max_accel, max_speed, dt, obstacle_radius, world_size: min, max - min
     double dr_max_accel, dr_max_speed, dr_dt, dr_world, dr_r_c, dr_r_o;
     float dr_std_thrust, dr_std_pos, dr_std_vel, dr_std_obst;
     float4* dr_params;            // [E][2] float4
-    const float* dr_qtable;       // [256] half-normal quantiles
+    const float* dr_qtable;       // [512] signed normal quantiles: entry f = the normal of the 9-bit field f
     int dr_delay_count, dr_delay_hist;   // control delay: number of choices, ring size H (0 = off)
     int dr_delay_values[4];
     double dr_delay_cum[4];

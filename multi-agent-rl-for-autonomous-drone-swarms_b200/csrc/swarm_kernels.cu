@@ -747,7 +747,9 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
             for (int idx = lane; idx < 2 * n_env; idx += 32)
                 cp_async16(sbase + dr_off4 * 16 + idx * 16, P.dr_params + (long long)env0 * 2 + idx);
         const float* act = P.actions + a0 * 3;
-        if ((((G * N) | n_ag) & 3) == 0) {  // 16-byte aligned, whole 16-byte chunks
+        // 16-byte copies need whole 16-byte chunks AND a 16-byte aligned base (a float32 view at a 4 / 8 / 12-byte
+        // storage offset is a legal `actions` argument: it takes the 4-byte path)
+        if ((((G * N) | n_ag) & 3) == 0 && (reinterpret_cast<unsigned long long>(P.actions) & 15ull) == 0) {
             if (lane * 4 < n_ag * 3) cp_async16(sbase + act_off4 * 16 + lane * 16, act + lane * 4);
         } else {
             for (int idx = lane; idx < n_ag * 3; idx += 32) cp_async4(sbase + act_off4 * 16 + idx * 4, act + idx);
@@ -885,11 +887,10 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                 }
                 ax = clipf(ax, -1.0f, 1.0f); ay = clipf(ay, -1.0f, 1.0f); az = clipf(az, -1.0f, 1.0f);
                 if (DR) {  // thrust noise: a <- a * (1 + sigma z), one normal per axis
-                    const uint4 r = philox4x32_10(genv, ekey, (unsigned)sc, (unsigned)i | (DR_STREAM_A << 16), P.dr_key0,
-                                                  P.dr_key1);
-                    ax = __fmul_rn(ax, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, dr_normal(P.dr_qtable, dr_field(r, 0)))));
-                    ay = __fmul_rn(ay, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, dr_normal(P.dr_qtable, dr_field(r, 1)))));
-                    az = __fmul_rn(az, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, dr_normal(P.dr_qtable, dr_field(r, 2)))));
+                    const uint4 r = philox4x32_7(genv, ekey, (unsigned)sc, (unsigned)i | (DR_STREAM_A << 16), P);
+                    ax = __fmul_rn(ax, __fmaf_rn(P.dr_std_thrust, dr_normal(P.dr_qtable, dr_field(r, 0)), 1.0f));
+                    ay = __fmul_rn(ay, __fmaf_rn(P.dr_std_thrust, dr_normal(P.dr_qtable, dr_field(r, 1)), 1.0f));
+                    az = __fmul_rn(az, __fmaf_rn(P.dr_std_thrust, dr_normal(P.dr_qtable, dr_field(r, 2)), 1.0f));
                 }
                 v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(ax, c_amax), c_dt));
                 v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(ay, c_amax), c_dt));
@@ -934,8 +935,8 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                 if (DR) {
                     // this episode's constants: 6 uniforms + an episode key from one counter per (env, reset)
                     const unsigned ge = (unsigned)(P.env_index_base + renv);
-                    const uint4 ra = philox4x32_10(ge, (unsigned)sl, (unsigned)(sl >> 32), DR_CTR_EPISODE, P.dr_key0, P.dr_key1);
-                    const uint4 rb = philox4x32_10(ge, (unsigned)sl, (unsigned)(sl >> 32), DR_CTR_EPISODE + 1u, P.dr_key0, P.dr_key1);
+                    const uint4 ra = philox4x32_10(ge, (unsigned)sl, (unsigned)(sl >> 32), DR_CTR_EPISODE, P);
+                    const uint4 rb = philox4x32_10(ge, (unsigned)sl, (unsigned)(sl >> 32), DR_CTR_EPISODE + 1u, P);
                     const double inv24 = 1.0 / 16777216.0;
                     const double s_mass = __dadd_rn(P.dr_lo[0], __dmul_rn(P.dr_span[0], __dmul_rn((double)(ra.x >> 8), inv24)));
                     const double s_acc = __dadd_rn(P.dr_lo[1], __dmul_rn(P.dr_span[1], __dmul_rn((double)(ra.y >> 8), inv24)));
@@ -1214,11 +1215,11 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
             // DR sensor noise of the observed state: blocks of counter (its step_count - 1), see swarm_device.cuh
             uint4 rA = make_uint4(0, 0, 0, 0), rB = rA;
             if (DR) {
-                rA = philox4x32_10(genv, ekey, (unsigned)(sc_obs - 1), (unsigned)i | (DR_STREAM_A << 16), P.dr_key0, P.dr_key1);
-                if (S > 4) rB = philox4x32_10(genv, ekey, (unsigned)(sc_obs - 1), (unsigned)i | (DR_STREAM_B << 16), P.dr_key0, P.dr_key1);
+                rA = philox4x32_7(genv, ekey, (unsigned)(sc_obs - 1), (unsigned)i | (DR_STREAM_A << 16), P);
+                if (S > 4) rB = philox4x32_7(genv, ekey, (unsigned)(sc_obs - 1), (unsigned)i | (DR_STREAM_B << 16), P);
             }
             auto noisy = [&](float x, float sigma, unsigned idx) {
-                return DR ? __fadd_rn(x, __fmul_rn(sigma, dr_normal(P.dr_qtable, idx))) : x;
+                return DR ? __fmaf_rn(sigma, dr_normal(P.dr_qtable, idx), x) : x;
             };
             auto obst_bits = [&](int q) { return q < 4 ? dr_field(rA, 9 + q) : dr_field(rB, q - 4); };
             row[0] = noisy(p.x, P.dr_std_pos, dr_field(rA, 3)); row[1] = noisy(p.y, P.dr_std_pos, dr_field(rA, 4));
@@ -1410,8 +1411,10 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                         if (all_reached) atomicAdd(wstats + SWARM_STAT_SUCCESS, 1ull);
                         if (any_col) atomicAdd(wstats + SWARM_STAT_COLLISION, 1ull);
                         if (all_trunc) atomicAdd(wstats + SWARM_STAT_TIMEOUT, 1ull);
-                    } else if (all_trunc && !all_term) {
-                        atomicAdd(wstats + SWARM_STAT_TIMEOUT, 1ull);
+                    } else {  // single env (:92-103): the one drone's flags are the episode's
+                        if (collided) atomicAdd(wstats + SWARM_STAT_COLLISION, 1ull);
+                        else if (reached) atomicAdd(wstats + SWARM_STAT_SUCCESS, 1ull);
+                        else if (all_trunc) atomicAdd(wstats + SWARM_STAT_TIMEOUT, 1ull);
                     }
                 }
                 if (P.episode_return) P.episode_return[env] = ep_over ? ret : 0.0f;

@@ -74,24 +74,108 @@ __device__ __forceinline__ unsigned merge_low(unsigned a, unsigned b) {
     return r;
 }
 
-// float32 -> float64 with two integer ops instead of the quarter-rate conversion unit.  Exact for
-// normal a >= 0; zero / denormal inputs come out as some value below 2^-125, which cannot change
-// the float64 sum of squares once that sum is >= 2^-28 (the rotation pass checks exactly that and
-// falls back to the exact path otherwise).
+// float32 -> float64 without the quarter-rate conversion unit (XU pipe: F2F, MUFU -- the busiest pipe of the pair
+// rounds): the float64 bit pattern of a normal a >= 0 is  bits(a) * 2^29 + 0x3800000000000000  (mantissa and
+// exponent shifted into place, exponent re-biased), ONE wide multiply-add on the FMA pipe (IMAD.WIDE.U32).
+// Zero / denormal inputs come out as some value below 2^-125, which cannot change the float64 sum of squares
+// once that sum is >= 2^-28 (the rotation pass checks exactly that and falls back to the exact path otherwise).
+// Which conversions take this route is a tuning knob:
+//   SWARM_ROT_CVT_SQ   bit k: the k-th square of a pair distance (x, y, z)
+//   SWARM_ROT_CVT_FORM bit 0 / 1: the forward / backward distance of the formation sum
 #ifndef SWARM_ROT_INT_CVT
 #define SWARM_ROT_INT_CVT 0
 #endif
-__device__ __forceinline__ double f64_of_pos_f32(float a) {
-#if SWARM_ROT_INT_CVT
-    const unsigned b = __float_as_uint(a);
-    return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
-#else
-    return (double)a;
+#ifndef SWARM_ROT_CVT_SQ
+#define SWARM_ROT_CVT_SQ 7
 #endif
+#ifndef SWARM_ROT_CVT_FORM
+#define SWARM_ROT_CVT_FORM (SWARM_ROT_INT_CVT ? 3 : 0)
+#endif
+template <bool INT>
+__device__ __forceinline__ double f64_of_pos_f32(float a) {
+    if (INT) {
+        const unsigned b = __float_as_uint(a);
+        return __longlong_as_double((long long)((unsigned long long)b * 0x20000000ull + 0x3800000000000000ull));
+    }
+    return (double)a;
 }
 __device__ __forceinline__ float sumsq1d_fast(float x, float y, float z) {
     const float px = __fmul_rn(x, x), py = __fmul_rn(y, y), pz = __fmul_rn(z, z);
-    return __double2float_rn(__dadd_rn(__dadd_rn(f64_of_pos_f32(px), f64_of_pos_f32(py)), f64_of_pos_f32(pz)));
+    return __double2float_rn(__dadd_rn(__dadd_rn(f64_of_pos_f32<(SWARM_ROT_CVT_SQ & 1) != 0>(px),
+                                                 f64_of_pos_f32<(SWARM_ROT_CVT_SQ & 2) != 0>(py)),
+                                       f64_of_pos_f32<(SWARM_ROT_CVT_SQ & 4) != 0>(pz)));
+}
+
+// ---- packed float32 pairs (Blackwell FADD2 / FMUL2 / FFMA2: two IEEE round-to-nearest operations per issue slot)
+#ifndef SWARM_ROT_PACKED
+#define SWARM_ROT_PACKED 1
+#endif
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// squares (dx^2, dy^2, dz^2) of q - p from two packed subtractions / multiplications; .w rides along unused
+__device__ __forceinline__ void sq_diff3(const float4& q, f32x2 p_xy, f32x2 p_z0, float& sx, float& sy, float& sz) {
+    const f32x2 dxy = sub2(pack2(q.x, q.y), p_xy), dzw = sub2(pack2(q.z, q.w), p_z0);
+    float junk;
+    unpack2(mul2(dxy, dxy), sx, sy);
+    unpack2(mul2(dzw, dzw), sz, junk);
+}
+// MINUS the sum of squares of np.linalg.norm(vec3) (BLAS sdot: float64 accumulate, cast back), squares given
+__device__ __forceinline__ float neg_sumsq1d_of_squares(float px, float py, float pz) {
+    return __double2float_rn(-__dadd_rn(__dadd_rn(f64_of_pos_f32<(SWARM_ROT_CVT_SQ & 1) != 0>(px),
+                                                  f64_of_pos_f32<(SWARM_ROT_CVT_SQ & 2) != 0>(py)),
+                                        f64_of_pos_f32<(SWARM_ROT_CVT_SQ & 4) != 0>(pz)));
+}
+// sqrt_rn_fast (swarm_device.cuh) of two values at once, on NEGATED inputs and with NEGATED results: with
+// ns = -s, y = rsqrt(s):  g' = ns y = -g,  r' = g' g' + ns = -(s - g g),  d' = r' h + g' = -(r h + g) -- every
+// operation is the mirror image of the scalar sequence (round-to-nearest is symmetric), so -d' has the same bits,
+// and no operand needs a sign flip (the packed instructions have no negate modifier in PTX)
+__device__ __forceinline__ f32x2 neg_sqrt_rn_fast2(float ns0, float ns1) {
+    float y0, y1;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(-ns0));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y1) : "f"(-ns1));
+    const f32x2 ns = pack2(ns0, ns1), y = pack2(y0, y1);
+    const f32x2 g = mul2(ns, y);
+    const f32x2 h = mul2(y, pack2(0.5f, 0.5f));
+    const f32x2 r = fma2(g, g, ns);
+    return fma2(r, h, g);
+}
+
+// atomicAdd(counter, 1) by ONE lane, without the compiler's warp-aggregation wrapper (vote / popc / elect /
+// broadcast shuffle): that wrapper consumes the result at once, so the warp sits out the full round trip of an
+// atomic on a contended address (12 % of the step kernel's stall samples).  `zero` must be a value that IS zero
+// but that the compiler cannot prove uniform (threadIdx.y of a one-dimensional CTA): it keeps ptxas from
+// recognising a uniform address.  The result is only waited for where it is first used.
+__device__ __forceinline__ unsigned atom_inc_lane(unsigned* counter, unsigned zero) {
+    unsigned r;
+    asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(r) : "l"(counter + zero) : "memory");
+    return r;
+}
+__device__ __forceinline__ unsigned atom_add_lane(unsigned* counter, unsigned n, unsigned zero) {
+    unsigned r;
+    asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(r) : "l"(counter + zero), "r"(n) : "memory");
+    return r;
 }
 
 __device__ __forceinline__ unsigned umin3(unsigned a, unsigned b, unsigned c) { return min(min(a, b), c); }

@@ -32,13 +32,20 @@ namespace swarm {
 
 
 // CTA shape (measured): N = 32 and N = 16 run best as 4 warps x 7 CTAs per SM (72 registers, 28 resident warps,
-// 7 per scheduler; N = 16: +4 % over 8 x 3), N = 8 as 8 warps x 3 CTAs (80 registers; 4 x 7 is 5 % slower there)
+// 7 per scheduler; N = 16: +4 % over 8 x 3), N = 8 as 8 warps x 3 CTAs (80 registers; 4 x 7 is 5 % slower there).
+// With domain randomisation every CTA carries the 2 KB quantile table, and seven copies of it do not fit beside
+// 28 warp slices: the DR kernels run the same 28 warps as ONE CTA per SM (there is no block barrier in the loop,
+// and 28 = 4 x 7 keeps the four schedulers evenly loaded).
 #ifndef SWARM_ROT_W32
 #define SWARM_ROT_W32 4
 #define SWARM_ROT_B32 7
 #endif
-__host__ __device__ constexpr int rot_warps(int n) { return n >= 16 ? SWARM_ROT_W32 : 8; }
-__host__ __device__ constexpr int rot_min_blocks(int n) { return n >= 16 ? SWARM_ROT_B32 : 3; }
+#ifndef SWARM_ROT_W32_DR
+#define SWARM_ROT_W32_DR 28
+#define SWARM_ROT_B32_DR 1
+#endif
+__host__ __device__ constexpr int rot_warps(int n, bool dr) { return n >= 16 ? (dr ? SWARM_ROT_W32_DR : SWARM_ROT_W32) : 8; }
+__host__ __device__ constexpr int rot_min_blocks(int n, bool dr) { return n >= 16 ? (dr ? SWARM_ROT_B32_DR : SWARM_ROT_B32) : 3; }
 
 // smem per warp: mbarriers (16 B) | agent inbox: pos4[32] vel4[32] actions[96] (single buffer, refilled as
 // soon as it has been read) | env inbox x 2: goal4[G] obst4[G*M] dr[2G] step_count[G] ep_return[G] |
@@ -53,14 +60,19 @@ __host__ __device__ constexpr int rot_smem_per_warp(int G, int M, bool dr) {
 // MT: number of obstacles when known at compile time (4 / 8: sorting-network selection), 0 = P.M
 // MODE: kRotStep = env.step() of every group (episode ends are put on the reset list);
 //       kRotReset = env.reset() + first observation of the listed envs (the auto-reset launch that follows)
-enum RotMode : int { kRotStep = 0, kRotReset = 1 };
+//       kRotFused = both in ONE launch: the warp that finds an episode over re-draws that env itself and runs the
+//                   table / rotation / obstacle / tile code a second time (the SAME code, a runtime pass flag --
+//                   a second copy would not fit the instruction cache) to produce the reset observation
+enum RotMode : int { kRotStep = 0, kRotReset = 1, kRotFused = 2 };
 
 template <int NT, int MT, bool DR, int MODE>
-__global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_step_rot_kernel(const DevParams P) {
+__global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)) swarm_step_rot_kernel(const DevParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int N = NT, G = 32 / NT, HALF = NT / 2;
     constexpr unsigned IDX = NT - 1;  // index bits of a neighbour key
-    constexpr int kRotWarps = rot_warps(NT);
+    constexpr int kRotWarps = rot_warps(NT, DR);
+    constexpr bool kStepLike = MODE != kRotReset;   // items = env groups of the batch, inputs by TMA, dynamic queue
+    constexpr bool kFused = MODE == kRotFused;
     // (the shuffle makes the warp index provably warp-uniform: addresses and branches that derive from
     //  it are then computed on the uniform datapath)
     const int warp = __shfl_sync(FULL_MASK, (int)(threadIdx.x >> 5), 0);
@@ -77,12 +89,29 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
     unsigned long long* wstats =
         reinterpret_cast<unsigned long long*>(smem_raw + (size_t)kRotWarps * per_warp) + warp * SWARM_STATS_WORDS;
     if (lane < SWARM_STATS_WORDS) wstats[lane] = 0ull;
-    // DR: the 256-entry half-normal quantile table lives in shared memory (13 lookups per agent-step)
+    // step launch: the groups with an env to reset are collected here and appended to the global list kLocalList
+    // at a time (one atomic per flush instead of one per group)
+    constexpr int kLocalList = 8;
+    int* wlist = reinterpret_cast<int*>(smem_raw + (size_t)kRotWarps * per_warp +
+                                        (size_t)kRotWarps * SWARM_STATS_WORDS * sizeof(unsigned long long)) + warp * kLocalList;
+    int n_local = 0;
+    const unsigned tid_y = threadIdx.y;   // zero (one-dimensional CTA), but not provably uniform: see atom_inc_lane
+    auto flush_list = [&]() {
+        __syncwarp();
+        unsigned base = 0u;
+        if (lane == 0) base = atom_add_lane(P.reset_count, (unsigned)n_local, tid_y);
+        base = __shfl_sync(FULL_MASK, base, 0);
+        if (lane < n_local) P.reset_list[base + lane] = wlist[lane];
+        __syncwarp();
+        n_local = 0;
+    };
+    // DR: the signed 512-entry normal quantile table lives in shared memory (13 lookups per agent-step)
     const float* qtab = reinterpret_cast<const float*>(smem_raw + (size_t)kRotWarps * per_warp +
-                                                       (size_t)kRotWarps * SWARM_STATS_WORDS * sizeof(unsigned long long));
+                                                       (size_t)kRotWarps * SWARM_STATS_WORDS * sizeof(unsigned long long) +
+                                                       (size_t)kRotWarps * kLocalList * sizeof(int));
     if (DR) {
         float* qw = const_cast<float*>(qtab);
-        for (int k = threadIdx.x; k < 256; k += kRotWarps * 32) qw[k] = P.dr_qtable[k];
+        for (int k = threadIdx.x; k < 512; k += kRotWarps * 32) qw[k] = P.dr_qtable[k];
         __syncthreads();
     }
 
@@ -102,9 +131,9 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
     //  it turns out to be inside the list -- so a warp's first item starts one memory round trip earlier)
     int env0_pref = 0;
     if (MODE == kRotReset) env0_pref = P.reset_list[min((int)(blockIdx.x * kRotWarps + warp), P.n_groups - 1)];
-    const int n_iter = MODE == kRotStep ? P.n_groups : (int)*reinterpret_cast<const volatile unsigned*>(P.reset_count);
+    const int n_iter = kStepLike ? P.n_groups : (int)*reinterpret_cast<const volatile unsigned*>(P.reset_count);
     const int env_end = P.env_begin + P.env_count;
-    unsigned* const queue = P.work_counter + (MODE == kRotStep ? 0 : 2);
+    unsigned* const queue = P.work_counter + (kStepLike ? 0 : 2);
 
     if (lane == 0) {
         mbar_init(bar0, 1);
@@ -117,7 +146,7 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
     const int goal_off = 0, obst_off = 16 * G, dr_off = 16 * G * (1 + M);
     const int sc_off = dr_off + (DR ? 32 * G : 0);
     auto issue = [&](int grp, int buf) {
-        if (MODE != kRotStep) return;
+        if (!kStepLike) return;
         const int env0 = P.env_begin + grp * G;
         const int n_env = G == 1 ? 1 : min(G, env_end - env0);
 #if SWARM_ROT_TMA_LOADS
@@ -171,12 +200,12 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
     int buf = 0;
     while (it < n_iter) {
         int it_next = 0;
-        if (MODE == kRotStep) {
-            if (lane == 0) it_next = warps_total + (int)atomicAdd(queue, 1u);
+        if (kStepLike) {
+            if (lane == 0) it_next = warps_total + (int)atom_inc_lane(queue, tid_y);
         } else {
             it_next = it + warps_total;
         }
-        const int env0 = MODE == kRotStep ? P.env_begin + it * G : env0_pref;
+        const int env0 = kStepLike ? P.env_begin + it * G : env0_pref;
         if (MODE == kRotReset) env0_pref = P.reset_list[min(it_next, P.n_groups - 1)];  // the next item's entry, early
         const int n_env = G == 1 ? 1 : min(G, env_end - env0);
         const bool lane_ok = G == 1 ? true : e_l < n_env;
@@ -206,9 +235,18 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
             else reset_envs = __ballot_sync(FULL_MASK, lane < n_env && P.env_mask[env0 + lane] != 0);
         }
 
-        constexpr auto step_pass = []() { return MODE == kRotStep; };
-        {
-            if (step_pass()) {
+        // fused launch: pass 0 = env.step(); pass 1 (only when an episode of the group ended) = env.reset() + its
+        // observation for those envs, through the same table / scan / tile code
+        int pass = 0;
+#pragma unroll 1
+        for (;; ++pass) {
+            // (the pass number is made opaque so that the compiler cannot specialise -- duplicate -- the scan / tile
+            //  code for each pass: ONE copy must serve both or the loop leaves the 32 KB instruction cache)
+            if (kFused) asm volatile("" : "+r"(pass));
+            const bool step_now = MODE == kRotStep || (kFused && pass == 0);
+            int step_flag = step_now ? 1 : 0;   // (re-read through an opaque copy after the input stage, see below)
+            auto step_pass = [&]() { return MODE == kRotStep || (kFused && step_flag != 0); };
+            if (step_now) {
                 cp_async_wait_all();
 #if SWARM_ROT_TMA_LOADS
                 mbar_wait(bar0 + 8 * buf, (phase >> buf) & 1u);
@@ -261,10 +299,10 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                     }
                     ax = clipf(ax, -1.0f, 1.0f); ay = clipf(ay, -1.0f, 1.0f); az = clipf(az, -1.0f, 1.0f);
                     if (DR) {  // thrust noise: a <- a * (1 + sigma z), one normal per axis
-                        rA = philox4x32_10(genv, ekey, (unsigned)sc, (unsigned)i | (DR_STREAM_A << 16), P.dr_key0, P.dr_key1);
-                        ax = __fmul_rn(ax, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, dr_normal(qtab, dr_field(rA, 0)))));
-                        ay = __fmul_rn(ay, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, dr_normal(qtab, dr_field(rA, 1)))));
-                        az = __fmul_rn(az, __fadd_rn(1.0f, __fmul_rn(P.dr_std_thrust, dr_normal(qtab, dr_field(rA, 2)))));
+                        rA = philox4x32_7(genv, ekey, (unsigned)sc, (unsigned)i | (DR_STREAM_A << 16), P);
+                        ax = __fmul_rn(ax, __fmaf_rn(P.dr_std_thrust, dr_normal_off(qtab, dr_field_off(rA, 0)), 1.0f));
+                        ay = __fmul_rn(ay, __fmaf_rn(P.dr_std_thrust, dr_normal_off(qtab, dr_field_off(rA, 1)), 1.0f));
+                        az = __fmul_rn(az, __fmaf_rn(P.dr_std_thrust, dr_normal_off(qtab, dr_field_off(rA, 2)), 1.0f));
                     }
                     v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(ax, c_amax), c_dt));
                     v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(ay, c_amax), c_dt));
@@ -298,8 +336,8 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                     if (DR) {
                         // this episode's constants: 6 uniforms + an episode key from one counter per (env, reset)
                         const unsigned ge = (unsigned)(P.env_index_base + renv);
-                        const uint4 ra = philox4x32_10(ge, (unsigned)sl, (unsigned)(sl >> 32), DR_CTR_EPISODE, P.dr_key0, P.dr_key1);
-                        const uint4 rb = philox4x32_10(ge, (unsigned)sl, (unsigned)(sl >> 32), DR_CTR_EPISODE + 1u, P.dr_key0, P.dr_key1);
+                        const uint4 ra = philox4x32_10(ge, (unsigned)sl, (unsigned)(sl >> 32), DR_CTR_EPISODE, P);
+                        const uint4 rb = philox4x32_10(ge, (unsigned)sl, (unsigned)(sl >> 32), DR_CTR_EPISODE + 1u, P);
                         const double inv24 = 1.0 / 16777216.0;
                         const double s_mass = __dadd_rn(P.dr_lo[0], __dmul_rn(P.dr_span[0], __dmul_rn((double)(ra.x >> 8), inv24)));
                         const double s_acc = __dadd_rn(P.dr_lo[1], __dmul_rn(P.dr_span[1], __dmul_rn((double)(ra.y >> 8), inv24)));
@@ -330,7 +368,7 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                         }
                         if (e_l == el) ekey = rb.z;  // (the dynamics constants are not needed to observe)
                     }
-#pragma unroll 4
+#pragma unroll (kFused ? 1 : 4)
                     for (int k = lane; k < P.n_draws; k += 32) {
                         unsigned long long oh, ol;
                         pcg_jump(P.jump[k + 1], sh, sl, ih, il, oh, ol);
@@ -375,6 +413,9 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                 __syncwarp();     // the drawn positions have been read before the table is rewritten
             }
 
+            // (fused: the two input stages above rejoin here; without this the compiler threads the later tests of
+            //  the pass flag back to them and emits the whole scan code twice)
+            if (kFused) asm volatile("" : "+r"(step_flag));
             // doubled position table: entry [2N e_l + i + r] is drone (i + r) mod N for 0 <= r <= N; .w = drone index
             {
                 const float4 t = make_float4(p.x, p.y, p.z, __int_as_float(i));
@@ -387,8 +428,10 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
             __syncwarp();
             // every lane has consumed the agent inbox (its values went through the integrator): refill it,
             // and the other env inbox, with the next group's inputs
-            it_next = __shfl_sync(FULL_MASK, it_next, 0);
-            if (step_pass() && it_next < n_iter) issue(it_next, buf ^ 1);
+            if (pass == 0) {
+                it_next = __shfl_sync(FULL_MASK, it_next, 0);
+                if (kStepLike && it_next < n_iter) issue(it_next, buf ^ 1);
+            }
             // velocity / previous goal distance wait in the tile row (slots 32-35) while the scans need the registers
             srow[32] = v.x; srow[33] = v.y; srow[34] = v.z; srow[35] = prev_d;
 
@@ -405,10 +448,72 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                 double acc_f = 0.0, acc_b = 0.0;
                 float smin = F32_INF;
                 const double d_star = P.d_star;
-                float4 qn = tp[1];
 #ifndef SWARM_ROT_DR_UNROLL
 #define SWARM_ROT_DR_UNROLL 5
 #endif
+#if SWARM_ROT_PACKED
+                // Rounds in pairs (r, r + 1), the last pair holding the half round N/2: the coordinate differences /
+                // squares of a round and the two square roots of a pair are packed float32x2 operations (same
+                // roundings, half the issue slots).  Distances travel NEGATED through the pair (neg_sqrt_rn_fast2):
+                // keys clear the sign in the LOP3 that packs them, the formation term is |(-d) + d*|, the stash holds
+                // -d and the three picks take |.| when they are read back.
+                const f32x2 p_xy = pack2(p.x, p.y), p_z0 = pack2(p.z, 0.0f);
+                constexpr unsigned KEYMASK = ~IDX & 0x7fffffffu;
+                auto full_round = [&](int r, const float4& q, float ndf) {
+                    const int src = lane + N - r;                                   // (i - r) mod N in the low bits
+                    const float ndb = __shfl_sync(FULL_MASK, ndf, src, N);          // -d((i - r) mod N, i)
+                    srow[r] = ndf;
+                    srow[HALF + r] = ndb;
+                    const unsigned kf = and_or<KEYMASK>(__float_as_uint(ndf), __float_as_uint(q.w));
+                    const unsigned kb = merge_low<IDX | 0x80000000u>(__float_as_uint(ndb), (unsigned)src);
+                    merge2(kf, kb, k0, k1, k2, k3);
+                    if (kStepLike) {   // |d - d*| = |(-d) + d*|
+                        if (SWARM_ROT_CVT_FORM & 1) acc_f = __dadd_rn(acc_f, fabs(__dsub_rn(f64_of_pos_f32<true>(fabsf(ndf)), d_star)));
+                        else acc_f = __dadd_rn(acc_f, fabs(__dadd_rn((double)ndf, d_star)));
+                        if (SWARM_ROT_CVT_FORM & 2) acc_b = __dadd_rn(acc_b, fabs(__dsub_rn(f64_of_pos_f32<true>(fabsf(ndb)), d_star)));
+                        else acc_b = __dadd_rn(acc_b, fabs(__dadd_rn((double)ndb, d_star)));
+                    }
+                };
+                constexpr int kPairs = HALF / 2;
+#ifndef SWARM_ROT_UNROLL_PAIRS
+#define SWARM_ROT_UNROLL_PAIRS 8
+#endif
+#ifndef SWARM_ROT_UNROLL_PAIRS_DR
+#define SWARM_ROT_UNROLL_PAIRS_DR 2
+#endif
+                // (the unroll factors are tuning knobs: the loop body must stay inside the instruction cache)
+                constexpr int kUnrollWant = DR ? SWARM_ROT_UNROLL_PAIRS_DR : SWARM_ROT_UNROLL_PAIRS;
+                constexpr int kUnroll = kPairs > kUnrollWant ? kUnrollWant : kPairs;
+#pragma unroll kUnroll
+                for (int u = 0; u < kPairs - 1; ++u) {
+                    const int ra = 2 * u + 1, rb = 2 * u + 2;
+                    const float4 qa = tp[ra], qb = tp[rb];
+                    float ax2, ay2, az2, bx2, by2, bz2;
+                    sq_diff3(qa, p_xy, p_z0, ax2, ay2, az2);
+                    sq_diff3(qb, p_xy, p_z0, bx2, by2, bz2);
+                    const float nsa = neg_sumsq1d_of_squares(ax2, ay2, az2), nsb = neg_sumsq1d_of_squares(bx2, by2, bz2);
+                    float nda, ndb;
+                    unpack2(neg_sqrt_rn_fast2(nsa, nsb), nda, ndb);
+                    if (!kStepLike) smin = fminf(smin, fminf(-nsa, -nsb));  // reset(): only the range check of the sum
+                    full_round(ra, qa, nda);
+                    full_round(rb, qb, ndb);
+                }
+                {   // last pair: round N/2 - 1 and the half round N/2 (visited from both ends, each end keeps its copy)
+                    const float4 qa = tp[HALF - 1], qb = tp[HALF];
+                    float ax2, ay2, az2, bx2, by2, bz2;
+                    sq_diff3(qa, p_xy, p_z0, ax2, ay2, az2);
+                    sq_diff3(qb, p_xy, p_z0, bx2, by2, bz2);
+                    const float nsa = neg_sumsq1d_of_squares(ax2, ay2, az2), nsb = neg_sumsq1d_of_squares(bx2, by2, bz2);
+                    float nda, ndb;
+                    unpack2(neg_sqrt_rn_fast2(nsa, nsb), nda, ndb);
+                    if (!kStepLike) smin = fminf(smin, fminf(-nsa, -nsb));
+                    full_round(HALF - 1, qa, nda);
+                    srow[HALF] = ndb;
+                    merge1(and_or<KEYMASK>(__float_as_uint(ndb), __float_as_uint(qb.w)), k0, k1, k2, k3);
+                    if (kStepLike) acc_f = __dadd_rn(acc_f, fabs(__dadd_rn((double)ndb, d_star)));
+                }
+#else
+                float4 qn = tp[1];
                 // (the DR variant's loop + noise code sits at the edge of the instruction cache: its unroll
                 //  factor is a tuning knob)
                 constexpr int kUnroll = DR ? (HALF > SWARM_ROT_DR_UNROLL ? SWARM_ROT_DR_UNROLL : HALF) : HALF;
@@ -424,9 +529,9 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                     const unsigned kf = and_or<~IDX>(__float_as_uint(d), __float_as_uint(q.w));
                     const unsigned kb = merge_low<IDX>(__float_as_uint(db), (unsigned)(lane - r));
                     merge2(kf, kb, k0, k1, k2, k3);
-                    if (step_pass()) {
-                        acc_f = __dadd_rn(acc_f, fabs(__dsub_rn(f64_of_pos_f32(d), d_star)));
-                        acc_b = __dadd_rn(acc_b, fabs(__dsub_rn(f64_of_pos_f32(db), d_star)));
+                    if (kStepLike) {
+                        acc_f = __dadd_rn(acc_f, fabs(__dsub_rn(f64_of_pos_f32<(SWARM_ROT_CVT_FORM & 1) != 0>(d), d_star)));
+                        acc_b = __dadd_rn(acc_b, fabs(__dsub_rn(f64_of_pos_f32<(SWARM_ROT_CVT_FORM & 2) != 0>(db), d_star)));
                     } else {
                         smin = fminf(smin, s);  // reset(): no reward, so no formation sum -- only its range check
                     }
@@ -437,9 +542,10 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                     const float d = sqrt_rn_fast(s);
                     srow[HALF] = d;
                     merge1(and_or<~IDX>(__float_as_uint(d), __float_as_uint(q.w)), k0, k1, k2, k3);
-                    if (step_pass()) acc_f = __dadd_rn(acc_f, fabs(__dsub_rn(f64_of_pos_f32(d), d_star)));
+                    if (kStepLike) acc_f = __dadd_rn(acc_f, fabs(__dsub_rn(f64_of_pos_f32<(SWARM_ROT_CVT_FORM & 1) != 0>(d), d_star)));
                     else smin = fminf(smin, s);
                 }
+#endif
                 form_sum = __dadd_rn(acc_f, acc_b);
                 // s < 2^-28 (a distance below 2^-14: fast sqrt / exact-sum preconditions) shows up either as the
                 // smallest key or, for s = 0 / denormal s (rsqrt -> inf -> NaN distance), as a NaN formation sum;
@@ -456,7 +562,8 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                     const int j = (int)(kk[q] & IDX);
                     const int t = (j - i) & (int)IDX;           // forward distance i -> j
                     nj[q] = j;
-                    nd[q] = srow[t <= HALF ? t : HALF + N - t];  // backward round N - t was stashed at HALF + (N - t)
+                    nd[q] = fabsf(srow[t <= HALF ? t : HALF + N - t]);  // backward round N - t was stashed at HALF + (N - t)
+                                                                         // (|.|: the packed rounds stash -d)
                 }
                 {
                     auto cex3 = [&](int a, int b) {
@@ -489,8 +596,16 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
 #pragma unroll
                     for (int m = 0; m < MT; m += 2) {
                         const float4 oa = tobs[m], ob = tobs[m + 1];
+#if SWARM_ROT_PACKED
+                        float oax, oay, oaz, obx, oby, obz;
+                        sq_diff3(oa, p_xy, p_z0, oax, oay, oaz);
+                        sq_diff3(ob, p_xy, p_z0, obx, oby, obz);
+                        const float sa = __fadd_rn(__fadd_rn(oax, oay), oaz);   // np.linalg.norm(axis=): sequential f32
+                        const float sb = __fadd_rn(__fadd_rn(obx, oby), obz);
+#else
                         const float sa = sumsq_axis(__fsub_rn(oa.x, p.x), __fsub_rn(oa.y, p.y), __fsub_rn(oa.z, p.z));
                         const float sb = sumsq_axis(__fsub_rn(ob.x, p.x), __fsub_rn(ob.y, p.y), __fsub_rn(ob.z, p.z));
+#endif
 #if SWARM_ROT_OBST_SQKEY
                         // keys from the SQUARED distance (sqrt is monotone; squares that a truncated key cannot
                         // tell apart -- which includes every pair whose roots could coincide -- are flagged
@@ -614,60 +729,15 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
             v.x = srow[32]; v.y = srow[33]; v.z = srow[34]; prev_d = srow[35];
             const float curr_d = norm1d<0>(__fsub_rn(gx, p.x), __fsub_rn(gy, p.y), __fsub_rn(gz, p.z));
 
-            // ============================ obs row -> staging tile (:226-243) ============================
-            // rows this launch delivers: step = every env, reset = the re-drawn ones
-            const unsigned out_envs = step_pass() ? ((1u << n_env) - 1u) : reset_envs;
-            if (out_envs != 0u) {
-                if (lane_ok) {
-                    float* row = srow;
-                    const float4 t0 = tab2[2 * e_base + nj[0]], t1 = tab2[2 * e_base + nj[1]], t2 = tab2[2 * e_base + nj[2]];
-                    const float4 b0 = tobs[om[0]], b1 = tobs[om[1]], b2 = tobs[om[2]], b3 = tobs[om[3]];
-                    if (DR) {  // sensor noise of the observed state (step_count sc + 1): the block of counter sc
-                        if (!step_pass() || !alive)  // (an active drone drew this block for its thrust already)
-                            rA = philox4x32_10(genv, ekey, (unsigned)sc, (unsigned)i | (DR_STREAM_A << 16), P.dr_key0, P.dr_key1);
-                    }
-                    auto noisy = [&](float x, float sigma, unsigned idx) {
-                        return DR ? __fadd_rn(x, __fmul_rn(sigma, dr_normal(qtab, idx))) : x;
-                    };
-                    row[0] = noisy(p.x, P.dr_std_pos, dr_field(rA, 3)); row[1] = noisy(p.y, P.dr_std_pos, dr_field(rA, 4));
-                    row[2] = noisy(p.z, P.dr_std_pos, dr_field(rA, 5));
-                    row[3] = noisy(v.x, P.dr_std_vel, dr_field(rA, 6)); row[4] = noisy(v.y, P.dr_std_vel, dr_field(rA, 7));
-                    row[5] = noisy(v.z, P.dr_std_vel, dr_field(rA, 8));
-                    row[6] = __fsub_rn(gx, p.x); row[7] = __fsub_rn(gy, p.y); row[8] = __fsub_rn(gz, p.z);
-                    row[9] = __fsub_rn(t0.x, p.x); row[10] = __fsub_rn(t0.y, p.y); row[11] = __fsub_rn(t0.z, p.z); row[12] = nd[0];
-                    row[13] = __fsub_rn(t1.x, p.x); row[14] = __fsub_rn(t1.y, p.y); row[15] = __fsub_rn(t1.z, p.z); row[16] = nd[1];
-                    row[17] = __fsub_rn(t2.x, p.x); row[18] = __fsub_rn(t2.y, p.y); row[19] = __fsub_rn(t2.z, p.z); row[20] = nd[2];
-                    row[21] = __fsub_rn(b0.x, p.x); row[22] = __fsub_rn(b0.y, p.y); row[23] = __fsub_rn(b0.z, p.z);
-                    row[24] = noisy(od[0], P.dr_std_obst, dr_field(rA, 9));
-                    row[25] = __fsub_rn(b1.x, p.x); row[26] = __fsub_rn(b1.y, p.y); row[27] = __fsub_rn(b1.z, p.z);
-                    row[28] = noisy(od[1], P.dr_std_obst, dr_field(rA, 10));
-                    row[29] = __fsub_rn(b2.x, p.x); row[30] = __fsub_rn(b2.y, p.y); row[31] = __fsub_rn(b2.z, p.z);
-                    row[32] = noisy(od[2], P.dr_std_obst, dr_field(rA, 11));
-                    row[33] = __fsub_rn(b3.x, p.x); row[34] = __fsub_rn(b3.y, p.y); row[35] = __fsub_rn(b3.z, p.z);
-                    row[36] = noisy(od[3], P.dr_std_obst, dr_field(rA, 12));
-                }
-                fence_async_smem();  // generic-proxy tile writes -> visible to the bulk-copy engine
-                __syncwarp();
-                if (lane == 0) {
-                    if (out_envs == (1u << n_env) - 1u) {  // whole tile, one TMA store
-                        bulk_s2g(P.obs + (long long)a0 * kD, smem_u32(tile), (unsigned)(n_env * N * kD * 4));
-                    } else {
-#pragma unroll 1
-                        for (int el = 0; el < n_env; ++el)
-                            if ((out_envs >> el) & 1u)
-                                bulk_s2g(P.obs + (long long)(a0 + el * N) * kD, smem_u32(tile + el * N * kD),
-                                         (unsigned)(N * kD * 4));
-                    }
-                    bulk_commit();
-                }
-            }
-
-            // ===================== rewards and flags (:120-172), pass 0 =====================
+            // ===================== rewards and flags (:120-172) =====================
+            // (before the observation: an env whose episode ends here and is re-drawn by the auto-reset does not
+            //  need this step's rows, so the tile / store below skip it)
             bool reached = false, collided = false, done_agent = false, any_col = false, time_limit = false;
             bool all_reached = false, all_term = false, all_trunc = false, ep_over = false, need_reset = false;
             bool env_active = false;
             double reward = 0.0;
             int sc_new = 0;
+            unsigned redraw_envs = 0u;   // fused launch: bit el = env el of the group is re-drawn in pass 1
             if (step_pass()) {
                 const bool obst_hit = od[0] <= c_thr_obst;
                 reached = alive && curr_d <= P.thr_goal;    // :124-127 (double compare)
@@ -696,6 +766,64 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                 all_trunc = env_active ? (time_limit && !episode_done) : false;
                 ep_over = env_active && (all_term || all_trunc);
                 need_reset = P.auto_reset && (ep_over || !env_active);
+                if (kFused) {
+                    const unsigned nr = __ballot_sync(FULL_MASK, leader && need_reset);
+                    if (G == 1) {
+                        redraw_envs = nr & 1u;
+                    } else {
+#pragma unroll
+                        for (int el = 0; el < G; ++el) redraw_envs |= ((nr >> (el * N)) & 1u) << el;
+                    }
+                }
+            }
+
+            // ============================ obs row -> staging tile (:226-243) ============================
+            // rows this launch delivers: step = every env (fused: minus the ones about to be re-drawn),
+            // reset = the re-drawn ones
+            const unsigned out_envs = step_pass() ? (((1u << n_env) - 1u) & ~redraw_envs) : reset_envs;
+            if (out_envs != 0u) {
+                if (lane_ok && (!kFused || ((out_envs >> e_l) & 1u))) {
+                    float* row = srow;
+                    const float4 t0 = tab2[2 * e_base + nj[0]], t1 = tab2[2 * e_base + nj[1]], t2 = tab2[2 * e_base + nj[2]];
+                    const float4 b0 = tobs[om[0]], b1 = tobs[om[1]], b2 = tobs[om[2]], b3 = tobs[om[3]];
+                    if (DR) {  // sensor noise of the observed state (step_count sc + 1): the block of counter sc
+                        if (!step_pass() || !alive)  // (an active drone drew this block for its thrust already)
+                            rA = philox4x32_7(genv, ekey, (unsigned)sc, (unsigned)i | (DR_STREAM_A << 16), P);
+                    }
+                    auto noisy = [&](float x, float sigma, unsigned idx) {
+                        return DR ? __fmaf_rn(sigma, dr_normal_off(qtab, idx), x) : x;
+                    };
+                    row[0] = noisy(p.x, P.dr_std_pos, dr_field_off(rA, 3)); row[1] = noisy(p.y, P.dr_std_pos, dr_field_off(rA, 4));
+                    row[2] = noisy(p.z, P.dr_std_pos, dr_field_off(rA, 5));
+                    row[3] = noisy(v.x, P.dr_std_vel, dr_field_off(rA, 6)); row[4] = noisy(v.y, P.dr_std_vel, dr_field_off(rA, 7));
+                    row[5] = noisy(v.z, P.dr_std_vel, dr_field_off(rA, 8));
+                    row[6] = __fsub_rn(gx, p.x); row[7] = __fsub_rn(gy, p.y); row[8] = __fsub_rn(gz, p.z);
+                    row[9] = __fsub_rn(t0.x, p.x); row[10] = __fsub_rn(t0.y, p.y); row[11] = __fsub_rn(t0.z, p.z); row[12] = nd[0];
+                    row[13] = __fsub_rn(t1.x, p.x); row[14] = __fsub_rn(t1.y, p.y); row[15] = __fsub_rn(t1.z, p.z); row[16] = nd[1];
+                    row[17] = __fsub_rn(t2.x, p.x); row[18] = __fsub_rn(t2.y, p.y); row[19] = __fsub_rn(t2.z, p.z); row[20] = nd[2];
+                    row[21] = __fsub_rn(b0.x, p.x); row[22] = __fsub_rn(b0.y, p.y); row[23] = __fsub_rn(b0.z, p.z);
+                    row[24] = noisy(od[0], P.dr_std_obst, dr_field_off(rA, 9));
+                    row[25] = __fsub_rn(b1.x, p.x); row[26] = __fsub_rn(b1.y, p.y); row[27] = __fsub_rn(b1.z, p.z);
+                    row[28] = noisy(od[1], P.dr_std_obst, dr_field_off(rA, 10));
+                    row[29] = __fsub_rn(b2.x, p.x); row[30] = __fsub_rn(b2.y, p.y); row[31] = __fsub_rn(b2.z, p.z);
+                    row[32] = noisy(od[2], P.dr_std_obst, dr_field_off(rA, 11));
+                    row[33] = __fsub_rn(b3.x, p.x); row[34] = __fsub_rn(b3.y, p.y); row[35] = __fsub_rn(b3.z, p.z);
+                    row[36] = noisy(od[3], P.dr_std_obst, dr_field_off(rA, 12));
+                }
+                fence_async_smem();  // generic-proxy tile writes -> visible to the bulk-copy engine
+                __syncwarp();
+                if (lane == 0) {
+                    if (out_envs == (1u << n_env) - 1u) {  // whole tile, one TMA store
+                        bulk_s2g(P.obs + (long long)a0 * kD, smem_u32(tile), (unsigned)(n_env * N * kD * 4));
+                    } else {
+#pragma unroll 1
+                        for (int el = 0; el < n_env; ++el)
+                            if ((out_envs >> el) & 1u)
+                                bulk_s2g(P.obs + (long long)(a0 + el * N) * kD, smem_u32(tile + el * N * kD),
+                                         (unsigned)(N * kD * 4));
+                    }
+                    bulk_commit();
+                }
             }
 
             if (step_pass()) {
@@ -715,7 +843,7 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                     if (P.reward64) P.reward64[a] = reward;
                     P.reached[a] = reached ? 1 : 0;
                     P.collision[a] = collided ? 1 : 0;
-                    if (!need_reset) {  // (a re-drawn env gets these from the reset launch that follows)
+                    if (!need_reset) {  // (a re-drawn env gets these from the reset pass / launch that follows)
                         P.dist[a] = curr_d;
                         P.obs_valid[a] = valid ? 1 : 0;
                         P.pos4[a] = make_float4(p.x, p.y, p.z, alive_next ? 1.0f : 0.0f);
@@ -731,7 +859,7 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                 if (leader) {
                     P.all_term[env] = all_term ? 1 : 0;
                     P.all_trunc[env] = all_trunc ? 1 : 0;
-                    if (P.reset_mask) P.reset_mask[env] = need_reset ? 1 : 0;
+                    if (!kFused && P.reset_mask) P.reset_mask[env] = need_reset ? 1 : 0;
                     const float ret = __fadd_rn(reinterpret_cast<const float*>(ib + sc_off)[G + e_l], x);
                     if (ep_over) {  // several env leaders per warp when G > 1: shared-memory atomics
                         atomicAdd(wstats + SWARM_STAT_EPISODES, 1ull);
@@ -759,9 +887,12 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                         wstats[SWARM_STAT_ENV_STEPS] += (unsigned long long)__popc(act_envs);
                     }
                 }
-                if (P.auto_reset) {  // groups with an env to reset go on the list the reset launch walks
+                if (!kFused && P.auto_reset) {  // groups with an env to reset go on the list the reset launch walks
                     const unsigned rl = __ballot_sync(FULL_MASK, leader && need_reset);
-                    if (rl != 0 && lane == 0) P.reset_list[atomicAdd(P.reset_count, 1u)] = env0;
+                    if (rl != 0) {
+                        if (lane == 0) wlist[n_local] = env0;
+                        if (++n_local == kLocalList) flush_list();
+                    }
                 }
             } else {
                 // =========== reset()'s obs / infos (:82-89) for the re-drawn envs; reward / flags stay ===========
@@ -779,15 +910,18 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
                     }
                 }
             }
+            if (!kFused || pass != 0 || redraw_envs == 0u) break;
+            reset_envs = redraw_envs;   // pass 1: env.reset() + observation of the envs whose episode just ended
         }
         it = it_next;
         buf ^= 1;
     }
+    if (MODE == kRotStep && n_local > 0) flush_list();
     // the last warp to leave re-arms the queue for the next launch
 #if SWARM_ROT_PDL
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
-    if (MODE == kRotStep) {
+    if (kStepLike) {
         if (lane == 0 && atomicAdd(queue + 1, 1u) == (unsigned)warps_total - 1u) {
             queue[0] = 0u;
             queue[1] = 0u;
@@ -798,7 +932,7 @@ __global__ void __launch_bounds__(rot_warps(NT) * 32, rot_min_blocks(NT)) swarm_
 
     if (lane == 0) bulk_wait0();  // the last obs tile must have left shared memory before the CTA retires
     __syncwarp();
-    if (MODE == kRotStep && P.stats && lane < SWARM_STATS_WORDS) {
+    if (kStepLike && P.stats && lane < SWARM_STATS_WORDS) {
         const unsigned long long w = wstats[lane];
         if (lane == SWARM_STAT_RETURN_SUM) {
             const double dv = __longlong_as_double((long long)w);
@@ -824,17 +958,19 @@ static RotKernel pick_rot_m(const DevParams& p) {
 
 static RotKernel pick_rot(const DevParams& p) {
     const bool reset = p.mode == kModeAutoReset;
+    const bool fused = p.mode == kModeStep && p.fused_reset != 0;
     switch (p.N) {
-        case 8: return reset ? pick_rot_m<8, kRotReset>(p) : pick_rot_m<8, kRotStep>(p);
-        case 16: return reset ? pick_rot_m<16, kRotReset>(p) : pick_rot_m<16, kRotStep>(p);
-        case 32: return reset ? pick_rot_m<32, kRotReset>(p) : pick_rot_m<32, kRotStep>(p);
+        case 8: return reset ? pick_rot_m<8, kRotReset>(p) : fused ? pick_rot_m<8, kRotFused>(p) : pick_rot_m<8, kRotStep>(p);
+        case 16: return reset ? pick_rot_m<16, kRotReset>(p) : fused ? pick_rot_m<16, kRotFused>(p) : pick_rot_m<16, kRotStep>(p);
+        case 32: return reset ? pick_rot_m<32, kRotReset>(p) : fused ? pick_rot_m<32, kRotFused>(p) : pick_rot_m<32, kRotStep>(p);
     }
     return nullptr;
 }
 
 size_t rot_smem_bytes(const DevParams& p) {
-    return (size_t)rot_warps(p.N) * rot_smem_per_warp(32 / p.N, p.M, p.dr_enabled != 0) +
-           (size_t)rot_warps(p.N) * SWARM_STATS_WORDS * sizeof(unsigned long long) + (p.dr_enabled ? 1024 : 0);
+    return (size_t)rot_warps(p.N, p.dr_enabled != 0) * rot_smem_per_warp(32 / p.N, p.M, p.dr_enabled != 0) +
+           (size_t)rot_warps(p.N, p.dr_enabled != 0) * (SWARM_STATS_WORDS * sizeof(unsigned long long) + 8 * sizeof(int)) +
+           (p.dr_enabled ? 2048 : 0);
 }
 
 cudaError_t launch_rot_kernel(const DevParams& p, int grid, cudaStream_t stream) {
@@ -846,7 +982,7 @@ cudaError_t launch_rot_kernel(const DevParams& p, int grid, cudaStream_t stream)
 #if SWARM_ROT_PDL
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3((unsigned)grid);
-    lc.blockDim = dim3((unsigned)(rot_warps(p.N) * 32));
+    lc.blockDim = dim3((unsigned)(rot_warps(p.N, p.dr_enabled != 0) * 32));
     lc.dynamicSmemBytes = smem;
     lc.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -856,7 +992,7 @@ cudaError_t launch_rot_kernel(const DevParams& p, int grid, cudaStream_t stream)
     lc.numAttrs = 1;
     return cudaLaunchKernelEx(&lc, k, p);
 #else
-    k<<<grid, rot_warps(p.N) * 32, smem, stream>>>(p);
+    k<<<grid, rot_warps(p.N, p.dr_enabled != 0) * 32, smem, stream>>>(p);
     return cudaGetLastError();
 #endif
 }
@@ -867,9 +1003,9 @@ cudaError_t rot_kernel_occupancy(const DevParams& p, int* blocks_per_sm) {
     const size_t smem = rot_smem_bytes(p);
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, rot_warps(p.N) * 32, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, rot_warps(p.N, p.dr_enabled != 0) * 32, smem);
 }
 
-int rot_warps_per_cta(const DevParams& p) { return rot_warps(p.N); }
+int rot_warps_per_cta(const DevParams& p) { return rot_warps(p.N, p.dr_enabled != 0); }
 
 }  // namespace swarm

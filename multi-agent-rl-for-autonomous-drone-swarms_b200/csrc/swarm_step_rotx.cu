@@ -279,7 +279,7 @@ swarm_step_rotx_kernel(const DevParams P) {
                     const float sq = STEP ? sumsq1d_fast(__fsub_rn(px[s2], px[s]), __fsub_rn(py[s2], py[s]), __fsub_rn(pz[s2], pz[s]))
                                           : sumsq_axis(__fsub_rn(px[s2], px[s]), __fsub_rn(py[s2], py[s]), __fsub_rn(pz[s2], pz[s]));
                     const float d = STEP ? sqrt_rn_fast(sq) : sq;
-                    const double t = STEP ? fabs(__dsub_rn(f64_of_pos_f32(d), d_star)) : 0.0;
+                    const double t = STEP ? fabs(__dsub_rn(f64_of_pos_f32<(SWARM_ROT_CVT_FORM & 1) != 0>(d), d_star)) : 0.0;
                     merge1((__float_as_uint(d) & ~IDX) | (unsigned)(s2 * 32 + lane), k0[s], k1[s], k2[s], k3[s]);
                     merge1((__float_as_uint(d) & ~IDX) | (unsigned)(s * 32 + lane), k0[s2], k1[s2], k2[s2], k3[s2]);
                     if (STEP) {
@@ -312,14 +312,14 @@ swarm_step_rotx_kernel(const DevParams P) {
                         const float d = STEP ? sqrt_rn_fast(sq) : sq;  // (reset launch: key = squared distance, see round 0)
                         kf[s][s2] = and_or<~IDX>(__float_as_uint(d), __float_as_uint(q.w));
                         if (STEP) {
-                            const double t = fabs(__dsub_rn(f64_of_pos_f32(d), d_star));
+                            const double t = fabs(__dsub_rn(f64_of_pos_f32<(SWARM_ROT_CVT_FORM & 1) != 0>(d), d_star));
                             acc[s] = __dadd_rn(acc[s], MASKED ? __dmul_rn(t, mf[s2]) : t);
                         }
                         if (!LAST) {
                             const float db = __shfl_sync(FULL_MASK, d, lb);  // d(drone s of lane l - r, my drone s2)
                             kb[s][s2] = and_or<~IDX>(__float_as_uint(db), (unsigned)(s * 32 + lb));
                             if (STEP) {
-                                const double tb = fabs(__dsub_rn(f64_of_pos_f32(db), d_star));
+                                const double tb = fabs(__dsub_rn(f64_of_pos_f32<(SWARM_ROT_CVT_FORM & 2) != 0>(db), d_star));
                                 acc[s2] = __dadd_rn(acc[s2], MASKED ? __dmul_rn(tb, mb[s]) : tb);
                             }
                         }

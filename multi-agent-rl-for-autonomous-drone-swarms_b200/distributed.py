@@ -89,6 +89,8 @@ class ShardedSwarm:
         self.lo, self.hi = shard_range(self.total_envs, rank, world_size)
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
+        # the domain-randomisation streams are keyed by the GLOBAL env index (same invariance as the seeds)
+        engine_kw.setdefault("env_index_base", self.lo)
         self.engine = SwarmEngine(self.hi - self.lo, config, kind=kind, device=device, **engine_kw)
         self.engine.seed(global_env_seeds(base_seed, self.lo, self.hi))
 

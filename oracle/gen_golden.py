@@ -207,6 +207,11 @@ CASES = {
                          _uniform_actions(-1.0, 1.0)),
     "swarm_c4_n32_w44": ("swarm", {"num_drones": 32, "num_obstacles": 8, "world_size": 44.0}, [30], 250,
                          _uniform_actions(-1.5, 1.5)),
+    # north_star's horizon ("over 1000 steps") at the DEFAULT world for the C3 / C4 shapes (one env each: repo size)
+    "swarm_c3_n16_w20_long": ("swarm", {"num_drones": 16, "num_obstacles": 8}, [12], 1000, _uniform_actions(-1.0, 1.0)),
+    "swarm_c4_n32_w20_long": ("swarm", {"num_drones": 32, "num_obstacles": 8}, [22], 1000, _uniform_actions(-1.0, 1.0)),
+    "swarm_c4_n32_w44_long": ("swarm", {"num_drones": 32, "num_obstacles": 8, "world_size": 44.0}, [31], 1000,
+                              _uniform_actions(-1.0, 1.0)),
     # C5 shape
     "swarm_c5_n128_w70": ("swarm", {"num_drones": 128, "num_obstacles": 8, "world_size": 70.0}, [40], 24,
                           _uniform_actions(-1.0, 1.0)),

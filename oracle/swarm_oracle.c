@@ -212,8 +212,10 @@ static float draw_uniform_f32(uint64_t rng[4], double lo, double range) {
 /* ------------------------------------------------------------------------- */
 /* Domain randomisation streams (engine semantics, see OracleConfig)          */
 /* ------------------------------------------------------------------------- */
-static void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
-    for (int r = 0; r < 10; ++r) {
+/* Philox4x32 (Salmon et al., SC'11) with `rounds` rounds: 10 for the per-episode block (one per reset), 7 for the
+ * per-step noise blocks (one per agent-step; 7 is the smallest round count the paper reports as Crush-resistant) */
+static void philox4x32_r(uint32_t c[4], uint32_t k0, uint32_t k1, int rounds) {
+    for (int r = 0; r < rounds; ++r) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
         uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1;
         uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
@@ -221,6 +223,8 @@ static void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
 }
+static void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) { philox4x32_r(c, k0, k1, 10); }
+static void philox4x32_7(uint32_t c[4], uint32_t k0, uint32_t k1) { philox4x32_r(c, k0, k1, 7); }
 
 static double inv_norm_cdf(double p) { /* Acklam's rational approximation */
     static const double a[] = {-3.969683028665376e+01, 2.209460984245205e+02, -2.759285104469687e+02,
@@ -428,19 +432,17 @@ static void build_obs(const OracleConfig *c, const DynConst *kc, int step_obs, c
          * stream B field q - 4 = sensed obstacle q >= 4 */
         uint32_t ra[4] = {kc->genv, kc->ekey, (uint32_t)(step_obs - 1), (uint32_t)index};
         uint32_t rb[4] = {kc->genv, kc->ekey, (uint32_t)(step_obs - 1), (uint32_t)index | (1u << 16)};
-        philox4x32_10(ra, kc->k0, kc->k1);
-        philox4x32_10(rb, kc->k0, kc->k1);
+        philox4x32_7(ra, kc->k0, kc->k1);
+        philox4x32_7(rb, kc->k0, kc->k1);
+        /* x + sigma z with ONE rounding (fused multiply-add) */
         for (int k = 0; k < 3; ++k) {
-            volatile float np_ = kc->std_pos * dr_normal(ra, 3 + k);
-            out[k] = out[k] + np_;
-            volatile float nv = kc->std_vel * dr_normal(ra, 6 + k);
-            out[3 + k] = out[3 + k] + nv;
+            out[k] = fmaf(kc->std_pos, dr_normal(ra, 3 + k), out[k]);
+            out[3 + k] = fmaf(kc->std_vel, dr_normal(ra, 6 + k), out[3 + k]);
         }
         int filled = c->sensed_obstacles < c->num_obstacles ? c->sensed_obstacles : c->num_obstacles;
-        for (int q = 0; q < filled; ++q) {
-            volatile float nd = kc->std_obst * (q < 4 ? dr_normal(ra, 9 + q) : dr_normal(rb, q - 4));
-            out[off + 4 * q + 3] = out[off + 4 * q + 3] + nd;
-        }
+        for (int q = 0; q < filled; ++q)
+            out[off + 4 * q + 3] = fmaf(kc->std_obst, q < 4 ? dr_normal(ra, 9 + q) : dr_normal(rb, q - 4),
+                                        out[off + 4 * q + 3]);
     }
 }
 
@@ -482,12 +484,11 @@ static void integrate(const OracleConfig *c, const DynConst *kc, int step_before
                       float *p, float *v) {
     float amax = kc->amax, dt = kc->dt;
     uint32_t ctr[4] = {kc->genv, kc->ekey, (uint32_t)step_before, (uint32_t)drone};
-    if (kc->dr) philox4x32_10(ctr, kc->k0, kc->k1);
+    if (kc->dr) philox4x32_7(ctr, kc->k0, kc->k1);
     for (int k = 0; k < 3; ++k) {
         float a = clipf(action[k], -1.0f, 1.0f);
         if (kc->dr) {
-            volatile float sz = kc->std_thrust * dr_normal(ctr, k);
-            volatile float one = 1.0f + sz;
+            volatile float one = fmaf(kc->std_thrust, dr_normal(ctr, k), 1.0f);   /* 1 + sigma z, one rounding */
             a = a * one;
         }
         volatile float accel = a * amax;
