@@ -20,8 +20,14 @@ one that is bit-identical to the reference -- and reports it under "dr_off".
   roofline  algorithmic bytes (B = 244 + (34 + 12 M)/N per slot-step) / kernel time vs measured HBM peak
   cpu_baseline  the C oracle (a port of the reference's algorithm) on all host cores, bounded sample
 
-`--impl reference` times that CPU port alone (the reference is pure Python: there is no
-oracle/_ref to compile, and /root/reference does not exist on the GPU box).
+`--impl reference` times the UNMODIFIED Python reference env (staged under oracle/_ref/ by oracle/make_ref.py, one
+worker process per host thread, >= 2 s) and reports the C port beside it; where the staged copy is missing it
+falls back to the port alone and says so (`reference_kind`).
+
+  --scaling strong   BASELINE config 4 as written: 65536 env instances IN TOTAL, sharded over the N GPUs
+  --graph T          time CUDA-graph replays of T captured steps (SwarmEngine.capture_steps) instead of a Python
+                     loop over step(): what the launch-bound batch sizes BASELINE names (4096 x 8 drones) need
+  named_sizes        the default run also reports C2 / C3 / C4-shard / C5 at BASELINE's own env counts
 """
 from __future__ import annotations
 
@@ -145,41 +151,56 @@ def cpu_port_rate(kind, cfg, n_envs, budget_s, threads, dr=False):
     return agent_steps / dt, steps, dt
 
 
+def python_reference_rate(kind, cfg, min_seconds, min_steps=1):
+    """The unmodified reference env on every host thread (oracle/ref_runner.py); None where it is not staged."""
+    try:
+        import ref_runner
+        if ref_runner.reference_src() is None:
+            return None
+        return ref_runner.time_reference(kind, cfg, min_seconds=min_seconds, min_steps=min_steps)
+    except Exception as exc:  # noqa: BLE001  (a baseline leg must never take the bench line down)
+        sys.stderr.write(f"python reference leg failed: {exc!r}\n")
+        return None
+
+
 def run_reference_arm(args, kind, cfg, wl_name, default_envs):
-    """--impl reference: the CPU port, all host threads, same config / metric / unit."""
+    """--impl reference: the reference's own CPU implementation on all host threads, same config / metric / unit.
+    Each "step" advances every worker's env instance once; the timed region is at least 2 s long (a 0.1 s region
+    measured the thread ramp-up, not the env)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import swarm_oracle as so
-
     threads = len(os.sched_getaffinity(0))
-    n_envs = args.cpu_envs
-    o = so.OracleSwarm(n_envs, cfg, kind=kind, dr=DR_V1 if dr_enabled(args) else None, dr_seed=2026)
-    o.seed(np.arange(n_envs, dtype=np.uint64))
-    o.reset()
-    rng = np.random.default_rng(1000)
-    acts = [rng.uniform(-1, 1, size=(n_envs, o.N, 3)).astype(np.float32) for _ in range(4)]
-    for w in range(args.warmup):
-        o.step(acts[w % 4], auto_reset=True, num_threads=threads)
-    agent_steps = 0
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        agent_steps += int(o.active.sum()) if kind == "swarm" else n_envs * o.N
-        o.step(acts[k % 4], auto_reset=True, num_threads=threads)
-    dt = time.perf_counter() - t0
-    val = agent_steps / dt
-    sample = (f"each step = {n_envs} env instances of the {wl_name} config (bounded sample of the {default_envs} "
-              f"per GPU the GPU arm steps), {args.steps} steps, {threads} threads; oracle/swarm_oracle.c")
+    dr = dr_enabled(args)
+    port_rate, port_steps, port_dt = cpu_port_rate(kind, cfg, args.cpu_envs, max(2.0, args.cpu_seconds / 4), threads, dr)
+    port = {"value": port_rate, "unit": "agent-steps/s", "cores": threads, "kind": "port",
+            "sample": f"{args.cpu_envs} env instances x {port_steps} steps in {port_dt:.1f} s (oracle/swarm_oracle.c, "
+                      f"scalar C port of the reference algorithm, {threads} threads" + (", randomisation on)" if dr else ")")}
+    ref = python_reference_rate(kind, cfg, min_seconds=max(2.0, args.cpu_seconds / 2), min_steps=args.steps)
+    if ref is not None:
+        val, ref_kind, steps_done, dt = ref["rate"], "python_reference", ref["steps_per_proc"], ref["seconds"]
+        base = {"value": val, "unit": "agent-steps/s", "cores": ref["procs"], "kind": "reference",
+                "sample": f"the unmodified reference env (oracle/_ref, pure Python + numpy), {ref['procs']} worker processes x "
+                          f"{ref['envs_per_proc']} env instance(s) of the {wl_name} config x {steps_done} steps in {dt:.1f} s, "
+                          f"randomisation off (no reference code implements it)"}
+        note = ("the reference's own env code, unmodified, one process per host thread (it has no vectorisation: "
+                "config_builders.py:19-23); `port` = oracle/swarm_oracle.c, a scalar C port of the same algorithm, "
+                "multi-threaded -- the stronger CPU baseline")
+    else:
+        val, ref_kind, steps_done, dt = port_rate, "c_port", port_steps, port_dt
+        base = port
+        note = ("oracle/_ref is not staged here (the reference is pure Python: oracle/make_ref.py copies it where "
+                "/root/reference exists): this is oracle/swarm_oracle.c, a scalar C port of its algorithm pinned "
+                "bit-exact to fixtures recorded from it")
     line = {
-        "impl": "reference", "metric": "agent_steps_per_sec", "value": val, "unit": "agent-steps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(wl_name, kind, cfg, default_envs, args.gpus, dr_enabled(args)),
-        "cpu_baseline": {"value": val, "unit": "agent-steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "impl": "reference", "reference_kind": ref_kind, "metric": "agent_steps_per_sec", "value": val,
+        "unit": "agent-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / max(steps_done, 1) * 1e3,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(wl_name, kind, cfg, default_envs, args.gpus, dr),
+        "cpu_baseline": base, "port": port,
         "e2e": {"value": val, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-        "note": "reference is pure Python (cannot travel to the GPU box); this is oracle/swarm_oracle.c, a scalar C "
-                "port of its algorithm pinned bit-exact to fixtures recorded from it",
+        "gpu_launches": 0, "note": note,
     }
     print(json.dumps(line), flush=True)
 
@@ -224,11 +245,19 @@ def main():
                     help="also randomise control_delay_steps ({0,1,2} with p {0.7,0.2,0.1}); runs on the general kernel")
     ap.add_argument("--dr", default="auto", choices=["auto", "on", "off"],
                     help="domain randomisation (domain_randomization_v1 ranges); auto = on for c4 (BASELINE configs[3])")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --envs-per-gpu on every GPU; strong: that many env instances IN TOTAL over the GPUs")
+    ap.add_argument("--graph", type=int, default=0, metavar="T",
+                    help="time CUDA-graph replays of T captured steps instead of a Python loop over step()")
+    ap.add_argument("--no-named-sizes", action="store_true", help="skip the block at BASELINE's own env counts")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     kind, cfg, default_envs = WORKLOADS[args.workload]
     E = args.envs_per_gpu or default_envs
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.scaling == "strong":
+        E = max(E // world_env, 1)   # the named batch, sharded (BASELINE config 4: 65536 envs over 8 GPUs)
 
     if args.impl == "reference":
         run_reference_arm(args, kind, cfg, args.workload, E)
@@ -250,12 +279,13 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    def make_engine(dr):
-        e = swarm_b200.SwarmEngine(E, cfg, kind=kind, device=dev, global_state=not args.no_global_state,
+    def make_engine(dr, kind_=None, cfg_=None, E_=None):
+        kind_, cfg_, E_ = kind_ or kind, cfg_ or cfg, E_ or E
+        e = swarm_b200.SwarmEngine(E_, cfg_, kind=kind_, device=dev, global_state=not args.no_global_state,
                                    domain_randomization=(dr if isinstance(dr, dict) else DR_V1) if dr else None,
-                                   dr_seed=2026, env_index_base=rank * E)
+                                   dr_seed=2026, env_index_base=rank * E_)
         # env e of rank r is global env r*E + e: seeds are a function of the GLOBAL env index
-        e.seed(np.arange(rank * E, (rank + 1) * E, dtype=np.uint64))
+        e.seed(np.arange(rank * E_, (rank + 1) * E_, dtype=np.uint64))
         e.reset()
         return e
 
@@ -268,10 +298,24 @@ def main():
     n_act = 4
     actions = [torch.rand((E, N, 3), generator=gen, device=dev) * 2.0 - 1.0 for _ in range(n_act)]
 
-    def timed(e, steps, warmup, sample_clocks):
-        """W untimed + K timed steps, CUDA events on the launching stream, max over ranks."""
-        for w in range(warmup):
-            e.step(actions[w % n_act], auto_reset=True)
+    def timed(e, steps, warmup, sample_clocks, graph_T=None, acts=None):
+        """W untimed + K timed steps, CUDA events on the launching stream, max over ranks.  graph_T > 0: the K steps
+        are K / T replays of a CUDA graph of T captured steps (K rounded down to a multiple of T)."""
+        graph_T = args.graph if graph_T is None else graph_T
+        acts = actions if acts is None else acts
+        E_, N_ = e.E, e.N
+        graph, launches_per_replay = None, 0
+        if graph_T > 0:
+            ring = torch.stack([acts[t % len(acts)] for t in range(graph_T)]).contiguous()
+            l_before = e.launch_count
+            graph = e.capture_steps(ring, auto_reset=True)
+            launches_per_replay = (e.launch_count - l_before) * graph_T // (graph_T + 1)   # capture = 1 warm-up step + T
+            steps = max(steps // graph_T, 1) * graph_T
+            for w in range(max(warmup // graph_T, 1)):
+                graph.replay()
+        else:
+            for w in range(warmup):
+                e.step(acts[w % len(acts)], auto_reset=True)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -283,33 +327,42 @@ def main():
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         ev0.record()
-        for k in range(steps):
-            e.step(actions[k % n_act], auto_reset=True)
+        if graph is not None:
+            for k in range(steps // graph_T):
+                graph.replay()
+        else:
+            for k in range(steps):
+                e.step(acts[k % len(acts)], auto_reset=True)
         ev1.record()
         torch.cuda.synchronize()
         ms = ev0.elapsed_time(ev1)
         clk = sampler.stop() if sampler else None
         st_ = e.stats()
+        n_launch = launches_per_replay * (steps // graph_T) if graph is not None else e.launch_count - l0
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        tot = torch.tensor([st_["agent_steps"], E * N * steps, st_["episodes"], e.launch_count - l0], dtype=torch.float64,
+        tot = torch.tensor([st_["agent_steps"], E_ * N_ * steps, st_["episodes"], n_launch, steps], dtype=torch.float64,
                            device=dev)
         if world > 1:
             # the one collective of the path: the episode-statistics reduction (NCCL, tiny)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        return float(t.item()), [float(x) for x in tot.tolist()], clk
+        tot = [float(x) for x in tot.tolist()]
+        tot[4] /= world
+        return float(t.item()), tot, clk
 
     timed(eng, 3, max(args.warmup, 3), False)   # (the first launches on a fresh box run cold: keep them out)
-    elapsed_ms, (agent_steps_all, slot_steps_all, episodes_all, launches_all), clocks = timed(eng, args.steps, args.warmup, True)
+    elapsed_ms, (agent_steps_all, slot_steps_all, episodes_all, launches_all, steps_done), clocks = \
+        timed(eng, args.steps, args.warmup, True)
+    steps_done = int(steps_done)
     value = agent_steps_all / (elapsed_ms * 1e-3)
 
     dr_off = None
     if dr_enabled(args) and not args.no_dr_off:
         # the reference-identical path (no reference code implements the randomisation): same shape, DR off
         eng0 = make_engine(False)
-        ms0, (as0, ss0, ep0, l0), _ = timed(eng0, max(args.steps // 4, 10), max(args.warmup, 3), False)
+        ms0, (as0, ss0, ep0, l0, sd0), _ = timed(eng0, max(args.steps // 2, 10), max(args.warmup, 3), False)
         B0 = eng0.algorithmic_bytes_per_agent_step()
-        dr_off = {"value": as0 / (ms0 * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms0 / max(args.steps // 4, 10),
+        dr_off = {"value": as0 / (ms0 * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms0 / sd0,
                   "roofline_frac": B0 * ss0 / (ms0 * 1e-3) / 1e9 / peaks()[0],
                   "note": "domain randomisation off: bit-identical to the reference's step (tests/)"}
         eng0.close()
@@ -319,13 +372,36 @@ def main():
     if dr_enabled(args) and not args.no_dr_off and not args.dr_delay:
         # the yaml's whole actuation block: control_delay_steps {0, 1, 2} on top (command ring in HBM, same kernel)
         eng1 = make_engine({**DR_V1, "control_delay_steps": ((0, 1, 2), (0.7, 0.2, 0.1))})
-        ms1, (as1, ss1, ep1, l1), _ = timed(eng1, max(args.steps // 4, 10), max(args.warmup, 3), False)
+        ms1, (as1, ss1, ep1, l1, sd1), _ = timed(eng1, max(args.steps // 4, 10), max(args.warmup, 3), False)
         B1 = eng1.algorithmic_bytes_per_agent_step()
-        dr_delay = {"value": as1 / (ms1 * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms1 / max(args.steps // 4, 10),
+        dr_delay = {"value": as1 / (ms1 * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms1 / sd1,
                     "roofline_frac": B1 * ss1 / (ms1 * 1e-3) / 1e9 / peaks()[0],
                     "note": "domain randomisation + control_delay_steps (0,1,2)/(0.7,0.2,0.1): command ring read + written"}
         eng1.close()
         del eng1
+
+    # ---- BASELINE's own env counts (launch-bound: a CUDA graph of 20 steps per replay, and the plain loop beside it)
+    named = None
+    if world == 1 and args.workload == "c4" and not args.envs_per_gpu and not args.no_named_sizes and not args.graph:
+        named = {}
+        for label, wl, En, dr_on in (("c2_4096_envs", "c2", 4096, False), ("c3_16384_envs", "c3", 16384, False),
+                                     ("c4_8192_envs_per_gpu", "c4", 8192, True),
+                                     ("c4_8192_envs_per_gpu_dr_off", "c4", 8192, False), ("c5_8192_envs", "c5", 8192, False)):
+            k2, c2, _ = WORKLOADS[wl]
+            e2 = make_engine(dr_on, k2, c2, En)
+            g2 = torch.Generator(device=dev)
+            g2.manual_seed(99)
+            acts2 = [torch.rand((En, e2.N, 3), generator=g2, device=dev) * 2.0 - 1.0 for _ in range(4)]
+            B2 = e2.algorithmic_bytes_per_agent_step()
+            msg, (asg, ssg, _, _, sdg), _ = timed(e2, 400, 20, False, graph_T=20, acts=acts2)
+            msl, (asl, ssl, _, _, sdl), _ = timed(e2, 200, 10, False, graph_T=0, acts=acts2)
+            named[label] = {"value": asg / (msg * 1e-3), "us_per_step": msg / sdg * 1e3,
+                            "roofline_frac": B2 * ssg / (msg * 1e-3) / 1e9 / peaks()[0],
+                            "mode": "CUDA graph, 20 steps per replay",
+                            "python_loop": {"value": asl / (msl * 1e-3), "us_per_step": msl / sdl * 1e3,
+                                            "roofline_frac": B2 * ssl / (msl * 1e-3) / 1e9 / peaks()[0]}}
+            e2.close()
+            del e2, acts2
 
     # ---- end-to-end through host buffers
     e2e = None
@@ -376,7 +452,7 @@ def main():
     if rank == 0:
         peak, peak_src = peaks()
         B = eng.algorithmic_bytes_per_agent_step()
-        kernel_ms = elapsed_ms / args.steps
+        kernel_ms = elapsed_ms / steps_done
         bytes_per_launch = B * E * N   # per GPU
         achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
         traffic = None
@@ -388,8 +464,8 @@ def main():
                 traffic = None
         line = {
             "metric": "agent_steps_per_sec", "value": value, "unit": "agent-steps/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "steps": steps_done, "warmup": args.warmup, "ms_per_step": elapsed_ms / steps_done,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.workload, kind, cfg, E, world, dr_enabled(args)),
             "slot_steps_per_sec": slot_steps_all / (elapsed_ms * 1e-3),
             "episodes_in_timed_region": episodes_all,
@@ -401,16 +477,27 @@ def main():
             "e2e": e2e,
             "dr_off": dr_off,
             "dr_delay": dr_delay,
+            "named_sizes": named,
             "gpu_launches": int(launches_all),
             "clocks": clocks,
         }
         if not args.no_cpu:
             threads = len(os.sched_getaffinity(0))
             rate, csteps, cdt = cpu_port_rate(kind, cfg, args.cpu_envs, args.cpu_seconds, threads, dr_enabled(args))
-            line["cpu_baseline"] = {
-                "value": rate, "unit": "agent-steps/s", "cores": threads, "kind": "port",
-                "sample": f"{args.cpu_envs} env instances x {csteps} steps of the same config in {cdt:.1f} s "
-                          f"(oracle/swarm_oracle.c, scalar C port of the reference algorithm, {threads} threads)"}
+            port = {"value": rate, "unit": "agent-steps/s", "cores": threads, "kind": "port",
+                    "sample": f"{args.cpu_envs} env instances x {csteps} steps of the same config in {cdt:.1f} s "
+                              f"(oracle/swarm_oracle.c, scalar C port of the reference algorithm, {threads} threads)"}
+            ref = python_reference_rate(kind, cfg, min_seconds=min(args.cpu_seconds, 8.0))
+            if ref is not None:
+                # the reference itself (pure Python, staged by oracle/make_ref.py) is the baseline; the port rides along
+                line["cpu_baseline"] = {
+                    "value": ref["rate"], "unit": "agent-steps/s", "cores": ref["procs"], "kind": "reference",
+                    "sample": f"the unmodified reference env (oracle/_ref), {ref['procs']} worker processes x "
+                              f"{ref['envs_per_proc']} env instance(s) x {ref['steps_per_proc']} steps of the same config in "
+                              f"{ref['seconds']:.1f} s (randomisation off: no reference code implements it)"}
+                line["cpu_port"] = port
+            else:
+                line["cpu_baseline"] = port
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

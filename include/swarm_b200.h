@@ -202,6 +202,14 @@ int swarm_observe(SwarmHandle *h, const SwarmBuffers *bufs, void *stream);
  * obs / dist / obs_valid / global_state describe the new episode. */
 int swarm_step(SwarmHandle *h, const SwarmBuffers *bufs, const float *actions, int auto_reset, void *stream);
 
+/* n_steps consecutive env.step() calls with ONE host call: step t applies actions[t] (device [n_steps][E][N][3]
+ * float32); launches are enqueued back to back on `stream` (what SURVEY 7 calls step_many: small batches are
+ * bound by the host's per-call cost, not by the device).  After the call the outputs describe the LAST step;
+ * episode statistics (stats, ep_return) accumulate over all of them.  No host state changes per launch, so the
+ * call -- like swarm_step -- can be captured into a CUDA graph and replayed. */
+int swarm_step_many(SwarmHandle *h, const SwarmBuffers *bufs, const float *actions, int n_steps, int auto_reset,
+                    void *stream);
+
 /* Same step through HOST buffers (the end-to-end path): copies actions host->device, steps,
  * copies the requested outputs device->host, chunked over the env axis on internal streams so
  * the copies overlap the kernel, and returns when the host buffers are valid.  Host pointers

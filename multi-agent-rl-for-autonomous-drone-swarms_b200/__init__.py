@@ -20,9 +20,9 @@ from . import _abi  # noqa: F401
 
 def __getattr__(name):
     # torch-dependent pieces are imported lazily so `import swarm_b200` stays cheap
-    if name == "SwarmEngine":
-        from .engine import SwarmEngine
-        return SwarmEngine
+    if name in ("SwarmEngine", "StepGraph"):
+        from . import engine
+        return getattr(engine, name)
     if name in ("DroneSwarmEnv", "SingleDroneEnv", "DronePhysicsEnv", "make_env_creator", "VectorSwarmEnv"):
         from . import envs
         return getattr(envs, name)

@@ -64,7 +64,8 @@ class SwarmHostOut(C.Structure):
 
 
 EXPORTS = ("swarm_abi_version", "swarm_last_error", "swarm_create", "swarm_destroy", "swarm_query_sizes",
-           "swarm_seed", "swarm_reset", "swarm_observe", "swarm_step", "swarm_step_host", "swarm_launch_count",
+           "swarm_seed", "swarm_reset", "swarm_observe", "swarm_step", "swarm_step_many", "swarm_step_host",
+           "swarm_launch_count",
            "swarm_dr_quantile_table")
 
 
@@ -96,13 +97,14 @@ def load():
     lib.swarm_reset.argtypes = [vp, C.POINTER(SwarmBuffers), vp, vp]
     lib.swarm_observe.argtypes = [vp, C.POINTER(SwarmBuffers), vp]
     lib.swarm_step.argtypes = [vp, C.POINTER(SwarmBuffers), vp, i32, vp]
+    lib.swarm_step_many.argtypes = [vp, C.POINTER(SwarmBuffers), vp, i32, i32, vp]
     lib.swarm_step_host.argtypes = [vp, C.POINTER(SwarmBuffers), vp, C.POINTER(SwarmHostOut), i32]
     lib.swarm_launch_count.argtypes = [vp]
     lib.swarm_launch_count.restype = C.c_int64
     lib.swarm_dr_quantile_table.argtypes = [vp]
     lib.swarm_dr_quantile_table.restype = i32
     for name in ("swarm_create", "swarm_destroy", "swarm_query_sizes", "swarm_seed", "swarm_reset",
-                 "swarm_observe", "swarm_step", "swarm_step_host"):
+                 "swarm_observe", "swarm_step", "swarm_step_many", "swarm_step_host"):
         getattr(lib, name).restype = i32
     if lib.swarm_abi_version() != ABI_VERSION:
         raise ImportError(f"libswarm_b200.so ABI {lib.swarm_abi_version()} != binding ABI {ABI_VERSION}; rebuild")

@@ -52,11 +52,12 @@ struct SwarmHandle {
     int rotx_min_envs;       // launches with fewer envs stay on the general kernel (SWARM_B200_ROTX_MIN_ENVS)
     JumpEntry* jump_dev;
     uint8_t* reset_mask_dev;  // [E]
-    unsigned* reset_count_dev;  // [(kHostChunks + 1) * 2] per launch slot, two parities
-    int* reset_list_dev;        // [number of groups]
+    unsigned* reset_count_dev;  // [(kHostChunks + 1) * 2] per launch slot: the counters of the two lists
+    unsigned* reset_epoch_dev;  // [kHostChunks + 1] per launch slot: which list is current (device-side parity)
+    int* reset_list_dev;        // [2][number of groups + 1]
+    int reset_list_stride;
     unsigned* work_counter_dev; // [(kHostChunks + 1) * 2] group queue of the rotation-pass step kernel, per launch slot
     float* qtable_dev;          // [512] signed quantile table (domain randomisation only)
-    unsigned step_parity[kHostChunks + 1];
     int64_t launches;
     // host-buffer path
     cudaStream_t chunk_stream[kHostChunks];
@@ -344,15 +345,12 @@ int launch(SwarmHandle* h, DevParams& p, int env_begin, int env_count, cudaStrea
     const int rotx_grid = rotx_needed < rotx_resident ? rotx_needed : rotx_resident;
     p.fused_reset = rot && p.auto_reset && h->rot_fused ? 1 : 0;
     const bool two_launch = p.mode == kModeStep && p.auto_reset && (p.N <= 32 || rotx) && !p.fused_reset;
-    if (two_launch) {
-        // the step kernel lists the groups that need a reset; counters alternate between steps so the
-        // aux launch can zero the next one while nobody uses it
-        const unsigned par = h->step_parity[slot];
-        p.reset_count = h->reset_count_dev + 2 * slot + par;
-        p.reset_count_other = h->reset_count_dev + 2 * slot + (par ^ 1u);
-        p.reset_list = h->reset_list_dev + env_begin / p.G;
-        h->step_parity[slot] = par ^ 1u;
-    }
+    // the step kernel lists the groups that need a reset for the launch behind it: two lists used alternately, the
+    // current one chosen on the device (reset_epoch), so there is no per-launch host state (CUDA-graph safe)
+    p.reset_count = h->reset_count_dev + 2 * slot;
+    p.reset_epoch = h->reset_epoch_dev + slot;
+    p.reset_list = h->reset_list_dev + env_begin / p.G;
+    p.reset_list_stride = h->reset_list_stride;
     p.work_counter = h->work_counter_dev + 4 * slot;  // {step queue, warps done, reset queue, warps done}
     if (rot) CUDA_TRY(launch_rot_kernel(p, rot_grid, stream));
     else if (rotx) CUDA_TRY(launch_rotx_kernel(p, rotx_grid, stream));
@@ -429,10 +427,10 @@ int swarm_create(const SwarmConfig* cfg, SwarmHandle** out) {
     h->jump_dev = nullptr;
     h->reset_mask_dev = nullptr;
     h->reset_count_dev = nullptr;
+    h->reset_epoch_dev = nullptr;
     h->reset_list_dev = nullptr;
     h->work_counter_dev = nullptr;
     h->qtable_dev = nullptr;
-    for (int c = 0; c <= kHostChunks; ++c) h->step_parity[c] = 0;
     h->actions_dev = nullptr;
     h->host_path_ready = false;
     fill_params(*cfg, h->base);
@@ -487,7 +485,10 @@ int swarm_create(const SwarmConfig* cfg, SwarmHandle** out) {
     const size_t n_groups_all = ((size_t)cfg->num_envs + h->base.G - 1) / h->base.G;
     if (e == cudaSuccess) e = cudaMalloc(&h->reset_count_dev, sizeof(unsigned) * 2 * (kHostChunks + 1));
     if (e == cudaSuccess) e = cudaMemset(h->reset_count_dev, 0, sizeof(unsigned) * 2 * (kHostChunks + 1));
-    if (e == cudaSuccess) e = cudaMalloc(&h->reset_list_dev, sizeof(int) * (n_groups_all + 1));
+    h->reset_list_stride = (int)(n_groups_all + 1);
+    if (e == cudaSuccess) e = cudaMalloc(&h->reset_list_dev, sizeof(int) * 2 * (n_groups_all + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&h->reset_epoch_dev, sizeof(unsigned) * (kHostChunks + 1));
+    if (e == cudaSuccess) e = cudaMemset(h->reset_epoch_dev, 0, sizeof(unsigned) * (kHostChunks + 1));
     if (e == cudaSuccess) e = cudaMalloc(&h->work_counter_dev, sizeof(unsigned) * 4 * (kHostChunks + 1));
     if (e == cudaSuccess) e = cudaMemset(h->work_counter_dev, 0, sizeof(unsigned) * 4 * (kHostChunks + 1));
     if (e == cudaSuccess && cfg->dr_enabled) {
@@ -501,6 +502,7 @@ int swarm_create(const SwarmConfig* cfg, SwarmHandle** out) {
         if (h->jump_dev) cudaFree(h->jump_dev);
         if (h->reset_mask_dev) cudaFree(h->reset_mask_dev);
         if (h->reset_count_dev) cudaFree(h->reset_count_dev);
+        if (h->reset_epoch_dev) cudaFree(h->reset_epoch_dev);
         if (h->reset_list_dev) cudaFree(h->reset_list_dev);
         if (h->work_counter_dev) cudaFree(h->work_counter_dev);
         if (h->qtable_dev) cudaFree(h->qtable_dev);
@@ -524,6 +526,7 @@ int swarm_destroy(SwarmHandle* h) {
     if (h->jump_dev) cudaFree(h->jump_dev);
     if (h->reset_mask_dev) cudaFree(h->reset_mask_dev);
     if (h->reset_count_dev) cudaFree(h->reset_count_dev);
+    if (h->reset_epoch_dev) cudaFree(h->reset_epoch_dev);
     if (h->reset_list_dev) cudaFree(h->reset_list_dev);
     if (h->work_counter_dev) cudaFree(h->work_counter_dev);
     if (h->qtable_dev) cudaFree(h->qtable_dev);
@@ -577,6 +580,27 @@ int swarm_step(SwarmHandle* h, const SwarmBuffers* bufs, const float* actions, i
     p.auto_reset = auto_reset ? 1 : 0;
     p.actions = actions;
     return launch(h, p, 0, p.E, static_cast<cudaStream_t>(stream));
+}
+
+int swarm_step_many(SwarmHandle* h, const SwarmBuffers* bufs, const float* actions, int n_steps, int auto_reset,
+                    void* stream) {
+    if (!h) return fail(SWARM_E_NULL, "handle is NULL");
+    if (!actions) return fail(SWARM_E_NULL, "actions is NULL");
+    if (n_steps < 0) return fail(SWARM_E_INVALID, "n_steps must be >= 0");
+    DeviceGuard guard(h->device);
+    DevParams p;
+    int rc = bind_buffers(h, bufs, p);
+    if (rc != SWARM_OK) return rc;
+    p.mode = kModeStep;
+    p.auto_reset = auto_reset ? 1 : 0;
+    const size_t per_step = (size_t)p.E * p.N * 3;
+    for (int t = 0; t < n_steps; ++t) {
+        DevParams q = p;
+        q.actions = actions + (size_t)t * per_step;
+        rc = launch(h, q, 0, p.E, static_cast<cudaStream_t>(stream));
+        if (rc != SWARM_OK) return rc;
+    }
+    return SWARM_OK;
 }
 
 int swarm_step_host(SwarmHandle* h, const SwarmBuffers* bufs, const float* actions_host, const SwarmHostOut* out,

@@ -65,9 +65,15 @@ struct DevParams {
     float* gs; float* episode_return; int* episode_length;
     unsigned long long* stats;
     uint8_t* reset_mask;          // [E] N <= 32 step kernel -> aux kernel: env needs its auto-reset
-    unsigned* reset_count;        // number of groups on reset_list (this step's counter)
-    unsigned* reset_count_other;  // the next step's counter (zeroed by the aux launch)
-    int* reset_list;              // first env of every group with an env to reset
+    // auto-reset hand-over between the step launch and the reset launch behind it: two compacted lists of
+    // groups with an env to reset, used alternately.  Which one is current is decided ON THE DEVICE by the parity of
+    // `reset_epoch` (incremented by the last warp to leave an auto-reset step launch, which also zeroes the other
+    // list's counter), so the host keeps no per-launch state and a captured CUDA graph can be replayed any number
+    // of times.  Step launch t appends to list (epoch & 1); the reset launch behind it reads list ((epoch - 1) & 1).
+    unsigned* reset_count;        // [2] entries on each list
+    unsigned* reset_epoch;        // auto-reset step launches completed so far (this launch slot)
+    int* reset_list;              // [2][reset_list_stride] first env of every group with an env to reset
+    int reset_list_stride;
     unsigned* work_counter;       // rotation-pass step kernel: {next group, warps done} of this launch slot
     const JumpEntry* jump;        // [n_draws + 1]
     // ---- domain randomisation (N <= 32 kernels, norm_mode 0)

@@ -721,8 +721,13 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
     const int gwarp = blockIdx.x * kWarpsPerCta + warp;
     // aux launches behind a step (auto-reset) walk the compacted list of groups that asked for a reset
     const bool listed = MODE == kSmallAux && P.mode == kModeAutoReset;
-    const int n_iter = listed ? (int)*reinterpret_cast<const volatile unsigned*>(P.reset_count) : P.n_groups;
-    if (listed && gwarp == 0 && lane == 0) *P.reset_count_other = 0u;  // the next step's counter
+    // auto-reset hand-over: list (epoch & 1) is appended to by the step launch, list ((epoch - 1) & 1) is walked by
+    // the aux launch behind it (swarm_internal.h)
+    const unsigned epoch = P.reset_epoch ? *reinterpret_cast<const volatile unsigned*>(P.reset_epoch) : 0u;
+    const unsigned lpar = MODE == kSmallStep ? (epoch & 1u) : ((epoch - 1u) & 1u);
+    unsigned* const rcount = P.reset_count + lpar;
+    int* const rlist = P.reset_list + lpar * P.reset_list_stride;
+    const int n_iter = listed ? (int)*reinterpret_cast<const volatile unsigned*>(rcount) : P.n_groups;
 
     // cp.async prefetch of one group's inputs into an inbox (step kernel only)
     auto prefetch = [&](int grp, int buf) {
@@ -767,7 +772,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
     while (it < n_iter) {
         int it_next = it + warps_total;
         if (dyn_queue && lane == 0) it_next = warps_total + (int)atomicAdd(P.work_counter, 1u);
-        const int env0 = listed ? P.reset_list[it] : P.env_begin + it * G;
+        const int env0 = listed ? rlist[it] : P.env_begin + it * G;
         const int n_env = min(G, P.env_begin + P.env_count - env0);
         const bool lane_ok = e_l < n_env;
         const int env = env0 + (lane_ok ? e_l : 0);
@@ -1430,7 +1435,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
             }
             if (P.auto_reset) {  // groups with an env to reset go on the list the aux launch walks
                 const unsigned rl = __ballot_sync(FULL_MASK, leader && need_reset);
-                if (rl != 0 && lane == 0) P.reset_list[atomicAdd(P.reset_count, 1u)] = env0;
+                if (rl != 0 && lane == 0) rlist[atomicAdd(rcount, 1u)] = env0;
             }
             {   // actions applied / envs stepped by this warp in this group
                 const unsigned act_envs = __ballot_sync(FULL_MASK, leader && env_active);
@@ -1465,10 +1470,16 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
         it = it_next;
         buf ^= 1;
     }
-    if (dyn_queue) {  // the last warp to leave re-arms the queue for the next launch
+    if (dyn_queue || (MODE == kSmallStep && P.auto_reset)) {
+        // the last warp to leave re-arms the queue for the next launch, hands the reset list over to the aux launch
+        // and clears the other list for the next step
         if (lane == 0 && atomicAdd(P.work_counter + 1, 1u) == (unsigned)warps_total - 1u) {
             P.work_counter[0] = 0u;
             P.work_counter[1] = 0u;
+            if (MODE == kSmallStep && P.auto_reset) {
+                P.reset_count[(epoch + 1u) & 1u] = 0u;
+                *P.reset_epoch = epoch + 1u;
+            }
         }
     }
 

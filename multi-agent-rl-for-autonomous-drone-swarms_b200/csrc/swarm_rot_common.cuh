@@ -79,14 +79,15 @@ __device__ __forceinline__ unsigned merge_low(unsigned a, unsigned b) {
 // exponent shifted into place, exponent re-biased), ONE wide multiply-add on the FMA pipe (IMAD.WIDE.U32).
 // Zero / denormal inputs come out as some value below 2^-125, which cannot change the float64 sum of squares
 // once that sum is >= 2^-28 (the rotation pass checks exactly that and falls back to the exact path otherwise).
-// Which conversions take this route is a tuning knob:
+// Which conversions take this route is a tuning knob (measured: N = 128, six conversions per pair -- all of them;
+// N <= 32 -- none: there the wide multiply's own pipe becomes the bottleneck, 0.1487 vs 0.1457 ms per C4 step):
 //   SWARM_ROT_CVT_SQ   bit k: the k-th square of a pair distance (x, y, z)
 //   SWARM_ROT_CVT_FORM bit 0 / 1: the forward / backward distance of the formation sum
 #ifndef SWARM_ROT_INT_CVT
 #define SWARM_ROT_INT_CVT 0
 #endif
 #ifndef SWARM_ROT_CVT_SQ
-#define SWARM_ROT_CVT_SQ 7
+#define SWARM_ROT_CVT_SQ (SWARM_ROT_INT_CVT ? 7 : 0)
 #endif
 #ifndef SWARM_ROT_CVT_FORM
 #define SWARM_ROT_CVT_FORM (SWARM_ROT_INT_CVT ? 3 : 0)

@@ -27,6 +27,10 @@
 #ifndef SWARM_ROT_PDL
 #define SWARM_ROT_PDL 1
 #endif
+// the step launch starts under the previous step's reset launch (see the kernel prologue)
+#ifndef SWARM_ROT_OVERLAP
+#define SWARM_ROT_OVERLAP 1
+#endif
 
 namespace swarm {
 
@@ -34,15 +38,15 @@ namespace swarm {
 // CTA shape (measured): N = 32 and N = 16 run best as 4 warps x 7 CTAs per SM (72 registers, 28 resident warps,
 // 7 per scheduler; N = 16: +4 % over 8 x 3), N = 8 as 8 warps x 3 CTAs (80 registers; 4 x 7 is 5 % slower there).
 // With domain randomisation every CTA carries the 2 KB quantile table, and seven copies of it do not fit beside
-// 28 warp slices: the DR kernels run the same 28 warps as ONE CTA per SM (there is no block barrier in the loop,
-// and 28 = 4 x 7 keeps the four schedulers evenly loaded).
+// 28 warp slices: the DR kernels run the same 28 warps as 4 CTAs of 7 (measured: 7 x 4 0.1620 ms per C4 step,
+// 14 x 2 0.1625, 28 x 1 0.1710 -- warps of one CTA start in phase and then contend for the same pipes).
 #ifndef SWARM_ROT_W32
 #define SWARM_ROT_W32 4
 #define SWARM_ROT_B32 7
 #endif
 #ifndef SWARM_ROT_W32_DR
-#define SWARM_ROT_W32_DR 28
-#define SWARM_ROT_B32_DR 1
+#define SWARM_ROT_W32_DR 7
+#define SWARM_ROT_B32_DR 4
 #endif
 __host__ __device__ constexpr int rot_warps(int n, bool dr) { return n >= 16 ? (dr ? SWARM_ROT_W32_DR : SWARM_ROT_W32) : 8; }
 __host__ __device__ constexpr int rot_min_blocks(int n, bool dr) { return n >= 16 ? (dr ? SWARM_ROT_B32_DR : SWARM_ROT_B32) : 3; }
@@ -99,9 +103,10 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
     auto flush_list = [&]() {
         __syncwarp();
         unsigned base = 0u;
-        if (lane == 0) base = atom_add_lane(P.reset_count, (unsigned)n_local, tid_y);
+        const unsigned par = *reinterpret_cast<const volatile unsigned*>(P.reset_epoch) & 1u;
+        if (lane == 0) base = atom_add_lane(P.reset_count + par, (unsigned)n_local, tid_y);
         base = __shfl_sync(FULL_MASK, base, 0);
-        if (lane < n_local) P.reset_list[base + lane] = wlist[lane];
+        if (lane < n_local) P.reset_list[par * P.reset_list_stride + base + lane] = wlist[lane];
         __syncwarp();
         n_local = 0;
     };
@@ -121,17 +126,35 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
     const unsigned env_lanes = N == 32 ? FULL_MASK : (((1u << N) - 1u) << e_base);
     float* srow = tile + lane * kD;  // this lane's tile row; before the obs is staged it stashes exact distances
 
+    // Programmatic dependent launch: this grid may start while the previous launch of the stream is still running.
+    //  * reset launch: waits for the step launch in front of it, reads its list, then lets the NEXT launch of the
+    //    stream start at once (it only writes the listed envs);
+    //  * step launch (kOverlap): does NOT wait at the top.  The launch in front of it is normally the previous
+    //    step's reset launch, which touches only the envs flagged in reset_mask by that step: a warp waits for it
+    //    the first time it is about to load a flagged group (issue()) and at the latest before it exits.  Every
+    //    other group was last written by the previous STEP launch, which had completed before the reset launch
+    //    released this one.  Anything else in front (a caller's kernel that never triggers early) has completed
+    //    before this grid starts.
+    constexpr bool kOverlap = SWARM_ROT_PDL && SWARM_ROT_OVERLAP && MODE == kRotStep;
+    bool dep_waited = !kOverlap;
 #if SWARM_ROT_PDL
-    // programmatic dependent launch: this grid may have been started while the previous launch of the
-    // stream (the reset launch of the last step / the step launch of this one) was still draining
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!kOverlap) asm volatile("griddepcontrol.wait;" ::: "memory");
 #endif
     // step: one item per env group; reset: one item per listed group
     // (reset launch: the first list entry is fetched together with the list length -- the entry is only used if
     //  it turns out to be inside the list -- so a warp's first item starts one memory round trip earlier)
     int env0_pref = 0;
-    if (MODE == kRotReset) env0_pref = P.reset_list[min((int)(blockIdx.x * kRotWarps + warp), P.n_groups - 1)];
-    const int n_iter = kStepLike ? P.n_groups : (int)*reinterpret_cast<const volatile unsigned*>(P.reset_count);
+    const int* rlist = P.reset_list;
+    int n_iter = P.n_groups;
+    if (MODE == kRotReset) {
+        const unsigned cur = (*reinterpret_cast<const volatile unsigned*>(P.reset_epoch) - 1u) & 1u;
+        rlist = P.reset_list + cur * P.reset_list_stride;
+        env0_pref = rlist[min((int)(blockIdx.x * kRotWarps + warp), P.n_groups - 1)];
+        n_iter = (int)*reinterpret_cast<const volatile unsigned*>(P.reset_count + cur);
+#if SWARM_ROT_PDL && SWARM_ROT_OVERLAP
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+    }
     const int env_end = P.env_begin + P.env_count;
     unsigned* const queue = P.work_counter + (kStepLike ? 0 : 2);
 
@@ -149,6 +172,13 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
         if (!kStepLike) return;
         const int env0 = P.env_begin + grp * G;
         const int n_env = G == 1 ? 1 : min(G, env_end - env0);
+        if (kOverlap && !dep_waited) {   // (warp-uniform) a group the running reset launch may still be writing?
+            const bool flagged = lane < n_env && P.reset_mask[env0 + lane] != 0;
+            if (__any_sync(FULL_MASK, flagged)) {
+                asm volatile("griddepcontrol.wait;" ::: "memory");
+                dep_waited = true;
+            }
+        }
 #if SWARM_ROT_TMA_LOADS
         if (lane == 0) {
             const unsigned n_ag = (unsigned)(n_env * N);
@@ -206,7 +236,7 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
             it_next = it + warps_total;
         }
         const int env0 = kStepLike ? P.env_begin + it * G : env0_pref;
-        if (MODE == kRotReset) env0_pref = P.reset_list[min(it_next, P.n_groups - 1)];  // the next item's entry, early
+        if (MODE == kRotReset) env0_pref = rlist[min(it_next, P.n_groups - 1)];  // the next item's entry, early
         const int n_env = G == 1 ? 1 : min(G, env_end - env0);
         const bool lane_ok = G == 1 ? true : e_l < n_env;
         const int env = env0 + (lane_ok ? e_l : 0);
@@ -917,6 +947,9 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
         buf ^= 1;
     }
     if (MODE == kRotStep && n_local > 0) flush_list();
+#if SWARM_ROT_PDL
+    if (kOverlap && !dep_waited) asm volatile("griddepcontrol.wait;" ::: "memory");   // never exit without it
+#endif
     // the last warp to leave re-arms the queue for the next launch
 #if SWARM_ROT_PDL
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -925,9 +958,14 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
         if (lane == 0 && atomicAdd(queue + 1, 1u) == (unsigned)warps_total - 1u) {
             queue[0] = 0u;
             queue[1] = 0u;
+            if (MODE == kRotStep && P.auto_reset) {
+                // every warp has flushed its list: hand it to the reset launch and clear the other list for the
+                // next step (its reader -- the previous step's reset launch -- is done: see the wait below)
+                const unsigned ep = *reinterpret_cast<const volatile unsigned*>(P.reset_epoch);
+                P.reset_count[(ep + 1u) & 1u] = 0u;
+                *P.reset_epoch = ep + 1u;
+            }
         }
-    } else if (blockIdx.x == 0 && warp == 0 && lane == 0) {
-        *P.reset_count_other = 0u;  // the next step's list counter (nobody reads it during this launch)
     }
 
     if (lane == 0) bulk_wait0();  // the last obs tile must have left shared memory before the CTA retires

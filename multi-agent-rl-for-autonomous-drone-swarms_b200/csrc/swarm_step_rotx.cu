@@ -80,7 +80,13 @@ swarm_step_rotx_kernel(const DevParams P) {
     float* srow = tile + lane * kD;
 
     asm volatile("griddepcontrol.wait;" ::: "memory");  // programmatic dependent launch (see swarm_step_rot.cu)
-    const int n_iter = STEP ? P.n_groups : (int)*reinterpret_cast<const volatile unsigned*>(P.reset_count);
+    // auto-reset hand-over: list (epoch & 1) is appended to by the step launch, list ((epoch - 1) & 1) is walked by
+    // the reset launch behind it (swarm_internal.h)
+    const unsigned epoch = *reinterpret_cast<const volatile unsigned*>(P.reset_epoch);
+    const unsigned lpar = STEP ? (epoch & 1u) : ((epoch - 1u) & 1u);
+    unsigned* const rcount = P.reset_count + lpar;
+    int* const rlist = P.reset_list + lpar * P.reset_list_stride;
+    const int n_iter = STEP ? P.n_groups : (int)*reinterpret_cast<const volatile unsigned*>(rcount);
     unsigned* const queue = P.work_counter + (STEP ? 0 : 2);
     if (lane == 0) {
         mbar_init(bar0, 1);
@@ -123,7 +129,7 @@ swarm_step_rotx_kernel(const DevParams P) {
         // so a static stride would leave a fifth of the warps one item short)
         int it_next = 0;
         if (lane == 0) it_next = warps_total + (int)atomicAdd(queue, 1u);
-        const int env = STEP ? P.env_begin + it : P.reset_list[it];
+        const int env = STEP ? P.env_begin + it : rlist[it];
         const int a0 = env * N;
         unsigned char* ib = envbox0 + (size_t)buf * envbox_bytes;
         float4* tgoal = reinterpret_cast<float4*>(ib);
@@ -648,7 +654,7 @@ swarm_step_rotx_kernel(const DevParams P) {
                 }
                 wstats[SWARM_STAT_AGENT_STEPS] += (unsigned long long)n_alive_env;
                 wstats[SWARM_STAT_ENV_STEPS] += env_active ? 1ull : 0ull;
-                if (P.auto_reset && need_reset) P.reset_list[atomicAdd(P.reset_count, 1u)] = env;
+                if (P.auto_reset && need_reset) rlist[atomicAdd(rcount, 1u)] = env;
             }
         } else {
             // reset()'s obs / infos (:82-89); reward / flags of the terminal step stay
@@ -675,8 +681,11 @@ swarm_step_rotx_kernel(const DevParams P) {
     if (lane == 0 && atomicAdd(queue + 1, 1u) == (unsigned)warps_total - 1u) {  // last warp out re-arms the queue
         queue[0] = 0u;
         queue[1] = 0u;
+        if (STEP && P.auto_reset) {  // hand the list over, clear the other one for the next step
+            P.reset_count[(epoch + 1u) & 1u] = 0u;
+            *P.reset_epoch = epoch + 1u;
+        }
     }
-    if (!STEP && blockIdx.x == 0 && warp == 0 && lane == 0) *P.reset_count_other = 0u;
     if (lane == 0) bulk_wait0();
     __syncwarp();
     if (STEP && P.stats && lane < SWARM_STATS_WORDS) {

@@ -231,6 +231,31 @@ class SwarmEngine:
         self._keep = a
         return self._step_result
 
+    def step_many(self, actions: torch.Tensor, auto_reset: bool = True):
+        """T consecutive `step` calls with ONE host call: `actions` is a [T,E,N,3] float32 CUDA tensor, step t
+        applies actions[t].  Outputs describe the last step; statistics accumulate.  For small batches (BASELINE's
+        4096 x 8 drones) the per-call host cost, not the device, bounds a Python loop over `step`."""
+        if not (torch.is_tensor(actions) and actions.is_cuda):
+            raise TypeError("actions must be a CUDA tensor")
+        a = actions
+        if a.dtype is not torch.float32 or not a.is_contiguous():
+            a = a.to(dtype=torch.float32).contiguous()
+        if a.dim() != 4 or a.numel() != a.shape[0] * self._n_actions:
+            raise ValueError(f"actions must have shape [T,{self.E},{self.N},3]")
+        rc = self._lib.swarm_step_many(self._handle, self._bufs_ref, a.data_ptr(), int(a.shape[0]),
+                                       1 if auto_reset else 0, self._stream())
+        if rc != 0:
+            _abi.check(rc, "swarm_step_many")
+        self._keep = a
+        return self._step_result
+
+    def capture_steps(self, actions: torch.Tensor, auto_reset: bool = True) -> "StepGraph":
+        """Capture `step_many(actions)` into a CUDA graph (the library keeps no per-launch host state, so the
+        graph can be replayed any number of times).  `actions` ([T,E,N,3] float32 CUDA) is the graph's INPUT
+        buffer: write the next T actions into it (e.g. `actions.copy_(...)`, or let a policy kernel fill
+        actions[t] between replays of single-step graphs) and call `.replay()`."""
+        return StepGraph(self, actions, auto_reset)
+
     def set_state(self, positions=None, velocities=None, goal=None, obstacles=None, alive=None, step_count=None,
                   observe: bool = True):
         """State injection (parity runs): arrays shaped like the reference attributes + env axis."""
@@ -345,3 +370,23 @@ class SwarmEngine:
         if self.dr_params is not None:
             per_env += 32   # this episode's randomised constants
         return per_agent + per_env / N
+
+
+class StepGraph:
+    """A captured sequence of T env steps (see `SwarmEngine.capture_steps`): one `cudaGraphLaunch` per replay instead
+    of 2 T kernel launches from Python.  Launch-bound batch sizes (a few thousand envs) gain the most."""
+
+    def __init__(self, engine: SwarmEngine, actions: torch.Tensor, auto_reset: bool = True):
+        if not (torch.is_tensor(actions) and actions.is_cuda and actions.dtype is torch.float32 and
+                actions.is_contiguous() and actions.dim() == 4):
+            raise TypeError("actions must be a contiguous [T,E,N,3] float32 CUDA tensor (it becomes the graph's input)")
+        self.engine, self.actions, self.steps = engine, actions, int(actions.shape[0])
+        engine.step_many(actions[:1], auto_reset=auto_reset)       # warm-up outside the capture (lazy attribute sets)
+        torch.cuda.synchronize(engine.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            engine.step_many(actions, auto_reset=auto_reset)
+
+    def replay(self):
+        self.graph.replay()
+        return self.engine._step_result

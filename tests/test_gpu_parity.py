@@ -427,6 +427,100 @@ def test_sharded_swarm_invariance_with_randomisation_and_delay(N, M):
     assert whole.engine.stats()["episodes"] > E   # the run went through resets (new per-episode constants)
 
 
+@pytest.mark.parametrize("cfg,E,dr", [({"num_drones": 8, "num_obstacles": 4, "max_steps": 25}, 1000, False),
+                                      ({"num_drones": 32, "num_obstacles": 8, "max_steps": 30}, 300, True),
+                                      ({"num_drones": 128, "num_obstacles": 8, "world_size": 60.0}, 64, False),
+                                      ({"num_drones": 5, "num_obstacles": 3, "max_steps": 20}, 500, False)])
+def test_step_many_and_graph_replay_match_the_step_loop(cfg, E, dr):
+    """`swarm_step_many` (one host call for T steps) and a captured CUDA graph of it, replayed several times with an
+    ODD number of steps per replay, leave every buffer exactly as a Python loop over `swarm_step` does: the library
+    keeps no per-launch host state (the reset-list parity lives on the device)."""
+    import torch
+    import swarm_b200
+    from test_domain_randomization import DR_DELAY
+
+    N, T, R = cfg["num_drones"], 7, 3
+    kw = dict(domain_randomization=DR_DELAY, dr_seed=5) if dr else {}
+    engines = []
+    for _ in range(3):
+        e = swarm_b200.SwarmEngine(E, cfg, device="cuda:0", reward64=True, **kw)
+        e.seed(np.arange(E, dtype=np.uint64))
+        e.reset()
+        engines.append(e)
+    loop, many, graphed = engines
+    gen = torch.Generator(device="cuda:0")
+    gen.manual_seed(21)
+    acts = [torch.rand((T, E, N, 3), generator=gen, device="cuda:0") * 2.4 - 1.2 for _ in range(R)]
+    buf = acts[0].clone()
+    graph = graphed.capture_steps(buf)      # (the capture's warm-up call already stepped once with buf[0])
+    loop.step(acts[0][0]); many.step(acts[0][0])
+    names = ["pos4", "vel4", "goal4", "obst4", "obs", "reward64", "dist", "terminated", "truncated", "reached", "collision",
+             "obs_valid", "all_terminated", "all_truncated", "global_state", "rng", "step_count", "ep_return"]
+    if dr:
+        names += ["dr_params", "act_hist"]
+    for r in range(R):
+        for t in range(T):
+            loop.step(acts[r][t])
+        many.step_many(acts[r])
+        buf.copy_(acts[r])
+        graph.replay()
+        for name in names:
+            want = getattr(loop, name).view(torch.uint8)
+            assert torch.equal(getattr(many, name).view(torch.uint8), want), ("step_many", name, r)
+            assert torch.equal(getattr(graphed, name).view(torch.uint8), want), ("graph", name, r)
+    assert loop.stats() == many.stats() == graphed.stats()
+
+
+def test_step_accepts_a_misaligned_actions_view():
+    """A float32 view at a 4-byte storage offset is a legal `actions` argument: the launch falls back to the general
+    kernel, whose 16-byte copies must then be skipped too (it used to fault with a misaligned address)."""
+    import torch
+    import swarm_b200
+    cfg = {"num_drones": 8, "num_obstacles": 4, "max_steps": 30}
+    E = 256
+    a, b = (swarm_b200.SwarmEngine(E, cfg, device="cuda:0") for _ in range(2))
+    for e in (a, b):
+        e.seed(np.arange(E, dtype=np.uint64))
+        e.reset()
+    gen = torch.Generator(device="cuda:0")
+    gen.manual_seed(4)
+    for t in range(12):
+        act = torch.rand((E, 8, 3), generator=gen, device="cuda:0") * 2 - 1
+        storage = torch.empty(act.numel() + 1, device="cuda:0")
+        view = storage[1:].view(E, 8, 3)
+        view.copy_(act)
+        assert view.data_ptr() % 16 == 4
+        a.step(act)
+        b.step(view)
+        for name in ("pos4", "vel4", "obs", "reward", "terminated", "all_terminated", "rng"):
+            assert torch.equal(getattr(a, name), getattr(b, name)), (name, t)
+
+
+def test_single_env_episode_statistics():
+    """kind='single': success / collision / timeout counters partition the ended episodes (they used to stay 0)."""
+    import torch
+    import swarm_b200
+    E, T = 2048, 120
+    eng = swarm_b200.SwarmEngine(E, {"num_obstacles": 8, "max_steps": 40, "world_size": 8.0}, kind="single", device="cuda:0")
+    eng.seed(np.arange(E, dtype=np.uint64))
+    eng.reset()
+    gen = torch.Generator(device="cuda:0")
+    gen.manual_seed(1)
+    succ = col = to = 0
+    for t in range(T):
+        # drive towards the goal so that all three endings occur
+        act = (eng.obs[:, :, 6:9] * 0.5 + torch.randn((E, 1, 3), generator=gen, device="cuda:0") * 0.3).clamp(-1, 1)
+        eng.step(act.contiguous())
+        done = (eng.all_terminated | eng.all_truncated).bool()
+        c = eng.collision[:, 0].bool() & done
+        s = eng.reached[:, 0].bool() & done & ~c
+        col += int(c.sum()); succ += int(s.sum()); to += int((done & ~c & ~s).sum())
+    st = eng.stats()
+    assert st["episodes"] == succ + col + to and st["episodes"] > 0
+    assert (st["success"], st["collision"], st["timeout"]) == (succ, col, to)
+    assert succ > 0 and col > 0 and to > 0
+
+
 def test_state_dict_roundtrip_continues_bit_exact():
     import torch
     import swarm_b200
