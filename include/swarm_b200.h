@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SWARM_ABI_VERSION 3
+#define SWARM_ABI_VERSION 4
 
 enum {
     SWARM_OK = 0,
@@ -157,7 +157,9 @@ enum {
     SWARM_STAT_RETURN_SUM = 5, /* sum of their returns (double bits) */
     SWARM_STAT_AGENT_STEPS = 6,/* actions applied (one per active drone per step) */
     SWARM_STAT_ENV_STEPS = 7,  /* env instances stepped */
-    SWARM_STATS_WORDS = 8
+    SWARM_STAT_NAN_ACTIONS = 8,/* applied actions with a NaN component (np.clip lets NaN through, drone_swarm_env.py:105:
+                                  the state of that env is NaN from then on -- this counter is the guard) */
+    SWARM_STATS_WORDS = 9
 };
 
 /* Host-side output pointers for swarm_step_host (any may be NULL = do not copy back). */
@@ -166,6 +168,10 @@ typedef struct SwarmHostOut {
     uint8_t *terminated; uint8_t *truncated; uint8_t *reached; uint8_t *collision; uint8_t *obs_valid;
     uint8_t *all_terminated; uint8_t *all_truncated;
     float *global_state;
+    /* block mode (block_bytes > 0; the fields above are then ignored): the caller keeps every output buffer inside
+     * ONE device allocation [block_dev, block_dev + block_bytes) and wants it mirrored byte for byte at block_host
+     * -- one device->host copy per step instead of one per field (small batches: the E = 1 facade envs) */
+    void *block_host; const void *block_dev; int64_t block_bytes;
 } SwarmHostOut;
 
 typedef struct SwarmHandle SwarmHandle;
@@ -213,9 +219,10 @@ int swarm_step_many(SwarmHandle *h, const SwarmBuffers *bufs, const float *actio
 /* Same step through HOST buffers (the end-to-end path): copies actions host->device, steps,
  * copies the requested outputs device->host, chunked over the env axis on internal streams so
  * the copies overlap the kernel, and returns when the host buffers are valid.  Host pointers
- * should be pinned for full PCIe rate. */
+ * should be pinned for full PCIe rate.  `stream`: the caller's stream -- the step starts behind the work already
+ * enqueued there (event, no device-wide synchronisation). */
 int swarm_step_host(SwarmHandle *h, const SwarmBuffers *bufs, const float *actions_host,
-                    const SwarmHostOut *out_host, int auto_reset);
+                    const SwarmHostOut *out_host, int auto_reset, void *stream);
 
 /* Number of kernel launches this handle has enqueued so far (bench bookkeeping). */
 int64_t swarm_launch_count(const SwarmHandle *h);

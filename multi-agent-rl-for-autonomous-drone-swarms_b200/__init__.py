@@ -6,6 +6,8 @@ hand-written sm_100a kernels behind the C ABI in include/swarm_b200.h.
 
     SwarmEngine      batched tensor API (E env instances per GPU, one step launch + a tiny auto-reset launch)
     evaluate_batched reference evaluation protocol (SR / CFR / TTG / FE / PE) for E episodes at once
+    collect_rollout  device-resident policy loop: [T,E,...] sample-batch columns incl. global_state, no host sync
+    VectorSwarmEnv   RLlib BaseEnv-shaped vector env (lazy dicts) + a batched array interface over one engine
     DroneSwarmEnv    reference-compatible multi-agent env (dict API) backed by the engine
     SingleDroneEnv   reference-compatible single-agent env backed by the engine
     DronePhysicsEnv  the PyBullet env's contract + force/drag/gravity model as point masses (parity unpinned)
@@ -26,6 +28,9 @@ def __getattr__(name):
     if name in ("DroneSwarmEnv", "SingleDroneEnv", "DronePhysicsEnv", "make_env_creator", "VectorSwarmEnv"):
         from . import envs
         return getattr(envs, name)
+    if name == "collect_rollout":
+        from .rollout import collect_rollout
+        return collect_rollout
     if name == "evaluate_batched":
         from .evaluation import evaluate_batched
         return evaluate_batched

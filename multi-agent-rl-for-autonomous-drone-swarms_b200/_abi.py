@@ -11,12 +11,12 @@ import os
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SWARM_B200_LIB") or os.path.join(_PKG_DIR, "libswarm_b200.so")  # override: tuning builds
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 KIND_SINGLE, KIND_SWARM, KIND_PHYSICS = 0, 1, 2
 MAX_DRONES, MAX_NEIGHBOR_K, MAX_SENSED = 128, 8, 8
 
 STAT_NAMES = ("episodes", "success", "collision", "timeout", "length_sum", "return_sum", "agent_steps",
-              "env_steps")
+              "env_steps", "nan_actions")
 
 _DOUBLES = ("world_size", "dt", "max_speed", "max_accel", "collision_radius", "goal_radius", "obstacle_radius",
             "desired_spacing", "reward_progress_scale", "reward_goal", "reward_collision",
@@ -60,7 +60,8 @@ HOST_OUT_FIELDS = ("obs", "reward", "reward64", "dist", "terminated", "truncated
 
 
 class SwarmHostOut(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in HOST_OUT_FIELDS]
+    _fields_ = [(n, C.c_void_p) for n in HOST_OUT_FIELDS] + \
+               [("block_host", C.c_void_p), ("block_dev", C.c_void_p), ("block_bytes", C.c_int64)]
 
 
 EXPORTS = ("swarm_abi_version", "swarm_last_error", "swarm_create", "swarm_destroy", "swarm_query_sizes",
@@ -98,7 +99,7 @@ def load():
     lib.swarm_observe.argtypes = [vp, C.POINTER(SwarmBuffers), vp]
     lib.swarm_step.argtypes = [vp, C.POINTER(SwarmBuffers), vp, i32, vp]
     lib.swarm_step_many.argtypes = [vp, C.POINTER(SwarmBuffers), vp, i32, i32, vp]
-    lib.swarm_step_host.argtypes = [vp, C.POINTER(SwarmBuffers), vp, C.POINTER(SwarmHostOut), i32]
+    lib.swarm_step_host.argtypes = [vp, C.POINTER(SwarmBuffers), vp, C.POINTER(SwarmHostOut), i32, vp]
     lib.swarm_launch_count.argtypes = [vp]
     lib.swarm_launch_count.restype = C.c_int64
     lib.swarm_dr_quantile_table.argtypes = [vp]

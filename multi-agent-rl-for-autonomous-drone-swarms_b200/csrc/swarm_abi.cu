@@ -9,6 +9,8 @@
 #include <new>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "swarm_internal.h"
 
 using namespace swarm;
@@ -62,6 +64,7 @@ struct SwarmHandle {
     // host-buffer path
     cudaStream_t chunk_stream[kHostChunks];
     cudaEvent_t chunk_done[kHostChunks];
+    cudaEvent_t caller_ready;   // recorded on the caller's stream: the chunk streams start behind it
     float* actions_dev;      // [E][N][3] staging for swarm_step_host
     bool host_path_ready;
 };
@@ -352,9 +355,16 @@ int launch(SwarmHandle* h, DevParams& p, int env_begin, int env_count, cudaStrea
     p.reset_list = h->reset_list_dev + env_begin / p.G;
     p.reset_list_stride = h->reset_list_stride;
     p.work_counter = h->work_counter_dev + 4 * slot;  // {step queue, warps done, reset queue, warps done}
-    if (rot) CUDA_TRY(launch_rot_kernel(p, rot_grid, stream));
-    else if (rotx) CUDA_TRY(launch_rotx_kernel(p, rotx_grid, stream));
-    else CUDA_TRY(launch_env_kernel(p, h->cfg.norm_mode, h->cfg.env_kind, grid, h->smem_bytes, stream));
+    // NVTX ranges around the launches (a few ns without a profiler attached): nsys / ncu timelines show which API call
+    // a kernel belongs to
+    static const char* const kRange[] = {"swarm_step", "swarm_reset", "swarm_observe", "swarm_auto_reset"};
+    nvtxRangePushA(kRange[p.mode & 3]);
+    cudaError_t lerr;
+    if (rot) lerr = launch_rot_kernel(p, rot_grid, stream);
+    else if (rotx) lerr = launch_rotx_kernel(p, rotx_grid, stream);
+    else lerr = launch_env_kernel(p, h->cfg.norm_mode, h->cfg.env_kind, grid, h->smem_bytes, stream);
+    nvtxRangePop();
+    CUDA_TRY(lerr);
     h->launches++;
     if (two_launch) {
         // N <= 32: the auto-reset runs as a second, tiny launch (kept out of the step kernel so each
@@ -362,12 +372,15 @@ int launch(SwarmHandle* h, DevParams& p, int env_begin, int env_count, cudaStrea
         DevParams q = p;
         q.mode = kModeAutoReset;
         q.env_mask = h->reset_mask_dev;
-        if (rot) CUDA_TRY(launch_rot_kernel(q, rot_grid, stream));
+        nvtxRangePushA(kRange[3]);
+        if (rot) lerr = launch_rot_kernel(q, rot_grid, stream);
         else if (rotx) {
             const int rr = h->num_sms * h->rotx_reset_blocks_per_sm;
-            CUDA_TRY(launch_rotx_kernel(q, rotx_needed < rr ? rotx_needed : rr, stream));
+            lerr = launch_rotx_kernel(q, rotx_needed < rr ? rotx_needed : rr, stream);
         }
-        else CUDA_TRY(launch_env_kernel(q, h->cfg.norm_mode, h->cfg.env_kind, grid, h->smem_bytes, stream));
+        else lerr = launch_env_kernel(q, h->cfg.norm_mode, h->cfg.env_kind, grid, h->smem_bytes, stream);
+        nvtxRangePop();
+        CUDA_TRY(lerr);
         h->launches++;
     }
     return SWARM_OK;
@@ -521,6 +534,7 @@ int swarm_destroy(SwarmHandle* h) {
             cudaStreamDestroy(h->chunk_stream[c]);
             cudaEventDestroy(h->chunk_done[c]);
         }
+        cudaEventDestroy(h->caller_ready);
     }
     if (h->actions_dev) cudaFree(h->actions_dev);
     if (h->jump_dev) cudaFree(h->jump_dev);
@@ -604,7 +618,7 @@ int swarm_step_many(SwarmHandle* h, const SwarmBuffers* bufs, const float* actio
 }
 
 int swarm_step_host(SwarmHandle* h, const SwarmBuffers* bufs, const float* actions_host, const SwarmHostOut* out,
-                    int auto_reset) {
+                    int auto_reset, void* stream) {
     if (!h) return fail(SWARM_E_NULL, "handle is NULL");
     if (!actions_host || !out) return fail(SWARM_E_NULL, "actions_host / out_host is NULL");
     DeviceGuard guard(h->device);
@@ -617,11 +631,13 @@ int swarm_step_host(SwarmHandle* h, const SwarmBuffers* bufs, const float* actio
             CUDA_TRY(cudaStreamCreateWithFlags(&h->chunk_stream[c], cudaStreamNonBlocking));
             CUDA_TRY(cudaEventCreateWithFlags(&h->chunk_done[c], cudaEventDisableTiming));
         }
+        CUDA_TRY(cudaEventCreateWithFlags(&h->caller_ready, cudaEventDisableTiming));
         CUDA_TRY(cudaMalloc(&h->actions_dev, (size_t)p.E * p.N * 3 * sizeof(float)));
         h->host_path_ready = true;
     }
-    // the internal chunk streams do not order against the caller's streams: drain prior work first
-    CUDA_TRY(cudaDeviceSynchronize());
+    // the internal chunk streams start behind whatever the caller has enqueued on `stream` (an event, not a
+    // device-wide drain); the call returns after a host wait on every chunk, so later work on any stream is behind it
+    CUDA_TRY(cudaEventRecord(h->caller_ready, static_cast<cudaStream_t>(stream)));
     p.mode = kModeStep;
     p.auto_reset = auto_reset ? 1 : 0;
     p.actions = h->actions_dev;
@@ -629,7 +645,7 @@ int swarm_step_host(SwarmHandle* h, const SwarmBuffers* bufs, const float* actio
     // chunk boundaries are multiples of G so a warp's env group never straddles two launches
     int chunks = kHostChunks;
     int groups_total = (E + p.G - 1) / p.G;
-    if (groups_total < chunks * 64) chunks = 1;
+    if (groups_total < chunks * 64 || out->block_bytes > 0) chunks = 1;
     const int groups_per_chunk = (groups_total + chunks - 1) / chunks;
     for (int c = 0; c < chunks; ++c) {
         const int e0 = c * groups_per_chunk * p.G;
@@ -637,11 +653,19 @@ int swarm_step_host(SwarmHandle* h, const SwarmBuffers* bufs, const float* actio
         const int e1 = (e0 + groups_per_chunk * p.G) < E ? (e0 + groups_per_chunk * p.G) : E;
         const size_t ne = (size_t)(e1 - e0);
         cudaStream_t s = h->chunk_stream[c];
+        CUDA_TRY(cudaStreamWaitEvent(s, h->caller_ready, 0));
         CUDA_TRY(cudaMemcpyAsync(h->actions_dev + (size_t)e0 * N * 3, actions_host + (size_t)e0 * N * 3,
                                  ne * N * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
         DevParams pc = p;
         rc = launch(h, pc, e0, e1 - e0, s, c + 1);
         if (rc != SWARM_OK) return rc;
+ if (out->block_bytes > 0) {
+            // small batches (the E = 1 facade envs): every output lives in ONE device block mirrored by one pinned
+            // host block -- one copy instead of twelve
+            CUDA_TRY(cudaMemcpyAsync(out->block_host, out->block_dev, (size_t)out->block_bytes, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaEventRecord(h->chunk_done[c], s));
+            continue;
+        }
 #define D2H(field, devptr, per_env_elems, type)                                                         \
         if (out->field)                                                                                 \
             CUDA_TRY(cudaMemcpyAsync(out->field + (size_t)e0 * (per_env_elems), (devptr) + (size_t)e0 * (per_env_elems), \

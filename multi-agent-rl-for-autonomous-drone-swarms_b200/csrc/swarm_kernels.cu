@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
         SMALLN ? (e_l < G ? (N == 32 ? FULL_MASK : (((1u << N) - 1u) << (e_l * N))) : 0u) : FULL_MASK;
 
     // per-lane statistics (flushed once per warp at the end)
-    unsigned st_eps = 0, st_succ = 0, st_col = 0, st_to = 0, st_len = 0, st_asteps = 0, st_esteps = 0;
+    unsigned st_eps = 0, st_succ = 0, st_col = 0, st_to = 0, st_len = 0, st_asteps = 0, st_esteps = 0, st_nan = 0;
     double st_ret = 0.0;
 
     asm volatile("griddepcontrol.wait;" ::: "memory");  // programmatic dependent launch: the previous launch is done
@@ -324,6 +324,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                         const float ax = clipf(P.actions[a * 3 + 0], -1.0f, 1.0f);
                         const float ay = clipf(P.actions[a * 3 + 1], -1.0f, 1.0f);
                         const float az = clipf(P.actions[a * 3 + 2], -1.0f, 1.0f);
+                        if (!(ax == ax && ay == ay && az == az)) ++st_nan;   // NaN-action guard counter
                         v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(ax, P.amax), P.dt));
                         v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(ay, P.amax), P.dt));
                         v.z = __fadd_rn(v.z, __fmul_rn(__fmul_rn(az, P.amax), P.dt));
@@ -646,6 +647,8 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
             atomicAdd(P.stats + SWARM_STAT_AGENT_STEPS, (unsigned long long)st_asteps);
             atomicAdd(P.stats + SWARM_STAT_ENV_STEPS, (unsigned long long)st_esteps);
         }
+        for (int off = 16; off >= 1; off >>= 1) st_nan += __shfl_xor_sync(FULL_MASK, st_nan, off);
+        if (lane == 0 && st_nan) atomicAdd(P.stats + SWARM_STAT_NAN_ACTIONS, (unsigned long long)st_nan);
     }
 }
 
@@ -839,6 +842,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
 
         bool alive = KIND == SWARM_KIND_SINGLE ? lane_ok : (lane_ok && p.w != 0.0f);
         float prev_d = 0.f;
+        bool nan_act = false;
         unsigned out_lanes = ok_lanes;  // lanes whose obs row is produced by this launch
         if (MODE == kSmallStep) {
             // =========================== phase A: integrate (:98-118) ===========================
@@ -891,6 +895,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                     wp[0] = sx; wp[1] = sy; wp[2] = sz;
                 }
                 ax = clipf(ax, -1.0f, 1.0f); ay = clipf(ay, -1.0f, 1.0f); az = clipf(az, -1.0f, 1.0f);
+                nan_act = !(ax == ax && ay == ay && az == az);   // (np.clip lets NaN through; counted below)
                 if (DR) {  // thrust noise: a <- a * (1 + sigma z), one normal per axis
                     const uint4 r = philox4x32_7(genv, ekey, (unsigned)sc, (unsigned)i | (DR_STREAM_A << 16), P);
                     ax = __fmul_rn(ax, __fmaf_rn(P.dr_std_thrust, dr_normal(P.dr_qtable, dr_field(r, 0)), 1.0f));
@@ -909,6 +914,11 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                 p.x = __fadd_rn(p.x, __fmul_rn(v.x, c_dt));
                 p.y = __fadd_rn(p.y, __fmul_rn(v.y, c_dt));
                 p.z = __fadd_rn(p.z, __fmul_rn(v.z, c_dt));
+            }
+            if (PHYS) nan_act = alive && !(ax == ax && ay == ay && az == az);   // (the physics env does not clip)
+            {   // NaN-action guard counter (rare: the vote is all a clean step pays)
+                const unsigned nan_m = __ballot_sync(FULL_MASK, nan_act);
+                if (nan_m != 0u && lane == 0) wstats[SWARM_STAT_NAN_ACTIONS] += (unsigned long long)__popc(nan_m);
             }
             // wall clip for ALL drones (:113-117); velocity is not zeroed at the wall (the physics env has no walls)
             if (!PHYS) {

@@ -31,6 +31,9 @@
 #ifndef SWARM_ROT_OVERLAP
 #define SWARM_ROT_OVERLAP 1
 #endif
+#ifndef SWARM_ROT_EARLY_TRIGGER
+#define SWARM_ROT_EARLY_TRIGGER 1
+#endif
 
 namespace swarm {
 
@@ -143,6 +146,11 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
     // step: one item per env group; reset: one item per listed group
     // (reset launch: the first list entry is fetched together with the list length -- the entry is only used if
     //  it turns out to be inside the list -- so a warp's first item starts one memory round trip earlier)
+#if SWARM_ROT_PDL && SWARM_ROT_EARLY_TRIGGER
+    // step launch: let the reset launch behind it place its CTAs as slots come free during this launch's tail (they
+    // sit in their griddepcontrol.wait until this launch has completed), instead of being launched only then
+    if (MODE == kRotStep) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
     int env0_pref = 0;
     const int* rlist = P.reset_list;
     int n_iter = P.n_groups;
@@ -287,6 +295,7 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
                 for (int idx = lane; idx < G * M; idx += 32)
                     reinterpret_cast<unsigned*>(tobs_all)[idx * 4 + 3] = (unsigned)(idx % M);
                 float ax = 0.f, ay = 0.f, az = 0.f;
+                bool nan_act = false;
                 if (lane_ok) {
                     p = in_pos[lane];
                     v = in_pos[32 + lane];
@@ -328,6 +337,7 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
                         wp[0] = sx; wp[1] = sy; wp[2] = sz;
                     }
                     ax = clipf(ax, -1.0f, 1.0f); ay = clipf(ay, -1.0f, 1.0f); az = clipf(az, -1.0f, 1.0f);
+                    nan_act = !(ax == ax && ay == ay && az == az);   // (np.clip lets NaN through; counted, see below)
                     if (DR) {  // thrust noise: a <- a * (1 + sigma z), one normal per axis
                         rA = philox4x32_7(genv, ekey, (unsigned)sc, (unsigned)i | (DR_STREAM_A << 16), P);
                         ax = __fmul_rn(ax, __fmaf_rn(P.dr_std_thrust, dr_normal_off(qtab, dr_field_off(rA, 0)), 1.0f));
@@ -346,6 +356,10 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
                     p.x = __fadd_rn(p.x, __fmul_rn(v.x, c_dt));
                     p.y = __fadd_rn(p.y, __fmul_rn(v.y, c_dt));
                     p.z = __fadd_rn(p.z, __fmul_rn(v.z, c_dt));
+                }
+                {   // NaN-action guard counter (rare: the vote is all a clean step pays)
+                    const unsigned nan_m = __ballot_sync(FULL_MASK, nan_act);
+                    if (nan_m != 0u && lane == 0) wstats[SWARM_STAT_NAN_ACTIONS] += (unsigned long long)__popc(nan_m);
                 }
                 // wall clip for ALL drones (:113-117); velocity is not zeroed at the wall
                 p.x = clipf(p.x, -c_bound, c_bound);

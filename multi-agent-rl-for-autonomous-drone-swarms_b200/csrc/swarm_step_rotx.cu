@@ -160,6 +160,7 @@ swarm_step_rotx_kernel(const DevParams P) {
             gx = g4.x; gy = g4.y; gz = g4.z;
             sc = reinterpret_cast<const int*>(ib + sc_off)[0];
             const float* act = reinterpret_cast<const float*>(in_pos + 2 * N);
+            bool nan_any = false;
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
                 const float4 p = SWARM_ROTX_DIRECT ? lp[s] : in_pos[s * 32 + lane];
@@ -172,6 +173,7 @@ swarm_step_rotx_kernel(const DevParams P) {
                 prev_d[s] = norm1d<0>(__fsub_rn(gx, p.x), __fsub_rn(gy, p.y), __fsub_rn(gz, p.z));  // :98-101
                 if (alive[s]) {  // integrate (:103-111)
                     ax = clipf(ax, -1.0f, 1.0f); ay = clipf(ay, -1.0f, 1.0f); az = clipf(az, -1.0f, 1.0f);
+                    nan_any = nan_any || !(ax == ax && ay == ay && az == az);   // (np.clip lets NaN through; counted)
                     v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(ax, P.amax), P.dt));
                     v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(ay, P.amax), P.dt));
                     v.z = __fadd_rn(v.z, __fmul_rn(__fmul_rn(az, P.amax), P.dt));
@@ -189,6 +191,10 @@ swarm_step_rotx_kernel(const DevParams P) {
                 py[s] = clipf(py[s], -P.bound, P.bound);
                 pz[s] = clipf(pz[s], -P.bound, P.bound);
                 vx[s] = v.x; vy[s] = v.y; vz[s] = v.z;
+            }
+            {   // NaN-action guard counter (rare: the vote is all a clean step pays); per lane: drones, not components
+                const unsigned nan_m = __ballot_sync(FULL_MASK, nan_any);
+                if (nan_m != 0u && lane == 0) wstats[SWARM_STAT_NAN_ACTIONS] += (unsigned long long)__popc(nan_m);
             }
         } else {
             // ================================ reset (:65-80) ================================
@@ -358,6 +364,9 @@ swarm_step_rotx_kernel(const DevParams P) {
         double rew[NS];
         float cd[NS];
         unsigned fl[NS];  // bit 0 reached, bit 1 collided
+        // step launch with auto-reset: the env is certain to be re-drawn (no active drone left, or the time limit is
+        // reached on this step; collisions are added slot pass by slot pass) -- its obs rows are not stored
+        bool doomed = STEP && P.auto_reset && (n_alive_env == 0 || sc + 1 >= P.max_steps);
 #pragma unroll 1
         for (int s = 0; s < NS; ++s) {
             if (s > 0) {  // the previous slot's tile must have left shared memory before this pass scribbles on it
@@ -525,30 +534,6 @@ swarm_step_rotx_kernel(const DevParams P) {
             }
             const float curr_d = norm1d<0>(__fsub_rn(gx, p_x), __fsub_rn(gy, p_y), __fsub_rn(gz, p_z));
 
-            // ---- obs row -> tile -> one TMA store per slot (:226-243)
-            {
-                float* row = srow;
-                const float4 t0 = tab2[nj[0]], t1 = tab2[nj[1]];
-                const float4 t2 = tab2[nj[2]];
-                const float4 b0 = tobs[om[0]], b1 = tobs[om[1]], b2 = tobs[om[2]], b3 = tobs[om[3]];
-                row[0] = p_x; row[1] = p_y; row[2] = p_z;
-                row[3] = vx[0]; row[4] = vy[0]; row[5] = vz[0];
-                row[6] = __fsub_rn(gx, p_x); row[7] = __fsub_rn(gy, p_y); row[8] = __fsub_rn(gz, p_z);
-                row[9] = __fsub_rn(t0.x, p_x); row[10] = __fsub_rn(t0.y, p_y); row[11] = __fsub_rn(t0.z, p_z); row[12] = nd[0];
-                row[13] = __fsub_rn(t1.x, p_x); row[14] = __fsub_rn(t1.y, p_y); row[15] = __fsub_rn(t1.z, p_z); row[16] = nd[1];
-                row[17] = __fsub_rn(t2.x, p_x); row[18] = __fsub_rn(t2.y, p_y); row[19] = __fsub_rn(t2.z, p_z); row[20] = nd[2];
-                row[21] = __fsub_rn(b0.x, p_x); row[22] = __fsub_rn(b0.y, p_y); row[23] = __fsub_rn(b0.z, p_z); row[24] = od[0];
-                row[25] = __fsub_rn(b1.x, p_x); row[26] = __fsub_rn(b1.y, p_y); row[27] = __fsub_rn(b1.z, p_z); row[28] = od[1];
-                row[29] = __fsub_rn(b2.x, p_x); row[30] = __fsub_rn(b2.y, p_y); row[31] = __fsub_rn(b2.z, p_z); row[32] = od[2];
-                row[33] = __fsub_rn(b3.x, p_x); row[34] = __fsub_rn(b3.y, p_y); row[35] = __fsub_rn(b3.z, p_z); row[36] = od[3];
-            }
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-                bulk_s2g(P.obs + (long long)(a0 + s * 32) * kD, smem_u32(tile), (unsigned)kTileBytes);
-                bulk_commit();
-            }
-
             // ---- per-drone reward pieces (:141-148); env-level flags need every slot: finished below
             double reward = 0.0;
             unsigned f = 0u;
@@ -570,6 +555,36 @@ swarm_step_rotx_kernel(const DevParams P) {
                 }
                 f = (reached ? 1u : 0u) | (collided ? 2u : 0u);
             }
+            // ---- obs row -> tile -> one TMA store per slot (:226-243)
+            // (an env that is certain to be re-drawn by the auto-reset behind this launch -- time limit reached, or a
+            //  collision seen in this or an earlier slot pass -- does not need this step's rows: the reset launch
+            //  writes the new episode's.  At BASELINE's density 97 % of the envs end every step, and their rows were
+            //  22 % of the launch's DRAM traffic.  An episode that ends because every drone reached the goal is only
+            //  known after the last pass; its rows are written twice, as before.)
+            if (STEP && P.auto_reset) doomed = doomed || __any_sync(FULL_MASK, (f & 2u) != 0u);
+            if (!doomed) {
+                float* row = srow;
+                const float4 t0 = tab2[nj[0]], t1 = tab2[nj[1]];
+                const float4 t2 = tab2[nj[2]];
+                const float4 b0 = tobs[om[0]], b1 = tobs[om[1]], b2 = tobs[om[2]], b3 = tobs[om[3]];
+                row[0] = p_x; row[1] = p_y; row[2] = p_z;
+                row[3] = vx[0]; row[4] = vy[0]; row[5] = vz[0];
+                row[6] = __fsub_rn(gx, p_x); row[7] = __fsub_rn(gy, p_y); row[8] = __fsub_rn(gz, p_z);
+                row[9] = __fsub_rn(t0.x, p_x); row[10] = __fsub_rn(t0.y, p_y); row[11] = __fsub_rn(t0.z, p_z); row[12] = nd[0];
+                row[13] = __fsub_rn(t1.x, p_x); row[14] = __fsub_rn(t1.y, p_y); row[15] = __fsub_rn(t1.z, p_z); row[16] = nd[1];
+                row[17] = __fsub_rn(t2.x, p_x); row[18] = __fsub_rn(t2.y, p_y); row[19] = __fsub_rn(t2.z, p_z); row[20] = nd[2];
+                row[21] = __fsub_rn(b0.x, p_x); row[22] = __fsub_rn(b0.y, p_y); row[23] = __fsub_rn(b0.z, p_z); row[24] = od[0];
+                row[25] = __fsub_rn(b1.x, p_x); row[26] = __fsub_rn(b1.y, p_y); row[27] = __fsub_rn(b1.z, p_z); row[28] = od[1];
+                row[29] = __fsub_rn(b2.x, p_x); row[30] = __fsub_rn(b2.y, p_y); row[31] = __fsub_rn(b2.z, p_z); row[32] = od[2];
+                row[33] = __fsub_rn(b3.x, p_x); row[34] = __fsub_rn(b3.y, p_y); row[35] = __fsub_rn(b3.z, p_z); row[36] = od[3];
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    bulk_s2g(P.obs + (long long)(a0 + s * 32) * kD, smem_u32(tile), (unsigned)kTileBytes);
+                    bulk_commit();
+                }
+            }
+
             rew[0] = reward; cd[0] = curr_d; fl[0] = f;
             rotate<NS>(px); rotate<NS>(py); rotate<NS>(pz); rotate<NS>(vx); rotate<NS>(vy); rotate<NS>(vz);
             rotate<NS>(prev_d); rotate<NS>(alive); rotate<NS>(k0); rotate<NS>(k1); rotate<NS>(k2); rotate<NS>(k3); rotate<NS>(acc);

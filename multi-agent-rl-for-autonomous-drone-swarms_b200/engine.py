@@ -99,18 +99,26 @@ class SwarmEngine:
         self.step_count = z((E,), torch.int32)
         self.rng = z((E, 4), torch.int64)
         self.ep_return = z((E,), torch.float32)
-        self.obs = z((E, N, D), torch.float32)
-        self.reward = z((E, N), torch.float32)
-        self.reward64 = z((E, N), torch.float64) if reward64 else None
-        self.dist = z((E, N), torch.float32)
-        self.terminated = z((E, N), torch.uint8)
-        self.truncated = z((E, N), torch.uint8)
-        self.reached = z((E, N), torch.uint8)
-        self.collision = z((E, N), torch.uint8)
-        self.obs_valid = z((E, N), torch.uint8)
-        self.all_terminated = z((E,), torch.uint8)
-        self.all_truncated = z((E,), torch.uint8)
-        self.global_state = z((E, R), torch.float32) if global_state else None
+        # every host-visible output is a view into ONE device allocation, so that a small batch (the E = 1 facade
+        # envs) comes back with a single device->host copy (SwarmHostOut block mode)
+        spec = [("obs", (E, N, D), torch.float32), ("reward", (E, N), torch.float32)]
+        if reward64:
+            spec.append(("reward64", (E, N), torch.float64))
+        spec += [("dist", (E, N), torch.float32)]
+        spec += [(n, (E, N), torch.uint8) for n in ("terminated", "truncated", "reached", "collision", "obs_valid")]
+        spec += [("all_terminated", (E,), torch.uint8), ("all_truncated", (E,), torch.uint8)]
+        if global_state:
+            spec.append(("global_state", (E, R), torch.float32))
+        self._out_layout, off = [], 0
+        for name, shape, dt in spec:
+            nbytes = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+            self._out_layout.append((name, shape, dt, off, nbytes))
+            off += (nbytes + 255) // 256 * 256
+        self._out_block = z((max(off, 256),), torch.uint8)
+        self.reward64 = None
+        self.global_state = None
+        for name, shape, dt, o, nbytes in self._out_layout:
+            setattr(self, name, self._out_block[o:o + nbytes].view(dt).view(shape))
         self.episode_return = z((E,), torch.float32)
         self.episode_length = z((E,), torch.int32)
         self.stats_words = z((len(_abi.STAT_NAMES),), torch.int64)
@@ -310,16 +318,13 @@ class SwarmEngine:
         if self._host is None:
             E, N, D, R = self.E, self.N, self.D, self.R
             pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()  # noqa: E731
-            h = dict(actions=pin((E, N, 3), torch.float32), obs=pin((E, N, D), torch.float32),
-                     reward=pin((E, N), torch.float32), dist=pin((E, N), torch.float32))
-            if self.reward64 is not None:
-                h["reward64"] = pin((E, N), torch.float64)
-            for name in ("terminated", "truncated", "reached", "collision", "obs_valid"):
-                h[name] = pin((E, N), torch.uint8)
-            h["all_terminated"] = pin((E,), torch.uint8)
-            h["all_truncated"] = pin((E,), torch.uint8)
-            if with_global_state and self.global_state is not None:
-                h["global_state"] = pin((E, R), torch.float32)
+            h = dict(actions=pin((E, N, 3), torch.float32))
+            # one pinned block mirroring the device output block (same offsets): views per field
+            self._host_block = pin((self._out_block.numel(),), torch.uint8)
+            for name, shape, dt, o, nbytes in self._out_layout:
+                if name == "global_state" and not with_global_state:
+                    continue
+                h[name] = self._host_block[o:o + nbytes].view(dt).view(shape)
             self._host = h
         return self._host
 
@@ -336,11 +341,28 @@ class SwarmEngine:
             else:
                 h["actions"].copy_(src)
         out = _abi.SwarmHostOut()
-        names = outputs if outputs is not None else tuple(n for n in _abi.HOST_OUT_FIELDS if n in h)
-        for name in names:
-            setattr(out, name, h[name].data_ptr())
-        _abi.check(self._lib.swarm_step_host(self._handle, C.byref(self._bufs), act.data_ptr(),
-                                             C.byref(out), int(auto_reset)), "swarm_step_host")
+        if outputs is None and self._out_block.numel() <= self.HOST_BLOCK_MAX_BYTES:
+            # small batch: the whole output block in one copy
+            out.block_host, out.block_dev = self._host_block.data_ptr(), self._out_block.data_ptr()
+            out.block_bytes = self._out_block.numel()
+        else:
+            names = outputs if outputs is not None else tuple(n for n in _abi.HOST_OUT_FIELDS if n in h)
+            for name in names:
+                setattr(out, name, h[name].data_ptr())
+        rc = self._lib.swarm_step_host(self._handle, self._bufs_ref, act.data_ptr(), C.byref(out), int(auto_reset),
+                                       self._stream())
+        if rc != 0:
+            _abi.check(rc, "swarm_step_host")
+        return h
+
+    HOST_BLOCK_MAX_BYTES = 1 << 20   # above this the env-axis chunk pipeline (copies under the kernel) wins
+
+    def fetch_outputs(self) -> dict[str, Any]:
+        """Copy the whole output block (obs, reward, flags, global_state ...) to the pinned host mirror in one
+        device->host copy and wait for it: what the facade envs call after `reset()`."""
+        h = self.host_buffers()
+        self._host_block.copy_(self._out_block, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
         return h
 
     def host_bytes_per_step(self, outputs: tuple[str, ...] | None = None) -> tuple[int, int]:

@@ -15,7 +15,8 @@ arithmetic runs in the sm_100a kernels (no CPU path).  For throughput use `Swarm
 from __future__ import annotations
 
 import os
-from typing import Any
+from collections.abc import Mapping
+from typing import Any, Callable
 
 import numpy as np
 
@@ -75,13 +76,15 @@ class _EngineBacked:
         seed = self.cfg.seed if self.cfg.seed is not None else _entropy_seed()
         self._engine.seed(np.asarray([seed], dtype=np.uint64))
         self._host = self._engine.host_buffers()
+        # numpy views of the pinned host block, made once (a step is then: write the action row, one C-ABI call --
+        # H2D, launches, ONE D2H of the whole output block -- and dict building from these views)
+        self._hn = {k: v.numpy() for k, v in self._host.items()}
 
     def _fetch_reset_outputs(self):
-        e = self._engine
-        import torch
-
-        torch.cuda.synchronize(e.device)
-        return (e.obs[0].cpu().numpy(), e.dist[0].cpu().numpy(), e.global_state[0].cpu().numpy())
+        """obs / dist / global_state after `reset()`: the output block comes back in one copy."""
+        self._engine.fetch_outputs()
+        hn = self._hn
+        return hn["obs"][0], hn["dist"][0], (hn["global_state"][0] if "global_state" in hn else None)
 
     # state attributes read by scripts/visualize_swarm.py:76-81,105-110
     @property
@@ -143,15 +146,20 @@ class DroneSwarmEnv(_EngineBacked, _MultiAgentEnv):
         active = list(self.agents)
         if not active:                                                            # :94-95
             return {}, {}, {"__all__": True}, {"__all__": False}, {}
-        act = self._host["actions"].numpy()
+        hn = self._hn
+        act = hn["actions"]
         act[...] = 0.0
         for a in active:                                                          # :103-106
-            raw = action_dict.get(a, np.zeros(3, dtype=np.float32))
-            act[0, self.agent_id_to_index[a]] = np.asarray(raw, dtype=np.float32).reshape(3)
-        h = self._engine.step_host(None, auto_reset=False)
-        rew = h["reward64"].numpy()[0]
-        term, trunc = h["terminated"].numpy()[0], h["truncated"].numpy()[0]
-        valid = h["obs_valid"].numpy()[0]
+            raw = action_dict.get(a)
+            if raw is not None:
+                act[0, self.agent_id_to_index[a]] = np.asarray(raw, dtype=np.float32).reshape(3)
+        self._engine.step_host(None, auto_reset=False)
+        rew = hn["reward64"][0].tolist()
+        term, trunc = hn["terminated"][0].tolist(), hn["truncated"][0].tolist()
+        valid = hn["obs_valid"][0].tolist()
+        obs_rows, dist = hn["obs"][0], hn["dist"][0].tolist()
+        reached, collision = hn["reached"][0].tolist(), hn["collision"][0].tolist()
+        gs = hn["global_state"][0]
         rewards: dict[str, float] = {}
         terminated: dict[str, bool] = {}
         truncated: dict[str, bool] = {}
@@ -160,20 +168,20 @@ class DroneSwarmEnv(_EngineBacked, _MultiAgentEnv):
         next_active: list[str] = []
         for a in active:                                                          # :141-162
             i = self.agent_id_to_index[a]
-            rewards[a] = float(rew[i])
+            rewards[a] = rew[i]
             terminated[a] = bool(term[i])
             truncated[a] = bool(trunc[i])
             if valid[i]:
-                obs[a] = h["obs"].numpy()[0, i].copy()
+                obs[a] = obs_rows[i].copy()
                 infos[a] = {
-                    "distance_to_goal": float(h["dist"].numpy()[0, i]),
-                    "reached_goal": bool(h["reached"].numpy()[0, i]),
-                    "collision": bool(h["collision"].numpy()[0, i]),
-                    "global_state": h["global_state"].numpy()[0].copy(),
+                    "distance_to_goal": dist[i],
+                    "reached_goal": bool(reached[i]),
+                    "collision": bool(collision[i]),
+                    "global_state": gs.copy(),
                 }
                 next_active.append(a)
-        terminated["__all__"] = bool(h["all_terminated"].numpy()[0])              # :164-167
-        truncated["__all__"] = bool(h["all_truncated"].numpy()[0])
+        terminated["__all__"] = bool(hn["all_terminated"][0])                     # :164-167
+        truncated["__all__"] = bool(hn["all_truncated"][0])
         self.agents = [] if (terminated["__all__"] or truncated["__all__"]) else next_active   # :169-172
         return obs, rewards, terminated, truncated, infos
 
@@ -211,16 +219,16 @@ class SingleDroneEnv(_EngineBacked, _GymEnv):
 
     def step(self, action: np.ndarray):
         """single_drone_env.py:73-111."""
-        act = self._host["actions"].numpy()
-        act[0, 0] = np.asarray(action, dtype=np.float32).reshape(3)
-        h = self._engine.step_host(None, auto_reset=False)
+        hn = self._hn
+        hn["actions"][0, 0] = np.asarray(action, dtype=np.float32).reshape(3)
+        self._engine.step_host(None, auto_reset=False)
         info = {
-            "distance_to_goal": float(h["dist"].numpy()[0, 0]),
-            "reached_goal": bool(h["reached"].numpy()[0, 0]),
-            "collision": bool(h["collision"].numpy()[0, 0]),
+            "distance_to_goal": float(hn["dist"][0, 0]),
+            "reached_goal": bool(hn["reached"][0, 0]),
+            "collision": bool(hn["collision"][0, 0]),
         }
-        return (h["obs"].numpy()[0, 0].copy(), float(h["reward64"].numpy()[0, 0]),
-                bool(h["terminated"].numpy()[0, 0]), bool(h["truncated"].numpy()[0, 0]), info)
+        return (hn["obs"][0, 0].copy(), float(hn["reward64"][0, 0]),
+                bool(hn["terminated"][0, 0]), bool(hn["truncated"][0, 0]), info)
 
 
 class DronePhysicsEnv(_EngineBacked, _MultiAgentEnv):
@@ -278,7 +286,8 @@ class DronePhysicsEnv(_EngineBacked, _MultiAgentEnv):
     def step(self, action_dict: dict[str, np.ndarray]):
         """drone_physics_env.py:279-419."""
         active = list(self.agents)
-        act = self._host["actions"].numpy()
+        hn = self._hn
+        act = hn["actions"]
         act[...] = 0.0
         for a, raw in action_dict.items():                                        # :325 (no clip, :336)
             act[0, self.agent_id_to_index[a]] = np.asarray(raw, dtype=np.float32).reshape(3)
@@ -287,20 +296,45 @@ class DronePhysicsEnv(_EngineBacked, _MultiAgentEnv):
             # empty rewards (:374, :398-411); the batched contract parks the env instead
             flags = {a: True for a in self.agent_ids}
             return {}, {}, {**flags, "__all__": True}, {**{a: False for a in self.agent_ids}, "__all__": False}, {}
-        h = self._engine.step_host(None, auto_reset=False)
-        gs = h["global_state"].numpy()[0]
-        obs = {a: h["obs"].numpy()[0, i].copy() for i, a in enumerate(self.agent_ids)}
-        infos = {a: {"global_state": gs.copy(), "distance_to_goal": float(h["dist"].numpy()[0, i]),
-                     "reached_goal": bool(h["reached"].numpy()[0, i]), "collision": bool(h["collision"].numpy()[0, i])}
+        self._engine.step_host(None, auto_reset=False)
+        gs = hn["global_state"][0]
+        obs_rows, dist = hn["obs"][0], hn["dist"][0].tolist()
+        reached, collision = hn["reached"][0].tolist(), hn["collision"][0].tolist()
+        rew, term, trunc = hn["reward64"][0].tolist(), hn["terminated"][0].tolist(), hn["truncated"][0].tolist()
+        obs = {a: obs_rows[i].copy() for i, a in enumerate(self.agent_ids)}
+        infos = {a: {"global_state": gs.copy(), "distance_to_goal": dist[i],
+                     "reached_goal": bool(reached[i]), "collision": bool(collision[i])}
                  for i, a in enumerate(self.agent_ids)}
-        rewards = {a: float(h["reward64"].numpy()[0, self.agent_id_to_index[a]]) for a in active}
-        terminated = {a: bool(h["terminated"].numpy()[0, i]) for i, a in enumerate(self.agent_ids)}
-        truncated = {a: bool(h["truncated"].numpy()[0, i]) for i, a in enumerate(self.agent_ids)}
-        terminated["__all__"] = bool(h["all_terminated"].numpy()[0])
-        truncated["__all__"] = bool(h["all_truncated"].numpy()[0])
+        rewards = {a: rew[self.agent_id_to_index[a]] for a in active}
+        terminated = {a: bool(term[i]) for i, a in enumerate(self.agent_ids)}
+        truncated = {a: bool(trunc[i]) for i, a in enumerate(self.agent_ids)}
+        terminated["__all__"] = bool(hn["all_terminated"][0])
+        truncated["__all__"] = bool(hn["all_truncated"][0])
         if terminated["__all__"] or truncated["__all__"]:
             self.agents = []                                                      # :411
         return obs, rewards, terminated, truncated, infos
+
+
+class _LazyEnvDicts(Mapping):
+    """{env_id: per-agent dict} whose values are built on first access: `poll()` itself does no per-agent Python
+    work, so a sampler that only touches some envs (or only some of the five dicts) pays only for those."""
+
+    def __init__(self, num_envs: int, build: Callable[[int], dict]):
+        self._n, self._build, self._cache = num_envs, build, {}
+
+    def __getitem__(self, e):
+        if not (0 <= e < self._n):
+            raise KeyError(e)
+        v = self._cache.get(e)
+        if v is None:
+            v = self._cache[e] = self._build(e)
+        return v
+
+    def __iter__(self):
+        return iter(range(self._n))
+
+    def __len__(self):
+        return self._n
 
 
 class VectorSwarmEnv:
@@ -309,10 +343,16 @@ class VectorSwarmEnv:
     stepped by ONE engine call per step instead of E Python envs (the reference runs
     one env per rollout worker, `training/config_builders.py:19-23`).  ray is not required.
 
-    Dicts are keyed by env id then agent id and populated by the reference's rules
-    (drone_swarm_env.py:141-172); `infos[...]["global_state"]` is the row the `GlobalStateCallback`
-    (`training/callbacks.py:51-57`) stacks.  An env whose episode ended is reset inside the same engine
-    step (auto-reset); its first observation is handed out by `try_reset(env_id)`, as RLlib expects."""
+    Per step there is one C-ABI call (pinned actions -> H2D -> step -> D2H of the output block into pinned host
+    memory) and O(E) vectorised numpy bookkeeping; the dicts `poll()` returns are LAZY (built per env on first
+    access, by the reference's population rules, drone_swarm_env.py:141-172).  `step_batch` / `last_batch` hand out
+    the same step as one dict of [E, ...] arrays -- including the `global_state` column [E, 6N+3] that the
+    reference's `GlobalStateCallback` (`training/callbacks.py:51-57`) stacks from per-agent infos in Python.  An
+    env whose episode ended is reset inside the same engine step (auto-reset); its first observation is handed
+    out by `try_reset(env_id)`, as RLlib expects."""
+
+    _FIELDS = ("obs", "dist", "global_state", "reward64", "terminated", "truncated", "reached", "collision",
+               "obs_valid", "all_terminated", "all_truncated")
 
     def __init__(self, num_envs: int, config: dict[str, Any] | None = None, device=None, base_seed: int | None = None):
         from .engine import SwarmEngine
@@ -330,76 +370,116 @@ class VectorSwarmEnv:
         seed0 = base_seed if base_seed is not None else (self.cfg.seed if self.cfg.seed is not None else _entropy_seed())
         self._engine.seed(np.uint64(seed0) + np.arange(self.num_envs, dtype=np.uint64))   # env e: seed0 + e
         self._engine.reset()
+        self._hn = {k: v.numpy() for k, v in self._engine.host_buffers().items()}   # pinned host views, made once
         self._active = np.ones((self.num_envs, self.num_drones), bool)   # membership in each env's .agents
-        self._pending = None       # outputs of the last step, not yet polled
+        self._pending = None       # (was_active) of the last step, not yet polled
         self._fresh = set(range(self.num_envs))   # envs whose (reset) observation has not been handed out
+        self._have_host = False
 
     def get_sub_environments(self):
         return []
 
-    def _snapshot(self):
-        import torch
+    # ------------------------------------------------------------------ batched (array) interface
+    def step_batch(self, actions) -> dict[str, np.ndarray]:
+        """One step of every env from an [E,N,3] float32 array (rows of drones outside `.agents` are ignored) ->
+        dict of pinned-host numpy VIEWS, valid until the next step: obs [E,N,D], reward [E,N] (float64),
+        terminated / truncated / reached / collision / obs_valid [E,N] u8, all_terminated / all_truncated [E] u8,
+        dist [E,N], global_state [E,6N+3], plus `was_active` [E,N] bool (the drones that were stepped)."""
+        act = self._hn["actions"]
+        act[...] = np.asarray(actions, dtype=np.float32).reshape(act.shape)
+        return self._step_from_host_actions()
 
-        e = self._engine
-        torch.cuda.synchronize(e.device)
-        return {k: getattr(e, k).cpu().numpy() for k in ("obs", "dist", "global_state", "reward64", "terminated",
-                                                         "truncated", "reached", "collision", "obs_valid",
-                                                         "all_terminated", "all_truncated")}
+    def _step_from_host_actions(self):
+        was_active = self._active.copy()
+        self._engine.step_host(None, auto_reset=True)
+        self._have_host = True
+        hn = self._hn
+        done = (hn["all_terminated"] | hn["all_truncated"]).astype(bool)
+        keep = hn["obs_valid"].astype(bool) & was_active & ~done[:, None]
+        self._active = np.where(done[:, None], True, keep)     # a finished env has already been reset by the engine
+        self._fresh.update(np.flatnonzero(done).tolist())
+        self._pending = (was_active, done, keep)
+        return self.last_batch()
 
-    def _reset_dicts(self, snap, e):
-        obs = {a: snap["obs"][e, i].copy() for i, a in enumerate(self.agent_ids)}
-        infos = {a: {"distance_to_goal": float(snap["dist"][e, i]), "global_state": snap["global_state"][e].copy()}
-                 for i, a in enumerate(self.agent_ids)}
+    def last_batch(self) -> dict[str, np.ndarray]:
+        hn = self._hn
+        out = {k: hn[k] for k in self._FIELDS}
+        out["reward"] = hn["reward64"]
+        if self._pending is not None:
+            out["was_active"] = self._pending[0]
+        return out
+
+    def global_state_column(self) -> np.ndarray:
+        """[E, 6N+3] float32: the centralized critic's input for every env (what `GlobalStateCallback` assembles)."""
+        return self._hn["global_state"]
+
+    # ------------------------------------------------------------------ RLlib BaseEnv-shaped interface
+    def _ensure_host(self):
+        if not self._have_host:
+            self._engine.fetch_outputs()
+            self._have_host = True
+
+    def _reset_dicts(self, e):
+        hn = self._hn
+        obs_rows, dist, gs = hn["obs"][e], hn["dist"][e].tolist(), hn["global_state"][e]
+        obs = {a: obs_rows[i].copy() for i, a in enumerate(self.agent_ids)}
+        infos = {a: {"distance_to_goal": dist[i], "global_state": gs.copy()} for i, a in enumerate(self.agent_ids)}
         return obs, infos
 
     def poll(self):
-        """-> (obs, rewards, terminateds, truncateds, infos, off_policy_actions), each {env_id: {agent_id: ...}}."""
-        obs, rew, term, trunc, infos = {}, {}, {}, {}, {}
+        """-> (obs, rewards, terminateds, truncateds, infos, off_policy_actions), each {env_id: {agent_id: ...}}
+        (lazy mappings over all env ids)."""
+        self._ensure_host()
+        E, hn, ids = self.num_envs, self._hn, self.agent_ids
         if self._pending is None:           # first poll: the reset observations
-            snap = self._snapshot()
-            for e in sorted(self._fresh):
-                obs[e], infos[e] = self._reset_dicts(snap, e)
-                rew[e], term[e], trunc[e] = {}, {"__all__": False}, {"__all__": False}
             self._fresh.clear()
-            self._last = snap
-            return obs, rew, term, trunc, infos, {}
-        snap, was_active = self._pending
+            cache: dict[int, tuple] = {}
+
+            def both(e):
+                if e not in cache:
+                    cache[e] = self._reset_dicts(e)
+                return cache[e]
+            return (_LazyEnvDicts(E, lambda e: both(e)[0]), _LazyEnvDicts(E, lambda e: {}),
+                    _LazyEnvDicts(E, lambda e: {"__all__": False}), _LazyEnvDicts(E, lambda e: {"__all__": False}),
+                    _LazyEnvDicts(E, lambda e: both(e)[1]), {})
+        was_active, done, keep = self._pending
         self._pending = None
-        self._last = snap
-        for e in range(self.num_envs):
-            done = bool(snap["all_terminated"][e] or snap["all_truncated"][e])
-            o, r, t, tr, inf = {}, {}, {}, {}, {}
-            for i, a in enumerate(self.agent_ids):
-                if not was_active[e, i]:
-                    continue
-                r[a] = float(snap["reward64"][e, i])
-                t[a] = bool(snap["terminated"][e, i])
-                tr[a] = bool(snap["truncated"][e, i])
-                keep = (not done) and bool(snap["obs_valid"][e, i])
-                if keep:   # drone_swarm_env.py:154-162 (after an auto-reset obs_valid describes the NEW episode)
-                    o[a] = snap["obs"][e, i].copy()
-                    inf[a] = {"distance_to_goal": float(snap["dist"][e, i]), "reached_goal": bool(snap["reached"][e, i]),
-                              "collision": bool(snap["collision"][e, i]), "global_state": snap["global_state"][e].copy()}
-                self._active[e, i] = keep
-            t["__all__"] = bool(snap["all_terminated"][e])
-            tr["__all__"] = bool(snap["all_truncated"][e])
-            if done:
-                self._active[e, :] = True      # the engine has already reset this env
-                self._fresh.add(e)
-            obs[e], rew[e], term[e], trunc[e], infos[e] = o, r, t, tr, inf
-        return obs, rew, term, trunc, infos, {}
+        # (the views below alias the pinned block: they stay valid until the next send_actions / step_batch)
+        rew64, term, trunc = hn["reward64"], hn["terminated"], hn["truncated"]
+
+        def obs_of(e):
+            rows = hn["obs"][e]
+            return {ids[i]: rows[i].copy() for i in np.flatnonzero(keep[e])}
+
+        def rew_of(e):
+            r = rew64[e].tolist()
+            return {ids[i]: r[i] for i in np.flatnonzero(was_active[e])}
+
+        def flags_of(arr, all_arr):
+            def f(e):
+                v = arr[e].tolist()
+                d = {ids[i]: bool(v[i]) for i in np.flatnonzero(was_active[e])}
+                d["__all__"] = bool(all_arr[e])
+                return d
+            return f
+
+        def infos_of(e):
+            dist, reached, col, gs = hn["dist"][e].tolist(), hn["reached"][e].tolist(), hn["collision"][e].tolist(), hn["global_state"][e]
+            return {ids[i]: {"distance_to_goal": dist[i], "reached_goal": bool(reached[i]), "collision": bool(col[i]),
+                             "global_state": gs.copy()} for i in np.flatnonzero(keep[e])}
+
+        return (_LazyEnvDicts(E, obs_of), _LazyEnvDicts(E, rew_of), _LazyEnvDicts(E, flags_of(term, hn["all_terminated"])),
+                _LazyEnvDicts(E, flags_of(trunc, hn["all_truncated"])), _LazyEnvDicts(E, infos_of), {})
 
     def send_actions(self, action_dict):
         """{env_id: {agent_id: action(3,)}}; agents without an action get zeros (drone_swarm_env.py:104)."""
-        import torch
-
-        act = np.zeros((self.num_envs, self.num_drones, 3), np.float32)
+        act = self._hn["actions"]
+        act[...] = 0.0
         for e, per_agent in action_dict.items():
+            row = act[e]
             for a, v in per_agent.items():
-                act[e, int(a.rsplit("_", 1)[1])] = np.asarray(v, dtype=np.float32).reshape(3)
-        was_active = self._active.copy()
-        self._engine.step(torch.from_numpy(act).to(self._engine.device), auto_reset=True)
-        self._pending = (self._snapshot(), was_active)
+                row[int(a.rsplit("_", 1)[1])] = v
+        self._step_from_host_actions()
 
     def try_reset(self, env_id=None, *, seed=None, options=None):
         """First observation of env `env_id`'s new episode -> ({env_id: obs}, {env_id: infos})."""
@@ -413,10 +493,11 @@ class VectorSwarmEnv:
                 seeds[env_id] = seed
                 self._engine.seed(seeds, mask)
             self._engine.reset(mask)
-            self._last = self._snapshot()
+            self._have_host = False
             self._active[env_id, :] = True
+        self._ensure_host()
         self._fresh.discard(env_id)
-        obs, infos = self._reset_dicts(self._last, env_id)
+        obs, infos = self._reset_dicts(env_id)
         return {env_id: obs}, {env_id: infos}
 
     def stop(self):

@@ -182,3 +182,102 @@ def test_vector_env_matches_per_env_facades():
     vec.stop()
     for r in refs:
         r.close()
+
+
+@pytest.mark.gpu
+def test_vector_env_batch_interface_and_lazy_dicts():
+    """`step_batch` hands out one dict of [E, ...] arrays (global_state column included) that agrees with the lazy
+    per-env dicts of `poll()` and with E separate facade envs; untouched envs cost no dict building."""
+    import swarm_b200
+
+    cfg = {"num_drones": 5, "num_obstacles": 4, "max_steps": 9, "world_size": 11.0}
+    E, base = 8, 900
+    vec = swarm_b200.VectorSwarmEnv(E, cfg, base_seed=base)
+    refs = [swarm_b200.DroneSwarmEnv({**cfg, "seed": base + e}) for e in range(E)]
+    obs0 = vec.poll()[0]
+    cur = []
+    for e, r in enumerate(refs):
+        o, _ = r.reset()
+        cur.append(o)
+        assert all(np.array_equal(obs0[e][a], o[a]) for a in o)
+    rng = np.random.default_rng(5)
+    for t in range(40):
+        act = rng.uniform(-1, 1, (E, 5, 3)).astype(np.float32)
+        b = vec.step_batch(act)
+        lazy = vec.poll()
+        assert lazy[0]._cache == {}                      # nothing built until somebody looks
+        assert b["global_state"].shape == (E, 6 * 5 + 3) and b["global_state"] is vec.global_state_column()
+        for e, r in enumerate(refs):
+            actions = {a: act[e, int(a[-1])] for a in cur[e]}
+            o, rw, te, tr, inf = r.step(actions)
+            done = te["__all__"] or tr["__all__"]
+            assert bool(b["all_terminated"][e]) == te["__all__"] and bool(b["all_truncated"][e]) == tr["__all__"]
+            for a in rw:
+                i = int(a[-1])
+                assert b["was_active"][e, i] and b["reward"][e, i] == rw[a]
+                assert bool(b["terminated"][e, i]) == te[a] and bool(b["truncated"][e, i]) == tr[a]
+            assert lazy[1][e] == rw and lazy[2][e] == te and lazy[3][e] == tr
+            assert set(lazy[0][e]) == set(o) and all(np.array_equal(lazy[0][e][a], o[a]) for a in o)
+            if not done:
+                for a in o:
+                    i = int(a[-1])
+                    assert np.array_equal(b["obs"][e, i], o[a])
+                    assert np.array_equal(b["global_state"][e], inf[a]["global_state"])
+                cur[e] = o
+            else:
+                ro, _ = vec.try_reset(e)
+                o2, _ = r.reset()
+                assert all(np.array_equal(ro[e][a], o2[a]) for a in o2)
+                cur[e] = o2
+    vec.stop()
+    for r in refs:
+        r.close()
+
+
+@pytest.mark.gpu
+def test_device_rollout_matches_the_per_env_facade_loop():
+    """`collect_rollout` (policy -> step -> [T,E,...] columns, all on the device, auto-reset on) against E facade
+    envs driven by the same deterministic policy in a Python loop with `env.reset()` on episode end: obs, rewards,
+    flags, the agent mask and the global_state column agree bit for bit (a fake RLlib sampler)."""
+    import torch
+    import swarm_b200
+
+    cfg = {"num_drones": 4, "num_obstacles": 5, "max_steps": 14, "world_size": 10.0}
+    E, T, base = 6, 45, 700
+
+    def policy_np(o):      # a deterministic stand-in for the actor: fly at the goal, wobble with the position
+        return np.tanh(0.4 * o[..., 6:9] + 0.2 * np.sin(3.0 * o[..., 0:3])).astype(np.float32)
+
+    def policy_t(obs, valid):
+        # (same arithmetic on the host for both sides, so the comparison is about the env, not about libm)
+        return torch.from_numpy(policy_np(obs.cpu().numpy())).to(obs.device)
+
+    eng = swarm_b200.SwarmEngine(E, cfg, device="cuda:0", reward64=True)
+    eng.seed(np.arange(base, base + E, dtype=np.uint64))
+    eng.reset()
+    ro = swarm_b200.collect_rollout(eng, policy_t, T, value_fn=lambda gs: gs.sum(-1))
+    got = {k: v.cpu().numpy() for k, v in ro.items()}
+    assert got["obs"].shape == (T, E, 4, eng.D) and got["global_state"].shape == (T, E, eng.R)
+    for e in range(E):
+        env = swarm_b200.DroneSwarmEnv({**cfg, "seed": base + e})
+        obs, infos = env.reset()
+        for t in range(T):
+            assert got["agent_mask"][t, e].tolist() == [a in obs for a in env.agent_ids], (e, t)
+            for a in obs:
+                i = env.agent_id_to_index[a]
+                assert np.array_equal(got["obs"][t, e, i], obs[a]), (e, t, a)
+                assert np.array_equal(got["global_state"][t, e], infos[a]["global_state"]), (e, t)
+            full = np.stack([obs.get(a, got["obs"][t, e, i]) for i, a in enumerate(env.agent_ids)])
+            act = policy_np(full)
+            actions = {a: act[env.agent_id_to_index[a]] for a in obs}
+            obs, rew, term, trunc, infos = env.step(actions)
+            for a in rew:
+                i = env.agent_id_to_index[a]
+                assert np.float32(rew[a]) == got["rewards"][t, e, i], (e, t, a)
+                assert term[a] == bool(got["terminateds"][t, e, i]) and trunc[a] == bool(got["truncateds"][t, e, i])
+            done = term["__all__"] or trunc["__all__"]
+            assert done == bool(got["dones"][t, e]), (e, t)
+            if done:
+                obs, infos = env.reset()
+        env.close()
+    assert np.allclose(got["values"], got["global_state"].sum(-1), rtol=1e-4, atol=1e-2)   # (a device-side sum)

@@ -521,6 +521,32 @@ def test_single_env_episode_statistics():
     assert succ > 0 and col > 0 and to > 0
 
 
+@pytest.mark.parametrize("kind,cfg", [("swarm", {"num_drones": 8, "num_obstacles": 4}),      # rotation-pass kernel
+                                      ("swarm", {"num_drones": 5, "num_obstacles": 3}),      # general kernel
+                                      ("swarm", {"num_drones": 64, "num_obstacles": 8, "world_size": 50.0}),   # wide kernel
+                                      ("single", {"num_obstacles": 8})])
+def test_nan_action_guard_counter(kind, cfg):
+    """np.clip lets a NaN action through (drone_swarm_env.py:105) and so does the engine -- the env's state is NaN
+    from then on, like the reference's; `stats()["nan_actions"]` counts the drones it was applied to."""
+    import torch
+    import swarm_b200
+    E = 64
+    eng = swarm_b200.SwarmEngine(E, cfg, kind=kind, device="cuda:0")
+    eng.seed(np.arange(E, dtype=np.uint64))
+    eng.reset()
+    N = eng.N
+    act = torch.zeros((E, N, 3), device="cuda:0")
+    eng.step(act, auto_reset=False)
+    assert eng.stats()["nan_actions"] == 0
+    act[3, 0, 1] = float("nan")
+    act[10, N - 1, :] = float("nan")
+    alive = eng.alive.clone()
+    eng.step(act, auto_reset=False)
+    want = int(alive[3, 0]) + int(alive[10, N - 1])
+    assert want == 2 and eng.stats()["nan_actions"] == want
+    assert bool(torch.isnan(eng.positions[3, 0]).any()) and not bool(torch.isnan(eng.positions[4]).any())
+
+
 def test_state_dict_roundtrip_continues_bit_exact():
     import torch
     import swarm_b200

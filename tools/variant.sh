@@ -20,5 +20,5 @@ for f in swarm_kernels.cu swarm_step_rot.cu swarm_step_rotx.cu swarm_abi.cu; do
   fi
 done
 wait
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $out/lib_$name.so $objs -lcudart
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $out/lib_$name.so $objs -lcudart -ldl
 echo "built $out/lib_$name.so ($flags)"
