@@ -433,19 +433,34 @@ def main():
             dist.all_reduce(se, op=dist.ReduceOp.SUM)
         h2d, d2h = eng.host_bytes_per_step()
         # what the link gives a bare pinned device->host copy of the largest output (explains the e2e number)
+        # (all ranks at once, behind a barrier: with several GPUs per host this is the ceiling the e2e number lives
+        #  under -- the ranks share the host's PCIe root complexes / memory controllers)
         pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         h["obs"].copy_(eng.obs, non_blocking=True)
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         pe0.record()
         for _ in range(4):
             h["obs"].copy_(eng.obs, non_blocking=True)
         pe1.record()
         torch.cuda.synchronize()
         link_gbs = 4 * eng.obs.numel() * 4 / (pe0.elapsed_time(pe1) * 1e-3) / 1e9
+        lk = torch.tensor([link_gbs, -link_gbs, link_gbs], dtype=torch.float64, device=dev)
+        if world > 1:
+            lmin = lk.clone()
+            dist.all_reduce(lmin, op=dist.ReduceOp.MIN)
+            dist.all_reduce(lk, op=dist.ReduceOp.SUM)
+            link_min, link_max, link_sum = float(lmin[0]), -float(lmin[1]), float(lk[2])
+        else:
+            link_min = link_max = link_sum = link_gbs
         e2e = {"value": float(se.item()) / (float(te.item()) * 1e-3), "unit": "agent-steps/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
                "ms_per_step": float(te.item()) / args.e2e_steps,
                "d2h_gbs": d2h / (float(te.item()) / args.e2e_steps * 1e-3) / 1e9, "link_d2h_gbs_measured": link_gbs,
+               "link_d2h_concurrent": {"ranks": world, "gbs_per_rank_min": link_min, "gbs_per_rank_max": link_max,
+                                       "gbs_total": link_sum,
+                                       "note": "bare pinned device->host copy of the obs tensor on every rank at once"},
                "path": "swarm_step_host: pinned host actions -> H2D -> fused step -> D2H of obs, reward, dist, "
                        "5 flag arrays, __all__ flags, global_state (4 env-axis chunks on side streams)"}
 

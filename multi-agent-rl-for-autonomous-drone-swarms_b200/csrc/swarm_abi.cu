@@ -48,6 +48,7 @@ struct SwarmHandle {
     bool rot_ok;             // the step launches run on swarm_step_rot_kernel (swarm_step_rot.cu)
     bool rot_fused;          // ... with the auto-reset inside the step launch (SWARM_B200_FUSED_RESET=0: second launch)
     int rot_blocks_per_sm;
+    int multi_step_max_groups;   // swarm_step_many: batches up to this many env groups run all steps in ONE launch
     bool rotx_ok;            // N = 64 / 128: swarm_step_rotx_kernel (swarm_step_rotx.cu)
     int rotx_blocks_per_sm;        // step launch
     int rotx_reset_blocks_per_sm;  // auto-reset launch (lighter kernel, more CTAs per SM)
@@ -346,7 +347,8 @@ int launch(SwarmHandle* h, DevParams& p, int env_begin, int env_count, cudaStrea
     const int rotx_needed = (p.n_groups + rotx_warps_per_cta() - 1) / rotx_warps_per_cta();
     const int rotx_resident = h->num_sms * h->rotx_blocks_per_sm;
     const int rotx_grid = rotx_needed < rotx_resident ? rotx_needed : rotx_resident;
-    p.fused_reset = rot && p.auto_reset && h->rot_fused ? 1 : 0;
+    if (p.n_steps < 1) p.n_steps = 1;
+    p.fused_reset = rot && ((p.auto_reset && h->rot_fused) || p.n_steps > 1) ? 1 : 0;
     const bool two_launch = p.mode == kModeStep && p.auto_reset && (p.N <= 32 || rotx) && !p.fused_reset;
     // the step kernel lists the groups that need a reset for the launch behind it: two lists used alternately, the
     // current one chosen on the device (reset_epoch), so there is no per-launch host state (CUDA-graph safe)
@@ -472,6 +474,8 @@ int swarm_create(const SwarmConfig* cfg, SwarmHandle** out) {
         h->rot_ok = h->rot_blocks_per_sm >= 1;
     }
     h->rot_fused = false;   // (measured slower than the second launch so far: see DESIGN.md)
+    h->multi_step_max_groups = 2 * h->num_sms * 28;   // up to ~2 groups per resident warp
+    if (const char* mg = std::getenv("SWARM_B200_MULTI_STEP_MAX_GROUPS")) h->multi_step_max_groups = std::atoi(mg);
     if (const char* fr = std::getenv("SWARM_B200_FUSED_RESET")) h->rot_fused = fr[0] != '0';
     h->rotx_ok = false;
     h->rotx_blocks_per_sm = 0;
@@ -608,6 +612,18 @@ int swarm_step_many(SwarmHandle* h, const SwarmBuffers* bufs, const float* actio
     p.mode = kModeStep;
     p.auto_reset = auto_reset ? 1 : 0;
     const size_t per_step = (size_t)p.E * p.N * 3;
+    // small batches are bound by launch latency and by the ramp / tail of every launch, not by the device: there ALL
+    // the steps run in one launch of the fused rotation-pass kernel (static env ownership per warp, in-warp
+    // auto-reset, no barrier between steps); larger ones are faster as one step + one reset launch per step
+    const int n_groups_all = (p.E + p.G - 1) / p.G;
+    if (n_steps > 1 && h->rot_ok && n_groups_all <= h->multi_step_max_groups &&
+        (reinterpret_cast<uintptr_t>(actions) & 15u) == 0 && (per_step & 3u) == 0) {
+        DevParams q = p;
+        q.actions = actions;
+        q.n_steps = n_steps;
+        q.action_step_stride = (long long)per_step;
+        return launch(h, q, 0, p.E, static_cast<cudaStream_t>(stream));
+    }
     for (int t = 0; t < n_steps; ++t) {
         DevParams q = p;
         q.actions = actions + (size_t)t * per_step;

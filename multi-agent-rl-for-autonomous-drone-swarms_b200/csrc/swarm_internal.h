@@ -41,6 +41,9 @@ struct DevParams {
     int mode;                     // Mode
     int auto_reset;
     int fused_reset;              // rotation-pass step launch: the auto-reset runs inside it (one launch per step)
+    int n_steps;                  // ... and that launch runs this many consecutive steps (swarm_step_many, small batches):
+                                  //   step t reads actions + t * action_step_stride
+    long long action_step_stride;
     int max_steps;
     // float32 constants the reference's numpy expressions effectively use
     float amax, dt, vmax, eps_speed, bound;

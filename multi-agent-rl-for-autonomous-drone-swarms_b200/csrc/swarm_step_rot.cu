@@ -149,7 +149,9 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
 #if SWARM_ROT_PDL && SWARM_ROT_EARLY_TRIGGER
     // step launch: let the reset launch behind it place its CTAs as slots come free during this launch's tail (they
     // sit in their griddepcontrol.wait until this launch has completed), instead of being launched only then
-    if (MODE == kRotStep) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // (only when that reset launch really follows: an early trigger releases whatever comes next in the stream, and a
+    //  step launch of this kernel does not wait at its top)
+    if (MODE == kRotStep && P.auto_reset) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
     int env0_pref = 0;
     const int* rlist = P.reset_list;
@@ -176,8 +178,9 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
     // env inbox: goal4[G] | obst4[G*M] | dr[2G] | step_count[G] | ep_return[G]
     const int goal_off = 0, obst_off = 16 * G, dr_off = 16 * G * (1 + M);
     const int sc_off = dr_off + (DR ? 32 * G : 0);
-    auto issue = [&](int grp, int buf) {
+    auto issue = [&](int grp, int buf, int t_step = 0) {
         if (!kStepLike) return;
+        const float* const actions = kFused ? P.actions + (long long)t_step * P.action_step_stride : P.actions;
         const int env0 = P.env_begin + grp * G;
         const int n_env = G == 1 ? 1 : min(G, env_end - env0);
         if (kOverlap && !dep_waited) {   // (warp-uniform) a group the running reset launch may still be writing?
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
             mbar_expect_tx(bar, n_ag * 44u + (unsigned)n_env * (16u + 16u * M + (DR ? 32u : 0u)));
             bulk_g2s(dsta, P.pos4 + a0, n_ag * 16u, bar);
             bulk_g2s(dsta + 512, P.vel4 + a0, n_ag * 16u, bar);
-            bulk_g2s(dsta + 1024, P.actions + a0 * 3, n_ag * 12u, bar);
+            bulk_g2s(dsta + 1024, actions + a0 * 3, n_ag * 12u, bar);
             bulk_g2s(dst + goal_off, P.goal4 + env0, (unsigned)n_env * 16u, bar);
             bulk_g2s(dst + obst_off, P.obst4 + (long long)env0 * M, (unsigned)(n_env * M) * 16u, bar);
             if (DR) bulk_g2s(dst + dr_off, P.dr_params + (long long)env0 * 2, (unsigned)n_env * 32u, bar);
@@ -212,7 +215,7 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
                 cp_async16(dsta + lane * 16, P.pos4 + a0 + lane);
                 cp_async16(dsta + 512 + lane * 16, P.vel4 + a0 + lane);
             }
-            if (lane * 4 < n_ag * 3) cp_async16(dsta + 1024 + lane * 16, P.actions + a0 * 3 + lane * 4);
+            if (lane * 4 < n_ag * 3) cp_async16(dsta + 1024 + lane * 16, actions + a0 * 3 + lane * 4);
             if (lane < n_env) cp_async16(dst + goal_off + lane * 16, P.goal4 + env0 + lane);
             for (int idx = lane; idx < n_env * M; idx += 32)
                 cp_async16(dst + obst_off + idx * 16, P.obst4 + (long long)env0 * M + idx);
@@ -232,13 +235,25 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
     //  one address; the reset launch has ~1-2 items per warp and keeps a static stride throughout)
     const int warps_total = gridDim.x * kRotWarps;
     int it = blockIdx.x * kRotWarps + warp;
-    if (it < n_iter) issue(it, 0);
+    // Fused launch: STATIC ownership -- this warp's groups are it, it + W, it + 2 W, ... -- and n_steps consecutive
+    // steps in one launch (swarm_step_many on small batches): the items of a warp are (step 0: its groups in order),
+    // (step 1: ...), ...  No warp ever touches another warp's envs, so the steps need no grid-wide barrier; a group's
+    // state goes through global memory between steps (written by this warp's generic stores, read back by its bulk
+    // copies: fence.proxy.async at the end of every item).
+    const int ms_steps = kFused ? max(P.n_steps, 1) : 1;
+    const int ms_own = (kFused && it < n_iter) ? (n_iter - it + warps_total - 1) / warps_total : 0;   // groups owned
+    int ms_t = 0, ms_j = 0;          // current item: step ms_t, own group number ms_j
+    if (it < n_iter) issue(it, 0, 0);
     unsigned phase = 0;  // bit b: parity the next wait on mbarrier b uses
 
     int buf = 0;
     while (it < n_iter) {
         int it_next = 0;
-        if (kStepLike) {
+        int ms_tn = ms_t, ms_jn = ms_j + 1;   // fused: the item after this one
+        if (kFused) {
+            if (ms_jn == ms_own) { ms_jn = 0; ++ms_tn; }
+            it_next = ms_tn < ms_steps ? (int)(blockIdx.x * kRotWarps + warp) + ms_jn * warps_total : n_iter;
+        } else if (kStepLike) {
             if (lane == 0) it_next = warps_total + (int)atom_inc_lane(queue, tid_y);
         } else {
             it_next = it + warps_total;
@@ -473,8 +488,10 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
             // every lane has consumed the agent inbox (its values went through the integrator): refill it,
             // and the other env inbox, with the next group's inputs
             if (pass == 0) {
-                it_next = __shfl_sync(FULL_MASK, it_next, 0);
-                if (kStepLike && it_next < n_iter) issue(it_next, buf ^ 1);
+                if (!kFused) it_next = __shfl_sync(FULL_MASK, it_next, 0);
+                // (fused, one group per warp: the next item is THIS group one step later -- its inputs are this
+                //  item's outputs, so they are fetched at the end of the item instead)
+                if (kStepLike && it_next < n_iter && !(kFused && ms_own == 1)) issue(it_next, buf ^ 1, ms_tn);
             }
             // velocity / previous goal distance wait in the tile row (slots 32-35) while the scans need the registers
             srow[32] = v.x; srow[33] = v.y; srow[34] = v.z; srow[35] = prev_d;
@@ -957,6 +974,14 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
             if (!kFused || pass != 0 || redraw_envs == 0u) break;
             reset_envs = redraw_envs;   // pass 1: env.reset() + observation of the envs whose episode just ended
         }
+        if (kFused && ms_steps > 1) {
+            // this item's state stores (generic proxy) must be visible to the bulk copies (async proxy) that read them
+            // back one step later
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            __syncwarp();
+            if (ms_own == 1 && it_next < n_iter) issue(it_next, buf ^ 1, ms_tn);
+        }
+        ms_t = ms_tn; ms_j = ms_jn;
         it = it_next;
         buf ^= 1;
     }
@@ -965,9 +990,8 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
     if (kOverlap && !dep_waited) asm volatile("griddepcontrol.wait;" ::: "memory");   // never exit without it
 #endif
     // the last warp to leave re-arms the queue for the next launch
-#if SWARM_ROT_PDL
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-#endif
+    // (no trigger here: a launch that has not triggered early releases its dependents when it has COMPLETED, with its
+    //  stores flushed -- the step launch behind it relies on that, it does not wait at its top)
     if (kStepLike) {
         if (lane == 0 && atomicAdd(queue + 1, 1u) == (unsigned)warps_total - 1u) {
             queue[0] = 0u;

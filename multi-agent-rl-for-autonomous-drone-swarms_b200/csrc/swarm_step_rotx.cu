@@ -692,7 +692,9 @@ swarm_step_rotx_kernel(const DevParams P) {
         it = it_next;
         buf ^= 1;
     }
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // (only a step launch with its reset launch behind it -- which waits at its top -- may release its dependents
+    //  before it has completed: see swarm_step_rot.cu)
+    if (STEP && P.auto_reset) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (lane == 0 && atomicAdd(queue + 1, 1u) == (unsigned)warps_total - 1u) {  // last warp out re-arms the queue
         queue[0] = 0u;
         queue[1] = 0u;

@@ -286,29 +286,60 @@ class SwarmEngine:
     # ------------------------------------------------------------------ (de)serialisation
     _STATE_KEYS = ("pos4", "vel4", "goal4", "obst4", "step_count", "rng", "ep_return", "stats_words")
 
+    def _meta(self) -> dict[str, Any]:
+        """Everything a trajectory depends on besides the state tensors: shapes, the whole env config, the
+        randomisation spec and its stream keys."""
+        import dataclasses
+        return dict(kind=self.kind, E=self.E, N=self.N, M=self.M, K=self.K, S=self.S,
+                    config=dataclasses.asdict(self.cfg), norm_mode=int(self._c.norm_mode),
+                    domain_randomization={k: (list(v) if isinstance(v, (tuple, list)) else v) for k, v in (self.dr or {}).items()},
+                    dr_seed=int(self._c.dr_seed), env_index_base=int(self._c.env_index_base),
+                    global_state=self.global_state is not None, reward64=self.reward64 is not None)
+
     def state_dict(self) -> dict[str, Any]:
         """Everything needed to continue every env bit-for-bit (the reference never checkpoints env
-        state; RLlib resumes only the policy).  CPU tensors, safe to `torch.save`."""
+        state; RLlib resumes only the policy): the state tensors, the output block of the last call
+        (obs, obs_valid, rewards, flags -- so that what a caller reads before the next step is restored too) and a
+        `meta` record that `load_state_dict` checks.  CPU tensors, safe to `torch.save`."""
         torch.cuda.synchronize(self.device)
         out = {k: getattr(self, k).detach().cpu().clone() for k in self._STATE_KEYS}
+        out["outputs"] = self._out_block.detach().cpu().clone()
+        for k in ("episode_return", "episode_length"):
+            out[k] = getattr(self, k).detach().cpu().clone()
         if self.dr_params is not None:
             out["dr_params"] = self.dr_params.detach().cpu().clone()
         if self.act_hist is not None:
             out["act_hist"] = self.act_hist.detach().cpu().clone()
-        out["meta"] = dict(kind=self.kind, E=self.E, N=self.N, M=self.M, K=self.K, S=self.S)
+        out["meta"] = self._meta()
         return out
 
-    def load_state_dict(self, state: dict[str, Any], observe: bool = True):
-        meta = state.get("meta", {})
-        mine = dict(kind=self.kind, E=self.E, N=self.N, M=self.M, K=self.K, S=self.S)
-        if meta and meta != mine:
-            raise ValueError(f"state_dict is for {meta}, this engine is {mine}")
+    def load_state_dict(self, state: dict[str, Any], observe: bool = False):
+        """Restore `state_dict()` output.  The engine must have been built with the same shapes, env config,
+        randomisation spec, `dr_seed` and `env_index_base` -- anything else would silently continue a different
+        trajectory, so a mismatch raises with the differing keys."""
+        meta, mine = dict(state.get("meta", {})), self._meta()
+
+        def canon(x):
+            if isinstance(x, dict):
+                return {k: canon(v) for k, v in x.items()}
+            return list(x) if isinstance(x, (tuple, list)) else x
+        diff = sorted(k for k in set(meta) | set(mine) if canon(meta.get(k)) != canon(mine.get(k)))
+        if diff:
+            raise ValueError("state_dict does not belong to an engine like this one; differing: " +
+                             ", ".join(f"{k}: saved {meta.get(k)!r} vs this {mine.get(k)!r}" for k in diff))
         for k in self._STATE_KEYS:
             getattr(self, k).copy_(state[k].to(self.device))
+        for k in ("episode_return", "episode_length"):
+            if k in state:
+                getattr(self, k).copy_(state[k].to(self.device))
         if self.dr_params is not None:
             self.dr_params.copy_(state["dr_params"].to(self.device))
         if self.act_hist is not None:
             self.act_hist.copy_(state["act_hist"].to(self.device))
+        if "outputs" in state and state["outputs"].numel() == self._out_block.numel():
+            self._out_block.copy_(state["outputs"].to(self.device))
+        elif not observe:
+            observe = True
         if observe:
             self.observe()
 

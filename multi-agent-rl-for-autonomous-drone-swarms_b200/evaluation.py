@@ -20,15 +20,24 @@ from typing import Callable
 import torch
 
 
-def _formation_error(pos: torch.Tensor, mask: torch.Tensor, spacing: float) -> torch.Tensor:
-    """evaluate_protocol.py:103-116 over the drones selected by `mask`: [E,N,3], [E,N] -> [E]."""
-    d = torch.linalg.vector_norm(pos[:, :, None, :] - pos[:, None, :, :], dim=-1).double()
-    pair = mask[:, :, None] & mask[:, None, :] & ~torch.eye(pos.shape[1], dtype=torch.bool, device=pos.device)
-    cnt = pair.sum(-1)
-    per = (torch.abs(d - spacing) * pair).sum(-1) / cnt.clamp(min=1)
-    n = mask.sum(-1)
-    fe = (per * mask).sum(-1) / n.clamp(min=1)
-    return torch.where(n > 1, fe, torch.zeros_like(fe))
+def _formation_error(pos: torch.Tensor, mask: torch.Tensor, spacing: float, chunk_bytes: int = 64 << 20) -> torch.Tensor:
+    """evaluate_protocol.py:103-116 over the drones selected by `mask`: [E,N,3], [E,N] -> [E].
+    Chunked over the env axis so that the [e, N, N, 3] difference temporary stays below `chunk_bytes` (at BASELINE
+    config 5 -- 8192 envs x 128 drones -- the unchunked temporary would be 1.6 GB per step)."""
+    E, N = pos.shape[0], pos.shape[1]
+    out = torch.zeros(E, dtype=torch.float64, device=pos.device)
+    eye = torch.eye(N, dtype=torch.bool, device=pos.device)
+    step = max(1, int(chunk_bytes // max(N * N * 3 * 4, 1)))
+    for lo in range(0, E, step):
+        p, m = pos[lo:lo + step], mask[lo:lo + step]
+        d = torch.linalg.vector_norm(p[:, :, None, :] - p[:, None, :, :], dim=-1).double()
+        pair = m[:, :, None] & m[:, None, :] & ~eye
+        cnt = pair.sum(-1)
+        per = (torch.abs(d - spacing) * pair).sum(-1) / cnt.clamp(min=1)
+        n = m.sum(-1)
+        fe = (per * m).sum(-1) / n.clamp(min=1)
+        out[lo:lo + step] = torch.where(n > 1, fe, torch.zeros_like(fe))
+    return out
 
 
 @torch.no_grad()
