@@ -726,11 +726,17 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
     const bool listed = MODE == kSmallAux && P.mode == kModeAutoReset;
     // auto-reset hand-over: list (epoch & 1) is appended to by the step launch, list ((epoch - 1) & 1) is walked by
     // the aux launch behind it (swarm_internal.h)
-    const unsigned epoch = P.reset_epoch ? *reinterpret_cast<const volatile unsigned*>(P.reset_epoch) : 0u;
-    const unsigned lpar = MODE == kSmallStep ? (epoch & 1u) : ((epoch - 1u) & 1u);
-    unsigned* const rcount = P.reset_count + lpar;
-    int* const rlist = P.reset_list + lpar * P.reset_list_stride;
-    const int n_iter = listed ? (int)*reinterpret_cast<const volatile unsigned*>(rcount) : P.n_groups;
+    // (the step launch re-reads the epoch where it needs it -- a rare path -- instead of carrying list pointers in
+    //  registers through the whole kernel: they cost the physics instantiation 48 bytes of spills and 13 %)
+    const int* rlist = P.reset_list;
+    int n_iter = P.n_groups;
+    unsigned aux_epoch = 0u;
+    if (listed) {
+        aux_epoch = *reinterpret_cast<const volatile unsigned*>(P.reset_epoch);
+        const unsigned lpar = (aux_epoch - 1u) & 1u;
+        rlist = P.reset_list + lpar * P.reset_list_stride;
+        n_iter = (int)*reinterpret_cast<const volatile unsigned*>(P.reset_count + lpar);
+    }
 
     // cp.async prefetch of one group's inputs into an inbox (step kernel only)
     auto prefetch = [&](int grp, int buf) {
@@ -1445,7 +1451,10 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
             }
             if (P.auto_reset) {  // groups with an env to reset go on the list the aux launch walks
                 const unsigned rl = __ballot_sync(FULL_MASK, leader && need_reset);
-                if (rl != 0 && lane == 0) rlist[atomicAdd(rcount, 1u)] = env0;
+                if (rl != 0 && lane == 0) {
+                    const unsigned lpar = *reinterpret_cast<const volatile unsigned*>(P.reset_epoch) & 1u;
+                    P.reset_list[lpar * P.reset_list_stride + atomicAdd(P.reset_count + lpar, 1u)] = env0;
+                }
             }
             {   // actions applied / envs stepped by this warp in this group
                 const unsigned act_envs = __ballot_sync(FULL_MASK, leader && env_active);
@@ -1487,6 +1496,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
             P.work_counter[0] = 0u;
             P.work_counter[1] = 0u;
             if (MODE == kSmallStep && P.auto_reset) {
+                const unsigned epoch = *reinterpret_cast<const volatile unsigned*>(P.reset_epoch);
                 P.reset_count[(epoch + 1u) & 1u] = 0u;
                 *P.reset_epoch = epoch + 1u;
             }

@@ -4,10 +4,11 @@ tag=$1
 out=gpurun_out
 tools/quick_bench.sh warm c4 >/dev/null 2>&1
 python bench.py > $out/bench_full_$tag.json 2> $out/bench_full_$tag.err
-python bench.py --impl reference --steps 3 --warmup 1 > $out/bench_ref_$tag.json 2> $out/bench_ref_$tag.err
+python bench.py --impl reference --steps 20 --warmup 5 > $out/bench_ref_$tag.json 2> $out/bench_ref_$tag.err
 tools/quick_bench.sh $tag c2 c3 c1 c5 c5_w70 c4_w44 phys phys8
+python tools/facade_latency.py > $out/facade_latency_$tag.json 2> $out/facade_latency_$tag.err
 for dr in on off; do
-  CMD="python bench.py --steps 12 --warmup 4 --no-cpu --no-e2e --no-dr-off --dr $dr"
+  CMD="python bench.py --steps 12 --warmup 4 --no-cpu --no-e2e --no-dr-off --no-named-sizes --dr $dr"
   $CMD > $out/plain_${tag}_$dr.log 2>&1 || { echo "plain run failed ($dr)"; continue; }
   if [ $dr = on ]; then
     ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $out/launches_$tag.csv $CMD > $out/ncu_${tag}_list.log 2>&1
