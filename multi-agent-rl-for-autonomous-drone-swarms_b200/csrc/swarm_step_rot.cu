@@ -178,11 +178,22 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
     // env inbox: goal4[G] | obst4[G*M] | dr[2G] | step_count[G] | ep_return[G]
     const int goal_off = 0, obst_off = 16 * G, dr_off = 16 * G * (1 + M);
     const int sc_off = dr_off + (DR ? 32 * G : 0);
-    auto issue = [&](int grp, int buf, int t_step = 0) {
+    // only_actions: the resident mode of the fused multi-step launch (one group per warp) -- the group's state is
+    // already in this warp's inboxes, written back there by the previous step; only the next step's actions are fetched
+    auto issue = [&](int grp, int buf, int t_step = 0, bool only_actions = false) {
         if (!kStepLike) return;
         const float* const actions = kFused ? P.actions + (long long)t_step * P.action_step_stride : P.actions;
         const int env0 = P.env_begin + grp * G;
         const int n_env = G == 1 ? 1 : min(G, env_end - env0);
+        if (kFused && only_actions) {
+            if (lane == 0) {
+                const unsigned n_ag = (unsigned)(n_env * N);
+                mbar_expect_tx(bar0 + 8 * buf, n_ag * 12u);
+                bulk_g2s(bar0 + 16 + 1024, actions + (long long)env0 * N * 3, n_ag * 12u, bar0 + 8 * buf);
+            }
+            cp_async_commit();
+            return;
+        }
         if (kOverlap && !dep_waited) {   // (warp-uniform) a group the running reset launch may still be writing?
             const bool flagged = lane < n_env && P.reset_mask[env0 + lane] != 0;
             if (__any_sync(FULL_MASK, flagged)) {
@@ -243,6 +254,12 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
     const int ms_steps = kFused ? max(P.n_steps, 1) : 1;
     const int ms_own = (kFused && it < n_iter) ? (n_iter - it + warps_total - 1) / warps_total : 0;   // groups owned
     int ms_t = 0, ms_j = 0;          // current item: step ms_t, own group number ms_j
+    // RESIDENT mode (one group per warp, several steps): the next item is the SAME group one step later, so its
+    // state does not go through global memory and back -- the epilogue also writes pos / vel / step count / return
+    // (and a reset its goal / obstacles / DR constants) into this warp's inboxes, the env inbox is not flipped, and
+    // only the next step's actions are fetched, half an item ahead as usual.  (The global state is still written
+    // every step: it is an output of the call.)
+    const bool resident = kFused && ms_own == 1 && ms_steps > 1 && SWARM_ROT_TMA_LOADS;
     if (it < n_iter) issue(it, 0, 0);
     unsigned phase = 0;  // bit b: parity the next wait on mbarrier b uses
 
@@ -417,13 +434,19 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
                                     if (uu < P.dr_delay_cum[k]) pick = k;
                                 delay = (float)P.dr_delay_values[pick];
                             }
-                            P.dr_params[(long long)renv * 2 + 0] =
+                            const float4 d0 =
                                 make_float4(__double2float_rn(__ddiv_rn(__dmul_rn(P.dr_max_accel, s_acc), s_mass)),
                                             __double2float_rn(__dmul_rn(P.dr_max_speed, s_spd)),
                                             __double2float_rn(__dmul_rn(P.dr_dt, s_dt)), __double2float_rn(half_w));
-                            P.dr_params[(long long)renv * 2 + 1] =
+                            const float4 d1 =
                                 make_float4(__double2float_rn(__dadd_rn(P.dr_r_c, __dmul_rn(P.dr_r_o, s_rad))),
                                             __uint_as_float(rb.z), __double2float_rn(world), delay);
+                            P.dr_params[(long long)renv * 2 + 0] = d0;
+                            P.dr_params[(long long)renv * 2 + 1] = d1;
+                            if (kFused) {   // (resident mode reads them from here on the next step)
+                                float4* drp = reinterpret_cast<float4*>(ib + dr_off) + 2 * el;
+                                drp[0] = d0; drp[1] = d1;
+                            }
                         }
                         if (e_l == el) ekey = rb.z;  // (the dynamics constants are not needed to observe)
                     }
@@ -491,7 +514,10 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
                 if (!kFused) it_next = __shfl_sync(FULL_MASK, it_next, 0);
                 // (fused, one group per warp: the next item is THIS group one step later -- its inputs are this
                 //  item's outputs, so they are fetched at the end of the item instead)
-                if (kStepLike && it_next < n_iter && !(kFused && ms_own == 1)) issue(it_next, buf ^ 1, ms_tn);
+                if (kStepLike && it_next < n_iter) {
+                    if (resident) issue(it_next, buf, ms_tn, true);
+                    else if (!(kFused && ms_own == 1)) issue(it_next, buf ^ 1, ms_tn);
+                }
             }
             // velocity / previous goal distance wait in the tile row (slots 32-35) while the scans need the registers
             srow[32] = v.x; srow[33] = v.y; srow[34] = v.z; srow[35] = prev_d;
@@ -909,6 +935,11 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
                         P.obs_valid[a] = valid ? 1 : 0;
                         P.pos4[a] = make_float4(p.x, p.y, p.z, alive_next ? 1.0f : 0.0f);
                         P.vel4[a] = make_float4(v.x, v.y, v.z, 0.0f);
+                        if (kFused && resident) {   // the next step reads its state from the inbox, not from global memory
+                            float4* box = const_cast<float4*>(in_pos);
+                            box[lane] = make_float4(p.x, p.y, p.z, alive_next ? 1.0f : 0.0f);
+                            box[32 + lane] = make_float4(v.x, v.y, v.z, 0.0f);
+                        }
                         if (P.gs) {
                             float* row = P.gs + (long long)env * P.R;
                             __stcs(row + 3 * i + 0, p.x); __stcs(row + 3 * i + 1, p.y); __stcs(row + 3 * i + 2, p.z);
@@ -935,6 +966,10 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
                     if (!need_reset) {
                         P.step_count[env] = sc_new;
                         P.ep_return[env] = ep_over ? 0.0f : ret;
+                        if (kFused && resident) {
+                            reinterpret_cast<int*>(ib + sc_off)[e_l] = sc_new;
+                            reinterpret_cast<float*>(ib + sc_off)[G + e_l] = ep_over ? 0.0f : ret;
+                        }
                         if (P.gs) {
                             float* row = P.gs + (long long)env * P.R + 6 * N;
                             __stcs(row + 0, gx); __stcs(row + 1, gy); __stcs(row + 2, gz);
@@ -962,6 +997,15 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
                     P.obs_valid[a] = 1;
                     P.pos4[a] = make_float4(p.x, p.y, p.z, 1.0f);
                     P.vel4[a] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (kFused && resident) {   // (goal / obstacles / DR constants of the new episode are in the env inbox already)
+                        float4* box = const_cast<float4*>(in_pos);
+                        box[lane] = make_float4(p.x, p.y, p.z, 1.0f);
+                        box[32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (i == 0) {
+                            reinterpret_cast<int*>(ib + sc_off)[e_l] = 0;
+                            reinterpret_cast<float*>(ib + sc_off)[G + e_l] = 0.0f;
+                        }
+                    }
                     if (P.gs) {
                         float* row = P.gs + (long long)env * P.R;
                         __stcs(row + 3 * i + 0, p.x); __stcs(row + 3 * i + 1, p.y); __stcs(row + 3 * i + 2, p.z);
@@ -977,13 +1021,15 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
         if (kFused && ms_steps > 1) {
             // this item's state stores (generic proxy) must be visible to the bulk copies (async proxy) that read them
             // back one step later
-            asm volatile("fence.proxy.async.global;" ::: "memory");
-            __syncwarp();
-            if (ms_own == 1 && it_next < n_iter) issue(it_next, buf ^ 1, ms_tn);
+            if (!resident) {
+                asm volatile("fence.proxy.async.global;" ::: "memory");
+                __syncwarp();
+                if (ms_own == 1 && it_next < n_iter) issue(it_next, buf ^ 1, ms_tn);
+            }
         }
         ms_t = ms_tn; ms_j = ms_jn;
         it = it_next;
-        buf ^= 1;
+        if (!resident) buf ^= 1;
     }
     if (MODE == kRotStep && n_local > 0) flush_list();
 #if SWARM_ROT_PDL

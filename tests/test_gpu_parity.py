@@ -429,6 +429,9 @@ def test_sharded_swarm_invariance_with_randomisation_and_delay(N, M):
 
 @pytest.mark.parametrize("cfg,E,dr", [({"num_drones": 8, "num_obstacles": 4, "max_steps": 25}, 1000, False),
                                       ({"num_drones": 32, "num_obstacles": 8, "max_steps": 30}, 300, True),
+                                      # more groups than resident warps: some warps own two groups (no resident state)
+                                      ({"num_drones": 32, "num_obstacles": 8, "max_steps": 30}, 6000, False),
+                                      ({"num_drones": 16, "num_obstacles": 4, "max_steps": 20}, 9001, True),
                                       ({"num_drones": 128, "num_obstacles": 8, "world_size": 60.0}, 64, False),
                                       ({"num_drones": 5, "num_obstacles": 3, "max_steps": 20}, 500, False)])
 def test_step_many_and_graph_replay_match_the_step_loop(cfg, E, dr):
