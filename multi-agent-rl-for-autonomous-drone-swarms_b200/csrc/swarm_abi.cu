@@ -107,8 +107,7 @@ int validate(const SwarmConfig* c) {
         return fail(SWARM_E_UNSUPPORTED, "neighbor_k %d outside [0, %d]", c->neighbor_k, SWARM_MAX_NEIGHBOR_K);
     if (c->norm_mode != 0 && c->norm_mode != 1) return fail(SWARM_E_INVALID, "norm_mode must be 0 or 1");
     if (c->dr_enabled) {
-        if (c->num_drones > 32 || c->norm_mode != 0)
-            return fail(SWARM_E_UNSUPPORTED, "domain randomisation needs num_drones <= 32 and norm_mode 0");
+        if (c->norm_mode != 0) return fail(SWARM_E_UNSUPPORTED, "domain randomisation needs norm_mode 0");
         const double* rng[6] = {c->dr_mass_scale, c->dr_max_accel_scale, c->dr_max_speed_scale, c->dr_dt_scale,
                                 c->dr_obstacle_radius_scale, c->dr_world_size_scale};
         for (int k = 0; k < 6; ++k)
@@ -316,13 +315,14 @@ bool rot_eligible(const SwarmConfig& c) {
 
 // The wide rotation-pass kernels (several drones per lane) cover the dense swarms of BASELINE config 5.
 bool rotx_eligible(const SwarmConfig& c) {
-    if (c.env_kind != SWARM_KIND_SWARM || c.norm_mode != 0 || c.dr_enabled) return false;
+    if (c.env_kind != SWARM_KIND_SWARM || c.norm_mode != 0) return false;
     if (c.num_drones != 64 && c.num_drones != 128) return false;
     if (c.neighbor_k != 3 || c.sensed_obstacles != 4) return false;
     if (c.num_obstacles < 4 || c.num_obstacles > 32 || (c.num_obstacles & 3)) return false;
     const double ds = c.desired_spacing;
     if (!(ds >= 0.0) || !(ds < 512.0) || std::ldexp(ds, 37) != std::floor(std::ldexp(ds, 37))) return false;
-    if (!(c.world_size < 256.0)) return false;   // 127 terms, each < 512: the float64 formation sum stays exact
+    const double wscale = c.dr_enabled ? c.dr_world_size_scale[1] : 1.0;
+    if (!(c.world_size * wscale < 256.0)) return false;   // 127 terms, each < 512: the float64 formation sum stays exact
     const char* off = std::getenv("SWARM_B200_NO_ROT");
     return !(off && off[0] == '1');
 }

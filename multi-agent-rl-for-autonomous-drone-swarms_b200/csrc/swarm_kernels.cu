@@ -247,12 +247,36 @@ __device__ __forceinline__ void write_gs_drone(float* __restrict__ row, int N, i
     __stcs(row + 3 * N + 3 * i + 0, vx); __stcs(row + 3 * N + 3 * i + 1, vy); __stcs(row + 3 * N + 3 * i + 2, vz);
 }
 
+// domain randomisation, sensor noise of one staged observation row: own position / velocity and the
+// sensed obstacle distances get x + sigma z from the Philox block of (env, episode key, step_count of the observed
+// state - 1, drone) -- the block the thrust noise of the step that produced the state was cut from
+template <int KT, int ST, bool EXACT, int KIND>
+__device__ __forceinline__ void add_sensor_noise(const DevParams& P, float* __restrict__ row, unsigned genv,
+                                                 unsigned ekey, int sc_obs, int i, const int (&om)[ST]) {
+    const int K = EXACT ? KT : P.K, S = EXACT ? ST : P.S;
+    const uint4 rA = philox4x32_7(genv, ekey, (unsigned)(sc_obs - 1), (unsigned)i | (DR_STREAM_A << 16), P);
+    uint4 rB = rA;
+    if (S > 4) rB = philox4x32_7(genv, ekey, (unsigned)(sc_obs - 1), (unsigned)i | (DR_STREAM_B << 16), P);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        row[c] = __fmaf_rn(P.dr_std_pos, dr_normal(P.dr_qtable, dr_field(rA, 3 + c)), row[c]);
+        row[3 + c] = __fmaf_rn(P.dr_std_vel, dr_normal(P.dr_qtable, dr_field(rA, 6 + c)), row[3 + c]);
+    }
+    const int off = 9 + (KIND == SWARM_KIND_SWARM ? 4 * K : 0);
+#pragma unroll
+    for (int q = 0; q < ST; ++q)
+        if (q < S && om[q] >= 0) {
+            const unsigned f = q < 4 ? dr_field(rA, 9 + (q < 4 ? q : 0)) : dr_field(rB, q >= 4 ? q - 4 : 0);
+            row[off + 4 * q + 3] = __fmaf_rn(P.dr_std_obst, dr_normal(P.dr_qtable, f), row[off + 4 * q + 3]);
+        }
+}
+
 // ------------------------------------------------------------------------------------------
 // the env kernel (step / reset / observe)
 //   KT, ST  capacity of the k-nearest lists; EXACT: K == KT and S == ST (D is compile-time)
 //   SMALLN  N <= 32: one drone per lane, drone state stays in registers between the phases
 // ------------------------------------------------------------------------------------------
-template <int KT, int ST, bool EXACT, int NORM, int KIND, bool SMALLN>
+template <int KT, int ST, bool EXACT, int NORM, int KIND, bool SMALLN, bool DR>
 __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_kernel(const DevParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5;
@@ -302,6 +326,17 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
         float4 g4 = lane_env_ok ? P.goal4[env] : make_float4(0.f, 0.f, 0.f, 0.f);
         float gx = g4.x, gy = g4.y, gz = g4.z;
         const int sc = lane_env_ok ? P.step_count[env] : 0;
+        // per-env dynamics constants: the config's, or this episode's randomised ones
+        float c_amax = P.amax, c_vmax = P.vmax, c_dt = P.dt, c_bound = P.bound, c_thr_obst = P.thr_obst;
+        unsigned ekey = 0u;
+        int ctrl_delay = 0;
+        if (DR && lane_env_ok) {
+            const float4 d0 = P.dr_params[(long long)env * 2 + 0], d1 = P.dr_params[(long long)env * 2 + 1];
+            c_amax = d0.x; c_vmax = d0.y; c_dt = d0.z; c_bound = d0.w;
+            c_thr_obst = d1.x; ekey = __float_as_uint(d1.y);
+            ctrl_delay = (int)d1.w;
+        }
+        const unsigned genv = DR ? (unsigned)(P.env_index_base + env) : 0u;
 
         unsigned reset_envs = 0;  // bit el: env el of this group is (re)drawn in this launch
 
@@ -321,27 +356,49 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                     // prev distance (:98-101)
                     const float prev_d = norm1d<NORM>(__fsub_rn(gx, p.x), __fsub_rn(gy, p.y), __fsub_rn(gz, p.z));
                     if (alive) {
-                        const float ax = clipf(P.actions[a * 3 + 0], -1.0f, 1.0f);
-                        const float ay = clipf(P.actions[a * 3 + 1], -1.0f, 1.0f);
-                        const float az = clipf(P.actions[a * 3 + 2], -1.0f, 1.0f);
-                        if (!(ax == ax && ay == ay && az == az)) ++st_nan;   // NaN-action guard counter
-                        v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(ax, P.amax), P.dt));
-                        v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(ay, P.amax), P.dt));
-                        v.z = __fadd_rn(v.z, __fmul_rn(__fmul_rn(az, P.amax), P.dt));
-                        const float speed = norm1d<NORM>(v.x, v.y, v.z);  // _clip_speed (:179-183)
-                        if (!(speed <= P.vmax || speed < P.eps_speed)) {
-                            v.x = __fmul_rn(__fdiv_rn(v.x, speed), P.vmax);
-                            v.y = __fmul_rn(__fdiv_rn(v.y, speed), P.vmax);
-                            v.z = __fmul_rn(__fdiv_rn(v.z, speed), P.vmax);
+                        float ax = P.actions[a * 3 + 0], ay = P.actions[a * 3 + 1], az = P.actions[a * 3 + 2];
+                        if (DR && P.dr_delay_hist > 0) {
+                            // control delay: apply the command submitted ctrl_delay steps ago (zero while the episode
+                            // is younger), then file the one submitted now in ring slot step_count % H
+                            const int H = P.dr_delay_hist;
+                            float* ring = P.act_hist + (long long)env * H * N * 3 + i * 3;
+                            const float sx = ax, sy = ay, sz = az;
+                            if (ctrl_delay > 0) {
+                                if (sc < ctrl_delay) {
+                                    ax = 0.f; ay = 0.f; az = 0.f;
+                                } else {
+                                    const float* hp = ring + (long long)((sc - ctrl_delay) % H) * N * 3;
+                                    ax = hp[0]; ay = hp[1]; az = hp[2];
+                                }
+                            }
+                            float* wp = ring + (long long)(sc % H) * N * 3;
+                            wp[0] = sx; wp[1] = sy; wp[2] = sz;
                         }
-                        p.x = __fadd_rn(p.x, __fmul_rn(v.x, P.dt));
-                        p.y = __fadd_rn(p.y, __fmul_rn(v.y, P.dt));
-                        p.z = __fadd_rn(p.z, __fmul_rn(v.z, P.dt));
+                        ax = clipf(ax, -1.0f, 1.0f); ay = clipf(ay, -1.0f, 1.0f); az = clipf(az, -1.0f, 1.0f);
+                        if (!(ax == ax && ay == ay && az == az)) ++st_nan;   // NaN-action guard counter
+                        if (DR) {  // thrust noise: a <- a * (1 + sigma z), one normal per axis
+                            const uint4 r = philox4x32_7(genv, ekey, (unsigned)sc, (unsigned)i | (DR_STREAM_A << 16), P);
+                            ax = __fmul_rn(ax, __fmaf_rn(P.dr_std_thrust, dr_normal(P.dr_qtable, dr_field(r, 0)), 1.0f));
+                            ay = __fmul_rn(ay, __fmaf_rn(P.dr_std_thrust, dr_normal(P.dr_qtable, dr_field(r, 1)), 1.0f));
+                            az = __fmul_rn(az, __fmaf_rn(P.dr_std_thrust, dr_normal(P.dr_qtable, dr_field(r, 2)), 1.0f));
+                        }
+                        v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(ax, c_amax), c_dt));
+                        v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(ay, c_amax), c_dt));
+                        v.z = __fadd_rn(v.z, __fmul_rn(__fmul_rn(az, c_amax), c_dt));
+                        const float speed = norm1d<NORM>(v.x, v.y, v.z);  // _clip_speed (:179-183)
+                        if (!(speed <= c_vmax || speed < P.eps_speed)) {
+                            v.x = __fmul_rn(__fdiv_rn(v.x, speed), c_vmax);
+                            v.y = __fmul_rn(__fdiv_rn(v.y, speed), c_vmax);
+                            v.z = __fmul_rn(__fdiv_rn(v.z, speed), c_vmax);
+                        }
+                        p.x = __fadd_rn(p.x, __fmul_rn(v.x, c_dt));
+                        p.y = __fadd_rn(p.y, __fmul_rn(v.y, c_dt));
+                        p.z = __fadd_rn(p.z, __fmul_rn(v.z, c_dt));
                     }
                     // wall clip for ALL drones (:113-117); velocity is not zeroed at the wall
-                    p.x = clipf(p.x, -P.bound, P.bound);
-                    p.y = clipf(p.y, -P.bound, P.bound);
-                    p.z = clipf(p.z, -P.bound, P.bound);
+                    p.x = clipf(p.x, -c_bound, c_bound);
+                    p.y = clipf(p.y, -c_bound, c_bound);
+                    p.z = clipf(p.z, -c_bound, c_bound);
                     p.w = alive ? 1.0f : 0.0f;
                     v.w = prev_d;
                     tab_pos[e_l * N + i] = p;
@@ -372,6 +429,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                     scan_drone<KT, ST, NORM, KIND, true>(P, tpos, tobs, i, p.x, p.y, p.z, alive, n_alive_env, nd, nj,
                                                          od, om, so);
                     reached = alive && curr_d <= P.thr_goal;           // :124-127 (double compare)
+                    if (DR) so.obst_hit = od[0] <= c_thr_obst;         // this episode's obstacle radius
                     collided = alive && (so.obst_hit || so.pair_hit);   // :128
                     double reward = 0.0;
                     if (alive) {
@@ -395,6 +453,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                     P.collision[a] = collided ? 1 : 0;
                     stage_obs_row<KT, ST, EXACT, KIND>(P, stage + lane * D, tpos, tobs, i, p.x, p.y, p.z, v.x, v.y,
                                                        v.z, gx, gy, gz, nd, nj, od, om);
+                    if (DR) add_sensor_noise<KT, ST, EXACT, KIND>(P, stage + lane * D, genv, ekey, sc + 1, i, om);
                 }
                 __syncwarp();
                 {
@@ -517,10 +576,45 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                 const int renv = env0 + el;
                 const unsigned long long sh = P.rng[(long long)renv * 4 + 0], sl = P.rng[(long long)renv * 4 + 1];
                 const unsigned long long ih = P.rng[(long long)renv * 4 + 2], il = P.rng[(long long)renv * 4 + 3];
+                double u_lo = P.rng_lo, u_range = P.rng_range;
+                if (DR) {
+                    // this episode's constants: 6 uniforms + an episode key from one counter per (env, reset)
+                    const unsigned ge = (unsigned)(P.env_index_base + renv);
+                    const uint4 ra = philox4x32_10(ge, (unsigned)sl, (unsigned)(sl >> 32), DR_CTR_EPISODE, P);
+                    const uint4 rb = philox4x32_10(ge, (unsigned)sl, (unsigned)(sl >> 32), DR_CTR_EPISODE + 1u, P);
+                    const double inv24 = 1.0 / 16777216.0;
+                    const double s_mass = __dadd_rn(P.dr_lo[0], __dmul_rn(P.dr_span[0], __dmul_rn((double)(ra.x >> 8), inv24)));
+                    const double s_acc = __dadd_rn(P.dr_lo[1], __dmul_rn(P.dr_span[1], __dmul_rn((double)(ra.y >> 8), inv24)));
+                    const double s_spd = __dadd_rn(P.dr_lo[2], __dmul_rn(P.dr_span[2], __dmul_rn((double)(ra.z >> 8), inv24)));
+                    const double s_dt = __dadd_rn(P.dr_lo[3], __dmul_rn(P.dr_span[3], __dmul_rn((double)(ra.w >> 8), inv24)));
+                    const double s_rad = __dadd_rn(P.dr_lo[4], __dmul_rn(P.dr_span[4], __dmul_rn((double)(rb.x >> 8), inv24)));
+                    const double s_wld = __dadd_rn(P.dr_lo[5], __dmul_rn(P.dr_span[5], __dmul_rn((double)(rb.y >> 8), inv24)));
+                    const double world = __dmul_rn(P.dr_world, s_wld);
+                    const double half_w = __dmul_rn(world, 0.5);
+                    u_lo = -half_w; u_range = __dsub_rn(half_w, -half_w);
+                    const float4 d0 = make_float4(__double2float_rn(__ddiv_rn(__dmul_rn(P.dr_max_accel, s_acc), s_mass)),
+                                                  __double2float_rn(__dmul_rn(P.dr_max_speed, s_spd)),
+                                                  __double2float_rn(__dmul_rn(P.dr_dt, s_dt)), __double2float_rn(half_w));
+                    float delay = 0.0f;  // this episode's control delay: 4th word of the second block
+                    if (P.dr_delay_count > 0) {
+                        const double uu = __dmul_rn((double)(rb.w >> 8), inv24);
+                        int pick = P.dr_delay_count - 1;
+                        for (int k = P.dr_delay_count - 1; k >= 0; --k)
+                            if (uu < P.dr_delay_cum[k]) pick = k;
+                        delay = (float)P.dr_delay_values[pick];
+                    }
+                    const float4 d1 = make_float4(__double2float_rn(__dadd_rn(P.dr_r_c, __dmul_rn(P.dr_r_o, s_rad))),
+                                                  __uint_as_float(rb.z), __double2float_rn(world), delay);
+                    if (lane == 0) {
+                        P.dr_params[(long long)renv * 2 + 0] = d0;
+                        P.dr_params[(long long)renv * 2 + 1] = d1;
+                    }
+                    if (lane_env_ok && e_l == el) ekey = rb.z;  // (the dynamics constants are not needed to observe)
+                }
                 for (int k = lane; k < P.n_draws; k += 32) {
                     unsigned long long oh, ol;
                     pcg_jump(P.jump[k + 1], sh, sl, ih, il, oh, ol);
-                    const float val = pcg_uniform_f32(oh, ol, P.rng_lo, P.rng_range);
+                    const float val = pcg_uniform_f32(oh, ol, u_lo, u_range);
                     // draw order: positions (N,3) -> goal (3,) -> obstacles (M,3)
                     if (k < 3 * N) {
                         reinterpret_cast<float*>(tab_pos + el * N + k / 3)[k % 3] = val;
@@ -585,6 +679,8 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                     if (gs_row) write_gs_drone(gs_row, N, i, p.x, p.y, p.z, v.x, v.y, v.z);
                     stage_obs_row<KT, ST, EXACT, KIND>(P, stage + lane * D, tpos, tobs, i, p.x, p.y, p.z, v.x, v.y, v.z,
                                                        gx, gy, gz, nd, nj, od, om);
+                    // (a re-drawn env is observed at step_count 0, swarm_observe at the env's current step_count)
+                    if (DR) add_sensor_noise<KT, ST, EXACT, KIND>(P, stage + lane * D, genv, ekey, fresh ? 0 : sc, i, om);
                 }
                 if (mine && i_base == 0 && slot == 0 && gs_row) {
                     __stcs(gs_row + 6 * N + 0, gx); __stcs(gs_row + 6 * N + 1, gy); __stcs(gs_row + 6 * N + 2, gz);
@@ -1602,8 +1698,10 @@ static EnvKernel pick_small(int norm_mode, bool step, bool dr) {
 }
 
 template <int KT, int ST, bool EXACT, int KIND>
-static EnvKernel pick_large(int norm_mode) {
-    return norm_mode == 0 ? swarm_env_kernel<KT, ST, EXACT, 0, KIND, false> : swarm_env_kernel<KT, ST, EXACT, 1, KIND, false>;
+static EnvKernel pick_large(int norm_mode, bool dr) {
+    if (dr) return swarm_env_kernel<KT, ST, EXACT, 0, KIND, false, true>;   // domain randomisation: norm_mode 0
+    return norm_mode == 0 ? swarm_env_kernel<KT, ST, EXACT, 0, KIND, false, false>
+                          : swarm_env_kernel<KT, ST, EXACT, 1, KIND, false, false>;
 }
 
 static EnvKernel resolve(const DevParams& p, int norm_mode, int env_kind) {
@@ -1612,13 +1710,13 @@ static EnvKernel resolve(const DevParams& p, int norm_mode, int env_kind) {
     const bool dr = p.dr_enabled != 0;
     if (env_kind == SWARM_KIND_SWARM) {
         if (p.K == 3 && p.S == 4) {
-            if (!small_n) return pick_large<3, 4, true, SWARM_KIND_SWARM>(norm_mode);
+            if (!small_n) return pick_large<3, 4, true, SWARM_KIND_SWARM>(norm_mode, dr);
             // (N = 32 measured faster on the runtime-N instantiation: 9.6e9 vs 9.1e9 agent-steps/s)
             if (p.N == 16) return pick_small<3, 4, true, SWARM_KIND_SWARM, 16>(norm_mode, step, dr);
             if (p.N == 8) return pick_small<3, 4, true, SWARM_KIND_SWARM, 8>(norm_mode, step, dr);
             return pick_small<3, 4, true, SWARM_KIND_SWARM, 0>(norm_mode, step, dr);
         }
-        if (!small_n) return pick_large<SWARM_MAX_NEIGHBOR_K, SWARM_MAX_SENSED, false, SWARM_KIND_SWARM>(norm_mode);
+        if (!small_n) return pick_large<SWARM_MAX_NEIGHBOR_K, SWARM_MAX_SENSED, false, SWARM_KIND_SWARM>(norm_mode, dr);
         return pick_small<SWARM_MAX_NEIGHBOR_K, SWARM_MAX_SENSED, false, SWARM_KIND_SWARM, 0>(norm_mode, step, dr);
     }
     if (env_kind == SWARM_KIND_PHYSICS) {  // point-mass DronePhysicsEnv: N <= 32, no domain randomisation

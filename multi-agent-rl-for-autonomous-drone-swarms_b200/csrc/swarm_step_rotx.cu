@@ -1,5 +1,6 @@
 // swarm_step_rotx.cu -- rotation-pass step / auto-reset kernels for the dense swarms: N = 64 / 128 drones
-// (BASELINE config 5), K = 3, S = 4, M a multiple of 4, norm_mode 0, no domain randomisation.
+// (BASELINE config 5), K = 3, S = 4, M a multiple of 4, norm_mode 0; DR = domain randomisation (per-episode
+// dynamics constants, thrust / sensor noise, control delay -- same bits as the general kernels and the oracle).
 // Reference: DroneSwarmEnv.step / reset, src/swarm_marl/envs/drone_swarm_env.py:92-174, 65-90.
 //
 // Same scheme as swarm_step_rot.cu (read its header first), with NS = N / 32 drones per lane:
@@ -35,12 +36,12 @@ namespace swarm {
 #endif
 constexpr int kXWarps = 4;  // warps per CTA
 
-__host__ __device__ constexpr int rotx_envbox_bytes(int M) { return 16 * (1 + M) + 16; }
+__host__ __device__ constexpr int rotx_envbox_bytes(int M, bool dr) { return 16 * (1 + M) + 16 + (dr ? 32 : 0); }
 // per warp: mbarriers (16) | agent inbox pos4[N] vel4[N] actions[3N] | env inbox x 2 | position table
 // (N float4; not doubled: the partner lane index is masked instead, which lets 4 CTAs = 16 warps fit an SM) |
 // obs tile (one slot at a time)
-__host__ __device__ constexpr int rotx_smem_per_warp(int N, int M) {
-    return 16 + (SWARM_ROTX_DIRECT ? 0 : 44 * N) + 2 * rotx_envbox_bytes(M) + (N / 32) * 32 * 16 + kTileBytes;
+__host__ __device__ constexpr int rotx_smem_per_warp(int N, int M, bool dr) {
+    return 16 + (SWARM_ROTX_DIRECT ? 0 : 44 * N) + 2 * rotx_envbox_bytes(M, dr) + (N / 32) * 32 * 16 + kTileBytes;
 }
 
 namespace {
@@ -55,7 +56,7 @@ __device__ __forceinline__ void rotate(T (&a)[NS]) {
 
 }  // namespace
 
-template <int NS, int MT, int MODE>
+template <int NS, int MT, int MODE, bool DR>
 __global__ void __launch_bounds__(kXWarps * 32, MODE == 0 ? SWARM_ROTX_MINB_STEP : SWARM_ROTX_MINB_RESET)
 swarm_step_rotx_kernel(const DevParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -65,7 +66,7 @@ swarm_step_rotx_kernel(const DevParams P) {
     const int warp = __shfl_sync(FULL_MASK, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
     const int M = MT ? MT : P.M;
-    const int envbox_bytes = rotx_envbox_bytes(M);
+    const int envbox_bytes = rotx_envbox_bytes(M, DR);
     constexpr int kAgentBox = SWARM_ROTX_DIRECT ? 0 : 44 * N;
     const int per_warp = 16 + kAgentBox + 2 * envbox_bytes + NS * 512 + kTileBytes;
     unsigned char* wslice = smem_raw + (size_t)warp * per_warp;
@@ -95,8 +96,8 @@ swarm_step_rotx_kernel(const DevParams P) {
     }
     __syncwarp();
 
-    // env inbox: goal4 | obst4[M] | step_count | ep_return
-    const int obst_off = 16, sc_off = 16 * (1 + M);
+    // env inbox: goal4 | obst4[M] | step_count | ep_return | (DR) this episode's constants, 2 x float4
+    const int obst_off = 16, sc_off = 16 * (1 + M), dr_off = 16 * (1 + M) + 16;
     auto issue = [&](int item, int buf) {
         if (!STEP) return;
         const int env0 = P.env_begin + item;
@@ -105,7 +106,7 @@ swarm_step_rotx_kernel(const DevParams P) {
             const unsigned dsta = bar0 + 16;
             const unsigned dst = smem_u32(envbox0 + (size_t)buf * envbox_bytes);
             const long long a0 = (long long)env0 * N;
-            mbar_expect_tx(bar, (SWARM_ROTX_DIRECT ? 0u : (unsigned)N * 44u) + 16u + 16u * M);
+            mbar_expect_tx(bar, (SWARM_ROTX_DIRECT ? 0u : (unsigned)N * 44u) + 16u + 16u * M + (DR ? 32u : 0u));
             if (!SWARM_ROTX_DIRECT) {
                 bulk_g2s(dsta, P.pos4 + a0, N * 16u, bar);
                 bulk_g2s(dsta + N * 16, P.vel4 + a0, N * 16u, bar);
@@ -113,6 +114,7 @@ swarm_step_rotx_kernel(const DevParams P) {
             }
             bulk_g2s(dst, P.goal4 + env0, 16u, bar);
             bulk_g2s(dst + obst_off, P.obst4 + (long long)env0 * M, (unsigned)M * 16u, bar);
+            if (DR) bulk_g2s(dst + dr_off, P.dr_params + (long long)env0 * 2, 32u, bar);
             cp_async4(dst + sc_off, P.step_count + env0);
             cp_async4(dst + sc_off + 4, P.ep_return + env0);
         }
@@ -139,6 +141,11 @@ swarm_step_rotx_kernel(const DevParams P) {
         bool alive[NS];
         float gx, gy, gz;
         int sc = 0;
+        // per-env dynamics constants: the config's, or this episode's randomised ones
+        float c_amax = P.amax, c_vmax = P.vmax, c_dt = P.dt, c_bound = P.bound, c_thr_obst = P.thr_obst;
+        unsigned ekey = 0u;
+        int ctrl_delay = 0;
+        const unsigned genv = DR ? (unsigned)(P.env_index_base + env) : 0u;
         if (STEP) {
             float4 lp[NS], lv[NS];
             float la[NS][3];
@@ -159,6 +166,13 @@ swarm_step_rotx_kernel(const DevParams P) {
             const float4 g4 = tgoal[0];
             gx = g4.x; gy = g4.y; gz = g4.z;
             sc = reinterpret_cast<const int*>(ib + sc_off)[0];
+            if (DR) {
+                const float4* drp = reinterpret_cast<const float4*>(ib + dr_off);
+                const float4 d0 = drp[0], d1 = drp[1];
+                c_amax = d0.x; c_vmax = d0.y; c_dt = d0.z; c_bound = d0.w;
+                c_thr_obst = d1.x; ekey = __float_as_uint(d1.y);
+                ctrl_delay = (int)d1.w;
+            }
             const float* act = reinterpret_cast<const float*>(in_pos + 2 * N);
             bool nan_any = false;
 #pragma unroll
@@ -172,24 +186,47 @@ swarm_step_rotx_kernel(const DevParams P) {
                 px[s] = p.x; py[s] = p.y; pz[s] = p.z;
                 prev_d[s] = norm1d<0>(__fsub_rn(gx, p.x), __fsub_rn(gy, p.y), __fsub_rn(gz, p.z));  // :98-101
                 if (alive[s]) {  // integrate (:103-111)
+                    if (DR && P.dr_delay_hist > 0) {
+                        // control delay: apply the command submitted ctrl_delay steps ago (zero while the episode is
+                        // younger), then file the one submitted now in ring slot step_count % H
+                        const int H = P.dr_delay_hist;
+                        float* ring = P.act_hist + ((long long)env * H * N + (s * 32 + lane)) * 3;
+                        const float sx = ax, sy = ay, sz = az;
+                        if (ctrl_delay > 0) {
+                            if (sc < ctrl_delay) {
+                                ax = 0.f; ay = 0.f; az = 0.f;
+                            } else {
+                                const float* hp = ring + (long long)((sc - ctrl_delay) % H) * N * 3;
+                                ax = hp[0]; ay = hp[1]; az = hp[2];
+                            }
+                        }
+                        float* wp = ring + (long long)(sc % H) * N * 3;
+                        wp[0] = sx; wp[1] = sy; wp[2] = sz;
+                    }
                     ax = clipf(ax, -1.0f, 1.0f); ay = clipf(ay, -1.0f, 1.0f); az = clipf(az, -1.0f, 1.0f);
                     nan_any = nan_any || !(ax == ax && ay == ay && az == az);   // (np.clip lets NaN through; counted)
-                    v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(ax, P.amax), P.dt));
-                    v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(ay, P.amax), P.dt));
-                    v.z = __fadd_rn(v.z, __fmul_rn(__fmul_rn(az, P.amax), P.dt));
-                    const float speed = norm1d<0>(v.x, v.y, v.z);  // _clip_speed (:179-183)
-                    if (!(speed <= P.vmax || speed < P.eps_speed)) {
-                        v.x = __fmul_rn(__fdiv_rn(v.x, speed), P.vmax);
-                        v.y = __fmul_rn(__fdiv_rn(v.y, speed), P.vmax);
-                        v.z = __fmul_rn(__fdiv_rn(v.z, speed), P.vmax);
+                    if (DR) {  // thrust noise: a <- a * (1 + sigma z), one normal per axis
+                        const uint4 r = philox4x32_7(genv, ekey, (unsigned)sc, (unsigned)(s * 32 + lane) | (DR_STREAM_A << 16), P);
+                        ax = __fmul_rn(ax, __fmaf_rn(P.dr_std_thrust, dr_normal(P.dr_qtable, dr_field(r, 0)), 1.0f));
+                        ay = __fmul_rn(ay, __fmaf_rn(P.dr_std_thrust, dr_normal(P.dr_qtable, dr_field(r, 1)), 1.0f));
+                        az = __fmul_rn(az, __fmaf_rn(P.dr_std_thrust, dr_normal(P.dr_qtable, dr_field(r, 2)), 1.0f));
                     }
-                    px[s] = __fadd_rn(px[s], __fmul_rn(v.x, P.dt));
-                    py[s] = __fadd_rn(py[s], __fmul_rn(v.y, P.dt));
-                    pz[s] = __fadd_rn(pz[s], __fmul_rn(v.z, P.dt));
+                    v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(ax, c_amax), c_dt));
+                    v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(ay, c_amax), c_dt));
+                    v.z = __fadd_rn(v.z, __fmul_rn(__fmul_rn(az, c_amax), c_dt));
+                    const float speed = norm1d<0>(v.x, v.y, v.z);  // _clip_speed (:179-183)
+                    if (!(speed <= c_vmax || speed < P.eps_speed)) {
+                        v.x = __fmul_rn(__fdiv_rn(v.x, speed), c_vmax);
+                        v.y = __fmul_rn(__fdiv_rn(v.y, speed), c_vmax);
+                        v.z = __fmul_rn(__fdiv_rn(v.z, speed), c_vmax);
+                    }
+                    px[s] = __fadd_rn(px[s], __fmul_rn(v.x, c_dt));
+                    py[s] = __fadd_rn(py[s], __fmul_rn(v.y, c_dt));
+                    pz[s] = __fadd_rn(pz[s], __fmul_rn(v.z, c_dt));
                 }
-                px[s] = clipf(px[s], -P.bound, P.bound);  // wall clip for ALL drones (:113-117)
-                py[s] = clipf(py[s], -P.bound, P.bound);
-                pz[s] = clipf(pz[s], -P.bound, P.bound);
+                px[s] = clipf(px[s], -c_bound, c_bound);  // wall clip for ALL drones (:113-117)
+                py[s] = clipf(py[s], -c_bound, c_bound);
+                pz[s] = clipf(pz[s], -c_bound, c_bound);
                 vx[s] = v.x; vy[s] = v.y; vz[s] = v.z;
             }
             {   // NaN-action guard counter (rare: the vote is all a clean step pays); per lane: drones, not components
@@ -201,11 +238,46 @@ swarm_step_rotx_kernel(const DevParams P) {
             __syncwarp();
             const unsigned long long sh = P.rng[(long long)env * 4 + 0], sl = P.rng[(long long)env * 4 + 1];
             const unsigned long long ih = P.rng[(long long)env * 4 + 2], il = P.rng[(long long)env * 4 + 3];
+            double u_lo = P.rng_lo, u_range = P.rng_range;
+            if (DR) {
+                // this episode's constants: 6 uniforms + an episode key from one counter per (env, reset)
+                const uint4 ra = philox4x32_10(genv, (unsigned)sl, (unsigned)(sl >> 32), DR_CTR_EPISODE, P);
+                const uint4 rb = philox4x32_10(genv, (unsigned)sl, (unsigned)(sl >> 32), DR_CTR_EPISODE + 1u, P);
+                const double inv24 = 1.0 / 16777216.0;
+                const double s_mass = __dadd_rn(P.dr_lo[0], __dmul_rn(P.dr_span[0], __dmul_rn((double)(ra.x >> 8), inv24)));
+                const double s_acc = __dadd_rn(P.dr_lo[1], __dmul_rn(P.dr_span[1], __dmul_rn((double)(ra.y >> 8), inv24)));
+                const double s_spd = __dadd_rn(P.dr_lo[2], __dmul_rn(P.dr_span[2], __dmul_rn((double)(ra.z >> 8), inv24)));
+                const double s_dt = __dadd_rn(P.dr_lo[3], __dmul_rn(P.dr_span[3], __dmul_rn((double)(ra.w >> 8), inv24)));
+                const double s_rad = __dadd_rn(P.dr_lo[4], __dmul_rn(P.dr_span[4], __dmul_rn((double)(rb.x >> 8), inv24)));
+                const double s_wld = __dadd_rn(P.dr_lo[5], __dmul_rn(P.dr_span[5], __dmul_rn((double)(rb.y >> 8), inv24)));
+                const double world = __dmul_rn(P.dr_world, s_wld);
+                const double half_w = __dmul_rn(world, 0.5);
+                u_lo = -half_w; u_range = __dsub_rn(half_w, -half_w);
+                if (lane == 0) {
+                    float delay = 0.0f;  // this episode's control delay: 4th word of the second block
+                    if (P.dr_delay_count > 0) {
+                        const double uu = __dmul_rn((double)(rb.w >> 8), inv24);
+                        int pick = P.dr_delay_count - 1;
+#pragma unroll 1
+                        for (int k = P.dr_delay_count - 1; k >= 0; --k)
+                            if (uu < P.dr_delay_cum[k]) pick = k;
+                        delay = (float)P.dr_delay_values[pick];
+                    }
+                    P.dr_params[(long long)env * 2 + 0] =
+                        make_float4(__double2float_rn(__ddiv_rn(__dmul_rn(P.dr_max_accel, s_acc), s_mass)),
+                                    __double2float_rn(__dmul_rn(P.dr_max_speed, s_spd)),
+                                    __double2float_rn(__dmul_rn(P.dr_dt, s_dt)), __double2float_rn(half_w));
+                    P.dr_params[(long long)env * 2 + 1] =
+                        make_float4(__double2float_rn(__dadd_rn(P.dr_r_c, __dmul_rn(P.dr_r_o, s_rad))),
+                                    __uint_as_float(rb.z), __double2float_rn(world), delay);
+                }
+                ekey = rb.z;  // (the dynamics constants are not needed to observe)
+            }
 #pragma unroll 4
             for (int k = lane; k < P.n_draws; k += 32) {
                 unsigned long long oh, ol;
                 pcg_jump(P.jump[k + 1], sh, sl, ih, il, oh, ol);
-                const float val = pcg_uniform_f32(oh, ol, P.rng_lo, P.rng_range);
+                const float val = pcg_uniform_f32(oh, ol, u_lo, u_range);
                 if (k < 3 * N) {  // drone j = k / 3 lives at [slot j / 32][lane j % 32]
                     const int j = k / 3;
                     reinterpret_cast<float*>(tab2 + j)[k - 3 * j] = val;
@@ -538,7 +610,7 @@ swarm_step_rotx_kernel(const DevParams P) {
             double reward = 0.0;
             unsigned f = 0u;
             if (STEP) {
-                const bool obst_hit = od[0] <= P.thr_obst;
+                const bool obst_hit = od[0] <= c_thr_obst;
                 const bool reached = alive[0] && curr_d <= P.thr_goal;
                 const bool collided = alive[0] && (obst_hit || pair_hit);
                 if (alive[0]) {
@@ -567,16 +639,23 @@ swarm_step_rotx_kernel(const DevParams P) {
                 const float4 t0 = tab2[nj[0]], t1 = tab2[nj[1]];
                 const float4 t2 = tab2[nj[2]];
                 const float4 b0 = tobs[om[0]], b1 = tobs[om[1]], b2 = tobs[om[2]], b3 = tobs[om[3]];
-                row[0] = p_x; row[1] = p_y; row[2] = p_z;
-                row[3] = vx[0]; row[4] = vy[0]; row[5] = vz[0];
+                // DR: sensor noise of the observed state -- the Philox block of counter (its step_count - 1), i.e. the
+                // block this step's thrust noise was cut from (a reset observation: step_count 0, counter 0xFFFFFFFF)
+                uint4 rA = make_uint4(0, 0, 0, 0);
+                if (DR) rA = philox4x32_7(genv, ekey, STEP ? (unsigned)sc : 0xFFFFFFFFu, (unsigned)me | (DR_STREAM_A << 16), P);
+                auto noisy = [&](float x, float sigma, int f) {
+                    return DR ? __fmaf_rn(sigma, dr_normal(P.dr_qtable, dr_field(rA, f)), x) : x;
+                };
+                row[0] = noisy(p_x, P.dr_std_pos, 3); row[1] = noisy(p_y, P.dr_std_pos, 4); row[2] = noisy(p_z, P.dr_std_pos, 5);
+                row[3] = noisy(vx[0], P.dr_std_vel, 6); row[4] = noisy(vy[0], P.dr_std_vel, 7); row[5] = noisy(vz[0], P.dr_std_vel, 8);
                 row[6] = __fsub_rn(gx, p_x); row[7] = __fsub_rn(gy, p_y); row[8] = __fsub_rn(gz, p_z);
                 row[9] = __fsub_rn(t0.x, p_x); row[10] = __fsub_rn(t0.y, p_y); row[11] = __fsub_rn(t0.z, p_z); row[12] = nd[0];
                 row[13] = __fsub_rn(t1.x, p_x); row[14] = __fsub_rn(t1.y, p_y); row[15] = __fsub_rn(t1.z, p_z); row[16] = nd[1];
                 row[17] = __fsub_rn(t2.x, p_x); row[18] = __fsub_rn(t2.y, p_y); row[19] = __fsub_rn(t2.z, p_z); row[20] = nd[2];
-                row[21] = __fsub_rn(b0.x, p_x); row[22] = __fsub_rn(b0.y, p_y); row[23] = __fsub_rn(b0.z, p_z); row[24] = od[0];
-                row[25] = __fsub_rn(b1.x, p_x); row[26] = __fsub_rn(b1.y, p_y); row[27] = __fsub_rn(b1.z, p_z); row[28] = od[1];
-                row[29] = __fsub_rn(b2.x, p_x); row[30] = __fsub_rn(b2.y, p_y); row[31] = __fsub_rn(b2.z, p_z); row[32] = od[2];
-                row[33] = __fsub_rn(b3.x, p_x); row[34] = __fsub_rn(b3.y, p_y); row[35] = __fsub_rn(b3.z, p_z); row[36] = od[3];
+                row[21] = __fsub_rn(b0.x, p_x); row[22] = __fsub_rn(b0.y, p_y); row[23] = __fsub_rn(b0.z, p_z); row[24] = noisy(od[0], P.dr_std_obst, 9);
+                row[25] = __fsub_rn(b1.x, p_x); row[26] = __fsub_rn(b1.y, p_y); row[27] = __fsub_rn(b1.z, p_z); row[28] = noisy(od[1], P.dr_std_obst, 10);
+                row[29] = __fsub_rn(b2.x, p_x); row[30] = __fsub_rn(b2.y, p_y); row[31] = __fsub_rn(b2.z, p_z); row[32] = noisy(od[2], P.dr_std_obst, 11);
+                row[33] = __fsub_rn(b3.x, p_x); row[34] = __fsub_rn(b3.y, p_y); row[35] = __fsub_rn(b3.z, p_z); row[36] = noisy(od[3], P.dr_std_obst, 12);
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) {
@@ -719,21 +798,23 @@ swarm_step_rotx_kernel(const DevParams P) {
 // ------------------------------------------------------------------------------------------
 typedef void (*RotxKernel)(const DevParams);
 
-template <int NS>
+template <int NS, bool DR>
 static RotxKernel pick_rotx_m(const DevParams& p) {
     const bool reset = p.mode == kModeAutoReset;
-    if (p.M == 8) return reset ? swarm_step_rotx_kernel<NS, 8, 1> : swarm_step_rotx_kernel<NS, 8, 0>;
-    if (p.M == 4) return reset ? swarm_step_rotx_kernel<NS, 4, 1> : swarm_step_rotx_kernel<NS, 4, 0>;
-    return reset ? swarm_step_rotx_kernel<NS, 0, 1> : swarm_step_rotx_kernel<NS, 0, 0>;
+    if (p.M == 8) return reset ? swarm_step_rotx_kernel<NS, 8, 1, DR> : swarm_step_rotx_kernel<NS, 8, 0, DR>;
+    if (p.M == 4) return reset ? swarm_step_rotx_kernel<NS, 4, 1, DR> : swarm_step_rotx_kernel<NS, 4, 0, DR>;
+    return reset ? swarm_step_rotx_kernel<NS, 0, 1, DR> : swarm_step_rotx_kernel<NS, 0, 0, DR>;
 }
 static RotxKernel pick_rotx(const DevParams& p) {
-    if (p.N == 128) return pick_rotx_m<4>(p);
-    if (p.N == 64) return pick_rotx_m<2>(p);
+    const bool dr = p.dr_enabled != 0;
+    if (p.N == 128) return dr ? pick_rotx_m<4, true>(p) : pick_rotx_m<4, false>(p);
+    if (p.N == 64) return dr ? pick_rotx_m<2, true>(p) : pick_rotx_m<2, false>(p);
     return nullptr;
 }
 
 size_t rotx_smem_bytes(const DevParams& p) {
-    return (size_t)kXWarps * rotx_smem_per_warp(p.N, p.M) + (size_t)kXWarps * SWARM_STATS_WORDS * sizeof(unsigned long long);
+    return (size_t)kXWarps * rotx_smem_per_warp(p.N, p.M, p.dr_enabled != 0) +
+           (size_t)kXWarps * SWARM_STATS_WORDS * sizeof(unsigned long long);
 }
 int rotx_warps_per_cta() { return kXWarps; }
 

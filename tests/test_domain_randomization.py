@@ -129,6 +129,13 @@ GPU_CASES = [
     ("single", {"num_obstacles": 8, "max_steps": 40}, 2000, 90),
     # curriculum_v1 stage 4 (configs/curriculum_v1.yaml:47-55) under domain_randomization_v1: BASELINE config 4's recipe
     ("swarm", {"num_drones": 8, "num_obstacles": 12, "max_steps": 450, "world_size": 28.0}, 512, 60),
+    # more than 32 drones (round 2): BASELINE config 5's shape, its density-matched world, odd sizes, generic K / S
+    ("swarm", {"num_drones": 128, "num_obstacles": 8}, 48, 12),
+    ("swarm", {"num_drones": 128, "num_obstacles": 8, "world_size": 70.0, "max_steps": 30}, 40, 45),
+    ("swarm", {"num_drones": 64, "num_obstacles": 8, "world_size": 50.0, "max_steps": 25}, 64, 40),
+    ("swarm", {"num_drones": 40, "num_obstacles": 5, "world_size": 45.0, "max_steps": 20}, 50, 45),
+    ("swarm", {"num_drones": 33, "num_obstacles": 6, "neighbor_k": 6, "sensed_obstacles": 6, "world_size": 40.0,
+               "max_steps": 20}, 40, 45),
 ]
 
 
@@ -152,6 +159,31 @@ def test_cuda_randomised_matches_oracle(kind, cfg, E, T):
         assert len(bad) == 0, f"obs rows differ at step {t}: {bad[:4]}"
 
     _roll(make, cfg, kind, E, T, N, check=check)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,E,T,dr", [(128, 24, 20, "v1"), (64, 40, 40, "delay")])
+def test_cuda_randomised_general_kernel_matches_oracle_above_32_drones(N, E, T, dr, monkeypatch):
+    """The shapes the wide rotation-pass kernel serves, forced onto the general kernel (SWARM_B200_NO_ROT=1): both
+    implement the randomisation, bit for bit."""
+    import swarm_oracle as so
+    from engine_backend import EngineBackend
+    monkeypatch.setenv("SWARM_B200_NO_ROT", "1")
+    cfg = {"num_drones": N, "num_obstacles": 8, "world_size": 60.0, "max_steps": 25}
+    spec = DR_V1 if dr == "v1" else {**DR_V1, "control_delay_steps": ((0, 1, 2), (0.7, 0.2, 0.1))}
+
+    def make():
+        return [so.OracleSwarm(E, cfg, dr=spec, dr_seed=31, env_index_base=100),
+                EngineBackend(E, cfg, domain_randomization=spec, dr_seed=31, env_index_base=100)]
+
+    def check(envs, t):
+        o, b = envs
+        for name in FIELDS + ("dr_params",):
+            pu.assert_biteq(name, getattr(b, name), getattr(o, name), t)
+        valid = o.obs_valid.astype(bool)
+        assert not ((pu.bits(b.obs) != pu.bits(o.obs)).any(axis=2) & valid).any(), t
+
+    _roll(make, cfg, "swarm", E, T, N, check=check)
 
 
 @pytest.mark.gpu
@@ -213,7 +245,11 @@ def test_flatten_accepts_the_yaml_delay_block():
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind,cfg,E,T", [("swarm", {"num_drones": 32, "num_obstacles": 8}, 256, 40),
                                           ("swarm", {"num_drones": 8, "num_obstacles": 4, "max_steps": 30}, 600, 70),
-                                          ("single", {"num_obstacles": 8, "max_steps": 40}, 1000, 90)])
+                                          ("single", {"num_obstacles": 8, "max_steps": 40}, 1000, 90),
+                                          ("swarm", {"num_drones": 128, "num_obstacles": 8, "world_size": 70.0,
+                                                     "max_steps": 30}, 32, 45),
+                                          ("swarm", {"num_drones": 48, "num_obstacles": 4, "world_size": 50.0,
+                                                     "max_steps": 20}, 40, 45)])
 def test_cuda_control_delay_matches_oracle(kind, cfg, E, T):
     import swarm_oracle as so
     from engine_backend import EngineBackend
