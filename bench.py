@@ -408,30 +408,44 @@ def main():
     if not args.no_e2e:
         h = eng.host_buffers()
         host_actions = [a.cpu().pin_memory() for a in actions[:2]]   # the caller's pinned action buffers
-        for w in range(3):
-            eng.step_host(host_actions[w % 2], auto_reset=True)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        eng.reset_stats()
-        t0 = time.perf_counter()
-        ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ee0.record()
-        for k in range(args.e2e_steps):
-            out = eng.step_host(host_actions[k % 2], auto_reset=True)
-            _ = float(out["reward"][0, 0])               # host reads the result
-        ee1.record()
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - t0
-        dev_ms = ee0.elapsed_time(ee1)
-        e2e_ms = max(wall * 1e3, dev_ms)
-        e2e_steps_done = eng.stats()["agent_steps"]
-        te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-        se = torch.tensor([e2e_steps_done], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-            dist.all_reduce(se, op=dist.ReduceOp.SUM)
-        h2d, d2h = eng.host_bytes_per_step()
+
+        def e2e_run(outputs, n_steps):
+            """n_steps of swarm_step_host with the named output set; (ms per step, agent-steps done), max / sum over ranks"""
+            for w in range(3):
+                eng.step_host(host_actions[w % 2], auto_reset=True, outputs=outputs)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            eng.reset_stats()
+            t0 = time.perf_counter()
+            ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ee0.record()
+            for k in range(n_steps):
+                out = eng.step_host(host_actions[k % 2], auto_reset=True, outputs=outputs)
+                _ = float(out["reward"][0, 0])               # host reads the result
+            ee1.record()
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - t0
+            ms = max(wall * 1e3, ee0.elapsed_time(ee1))
+            te_ = torch.tensor([ms], dtype=torch.float64, device=dev)
+            se_ = torch.tensor([eng.stats()["agent_steps"]], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(te_, op=dist.ReduceOp.MAX)
+                dist.all_reduce(se_, op=dist.ReduceOp.SUM)
+            return te_, se_
+
+        # headline: every output of env.step() -- obs, reward, distance, the five flag arrays (one packed byte per
+        # agent, ABI 5), the __all__ flags and global_state; beside it the same with unpacked flag arrays (round 1 / 2a)
+        # and the "lean" set (obs, reward, flags: env.step() without the info dicts)
+        e2e_set = "packed"
+        te, se = e2e_run(e2e_set, args.e2e_steps)
+        variants = {}
+        for vname, vset in (("unpacked_flag_arrays", None), ("lean_obs_reward_flags", "lean")):
+            tv, sv = e2e_run(vset, max(args.e2e_steps // 2, 4))
+            vb = eng.host_bytes_per_step(vset)
+            variants[vname] = {"value": float(sv.item()) / (float(tv.item()) * 1e-3), "unit": "agent-steps/s",
+                               "h2d_bytes_per_step": vb[0], "d2h_bytes_per_step": vb[1]}
+        h2d, d2h = eng.host_bytes_per_step(e2e_set)
         # what the link gives a bare pinned device->host copy of the largest output (explains the e2e number)
         # (all ranks at once, behind a barrier: with several GPUs per host this is the ceiling the e2e number lives
         #  under -- the ranks share the host's PCIe root complexes / memory controllers)
@@ -461,8 +475,10 @@ def main():
                "link_d2h_concurrent": {"ranks": world, "gbs_per_rank_min": link_min, "gbs_per_rank_max": link_max,
                                        "gbs_total": link_sum,
                                        "note": "bare pinned device->host copy of the obs tensor on every rank at once"},
+               "variants": variants,
                "path": "swarm_step_host: pinned host actions -> H2D -> fused step -> D2H of obs, reward, dist, "
-                       "5 flag arrays, __all__ flags, global_state (4 env-axis chunks on side streams)"}
+                       "the 5 per-agent flag arrays as one packed byte, __all__ flags, global_state "
+                       "(4 env-axis chunks on side streams)"}
 
     if rank == 0:
         peak, peak_src = peaks()

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SWARM_ABI_VERSION 4
+#define SWARM_ABI_VERSION 5
 
 enum {
     SWARM_OK = 0,
@@ -172,7 +172,17 @@ typedef struct SwarmHostOut {
      * ONE device allocation [block_dev, block_dev + block_bytes) and wants it mirrored byte for byte at block_host
      * -- one device->host copy per step instead of one per field (small batches: the E = 1 facade envs) */
     void *block_host; const void *block_dev; int64_t block_bytes;
+    /* ABI 5: the five per-agent flag arrays as ONE byte per agent, packed on the device right behind the step
+     * (SWARM_FLAG_* bits) -- a host consumer that wants every flag reads 1 byte per agent over the link instead
+     * of 5.  Independent of the unpacked fields above (either, both or neither may be requested). */
+    uint8_t *flags;      /* [E][N] */
 } SwarmHostOut;
+
+/* bits of SwarmHostOut.flags */
+enum {
+    SWARM_FLAG_TERMINATED = 1, SWARM_FLAG_TRUNCATED = 2, SWARM_FLAG_REACHED = 4, SWARM_FLAG_COLLISION = 8,
+    SWARM_FLAG_OBS_VALID = 16
+};
 
 typedef struct SwarmHandle SwarmHandle;
 

@@ -11,7 +11,7 @@ import os
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SWARM_B200_LIB") or os.path.join(_PKG_DIR, "libswarm_b200.so")  # override: tuning builds
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 KIND_SINGLE, KIND_SWARM, KIND_PHYSICS = 0, 1, 2
 MAX_DRONES, MAX_NEIGHBOR_K, MAX_SENSED = 128, 8, 8
 
@@ -61,7 +61,12 @@ HOST_OUT_FIELDS = ("obs", "reward", "reward64", "dist", "terminated", "truncated
 
 class SwarmHostOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in HOST_OUT_FIELDS] + \
-               [("block_host", C.c_void_p), ("block_dev", C.c_void_p), ("block_bytes", C.c_int64)]
+               [("block_host", C.c_void_p), ("block_dev", C.c_void_p), ("block_bytes", C.c_int64),
+                ("flags", C.c_void_p)]   # ABI 5: the five per-agent flag arrays packed into one byte (FLAG_* bits)
+
+
+FLAG_TERMINATED, FLAG_TRUNCATED, FLAG_REACHED, FLAG_COLLISION, FLAG_OBS_VALID = 1, 2, 4, 8, 16
+FLAG_FIELDS = ("terminated", "truncated", "reached", "collision", "obs_valid")   # bit k = FLAG_FIELDS[k]
 
 
 EXPORTS = ("swarm_abi_version", "swarm_last_error", "swarm_create", "swarm_destroy", "swarm_query_sizes",

@@ -67,10 +67,36 @@ struct SwarmHandle {
     cudaEvent_t chunk_done[kHostChunks];
     cudaEvent_t caller_ready;   // recorded on the caller's stream: the chunk streams start behind it
     float* actions_dev;      // [E][N][3] staging for swarm_step_host
+    uint8_t* flags_dev;      // [E][N] packed flag bytes (SwarmHostOut.flags), allocated on first use
     bool host_path_ready;
 };
 
 namespace {
+
+// SwarmHostOut.flags: terminated | truncated << 1 | reached << 2 | collision << 3 | obs_valid << 4, one byte per agent
+// (host-buffer path only: runs on the chunk's stream between the step and the device->host copies; 4 agents per
+//  thread when the chunk is 4-byte aligned)
+__global__ void swarm_pack_flags_kernel(const uint8_t* __restrict__ term, const uint8_t* __restrict__ trunc,
+                                        const uint8_t* __restrict__ reached, const uint8_t* __restrict__ col,
+                                        const uint8_t* __restrict__ valid, uint8_t* __restrict__ out, long long a0,
+                                        long long n) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (((a0 | n) & 3) == 0) {
+        if (t * 4 >= n) return;
+        const long long w = (a0 >> 2) + t;
+        const unsigned m = 0x01010101u;
+        const unsigned v = (reinterpret_cast<const unsigned*>(term)[w] & m) | ((reinterpret_cast<const unsigned*>(trunc)[w] & m) << 1) |
+                           ((reinterpret_cast<const unsigned*>(reached)[w] & m) << 2) |
+                           ((reinterpret_cast<const unsigned*>(col)[w] & m) << 3) |
+                           ((reinterpret_cast<const unsigned*>(valid)[w] & m) << 4);
+        reinterpret_cast<unsigned*>(out)[w] = v;
+    } else {
+        if (t >= n) return;
+        const long long a = a0 + t;
+        out[a] = (uint8_t)((term[a] & 1) | ((trunc[a] & 1) << 1) | ((reached[a] & 1) << 2) | ((col[a] & 1) << 3) |
+                           ((valid[a] & 1) << 4));
+    }
+}
 
 int obs_dim_of(const SwarmConfig& c) {
     return c.env_kind != SWARM_KIND_SINGLE ? 9 + 4 * c.neighbor_k + 4 * c.sensed_obstacles
@@ -447,6 +473,7 @@ int swarm_create(const SwarmConfig* cfg, SwarmHandle** out) {
     h->work_counter_dev = nullptr;
     h->qtable_dev = nullptr;
     h->actions_dev = nullptr;
+    h->flags_dev = nullptr;
     h->host_path_ready = false;
     fill_params(*cfg, h->base);
     h->smem_bytes = (size_t)h->base.smem_per_warp * kWarpsPerCta + (size_t)kWarpsPerCta * SWARM_STATS_WORDS * 8;
@@ -542,6 +569,7 @@ int swarm_destroy(SwarmHandle* h) {
         cudaEventDestroy(h->caller_ready);
     }
     if (h->actions_dev) cudaFree(h->actions_dev);
+    if (h->flags_dev) cudaFree(h->flags_dev);
     if (h->jump_dev) cudaFree(h->jump_dev);
     if (h->reset_mask_dev) cudaFree(h->reset_mask_dev);
     if (h->reset_count_dev) cudaFree(h->reset_count_dev);
@@ -652,6 +680,8 @@ int swarm_step_host(SwarmHandle* h, const SwarmBuffers* bufs, const float* actio
         CUDA_TRY(cudaMalloc(&h->actions_dev, (size_t)p.E * p.N * 3 * sizeof(float)));
         h->host_path_ready = true;
     }
+    if (out->flags && out->block_bytes == 0 && !h->flags_dev)
+        CUDA_TRY(cudaMalloc(&h->flags_dev, ((size_t)p.E * p.N + 3) & ~(size_t)3));
     // the internal chunk streams start behind whatever the caller has enqueued on `stream` (an event, not a
     // device-wide drain); the call returns after a host wait on every chunk, so later work on any stream is behind it
     CUDA_TRY(cudaEventRecord(h->caller_ready, static_cast<cudaStream_t>(stream)));
@@ -699,6 +729,16 @@ int swarm_step_host(SwarmHandle* h, const SwarmBuffers* bufs, const float* actio
         D2H(reached, p.reached, (size_t)N, uint8_t);
         D2H(collision, p.collision, (size_t)N, uint8_t);
         D2H(obs_valid, p.obs_valid, (size_t)N, uint8_t);
+        if (out->flags) {
+            const long long a_first = (long long)e0 * N, n_ag = (long long)ne * N;
+            const bool vec = ((a_first | n_ag) & 3) == 0;
+            const long long threads = vec ? n_ag / 4 : n_ag;
+            swarm_pack_flags_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(
+                p.terminated, p.truncated, p.reached, p.collision, p.obs_valid, h->flags_dev, a_first, n_ag);
+            CUDA_TRY(cudaGetLastError());
+            ++h->launches;
+            CUDA_TRY(cudaMemcpyAsync(out->flags + a_first, h->flags_dev + a_first, (size_t)n_ag, cudaMemcpyDeviceToHost, s));
+        }
         D2H(all_terminated, p.all_term, (size_t)1, uint8_t);
         D2H(all_truncated, p.all_trunc, (size_t)1, uint8_t);
         D2H(global_state, p.gs, (size_t)R, float);

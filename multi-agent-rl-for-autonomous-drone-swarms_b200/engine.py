@@ -356,13 +356,37 @@ class SwarmEngine:
                 if name == "global_state" and not with_global_state:
                     continue
                 h[name] = self._host_block[o:o + nbytes].view(dt).view(shape)
+            h["flags"] = pin((E, N), torch.uint8)   # ABI 5: terminated | truncated | reached | collision | obs_valid bits
             self._host = h
         return self._host
 
-    def step_host(self, actions_host=None, auto_reset: bool = True, outputs: tuple[str, ...] | None = None):
+    # named output sets of `step_host` (what crosses the link per agent-step, N = 32, M = 8):
+    #   None      every field, flags as five byte arrays                                   185 B
+    #   "packed"  the same information, the five flag arrays as one byte (`unpack_flags`)  181 B
+    #   "lean"    what env.step() returns without the info dicts: obs, reward, flags       153 B
+    OUTPUT_SETS = {
+        "packed": ("obs", "reward", "dist", "flags", "all_terminated", "all_truncated", "global_state"),
+        "lean": ("obs", "reward", "flags", "all_terminated", "all_truncated"),
+    }
+
+    def _output_names(self, outputs) -> tuple[str, ...]:
+        h = self.host_buffers()
+        if outputs is None:
+            return tuple(n for n in _abi.HOST_OUT_FIELDS if n in h)
+        if isinstance(outputs, str):
+            outputs = self.OUTPUT_SETS[outputs]
+        return tuple(n for n in outputs if n in h)
+
+    @staticmethod
+    def unpack_flags(flags) -> dict[str, Any]:
+        """The five per-agent flag arrays (bool, same shape) of a packed `flags` byte array."""
+        return {name: (flags & (1 << k)) != 0 for k, name in enumerate(_abi.FLAG_FIELDS)}
+
+    def step_host(self, actions_host=None, auto_reset: bool = True, outputs: tuple[str, ...] | str | None = None):
         """One step through HOST buffers: H2D actions, kernel, D2H outputs (chunk-pipelined in the
         library).  `actions_host`: [E,N,3] float32 numpy / CPU tensor, or None to use the pinned
-        `host_buffers()['actions']` in place.  Returns the dict of pinned host tensors."""
+        `host_buffers()['actions']` in place.  `outputs`: field names, or one of `OUTPUT_SETS` ("packed", "lean");
+        only those fields of the returned dict are fresh.  Returns the dict of pinned host tensors."""
         h = self.host_buffers()
         act = h["actions"]
         if actions_host is not None:
@@ -377,8 +401,7 @@ class SwarmEngine:
             out.block_host, out.block_dev = self._host_block.data_ptr(), self._out_block.data_ptr()
             out.block_bytes = self._out_block.numel()
         else:
-            names = outputs if outputs is not None else tuple(n for n in _abi.HOST_OUT_FIELDS if n in h)
-            for name in names:
+            for name in self._output_names(outputs):
                 setattr(out, name, h[name].data_ptr())
         rc = self._lib.swarm_step_host(self._handle, self._bufs_ref, act.data_ptr(), C.byref(out), int(auto_reset),
                                        self._stream())
@@ -396,10 +419,9 @@ class SwarmEngine:
         torch.cuda.current_stream(self.device).synchronize()
         return h
 
-    def host_bytes_per_step(self, outputs: tuple[str, ...] | None = None) -> tuple[int, int]:
+    def host_bytes_per_step(self, outputs: tuple[str, ...] | str | None = None) -> tuple[int, int]:
         h = self.host_buffers()
-        names = outputs if outputs is not None else tuple(n for n in _abi.HOST_OUT_FIELDS if n in h)
-        return h["actions"].numel() * 4, sum(h[n].numel() * h[n].element_size() for n in names)
+        return h["actions"].numel() * 4, sum(h[n].numel() * h[n].element_size() for n in self._output_names(outputs))
 
     # ------------------------------------------------------------------ statistics
     def stats(self) -> dict[str, float]:

@@ -26,8 +26,10 @@ def test_struct_layouts_match_header_field_order():
     names = re.findall(r"\*\s*([a-z_0-9]+)\s*;", body)
     assert tuple(names) == _abi.BUFFER_FIELDS
     body = header[header.index("typedef struct SwarmHostOut {"):header.index("} SwarmHostOut;")]
-    assert tuple(re.findall(r"\*\s*([a-z_0-9]+)\s*;", body)) == _abi.HOST_OUT_FIELDS + ("block_host", "block_dev")
-    assert [n for n, _ in _abi.SwarmHostOut._fields_][-3:] == ["block_host", "block_dev", "block_bytes"]
+    assert tuple(re.findall(r"\*\s*([a-z_0-9]+)\s*;", body)) == _abi.HOST_OUT_FIELDS + ("block_host", "block_dev", "flags")
+    assert [n for n, _ in _abi.SwarmHostOut._fields_][-4:] == ["block_host", "block_dev", "block_bytes", "flags"]
+    bits = dict(re.findall(r"SWARM_FLAG_([A-Z_]+) = (\d+)", header))
+    assert [int(bits[n.upper()]) for n in _abi.FLAG_FIELDS] == [1, 2, 4, 8, 16]
     body = header[header.index("typedef struct SwarmSizes {"):header.index("} SwarmSizes;")]
     assert tuple(re.findall(r"int64_t\s+([a-z_0-9]+)\s*;", body)) == tuple(n for n, _ in _abi.SwarmSizes._fields_)
 

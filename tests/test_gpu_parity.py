@@ -321,6 +321,44 @@ def test_step_host_matches_device_step():
             assert np.array_equal(pu.bits(h[name].numpy()), pu.bits(getattr(a, name).cpu().numpy())), (name, t)
 
 
+@pytest.mark.parametrize("cfg,E", [({"num_drones": 32, "num_obstacles": 8, "max_steps": 9, "world_size": 60.0}, 2048),   # four pipelined chunks
+                                   ({"num_drones": 5, "num_obstacles": 3, "max_steps": 12}, 333)])  # unaligned chunk
+def test_step_host_packed_flags_and_output_sets(cfg, E):
+    """ABI 5: `flags` is the five per-agent flag arrays in one byte, packed on the device behind the step; the
+    "packed" / "lean" output sets copy it instead of them and leave the other host fields alone."""
+    import torch
+    import swarm_b200
+    from swarm_b200 import _abi
+
+    N = cfg["num_drones"]
+    a = swarm_b200.SwarmEngine(E, cfg, device="cuda:0")
+    b = swarm_b200.SwarmEngine(E, cfg, device="cuda:0")
+    for x in (a, b):
+        x.seed(np.arange(E, dtype=np.uint64))
+        x.reset()
+    rng = np.random.default_rng(4)
+    names = ("terminated", "truncated", "reached", "collision", "obs_valid")
+    assert names == _abi.FLAG_FIELDS
+    seen = np.zeros(5, bool)
+    for t in range(30):
+        act = rng.uniform(-1.5, 1.5, size=(E, N, 3)).astype(np.float32)
+        a.step(torch.from_numpy(act).cuda())
+        mode = ("packed", "lean", ("flags", "terminated"))[t % 3]
+        h = b.step_host(act, outputs=mode)
+        want = sum((getattr(a, n).cpu().numpy().astype(np.uint8) & 1) << k for k, n in enumerate(names))
+        assert np.array_equal(h["flags"].numpy(), want), (t, mode)
+        un = swarm_b200.SwarmEngine.unpack_flags(h["flags"].numpy())
+        for k, n in enumerate(names):
+            assert np.array_equal(un[n], getattr(a, n).cpu().numpy().astype(bool)), (n, t)
+            seen[k] |= un[n].any()
+        for n in ("obs", "reward"):
+            if mode != ("flags", "terminated"):
+                assert np.array_equal(pu.bits(h[n].numpy()), pu.bits(getattr(a, n).cpu().numpy())), (n, t)
+    assert seen.all()
+    h2d, d2h = b.host_bytes_per_step("lean")
+    assert h2d == E * N * 12 and d2h == E * N * (a.D * 4 + 4 + 1) + 2 * E
+
+
 def test_engine_stats_and_episode_outputs():
     import torch
     import swarm_b200
