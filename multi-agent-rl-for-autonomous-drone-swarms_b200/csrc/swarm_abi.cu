@@ -117,8 +117,8 @@ int validate(const SwarmConfig* c) {
         return fail(SWARM_E_INVALID, "abi_version %d != %d", c->abi_version, SWARM_ABI_VERSION);
     if (c->env_kind != SWARM_KIND_SINGLE && c->env_kind != SWARM_KIND_SWARM && c->env_kind != SWARM_KIND_PHYSICS)
         return fail(SWARM_E_INVALID, "env_kind %d unknown", c->env_kind);
-    if (c->env_kind == SWARM_KIND_PHYSICS && (c->num_drones > 32 || c->dr_enabled))
-        return fail(SWARM_E_UNSUPPORTED, "SWARM_KIND_PHYSICS needs num_drones <= 32 and no domain randomisation");
+    if (c->env_kind == SWARM_KIND_PHYSICS && c->num_drones > 32)
+        return fail(SWARM_E_UNSUPPORTED, "SWARM_KIND_PHYSICS needs num_drones <= 32");
     if (c->num_envs < 1) return fail(SWARM_E_INVALID, "num_envs must be >= 1");
     if (c->num_drones < 1) return fail(SWARM_E_INVALID, "num_drones must be >= 1");
     if (c->env_kind == SWARM_KIND_SINGLE && c->num_drones != 1)
@@ -285,6 +285,9 @@ void fill_params(const SwarmConfig& c, DevParams& p) {
         p.thr_obst = (float)(c.obstacle_radius + 0.15);
         p.thr_pair = (float)(2.0 * 0.15);
         p.goal_radius_d = c.goal_radius;
+        // domain randomisation on top: the sub-step length and the drone's contact radius take the place of dt / r_c
+        p.dr_dt = 1.0 / 240.0;
+        p.dr_r_c = 0.15;
     }
 }
 

@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
     int grp = blockIdx.x * kWarpsPerCta + warp;
     while (grp < P.n_groups) {
         int grp_next = 0;
-        if (lane == 0) grp_next = warps_total + (int)atomicAdd(P.work_counter, 1u);
+        if (lane == 0) grp_next = (int)atomicAdd(P.work_counter, 1u);   // raw; + warps_total behind the shuffle
         const int env0 = P.env_begin + grp * G;
         const int n_env = min(G, P.env_begin + P.env_count - env0);
         const bool lane_env_ok = e_l < n_env;
@@ -710,7 +710,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                 if (P.episode_length) P.episode_length[env0 + lane] = 0;
             }
         }
-        grp = __shfl_sync(FULL_MASK, grp_next, 0);
+        grp = warps_total + __shfl_sync(FULL_MASK, grp_next, 0);
     }
     // the last warp to leave re-arms the queue for the next launch
     if (lane == 0 && atomicAdd(P.work_counter + 1, 1u) == (unsigned)warps_total - 1u) {
@@ -876,7 +876,8 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
     int it = gwarp;
     while (it < n_iter) {
         int it_next = it + warps_total;
-        if (dyn_queue && lane == 0) it_next = warps_total + (int)atomicAdd(P.work_counter, 1u);
+        // (the raw counter value: an add placed here is scheduled right behind the atomic and waits out its round trip)
+        if (dyn_queue && lane == 0) it_next = (int)atomicAdd(P.work_counter, 1u);
         const int env0 = listed ? rlist[it] : P.env_begin + it * G;
         const int n_env = min(G, P.env_begin + P.env_count - env0);
         const bool lane_ok = e_l < n_env;
@@ -954,7 +955,30 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                 // (action neither clipped nor cast; the mass cancels) + 9.5 - 9.81 on z, Bullet's
                 // integrateVelocities -> applyDamping -> integrateTransforms; v.w = this drone's damping factor
                 if (alive) {
-                    const float h = P.phys_h, f = v.w, gnet = P.phys_g_net;
+                    // DR on top: the episode's sub-step length rides in c_dt; control delay and thrust
+                    // noise act on the command, which is then held for the whole step (no clip: :336)
+                    if (DR && P.dr_delay_hist > 0) {
+                        const int H = P.dr_delay_hist;
+                        float* ring = P.act_hist + (long long)env * H * N * 3 + i * 3;
+                        const float sx = ax, sy = ay, sz = az;
+                        if (ctrl_delay > 0) {
+                            if (sc < ctrl_delay) {
+                                ax = 0.f; ay = 0.f; az = 0.f;
+                            } else {
+                                const float* hp = ring + (long long)((sc - ctrl_delay) % H) * N * 3;
+                                ax = hp[0]; ay = hp[1]; az = hp[2];
+                            }
+                        }
+                        float* wp = ring + (long long)(sc % H) * N * 3;
+                        wp[0] = sx; wp[1] = sy; wp[2] = sz;
+                    }
+                    if (DR) {
+                        const uint4 r = philox4x32_7(genv, ekey, (unsigned)sc, (unsigned)i | (DR_STREAM_A << 16), P);
+                        ax = __fmul_rn(ax, __fmaf_rn(P.dr_std_thrust, dr_normal(P.dr_qtable, dr_field(r, 0)), 1.0f));
+                        ay = __fmul_rn(ay, __fmaf_rn(P.dr_std_thrust, dr_normal(P.dr_qtable, dr_field(r, 1)), 1.0f));
+                        az = __fmul_rn(az, __fmaf_rn(P.dr_std_thrust, dr_normal(P.dr_qtable, dr_field(r, 2)), 1.0f));
+                    }
+                    const float h = DR ? c_dt : P.phys_h, f = v.w, gnet = P.phys_g_net;
                     // |v| can exceed max_speed only if the plain float32 sum of squares (within 2^-22 of the exact
                     // one, like the reference's norm) comes within 2^-19 of max_speed^2: the exact norm -- float64
                     // accumulate + IEEE sqrt, 24 times per step -- is evaluated only then (NaN compares false on
@@ -1030,7 +1054,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
             }
         }
         if (MODE == kSmallStep) {  // next group's inputs -> the other inbox
-            if (dyn_queue) it_next = __shfl_sync(FULL_MASK, it_next, 0);
+            if (dyn_queue) it_next = warps_total + __shfl_sync(FULL_MASK, it_next, 0);
             if (it_next < n_iter) prefetch(it_next, buf ^ 1);
         }
         float damp = v.w;  // physics env: per-drone damping factor rides in vel4.w
@@ -1719,9 +1743,9 @@ static EnvKernel resolve(const DevParams& p, int norm_mode, int env_kind) {
         if (!small_n) return pick_large<SWARM_MAX_NEIGHBOR_K, SWARM_MAX_SENSED, false, SWARM_KIND_SWARM>(norm_mode, dr);
         return pick_small<SWARM_MAX_NEIGHBOR_K, SWARM_MAX_SENSED, false, SWARM_KIND_SWARM, 0>(norm_mode, step, dr);
     }
-    if (env_kind == SWARM_KIND_PHYSICS) {  // point-mass DronePhysicsEnv: N <= 32, no domain randomisation
-        if (p.K == 3 && p.S == 4) return pick_small<3, 4, true, SWARM_KIND_PHYSICS, 0>(norm_mode, step, false);
-        return pick_small<SWARM_MAX_NEIGHBOR_K, SWARM_MAX_SENSED, false, SWARM_KIND_PHYSICS, 0>(norm_mode, step, false);
+    if (env_kind == SWARM_KIND_PHYSICS) {  // point-mass DronePhysicsEnv: N <= 32
+        if (p.K == 3 && p.S == 4) return pick_small<3, 4, true, SWARM_KIND_PHYSICS, 0>(norm_mode, step, dr);
+        return pick_small<SWARM_MAX_NEIGHBOR_K, SWARM_MAX_SENSED, false, SWARM_KIND_PHYSICS, 0>(norm_mode, step, dr);
     }
     if (p.S == 4) return pick_small<1, 4, true, SWARM_KIND_SINGLE, 1>(norm_mode, step, dr);
     return pick_small<1, SWARM_MAX_SENSED, false, SWARM_KIND_SINGLE, 0>(norm_mode, step, dr);

@@ -130,7 +130,7 @@ swarm_step_rotx_kernel(const DevParams P) {
         // dynamic item queue in both launches (an item is >= 10k warp instructions and a warp sees only ~5 of them,
         // so a static stride would leave a fifth of the warps one item short)
         int it_next = 0;
-        if (lane == 0) it_next = warps_total + (int)atomicAdd(queue, 1u);
+        if (lane == 0) it_next = (int)atomicAdd(queue, 1u);   // raw: "+ warps_total" placed here would wait for the atomic
         const int env = STEP ? P.env_begin + it : rlist[it];
         const int a0 = env * N;
         unsigned char* ib = envbox0 + (size_t)buf * envbox_bytes;
@@ -336,7 +336,7 @@ swarm_step_rotx_kernel(const DevParams P) {
         for (int off = 16; off >= 1; off >>= 1) n_alive_env += __shfl_xor_sync(FULL_MASK, n_alive_env, off);
         if (lane == 0) bulk_wait_read0();
         __syncwarp();
-        it_next = __shfl_sync(FULL_MASK, it_next, 0);
+        it_next = warps_total + __shfl_sync(FULL_MASK, it_next, 0);
         if (STEP && it_next < n_iter) issue(it_next, buf ^ 1);
 
         // ================= rotation pass =================

@@ -412,7 +412,7 @@ static void build_obs(const OracleConfig *c, const DynConst *kc, int step_obs, c
     out[3] = v[0]; out[4] = v[1]; out[5] = v[2];
     if (c->env_kind == 2) { /* drone_physics_env.py:436-439: the observed velocity is clamped to max_speed */
         float speed = norm1d(c, v[0], v[1], v[2]);
-        float vmax = (float)c->max_speed;
+        float vmax = kc->vmax;   /* (DR: this episode's) */
         if (speed > vmax)
             for (int k = 0; k < 3; ++k) {
                 volatile float q = v[k] / speed;
@@ -606,6 +606,51 @@ static void observe_env(const OracleConfig *c, EnvView *v) {
     if (v->gs) global_state(c, v->pos, v->vel, v->goal, v->gs);
 }
 
+/* DR: this episode's constants from one Philox counter per (global env, PCG64 state_lo before the reset draws):
+ * dr[0..7] = {max_accel s_acc / s_mass, max_speed s_spd, dt s_dt, world s_wld / 2, r_c + r_o s_rad, episode key,
+ * world s_wld, control delay}.  base_dt / r_c: the kinematic envs pass cfg.dt / cfg.collision_radius, the physics env
+ * its sub-step 1/240 s / the drone's contact radius.  Returns the half width of this episode's world. */
+static double draw_episode_constants(const OracleConfig *c, EnvView *v, double base_dt, double r_c) {
+    /* counter = (genv, PCG64 state_lo before the draws, 0xD5D5D5D5 [+1]) */
+    uint32_t genv = (uint32_t)(c->env_index_base + v->env_index);
+    uint32_t k0 = (uint32_t)(c->dr_seed & 0xffffffffu), k1 = (uint32_t)(c->dr_seed >> 32);
+    uint64_t sl = v->rng[1];
+    uint32_t ra[4] = {genv, (uint32_t)sl, (uint32_t)(sl >> 32), 0xD5D5D5D5u};
+    uint32_t rb[4] = {genv, (uint32_t)sl, (uint32_t)(sl >> 32), 0xD5D5D5D5u + 1u};
+    philox4x32_10(ra, k0, k1);
+    philox4x32_10(rb, k0, k1);
+    const double inv24 = 1.0 / 16777216.0;
+    uint32_t u[6] = {ra[0], ra[1], ra[2], ra[3], rb[0], rb[1]};
+    double sc[6];
+    for (int k = 0; k < 6; ++k) {
+        volatile double uu = (double)(u[k] >> 8) * inv24;
+        volatile double sp = c->dr_span[k] * uu;
+        sc[k] = c->dr_lo[k] + sp;
+    }
+    volatile double acc = c->max_accel * sc[1];
+    volatile double spd = c->max_speed * sc[2];
+    volatile double dtt = base_dt * sc[3];
+    volatile double rad = c->obstacle_radius * sc[4];
+    volatile double world = c->world_size * sc[5];
+    volatile double half_w = world * 0.5;
+    v->dr[0] = (float)(acc / sc[0]);
+    v->dr[1] = (float)spd;
+    v->dr[2] = (float)dtt;
+    v->dr[3] = (float)half_w;
+    v->dr[4] = (float)(r_c + rad);
+    memcpy(v->dr + 5, &rb[2], 4);
+    v->dr[6] = (float)world;
+    v->dr[7] = 0.0f;
+    if (c->dr_delay_count > 0) { /* this episode's control delay from the 4th word of the second block */
+        double uu = (double)(rb[3] >> 8) * inv24;
+        int pick = c->dr_delay_count - 1;
+        for (int k = 0; k < c->dr_delay_count; ++k)
+            if (uu < c->dr_delay_cum[k]) { pick = k; break; }
+        v->dr[7] = (float)c->dr_delay_values[pick];
+    }
+    return half_w;
+}
+
 /* reset  drone_swarm_env.py:65-90 / single_drone_env.py:53-71.
  * Draw order: positions (N,3) -> goal (3,) -> obstacles (M,3). */
 static void reset_env_physics(const OracleConfig *c, EnvView *v);
@@ -613,46 +658,7 @@ static void reset_env(const OracleConfig *c, EnvView *v) {
     int N = c->num_drones, M = c->num_obstacles;
     double bound = c->world_size / 2.0;
     if (c->env_kind == 2) { reset_env_physics(c, v); return; }
-    if (c->dr_enabled && v->dr) {
-        /* this episode's constants: counter = (genv, PCG64 state_lo before the draws, 0xD5D5D5D5 [+1]) */
-        uint32_t genv = (uint32_t)(c->env_index_base + v->env_index);
-        uint32_t k0 = (uint32_t)(c->dr_seed & 0xffffffffu), k1 = (uint32_t)(c->dr_seed >> 32);
-        uint64_t sl = v->rng[1];
-        uint32_t ra[4] = {genv, (uint32_t)sl, (uint32_t)(sl >> 32), 0xD5D5D5D5u};
-        uint32_t rb[4] = {genv, (uint32_t)sl, (uint32_t)(sl >> 32), 0xD5D5D5D5u + 1u};
-        philox4x32_10(ra, k0, k1);
-        philox4x32_10(rb, k0, k1);
-        const double inv24 = 1.0 / 16777216.0;
-        uint32_t u[6] = {ra[0], ra[1], ra[2], ra[3], rb[0], rb[1]};
-        double sc[6];
-        for (int k = 0; k < 6; ++k) {
-            volatile double uu = (double)(u[k] >> 8) * inv24;
-            volatile double sp = c->dr_span[k] * uu;
-            sc[k] = c->dr_lo[k] + sp;
-        }
-        volatile double acc = c->max_accel * sc[1];
-        volatile double spd = c->max_speed * sc[2];
-        volatile double dtt = c->dt * sc[3];
-        volatile double rad = c->obstacle_radius * sc[4];
-        volatile double world = c->world_size * sc[5];
-        volatile double half_w = world * 0.5;
-        v->dr[0] = (float)(acc / sc[0]);
-        v->dr[1] = (float)spd;
-        v->dr[2] = (float)dtt;
-        v->dr[3] = (float)half_w;
-        v->dr[4] = (float)(c->collision_radius + rad);
-        memcpy(v->dr + 5, &rb[2], 4);
-        v->dr[6] = (float)world;
-        v->dr[7] = 0.0f;
-        if (c->dr_delay_count > 0) { /* this episode's control delay from the 4th word of the second block */
-            double uu = (double)(rb[3] >> 8) * inv24;
-            int pick = c->dr_delay_count - 1;
-            for (int k = 0; k < c->dr_delay_count; ++k)
-                if (uu < c->dr_delay_cum[k]) { pick = k; break; }
-            v->dr[7] = (float)c->dr_delay_values[pick];
-        }
-        bound = half_w;
-    }
+    if (c->dr_enabled && v->dr) bound = draw_episode_constants(c, v, c->dt, c->collision_radius);
     double lo = -bound, range = bound - (-bound);
     for (int i = 0; i < N; ++i) v->active[i] = 1;
     *v->step_count = 0;
@@ -892,6 +898,8 @@ static double draw_uniform_f64(uint64_t rng[4], double lo, double range) {
 static void reset_env_physics(const OracleConfig *c, EnvView *v) {
     int N = c->num_drones, M = c->num_obstacles;
     double bound = c->world_size / 2.0;
+    /* DR on top (engine semantics): the sub-step length and the contact radius take the place of dt / r_c */
+    if (c->dr_enabled && v->dr) bound = draw_episode_constants(c, v, 1.0 / PHYS_SUBSTEP_HZ, PHYS_R_DRONE);
     double lo = -bound, range = bound - (-bound);
     for (int i = 0; i < N; ++i) v->active[i] = 1;
     *v->step_count = 0;
@@ -933,12 +941,22 @@ static void step_physics_env(const OracleConfig *c, EnvView *v, const float *act
         return;
     }
     const int substeps = (int)(c->dt * PHYS_SUBSTEP_HZ);                /* :323 */
-    const float h = (float)(1.0 / PHYS_SUBSTEP_HZ);
-    const float amax = (float)c->max_accel, vmax = (float)c->max_speed;
+    const DynConst kd = dyn_const(c, v);   /* DR: this episode's max_accel / max_speed / sub-step length / obstacle radius */
+    const float h = kd.dr ? kd.dt : (float)(1.0 / PHYS_SUBSTEP_HZ);
+    const float amax = kd.amax, vmax = kd.vmax;
     const float g_net = (float)(PHYS_G_COMP - PHYS_GRAVITY);            /* :343 minus :197 */
     for (int i = 0; i < N; ++i) {
         float *p = v->pos + 3 * i, *vel = v->vel + 3 * i;
-        const float *a = action + 3 * i;
+        float a[3];
+        delayed_command(c, v, i, action + 3 * i, a);                    /* DR control delay (identity without it) */
+        if (kd.dr) {  /* thrust noise a (1 + sigma z): one normal per axis, held for the whole step; no clip (:336) */
+            uint32_t ctr[4] = {kd.genv, kd.ekey, (uint32_t)*v->step_count, (uint32_t)i};
+            philox4x32_7(ctr, kd.k0, kd.k1);
+            for (int k = 0; k < 3; ++k) {
+                volatile float one = fmaf(kd.std_thrust, dr_normal(ctr, k), 1.0f);
+                a[k] = a[k] * one;
+            }
+        }
         const float f = v->damp[i];
         for (int s = 0; s < substeps; ++s) {
             float speed = norm1d(c, vel[0], vel[1], vel[2]);            /* :349-358 */
@@ -961,7 +979,7 @@ static void step_physics_env(const OracleConfig *c, EnvView *v, const float *act
         }
     }
     *v->step_count += 1;                                                /* :363 */
-    const float thr_obst = (float)(c->obstacle_radius + PHYS_R_DRONE);
+    const float thr_obst = kd.dr ? kd.thr_obst : (float)(c->obstacle_radius + PHYS_R_DRONE);
     const float thr_pair = (float)(2.0 * PHYS_R_DRONE);
     int any_collision = 0, all_goals = 1;
     for (int i = 0; i < N; ++i) {
