@@ -117,8 +117,6 @@ int validate(const SwarmConfig* c) {
         return fail(SWARM_E_INVALID, "abi_version %d != %d", c->abi_version, SWARM_ABI_VERSION);
     if (c->env_kind != SWARM_KIND_SINGLE && c->env_kind != SWARM_KIND_SWARM && c->env_kind != SWARM_KIND_PHYSICS)
         return fail(SWARM_E_INVALID, "env_kind %d unknown", c->env_kind);
-    if (c->env_kind == SWARM_KIND_PHYSICS && c->num_drones > 32)
-        return fail(SWARM_E_UNSUPPORTED, "SWARM_KIND_PHYSICS needs num_drones <= 32");
     if (c->num_envs < 1) return fail(SWARM_E_INVALID, "num_envs must be >= 1");
     if (c->num_drones < 1) return fail(SWARM_E_INVALID, "num_drones must be >= 1");
     if (c->env_kind == SWARM_KIND_SINGLE && c->num_drones != 1)

@@ -195,7 +195,7 @@ __device__ __forceinline__ void stage_obs_row(const DevParams& P, float* __restr
     row[3] = vx; row[4] = vy; row[5] = vz;
     row[6] = __fsub_rn(gx, px); row[7] = __fsub_rn(gy, py); row[8] = __fsub_rn(gz, pz);
     int off = 9;
-    if (KIND == SWARM_KIND_SWARM) {
+    if (KIND != SWARM_KIND_SINGLE) {
 #pragma unroll
         for (int q = 0; q < KT; ++q) {
             if (q < K) {
@@ -262,7 +262,7 @@ __device__ __forceinline__ void add_sensor_noise(const DevParams& P, float* __re
         row[c] = __fmaf_rn(P.dr_std_pos, dr_normal(P.dr_qtable, dr_field(rA, 3 + c)), row[c]);
         row[3 + c] = __fmaf_rn(P.dr_std_vel, dr_normal(P.dr_qtable, dr_field(rA, 6 + c)), row[3 + c]);
     }
-    const int off = 9 + (KIND == SWARM_KIND_SWARM ? 4 * K : 0);
+    const int off = 9 + (KIND != SWARM_KIND_SINGLE ? 4 * K : 0);
 #pragma unroll
     for (int q = 0; q < ST; ++q)
         if (q < S && om[q] >= 0) {
@@ -289,7 +289,8 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
     float* stage = reinterpret_cast<float*>(tab_obst + P.G * P.m_pad);
 
     const int N = P.N, M = P.M, G = P.G;
-    const int D = EXACT ? (KIND == SWARM_KIND_SWARM ? 9 + 4 * KT + 4 * ST : 9 + 4 * ST) : P.D;
+    constexpr bool PHYS = KIND == SWARM_KIND_PHYSICS;   // DronePhysicsEnv as a point mass, above 32 drones
+    const int D = EXACT ? (KIND != SWARM_KIND_SINGLE ? 9 + 4 * KT + 4 * ST : 9 + 4 * ST) : P.D;
     const int nslots = SMALLN ? 1 : P.nslots;
     const int e_l = SMALLN ? lane / N : 0;  // env-local index of this lane
     const int i_base = SMALLN ? lane - e_l * N : lane;
@@ -357,6 +358,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                     const float prev_d = norm1d<NORM>(__fsub_rn(gx, p.x), __fsub_rn(gy, p.y), __fsub_rn(gz, p.z));
                     if (alive) {
                         float ax = P.actions[a * 3 + 0], ay = P.actions[a * 3 + 1], az = P.actions[a * 3 + 2];
+                        const bool clip_cmd = !PHYS;   // (the physics env neither clips nor casts the action, :336)
                         if (DR && P.dr_delay_hist > 0) {
                             // control delay: apply the command submitted ctrl_delay steps ago (zero while the episode
                             // is younger), then file the one submitted now in ring slot step_count % H
@@ -374,7 +376,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                             float* wp = ring + (long long)(sc % H) * N * 3;
                             wp[0] = sx; wp[1] = sy; wp[2] = sz;
                         }
-                        ax = clipf(ax, -1.0f, 1.0f); ay = clipf(ay, -1.0f, 1.0f); az = clipf(az, -1.0f, 1.0f);
+                        if (clip_cmd) { ax = clipf(ax, -1.0f, 1.0f); ay = clipf(ay, -1.0f, 1.0f); az = clipf(az, -1.0f, 1.0f); }
                         if (!(ax == ax && ay == ay && az == az)) ++st_nan;   // NaN-action guard counter
                         if (DR) {  // thrust noise: a <- a * (1 + sigma z), one normal per axis
                             const uint4 r = philox4x32_7(genv, ekey, (unsigned)sc, (unsigned)i | (DR_STREAM_A << 16), P);
@@ -382,6 +384,30 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                             ay = __fmul_rn(ay, __fmaf_rn(P.dr_std_thrust, dr_normal(P.dr_qtable, dr_field(r, 1)), 1.0f));
                             az = __fmul_rn(az, __fmaf_rn(P.dr_std_thrust, dr_normal(P.dr_qtable, dr_field(r, 2)), 1.0f));
                         }
+                      if (PHYS) {
+                        // drone_physics_env.py:323-360 as a point mass (see the N <= 32 kernel below): per 1/240 s sub-step
+                        // speed clamp, thrust + 9.5 - 9.81 on z, Bullet's integrateVelocities -> applyDamping ->
+                        // integrateTransforms; v.w = this drone's damping factor
+                        const float h = DR ? c_dt : P.phys_h, f = v.w, gnet = P.phys_g_net;
+                        const float clamp_gate = __fmul_rn(__fmul_rn(c_vmax, c_vmax), 0.99999809265136719f /* 1 - 2^-19 */);
+#pragma unroll 1
+                        for (int sub = 0; sub < P.phys_substeps; ++sub) {
+                            if (sumsq_axis(v.x, v.y, v.z) > clamp_gate) {
+                                const float speed = norm1d<NORM>(v.x, v.y, v.z);
+                                if (speed > c_vmax) {
+                                    v.x = __fmul_rn(__fdiv_rn(v.x, speed), c_vmax);
+                                    v.y = __fmul_rn(__fdiv_rn(v.y, speed), c_vmax);
+                                    v.z = __fmul_rn(__fdiv_rn(v.z, speed), c_vmax);
+                                }
+                            }
+                            v.x = __fmul_rn(__fadd_rn(v.x, __fmul_rn(__fmul_rn(ax, c_amax), h)), f);
+                            v.y = __fmul_rn(__fadd_rn(v.y, __fmul_rn(__fmul_rn(ay, c_amax), h)), f);
+                            v.z = __fmul_rn(__fadd_rn(v.z, __fmul_rn(__fadd_rn(__fmul_rn(az, c_amax), gnet), h)), f);
+                            p.x = __fadd_rn(p.x, __fmul_rn(v.x, h));
+                            p.y = __fadd_rn(p.y, __fmul_rn(v.y, h));
+                            p.z = __fadd_rn(p.z, __fmul_rn(v.z, h));
+                        }
+                      } else {
                         v.x = __fadd_rn(v.x, __fmul_rn(__fmul_rn(ax, c_amax), c_dt));
                         v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(ay, c_amax), c_dt));
                         v.z = __fadd_rn(v.z, __fmul_rn(__fmul_rn(az, c_amax), c_dt));
@@ -394,13 +420,16 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                         p.x = __fadd_rn(p.x, __fmul_rn(v.x, c_dt));
                         p.y = __fadd_rn(p.y, __fmul_rn(v.y, c_dt));
                         p.z = __fadd_rn(p.z, __fmul_rn(v.z, c_dt));
+                      }
                     }
-                    // wall clip for ALL drones (:113-117); velocity is not zeroed at the wall
-                    p.x = clipf(p.x, -c_bound, c_bound);
-                    p.y = clipf(p.y, -c_bound, c_bound);
-                    p.z = clipf(p.z, -c_bound, c_bound);
+                    // wall clip for ALL drones (:113-117); velocity is not zeroed at the wall (the physics env has no walls)
+                    if (!PHYS) {
+                        p.x = clipf(p.x, -c_bound, c_bound);
+                        p.y = clipf(p.y, -c_bound, c_bound);
+                        p.z = clipf(p.z, -c_bound, c_bound);
+                    }
                     p.w = alive ? 1.0f : 0.0f;
-                    v.w = prev_d;
+                    if (!PHYS) v.w = prev_d;   // (physics: .w keeps the drone's damping factor; its reward has no progress term)
                     tab_pos[e_l * N + i] = p;
                     if (SMALLN) { p_reg = p; v_reg = v; }
                     else tab_vel[e_l * N + i] = v;
@@ -413,7 +442,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
             unsigned m_alive = 0, m_done = 0;  // bit = slot
             float rew_sum = 0.0f;
             bool any_col = false;
-            int n_cont = 0;
+            int n_cont = 0, n_open = 0;   // n_open (physics): active drones neither at the goal nor in contact
             for (int slot = 0; slot < nslots; ++slot) {
                 const int i = slot * 32 + i_base;
                 const bool ok = lane_env_ok && i < N;
@@ -428,11 +457,20 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                     ScanOut so;
                     scan_drone<KT, ST, NORM, KIND, true>(P, tpos, tobs, i, p.x, p.y, p.z, alive, n_alive_env, nd, nj,
                                                          od, om, so);
-                    reached = alive && curr_d <= P.thr_goal;           // :124-127 (double compare)
+                    // physics env: reached = dist < goal_radius (strict, drone_physics_env.py:389); contact with the
+                    // ground plane, an obstacle sphere or another drone (:368-372, point-mass radii set by the host)
+                    reached = PHYS ? (alive && (double)curr_d < P.goal_radius_d)
+                                   : (alive && curr_d <= P.thr_goal);   // :124-127 (double compare)
                     if (DR) so.obst_hit = od[0] <= c_thr_obst;         // this episode's obstacle radius
-                    collided = alive && (so.obst_hit || so.pair_hit);   // :128
+                    collided = alive && (so.obst_hit || so.pair_hit || (PHYS && p.z <= P.phys_ground_z));   // :128
                     double reward = 0.0;
-                    if (alive) {
+                    if (PHYS) {
+                        if (alive) {  // drone_physics_env.py:378-392
+                            reward = __dmul_rn(-(double)curr_d, 0.1);
+                            if (collided) reward = __dsub_rn(reward, 10.0);
+                            else if (reached) reward = __dadd_rn(reward, 50.0);
+                        }
+                    } else if (alive) {
                         const double progress = __dmul_rn(__dsub_rn((double)v.w, (double)curr_d), P.k_p);  // :142
                         if (KIND == SWARM_KIND_SWARM) {
                             double pen = 0.0;  // :210-224
@@ -451,8 +489,17 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                     P.dist[a] = curr_d;
                     P.reached[a] = reached ? 1 : 0;
                     P.collision[a] = collided ? 1 : 0;
-                    stage_obs_row<KT, ST, EXACT, KIND>(P, stage + lane * D, tpos, tobs, i, p.x, p.y, p.z, v.x, v.y,
-                                                       v.z, gx, gy, gz, nd, nj, od, om);
+                    float ovx = v.x, ovy = v.y, ovz = v.z;
+                    if (PHYS) {  // drone_physics_env.py:436-439: the observed velocity is clamped to max_speed
+                        const float speed = norm1d<NORM>(v.x, v.y, v.z);
+                        if (speed > c_vmax) {
+                            ovx = __fmul_rn(__fdiv_rn(v.x, speed), c_vmax);
+                            ovy = __fmul_rn(__fdiv_rn(v.y, speed), c_vmax);
+                            ovz = __fmul_rn(__fdiv_rn(v.z, speed), c_vmax);
+                        }
+                    }
+                    stage_obs_row<KT, ST, EXACT, KIND>(P, stage + lane * D, tpos, tobs, i, p.x, p.y, p.z, ovx, ovy,
+                                                       ovz, gx, gy, gz, nd, nj, od, om);
                     if (DR) add_sensor_noise<KT, ST, EXACT, KIND>(P, stage + lane * D, genv, ekey, sc + 1, i, om);
                 }
                 __syncwarp();
@@ -467,6 +514,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                 m_done |= (done_agent ? 1u : 0u) << slot;
                 any_col |= (__ballot_sync(FULL_MASK, collided) & env_lanes) != 0;
                 n_cont += __popc(__ballot_sync(FULL_MASK, alive && !done_agent) & env_lanes);
+                if (PHYS) n_open += __popc(__ballot_sync(FULL_MASK, alive && !collided && !reached) & env_lanes);
                 // deterministic per-env reward sum (segmented tree over the env's lanes)
                 float x = rew32;
 #pragma unroll
@@ -482,7 +530,15 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
             const int sc_new = env_active ? sc + 1 : sc;
             const bool time_limit = env_active && sc_new >= P.max_steps;
             bool all_term, all_trunc, ep_over;
-            if (KIND == SWARM_KIND_SWARM) {
+            if (PHYS) {  // drone_physics_env.py:397-417: one flag pair for every drone
+                const bool all_goals = n_open == 0;
+                all_trunc = env_active && time_limit && !any_col && !all_goals;
+                all_term = env_active ? (any_col || all_goals) : true;
+                ep_over = env_active && (any_col || all_goals || time_limit);
+                if (lane_env_ok && i_base == 0 && ep_over) {
+                    st_eps++; st_succ += (all_goals && !any_col) ? 1 : 0; st_col += any_col ? 1 : 0; st_to += all_trunc ? 1 : 0;
+                }
+            } else if (KIND == SWARM_KIND_SWARM) {
                 const bool all_reached = n_cont == 0 && !any_col && !time_limit;
                 const bool episode_done = all_reached || any_col;
                 all_term = env_active ? episode_done : true;  // :94-95 when no agent is left
@@ -507,7 +563,12 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                 const bool alive = (m_alive >> slot) & 1u, done_agent = (m_done >> slot) & 1u;
                 const long long a = (long long)env * N + i;
                 bool valid, alive_next;
-                if (KIND == SWARM_KIND_SWARM) {
+                if (PHYS) {
+                    P.terminated[a] = (alive && ep_over && !all_trunc) ? 1 : 0;
+                    P.truncated[a] = (alive && ep_over && all_trunc) ? 1 : 0;
+                    valid = alive;              // every drone is observed on every step
+                    alive_next = alive && !ep_over;
+                } else if (KIND == SWARM_KIND_SWARM) {
                     P.terminated[a] = (alive && done_agent) ? 1 : 0;                 // :150-151
                     P.truncated[a] = (alive && time_limit && !done_agent) ? 1 : 0;   // :152
                     valid = alive && !done_agent && cont_ok;                         // :154
@@ -523,7 +584,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                     float4 p = SMALLN ? p_reg : tab_pos[e_l * N + i];
                     float4 v = SMALLN ? v_reg : tab_vel[e_l * N + i];
                     p.w = alive_next ? 1.0f : 0.0f;
-                    v.w = 0.0f;
+                    if (!PHYS) v.w = 0.0f;   // (physics: the damping factor stays in .w)
                     P.pos4[a] = p;
                     P.vel4[a] = v;
                     if (gs_row) write_gs_drone(gs_row, N, i, p.x, p.y, p.z, v.x, v.y, v.z);
@@ -609,11 +670,39 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                         P.dr_params[(long long)renv * 2 + 0] = d0;
                         P.dr_params[(long long)renv * 2 + 1] = d1;
                     }
-                    if (lane_env_ok && e_l == el) ekey = rb.z;  // (the dynamics constants are not needed to observe)
+                    if (lane_env_ok && e_l == el) {
+                        ekey = rb.z;
+                        c_vmax = d0.y;   // (physics: the observed velocity is clamped to this episode's max_speed)
+                    }
                 }
                 for (int k = lane; k < P.n_draws; k += 32) {
                     unsigned long long oh, ol;
                     pcg_jump(P.jump[k + 1], sh, sl, ih, il, oh, ol);
+                    if (PHYS) {
+                        // drone_physics_env.py:207-242: per drone position (z >= 1), mass noise (cancels), damping
+                        // noise; obstacles (z >= 0.5); goal xy, one discarded draw, goal z in [0.5, 2]
+                        if (k < 5 * N) {
+                            const int dr_ = k / 5, c5 = k - 5 * dr_;
+                            if (c5 < 3) {
+                                float val = pcg_uniform_f32(oh, ol, u_lo, u_range);
+                                if (c5 == 2) val = fmaxf(val, 1.0f);
+                                reinterpret_cast<float*>(tab_pos + el * N + dr_)[c5] = val;
+                            } else if (c5 == 4) {
+                                const double c_lin = __dmul_rn(0.5, pcg_uniform_f64(oh, ol, 0.8, 1.2 - 0.8));
+                                reinterpret_cast<float*>(tab_vel + el * N + dr_)[3] = __double2float_rn(phys_damp_factor(c_lin));
+                            }
+                        } else if (k < 5 * N + 3 * M) {
+                            const int kk = k - 5 * N, m_ = kk / 3, c3 = kk - 3 * m_;
+                            float val = pcg_uniform_f32(oh, ol, u_lo, u_range);
+                            if (c3 == 2) val = fmaxf(val, 0.5f);
+                            reinterpret_cast<float*>(tab_obst + el * P.m_pad + m_)[c3] = val;
+                        } else {
+                            const int g_ = k - 5 * N - 3 * M;
+                            if (g_ < 2) reinterpret_cast<float*>(tab_goal + el)[g_] = pcg_uniform_f32(oh, ol, u_lo, u_range);
+                            else if (g_ == 3) reinterpret_cast<float*>(tab_goal + el)[2] = pcg_uniform_f32(oh, ol, 0.5, 2.0 - 0.5);
+                        }
+                        continue;
+                    }
                     const float val = pcg_uniform_f32(oh, ol, u_lo, u_range);
                     // draw order: positions (N,3) -> goal (3,) -> obstacles (M,3)
                     if (k < 3 * N) {
@@ -627,7 +716,9 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                 }
                 for (int k = lane; k < N; k += 32) {
                     reinterpret_cast<float*>(tab_pos + el * N + k)[3] = 1.0f;
-                    tab_vel[el * N + k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float* tv = reinterpret_cast<float*>(tab_vel + el * N + k);
+                    tv[0] = 0.f; tv[1] = 0.f; tv[2] = 0.f;
+                    if (!PHYS) tv[3] = 0.f;  // (physics: .w holds this drone's new damping factor)
                 }
                 if (lane == 0) {
                     unsigned long long oh, ol;
@@ -666,10 +757,11 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                     scan_drone<KT, ST, NORM, KIND, false>(P, tpos, tobs, i, p.x, p.y, p.z, true, N, nd, nj, od, om, so);
                     const long long a = (long long)env * N + i;
                     P.dist[a] = norm1d<NORM>(__fsub_rn(gx, p.x), __fsub_rn(gy, p.y), __fsub_rn(gz, p.z));
-                    P.obs_valid[a] = KIND == SWARM_KIND_SINGLE ? 1 : (p.w != 0.0f ? 1 : 0);
+                    // (the physics env observes every drone, always: drone_physics_env.py:421-462)
+                    P.obs_valid[a] = KIND != SWARM_KIND_SWARM ? 1 : (p.w != 0.0f ? 1 : 0);
                     if (fresh) {
                         P.pos4[a] = p;
-                        P.vel4[a] = make_float4(v.x, v.y, v.z, 0.0f);
+                        P.vel4[a] = make_float4(v.x, v.y, v.z, PHYS ? v.w : 0.0f);
                     }
                     if (P.mode != kModeStep) {
                         P.reward[a] = 0.0f;
@@ -677,7 +769,16 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinBlocksPerSm) swarm_env_ker
                         P.terminated[a] = 0; P.truncated[a] = 0; P.reached[a] = 0; P.collision[a] = 0;
                     }
                     if (gs_row) write_gs_drone(gs_row, N, i, p.x, p.y, p.z, v.x, v.y, v.z);
-                    stage_obs_row<KT, ST, EXACT, KIND>(P, stage + lane * D, tpos, tobs, i, p.x, p.y, p.z, v.x, v.y, v.z,
+                    float ovx = v.x, ovy = v.y, ovz = v.z;
+                    if (PHYS) {  // the observed velocity is clamped to max_speed (:436-439)
+                        const float speed = norm1d<NORM>(v.x, v.y, v.z);
+                        if (speed > c_vmax) {
+                            ovx = __fmul_rn(__fdiv_rn(v.x, speed), c_vmax);
+                            ovy = __fmul_rn(__fdiv_rn(v.y, speed), c_vmax);
+                            ovz = __fmul_rn(__fdiv_rn(v.z, speed), c_vmax);
+                        }
+                    }
+                    stage_obs_row<KT, ST, EXACT, KIND>(P, stage + lane * D, tpos, tobs, i, p.x, p.y, p.z, ovx, ovy, ovz,
                                                        gx, gy, gz, nd, nj, od, om);
                     // (a re-drawn env is observed at step_count 0, swarm_observe at the env's current step_count)
                     if (DR) add_sensor_noise<KT, ST, EXACT, KIND>(P, stage + lane * D, genv, ekey, fresh ? 0 : sc, i, om);
@@ -1743,8 +1844,12 @@ static EnvKernel resolve(const DevParams& p, int norm_mode, int env_kind) {
         if (!small_n) return pick_large<SWARM_MAX_NEIGHBOR_K, SWARM_MAX_SENSED, false, SWARM_KIND_SWARM>(norm_mode, dr);
         return pick_small<SWARM_MAX_NEIGHBOR_K, SWARM_MAX_SENSED, false, SWARM_KIND_SWARM, 0>(norm_mode, step, dr);
     }
-    if (env_kind == SWARM_KIND_PHYSICS) {  // point-mass DronePhysicsEnv: N <= 32
-        if (p.K == 3 && p.S == 4) return pick_small<3, 4, true, SWARM_KIND_PHYSICS, 0>(norm_mode, step, dr);
+    if (env_kind == SWARM_KIND_PHYSICS) {  // point-mass DronePhysicsEnv
+        if (p.K == 3 && p.S == 4) {
+            if (!small_n) return pick_large<3, 4, true, SWARM_KIND_PHYSICS>(norm_mode, dr);
+            return pick_small<3, 4, true, SWARM_KIND_PHYSICS, 0>(norm_mode, step, dr);
+        }
+        if (!small_n) return pick_large<SWARM_MAX_NEIGHBOR_K, SWARM_MAX_SENSED, false, SWARM_KIND_PHYSICS>(norm_mode, dr);
         return pick_small<SWARM_MAX_NEIGHBOR_K, SWARM_MAX_SENSED, false, SWARM_KIND_PHYSICS, 0>(norm_mode, step, dr);
     }
     if (p.S == 4) return pick_small<1, 4, true, SWARM_KIND_SINGLE, 1>(norm_mode, step, dr);

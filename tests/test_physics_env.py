@@ -85,6 +85,9 @@ GPU_CASES = [
     ({"num_drones": 5, "num_obstacles": 0, "max_steps": 30, "neighbor_k": 2, "sensed_obstacles": 3}, 333, 50),
     ({"num_drones": 32, "num_obstacles": 8, "world_size": 44.0, "max_steps": 20}, 128, 30),
     ({"num_drones": 1, "num_obstacles": 3, "max_steps": 20}, 500, 40),
+    # more than 32 drones (round 2): the general large-N kernel
+    ({"num_drones": 40, "num_obstacles": 4, "world_size": 60.0, "max_steps": 20}, 48, 45),
+    ({"num_drones": 64, "num_obstacles": 8, "world_size": 80.0, "max_steps": 15, "neighbor_k": 4, "sensed_obstacles": 5}, 32, 35),
 ]
 
 
@@ -160,7 +163,8 @@ def test_oracle_physics_neutral_randomisation_is_the_plain_path_and_constants_sc
                                      ({"num_drones": 8, "num_obstacles": 4, "max_steps": 30}, 400, 70),
                                      ({"num_drones": 32, "num_obstacles": 8, "world_size": 44.0, "max_steps": 20}, 96, 30),
                                      ({"num_drones": 5, "num_obstacles": 6, "max_steps": 25, "neighbor_k": 2,
-                                       "sensed_obstacles": 6}, 200, 50)])
+                                       "sensed_obstacles": 6}, 200, 50),
+                                     ({"num_drones": 48, "num_obstacles": 6, "world_size": 70.0, "max_steps": 20}, 40, 45)])
 def test_cuda_physics_with_domain_randomisation_matches_oracle(cfg, E, T):
     """DR on top of the physics env (round 2): per-episode max_accel / max_speed / sub-step length / obstacle radius /
     world, thrust + sensor noise, control delay -- CUDA and the C restatement agree bit for bit."""
