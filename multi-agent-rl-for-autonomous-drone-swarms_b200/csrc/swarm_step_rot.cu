@@ -47,6 +47,11 @@ namespace swarm {
 #define SWARM_ROT_W32 4
 #define SWARM_ROT_B32 7
 #endif
+// SWARM_ROT_DR_QTAB_GLOBAL = 1: the table is read from global memory (L1) instead, no per-CTA copy (measured slower:
+// 0.1571 ms per C4 step as 7 x 4, 0.1557 as 4 x 7 -- which the missing copy makes possible -- against 0.1545)
+#ifndef SWARM_ROT_DR_QTAB_GLOBAL
+#define SWARM_ROT_DR_QTAB_GLOBAL 0
+#endif
 #ifndef SWARM_ROT_W32_DR
 #define SWARM_ROT_W32_DR 7
 #define SWARM_ROT_B32_DR 4
@@ -114,10 +119,11 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
         n_local = 0;
     };
     // DR: the signed 512-entry normal quantile table lives in shared memory (13 lookups per agent-step)
-    const float* qtab = reinterpret_cast<const float*>(smem_raw + (size_t)kRotWarps * per_warp +
+    const float* qtab = SWARM_ROT_DR_QTAB_GLOBAL ? P.dr_qtable :
+                        reinterpret_cast<const float*>(smem_raw + (size_t)kRotWarps * per_warp +
                                                        (size_t)kRotWarps * SWARM_STATS_WORDS * sizeof(unsigned long long) +
                                                        (size_t)kRotWarps * kLocalList * sizeof(int));
-    if (DR) {
+    if (DR && !SWARM_ROT_DR_QTAB_GLOBAL) {
         float* qw = const_cast<float*>(qtab);
         for (int k = threadIdx.x; k < 512; k += kRotWarps * 32) qw[k] = P.dr_qtable[k];
         __syncthreads();
@@ -1103,7 +1109,7 @@ static RotKernel pick_rot(const DevParams& p) {
 size_t rot_smem_bytes(const DevParams& p) {
     return (size_t)rot_warps(p.N, p.dr_enabled != 0) * rot_smem_per_warp(32 / p.N, p.M, p.dr_enabled != 0) +
            (size_t)rot_warps(p.N, p.dr_enabled != 0) * (SWARM_STATS_WORDS * sizeof(unsigned long long) + 8 * sizeof(int)) +
-           (p.dr_enabled ? 2048 : 0);
+           ((p.dr_enabled && !SWARM_ROT_DR_QTAB_GLOBAL) ? 2048 : 0);
 }
 
 cudaError_t launch_rot_kernel(const DevParams& p, int grid, cudaStream_t stream) {

@@ -6,6 +6,10 @@ tools/quick_bench.sh warm c4 >/dev/null 2>&1
 python bench.py > $out/bench_full_$tag.json 2> $out/bench_full_$tag.err
 python bench.py --impl reference --steps 20 --warmup 5 > $out/bench_ref_$tag.json 2> $out/bench_ref_$tag.err
 tools/quick_bench.sh $tag c2 c3 c1 c5 c5_w70 c4_w44 phys phys8
+# round 2b: randomisation above 32 drones and on the physics env
+python bench.py --steps 300 --warmup 10 --no-cpu --no-e2e --no-dr-off --workload c5_w70 --dr on > $out/bench_${tag}_c5_w70_dr.json 2> $out/bench_${tag}_c5_w70_dr.err
+python bench.py --steps 300 --warmup 10 --no-cpu --no-e2e --no-dr-off --workload c5 --dr on > $out/bench_${tag}_c5_dr.json 2> $out/bench_${tag}_c5_dr.err
+python bench.py --steps 300 --warmup 10 --no-cpu --no-e2e --no-dr-off --workload phys8 --dr on > $out/bench_${tag}_phys8_dr.json 2> $out/bench_${tag}_phys8_dr.err
 python tools/facade_latency.py > $out/facade_latency_$tag.json 2> $out/facade_latency_$tag.err
 for dr in on off; do
   CMD="python bench.py --steps 12 --warmup 4 --no-cpu --no-e2e --no-dr-off --no-named-sizes --dr $dr"
