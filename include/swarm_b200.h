@@ -43,8 +43,9 @@ enum {
     SWARM_KIND_SINGLE = 0, /* SingleDroneEnv  (single_drone_env.py:12) */
     SWARM_KIND_SWARM = 1,  /* DroneSwarmEnv   (drone_swarm_env.py:17) */
     SWARM_KIND_PHYSICS = 2 /* DronePhysicsEnv (drone_physics_env.py:22) as a point mass: its env contract and the
-                              force / drag / gravity / speed-clamp model around PyBullet's solver; num_drones <= 32,
-                              no domain randomisation.  PyBullet is not vendored: parity unpinned */
+                              force / drag / gravity / speed-clamp model around PyBullet's solver; any num_drones up
+                              to SWARM_MAX_DRONES, domain randomisation allowed on top (round 2).  PyBullet is not
+                              vendored: parity unpinned */
 };
 
 #define SWARM_MAX_DRONES 128    /* np.mean's pairwise sum is restated exactly for n <= 128 */

@@ -84,6 +84,10 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
     constexpr unsigned IDX = NT - 1;  // index bits of a neighbour key
     constexpr int kRotWarps = rot_warps(NT, DR);
     constexpr bool kStepLike = MODE != kRotReset;   // items = env groups of the batch, inputs by TMA, dynamic queue
+#ifndef SWARM_ROT_RAW_DRAW_MIN_N
+#define SWARM_ROT_RAW_DRAW_MIN_N 16
+#endif
+    constexpr bool kRawDraw = NT >= SWARM_ROT_RAW_DRAW_MIN_N;   // queue draws keep the raw counter value until the shuffle
     constexpr bool kFused = MODE == kRotFused;
     // (the shuffle makes the warp index provably warp-uniform: addresses and branches that derive from
     //  it are then computed on the uniform datapath)
@@ -279,8 +283,9 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
         } else if (kStepLike) {
             // (the RAW counter value: "+ warps_total" written here is scheduled right behind the atomic and waits out
             //  its round trip -- 4.6 % of the launch's stall samples in the ncu source view; it is added behind the
-            //  shuffle that broadcasts the value, half an item later)
-            if (lane == 0) it_next = (int)atom_inc_lane(queue, tid_y);
+            //  shuffle that broadcasts the value, half an item later.  N = 8 keeps the add in place: its short items
+            //  measured 4 % slower with the deferred add, N = 16 / 32 1.5 % / 1 % faster)
+            if (lane == 0) it_next = (kRawDraw ? 0 : warps_total) + (int)atom_inc_lane(queue, tid_y);
         } else {
             it_next = it + warps_total;
         }
@@ -522,7 +527,7 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
             if (pass == 0) {
                 if (!kFused) {
                     it_next = __shfl_sync(FULL_MASK, it_next, 0);
-                    if (kStepLike) it_next += warps_total;
+                    if (kStepLike && kRawDraw) it_next += warps_total;
                 }
                 // (fused, one group per warp: the next item is THIS group one step later -- its inputs are this
                 //  item's outputs, so they are fetched at the end of the item instead)
