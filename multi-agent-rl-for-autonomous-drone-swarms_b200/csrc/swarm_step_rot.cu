@@ -674,7 +674,13 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
                     nd[q] = fabsf(srow[t <= HALF ? t : HALF + N - t]);  // backward round N - t was stashed at HALF + (N - t)
                                                                          // (|.|: the packed rounds stash -d)
                 }
-                {
+#ifndef SWARM_ROT_SORT_ALWAYS
+#define SWARM_ROT_SORT_ALWAYS 0
+#endif
+                // keys in different buckets order their exact distances strictly (the truncation is monotone), so the
+                // exact (distance, index) sort of the picks is only needed when two of the first three keys share a
+                // bucket -- about one warp in a thousand (ncu source view: the sort was ~35 instructions per env-step)
+                if (SWARM_ROT_SORT_ALWAYS || __any_sync(FULL_MASK, (k0 ^ k1) <= IDX || (k1 ^ k2) <= IDX)) {
                     auto cex3 = [&](int a, int b) {
                         const bool sw = nd[a] > nd[b] || (nd[a] == nd[b] && nj[a] > nj[b]);
                         const float td = sw ? nd[b] : nd[a], tD = sw ? nd[a] : nd[b];
