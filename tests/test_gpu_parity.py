@@ -745,6 +745,9 @@ FULL_SIZE = [
     ("c4_dr_delay", {"num_drones": 32, "num_obstacles": 8}, 65536, 12, "v1+delay"),   # the yaml's whole actuation block
     ("c5_w20", {"num_drones": 128, "num_obstacles": 8}, 8192, 5, None),              # C5 as named: every env resets every step
     ("c5", {"num_drones": 128, "num_obstacles": 8, "world_size": 70.0}, 8192, 6, None),
+    # round 2: BASELINE config 5 under domain_randomization_v1 (+ control delay) -- the wide kernel's DR instantiations
+    ("c5_dr_delay", {"num_drones": 128, "num_obstacles": 8, "world_size": 70.0, "max_steps": 6}, 8192, 8, "v1+delay"),
+    ("c5_w20_dr", {"num_drones": 128, "num_obstacles": 8}, 4096, 4, "v1"),
 ]
 
 
