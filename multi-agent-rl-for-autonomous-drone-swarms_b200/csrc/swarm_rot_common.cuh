@@ -100,6 +100,15 @@ __device__ __forceinline__ double f64_of_pos_f32(float a) {
     }
     return (double)a;
 }
+// the same for a NEGATIVE normal float32 (the negated distances of the packed rounds): the sign bit of the float32
+// pattern lands on bit 60 of the product, so the constant takes 2^60 back out and sets bit 63
+__device__ __forceinline__ double f64_of_neg_f32(float a) {
+    if (SWARM_ROT_CVT_FORM & 1) {
+        const unsigned b = __float_as_uint(a);
+        return __longlong_as_double((long long)((unsigned long long)b * 0x20000000ull + 0xA800000000000000ull));
+    }
+    return (double)a;
+}
 __device__ __forceinline__ float sumsq1d_fast(float x, float y, float z) {
     const float px = __fmul_rn(x, x), py = __fmul_rn(y, y), pz = __fmul_rn(z, z);
     return __double2float_rn(__dadd_rn(__dadd_rn(f64_of_pos_f32<(SWARM_ROT_CVT_SQ & 1) != 0>(px),

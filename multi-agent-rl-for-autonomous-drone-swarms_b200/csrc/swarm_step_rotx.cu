@@ -34,13 +34,21 @@ namespace swarm {
 #ifndef SWARM_ROTX_DIRECT
 #define SWARM_ROTX_DIRECT 0
 #endif
+// step launch: the rounds run on packed float32x2 instructions (FADD2 / FMUL2 / FFMA2, same roundings) like the N <= 32
+// kernel -- (x, y) and (z, .) of a coordinate difference are one packed subtract + one packed multiply each, the square
+// roots of two distances four packed operations; distances travel NEGATED (see neg_sqrt_rn_fast2).  The velocities and
+// previous goal distances (16 values per lane at N = 128) wait in shared memory during the pass, which pays for the
+// registers of the packed operands.
+#ifndef SWARM_ROTX_PACKED
+#define SWARM_ROTX_PACKED 1
+#endif
 constexpr int kXWarps = 4;  // warps per CTA
 
 __host__ __device__ constexpr int rotx_envbox_bytes(int M, bool dr) { return 16 * (1 + M) + 16 + (dr ? 32 : 0); }
 // per warp: mbarriers (16) | agent inbox pos4[N] vel4[N] actions[3N] | env inbox x 2 | position table
 // (N float4; not doubled: the partner lane index is masked instead, which lets 4 CTAs = 16 warps fit an SM) |
 // obs tile (one slot at a time)
-__host__ __device__ constexpr int rotx_smem_per_warp(int N, int M, bool dr) {
+__host__ __device__ constexpr int rotx_smem_per_warp(int N, int M, bool dr, bool step) {
     return 16 + (SWARM_ROTX_DIRECT ? 0 : 44 * N) + 2 * rotx_envbox_bytes(M, dr) + (N / 32) * 32 * 16 + kTileBytes;
 }
 
@@ -68,6 +76,7 @@ swarm_step_rotx_kernel(const DevParams P) {
     const int M = MT ? MT : P.M;
     const int envbox_bytes = rotx_envbox_bytes(M, DR);
     constexpr int kAgentBox = SWARM_ROTX_DIRECT ? 0 : 44 * N;
+    constexpr bool kPacked = SWARM_ROTX_PACKED && STEP;
     const int per_warp = 16 + kAgentBox + 2 * envbox_bytes + NS * 512 + kTileBytes;
     unsigned char* wslice = smem_raw + (size_t)warp * per_warp;
     const unsigned bar0 = smem_u32(wslice);
@@ -79,6 +88,9 @@ swarm_step_rotx_kernel(const DevParams P) {
         reinterpret_cast<unsigned long long*>(smem_raw + (size_t)kXWarps * per_warp) + warp * SWARM_STATS_WORDS;
     if (lane < SWARM_STATS_WORDS) wstats[lane] = 0ull;
     float* srow = tile + lane * kD;
+    // kPacked: the obs tile is idle during the rotation pass -- velocities / previous goal distances wait there,
+    // [4 * NS][32] floats, this lane's column (written once the previous item's tile has left, read back before the tail)
+    float* const vstash = tile + lane;
 
     asm volatile("griddepcontrol.wait;" ::: "memory");  // programmatic dependent launch (see swarm_step_rot.cu)
     // auto-reset hand-over: list (epoch & 1) is appended to by the step launch, list ((epoch - 1) & 1) is walked by
@@ -338,6 +350,13 @@ swarm_step_rotx_kernel(const DevParams P) {
         __syncwarp();
         it_next = warps_total + __shfl_sync(FULL_MASK, it_next, 0);
         if (STEP && it_next < n_iter) issue(it_next, buf ^ 1);
+        if (kPacked) {   // not needed before the per-drone tail: out of the registers during the rotation pass
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                vstash[(4 * s + 0) * 32] = vx[s]; vstash[(4 * s + 1) * 32] = vy[s];
+                vstash[(4 * s + 2) * 32] = vz[s]; vstash[(4 * s + 3) * 32] = prev_d[s];
+            }
+        }
 
         // ================= rotation pass =================
         // MASKED = some drone of the env is parked (it reached the goal earlier): neighbour keys still cover every
@@ -352,6 +371,16 @@ swarm_step_rotx_kernel(const DevParams P) {
         auto rotation_pass = [&](auto masked_tag) {
             constexpr bool MASKED = decltype(masked_tag)::value;
             const double d_star = P.d_star;
+            constexpr unsigned KEYMASK = ~IDX & 0x7fffffffu;   // packed rounds: keys drop the sign of the negated distance
+            f32x2 pxy[NS], pz0[NS];
+#ifndef SWARM_ROTX_PACKED_RESET
+#define SWARM_ROTX_PACKED_RESET 1
+#endif
+            constexpr bool kPackedReset = SWARM_ROTX_PACKED && SWARM_ROTX_PACKED_RESET && !STEP;   // packed differences / squares only
+            if (kPacked || kPackedReset) {
+#pragma unroll
+                for (int s = 0; s < NS; ++s) { pxy[s] = pack2(px[s], py[s]); pz0[s] = pack2(pz[s], 0.0f); }
+            }
             // round 0: the pairs inside a lane
 #pragma unroll
             for (int s = 0; s < NS; ++s)
@@ -389,10 +418,42 @@ swarm_step_rotx_kernel(const DevParams P) {
 #pragma unroll
                 for (int s2 = 0; s2 < NS; ++s2) {
                     const float4 q = tq[s2 * 32];
+                    if (kPacked) {
+                        // NS distances to q: packed differences / squares, float64 accumulate (BLAS sdot), two packed
+                        // square roots at a time; nd[] = MINUS the distance
+                        float nd[NS];
 #pragma unroll
-                    for (int s = 0; s < NS; ++s) {
-                        const float sq = STEP ? sumsq1d_fast(__fsub_rn(q.x, px[s]), __fsub_rn(q.y, py[s]), __fsub_rn(q.z, pz[s]))
-                                              : sumsq_axis(__fsub_rn(q.x, px[s]), __fsub_rn(q.y, py[s]), __fsub_rn(q.z, pz[s]));
+                        for (int s = 0; s < NS; s += 2) {
+                            float ax2, ay2, az2, bx2, by2, bz2;
+                            sq_diff3(q, pxy[s], pz0[s], ax2, ay2, az2);
+                            sq_diff3(q, pxy[s + 1], pz0[s + 1], bx2, by2, bz2);
+                            unpack2(neg_sqrt_rn_fast2(neg_sumsq1d_of_squares(ax2, ay2, az2), neg_sumsq1d_of_squares(bx2, by2, bz2)),
+                                    nd[s], nd[s + 1]);
+                        }
+#pragma unroll
+                        for (int s = 0; s < NS; ++s) {
+                            kf[s][s2] = and_or<KEYMASK>(__float_as_uint(nd[s]), __float_as_uint(q.w));
+                            const double t = fabs(__dadd_rn(f64_of_neg_f32(nd[s]), d_star));   // |(-d) + d*|
+                            acc[s] = __dadd_rn(acc[s], MASKED ? __dmul_rn(t, mf[s2]) : t);
+                            if (!LAST) {
+                                const float db = __shfl_sync(FULL_MASK, nd[s], lb);  // -d(drone s of lane l - r, my drone s2)
+                                kb[s][s2] = and_or<KEYMASK>(__float_as_uint(db), (unsigned)(s * 32 + lb));
+                                const double tb = fabs(__dadd_rn(f64_of_neg_f32(db), d_star));
+                                acc[s2] = __dadd_rn(acc[s2], MASKED ? __dmul_rn(tb, mb[s]) : tb);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int s = 0; s < (kPacked ? 0 : NS); ++s) {   // (scalar rounds: the reset launch, or SWARM_ROTX_PACKED = 0)
+                        float sq;
+                        if (kPackedReset) {   // sumsq_axis with packed differences / squares (same operations, same order)
+                            float sx, sy, sz;
+                            sq_diff3(q, pxy[s], pz0[s], sx, sy, sz);
+                            sq = __fadd_rn(__fadd_rn(sx, sy), sz);
+                        } else {
+                            sq = STEP ? sumsq1d_fast(__fsub_rn(q.x, px[s]), __fsub_rn(q.y, py[s]), __fsub_rn(q.z, pz[s]))
+                                      : sumsq_axis(__fsub_rn(q.x, px[s]), __fsub_rn(q.y, py[s]), __fsub_rn(q.z, pz[s]));
+                        }
                         const float d = STEP ? sqrt_rn_fast(sq) : sq;  // (reset launch: key = squared distance, see round 0)
                         kf[s][s2] = and_or<~IDX>(__float_as_uint(d), __float_as_uint(q.w));
                         if (STEP) {
@@ -431,6 +492,13 @@ swarm_step_rotx_kernel(const DevParams P) {
         if (all_alive) rotation_pass(std::false_type{});
         else rotation_pass(std::true_type{});
         const bool exact = __any_sync(FULL_MASK, bad);
+        if (kPacked) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                vx[s] = vstash[(4 * s + 0) * 32]; vy[s] = vstash[(4 * s + 1) * 32];
+                vz[s] = vstash[(4 * s + 2) * 32]; prev_d[s] = vstash[(4 * s + 3) * 32];
+            }
+        }
 
         // ================= per-drone tail: one copy of code, NS passes over rotated register arrays =================
         double rew[NS];
@@ -813,7 +881,7 @@ static RotxKernel pick_rotx(const DevParams& p) {
 }
 
 size_t rotx_smem_bytes(const DevParams& p) {
-    return (size_t)kXWarps * rotx_smem_per_warp(p.N, p.M, p.dr_enabled != 0) +
+    return (size_t)kXWarps * rotx_smem_per_warp(p.N, p.M, p.dr_enabled != 0, p.mode != kModeAutoReset) +
            (size_t)kXWarps * SWARM_STATS_WORDS * sizeof(unsigned long long);
 }
 int rotx_warps_per_cta() { return kXWarps; }
