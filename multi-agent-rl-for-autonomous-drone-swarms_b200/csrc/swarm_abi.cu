@@ -34,7 +34,10 @@ int fail(int code, const char* fmt, ...) {
             return fail(SWARM_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
 
-constexpr int kHostChunks = 4;
+#ifndef SWARM_HOST_CHUNKS
+#define SWARM_HOST_CHUNKS 4
+#endif
+constexpr int kHostChunks = SWARM_HOST_CHUNKS;
 
 }  // namespace
 
