@@ -21,6 +21,7 @@
 //             d >= 2^-14; otherwise the exact path runs).
 //   outputs   the 32 x 37 observation tile is staged in shared memory and leaves with ONE TMA bulk
 //             store per group; state / flags are float4 / byte stores straight from registers.
+#include <type_traits>
 #include "swarm_rot_common.cuh"
 
 // programmatic dependent launch of the step / reset kernels (hides the launch latency between them)
@@ -582,8 +583,19 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
             int form_n = 0;
             const float4* tp = tab2 + 2 * e_base + i;  // tp[r] = drone (i + r) mod N
             bool bad = false;
-            if (alive_mask == ok_lanes) {
-                // ================= rotation pass: every drone of the group is active =================
+            // Groups with PARKED drones (they reached the goal earlier, the episode goes on) stay on the rotation pass
+            // (round 2b, as in the wide kernel): neighbour keys cover every drone, each formation term is multiplied by
+            // the partner's 0.0 / 1.0 activity flag (the float64 sum is exact, so the masked sum IS the reference's sum
+            // over active pairs), collisions among ACTIVE drones are read off the three picks.  That instantiation of the
+            // rounds is a rolled loop (it is the rarer one, and the hot loop must keep the instruction cache).  Under
+            // goal-seeking actions 10 - 25 % of the groups hold a parked drone, and the serial exact path they used to
+            // take (~2 000 instructions per item) made the whole launch 32 - 40 % slower (tools/parked_bench.py).
+#ifndef SWARM_ROT_MASKED_PASS
+#define SWARM_ROT_MASKED_PASS 1
+#endif
+            const bool masked = SWARM_ROT_MASKED_PASS && SWARM_ROT_PACKED && alive_mask != ok_lanes;   // (warp-uniform)
+            if (alive_mask == ok_lanes || masked) {
+                // ================= rotation pass: every drone of the group is active, or masked =================
                 unsigned k0 = ~0u, k1 = ~0u, k2 = ~0u, k3 = ~0u;
                 double acc_f = 0.0, acc_b = 0.0;
                 float smin = F32_INF;
@@ -599,7 +611,9 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
                 // -d and the three picks take |.| when they are read back.
                 const f32x2 p_xy = pack2(p.x, p.y), p_z0 = pack2(p.z, 0.0f);
                 constexpr unsigned KEYMASK = ~IDX & 0x7fffffffu;
-                auto full_round = [&](int r, const float4& q, float ndf) {
+                const unsigned env_alive = alive_mask >> e_base;   // bit j: drone j of this lane's env is active
+                auto full_round = [&](auto masked_tag, int r, const float4& q, float ndf) {
+                    constexpr bool MASKED = decltype(masked_tag)::value;
                     const int src = lane + N - r;                                   // (i - r) mod N in the low bits
                     const float ndb = __shfl_sync(FULL_MASK, ndf, src, N);          // -d((i - r) mod N, i)
                     srow[r] = ndf;
@@ -608,10 +622,17 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
                     const unsigned kb = merge_low<IDX | 0x80000000u>(__float_as_uint(ndb), (unsigned)src);
                     merge2(kf, kb, k0, k1, k2, k3);
                     if (kStepLike) {   // |d - d*| = |(-d) + d*|
-                        if (SWARM_ROT_CVT_FORM & 1) acc_f = __dadd_rn(acc_f, fabs(__dsub_rn(f64_of_pos_f32<true>(fabsf(ndf)), d_star)));
-                        else acc_f = __dadd_rn(acc_f, fabs(__dadd_rn((double)ndf, d_star)));
-                        if (SWARM_ROT_CVT_FORM & 2) acc_b = __dadd_rn(acc_b, fabs(__dsub_rn(f64_of_pos_f32<true>(fabsf(ndb)), d_star)));
-                        else acc_b = __dadd_rn(acc_b, fabs(__dadd_rn((double)ndb, d_star)));
+                        double tf, tb;
+                        if (SWARM_ROT_CVT_FORM & 1) tf = fabs(__dsub_rn(f64_of_pos_f32<true>(fabsf(ndf)), d_star));
+                        else tf = fabs(__dadd_rn((double)ndf, d_star));
+                        if (SWARM_ROT_CVT_FORM & 2) tb = fabs(__dsub_rn(f64_of_pos_f32<true>(fabsf(ndb)), d_star));
+                        else tb = fabs(__dadd_rn((double)ndb, d_star));
+                        if (MASKED) {   // only ACTIVE partners count (:210-224); q.w = the forward partner's index
+                            tf = __dmul_rn(tf, ((env_alive >> (__float_as_uint(q.w) & IDX)) & 1u) ? 1.0 : 0.0);
+                            tb = __dmul_rn(tb, ((env_alive >> ((unsigned)src & IDX)) & 1u) ? 1.0 : 0.0);
+                        }
+                        acc_f = __dadd_rn(acc_f, tf);
+                        acc_b = __dadd_rn(acc_b, tb);
                     }
                 };
                 constexpr int kPairs = HALF / 2;
@@ -629,34 +650,44 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
 #endif
                 constexpr int kUnrollWant = kFused ? SWARM_ROT_UNROLL_PAIRS_FUSED : (DR ? SWARM_ROT_UNROLL_PAIRS_DR : SWARM_ROT_UNROLL_PAIRS);
                 constexpr int kUnroll = kPairs > kUnrollWant ? kUnrollWant : kPairs;
-#pragma unroll kUnroll
-                for (int u = 0; u < kPairs - 1; ++u) {
-                    const int ra = 2 * u + 1, rb = 2 * u + 2;
-                    const float4 qa = tp[ra], qb = tp[rb];
-                    float ax2, ay2, az2, bx2, by2, bz2;
-                    sq_diff3(qa, p_xy, p_z0, ax2, ay2, az2);
-                    sq_diff3(qb, p_xy, p_z0, bx2, by2, bz2);
-                    const float nsa = neg_sumsq1d_of_squares(ax2, ay2, az2), nsb = neg_sumsq1d_of_squares(bx2, by2, bz2);
-                    float nda, ndb;
-                    unpack2(neg_sqrt_rn_fast2(nsa, nsb), nda, ndb);
-                    if (!kStepLike) smin = fminf(smin, fminf(-nsa, -nsb));  // reset(): only the range check of the sum
-                    full_round(ra, qa, nda);
-                    full_round(rb, qb, ndb);
-                }
-                {   // last pair: round N/2 - 1 and the half round N/2 (visited from both ends, each end keeps its copy)
-                    const float4 qa = tp[HALF - 1], qb = tp[HALF];
-                    float ax2, ay2, az2, bx2, by2, bz2;
-                    sq_diff3(qa, p_xy, p_z0, ax2, ay2, az2);
-                    sq_diff3(qb, p_xy, p_z0, bx2, by2, bz2);
-                    const float nsa = neg_sumsq1d_of_squares(ax2, ay2, az2), nsb = neg_sumsq1d_of_squares(bx2, by2, bz2);
-                    float nda, ndb;
-                    unpack2(neg_sqrt_rn_fast2(nsa, nsb), nda, ndb);
-                    if (!kStepLike) smin = fminf(smin, fminf(-nsa, -nsb));
-                    full_round(HALF - 1, qa, nda);
-                    srow[HALF] = ndb;
-                    merge1(and_or<KEYMASK>(__float_as_uint(ndb), __float_as_uint(qb.w)), k0, k1, k2, k3);
-                    if (kStepLike) acc_f = __dadd_rn(acc_f, fabs(__dadd_rn((double)ndb, d_star)));
-                }
+                auto pair_rounds = [&](auto masked_tag) {
+                    constexpr bool MASKED = decltype(masked_tag)::value;
+                    constexpr int kUnrollHere = MASKED ? 1 : kUnroll;
+#pragma unroll kUnrollHere
+                    for (int u = 0; u < kPairs - 1; ++u) {
+                        const int ra = 2 * u + 1, rb = 2 * u + 2;
+                        const float4 qa = tp[ra], qb = tp[rb];
+                        float ax2, ay2, az2, bx2, by2, bz2;
+                        sq_diff3(qa, p_xy, p_z0, ax2, ay2, az2);
+                        sq_diff3(qb, p_xy, p_z0, bx2, by2, bz2);
+                        const float nsa = neg_sumsq1d_of_squares(ax2, ay2, az2), nsb = neg_sumsq1d_of_squares(bx2, by2, bz2);
+                        float nda, ndb;
+                        unpack2(neg_sqrt_rn_fast2(nsa, nsb), nda, ndb);
+                        if (!kStepLike) smin = fminf(smin, fminf(-nsa, -nsb));  // reset(): only the range check of the sum
+                        full_round(masked_tag, ra, qa, nda);
+                        full_round(masked_tag, rb, qb, ndb);
+                    }
+                    {   // last pair: round N/2 - 1 and the half round N/2 (visited from both ends, each end keeps its copy)
+                        const float4 qa = tp[HALF - 1], qb = tp[HALF];
+                        float ax2, ay2, az2, bx2, by2, bz2;
+                        sq_diff3(qa, p_xy, p_z0, ax2, ay2, az2);
+                        sq_diff3(qb, p_xy, p_z0, bx2, by2, bz2);
+                        const float nsa = neg_sumsq1d_of_squares(ax2, ay2, az2), nsb = neg_sumsq1d_of_squares(bx2, by2, bz2);
+                        float nda, ndb;
+                        unpack2(neg_sqrt_rn_fast2(nsa, nsb), nda, ndb);
+                        if (!kStepLike) smin = fminf(smin, fminf(-nsa, -nsb));
+                        full_round(masked_tag, HALF - 1, qa, nda);
+                        srow[HALF] = ndb;
+                        merge1(and_or<KEYMASK>(__float_as_uint(ndb), __float_as_uint(qb.w)), k0, k1, k2, k3);
+                        if (kStepLike) {
+                            double th = fabs(__dadd_rn((double)ndb, d_star));
+                            if (MASKED) th = __dmul_rn(th, ((env_alive >> (__float_as_uint(qb.w) & IDX)) & 1u) ? 1.0 : 0.0);
+                            acc_f = __dadd_rn(acc_f, th);
+                        }
+                    }
+                };
+                if (!masked) pair_rounds(std::false_type{});
+                else pair_rounds(std::true_type{});
 #else
                 float4 qn = tp[1];
                 // (the DR variant's loop + noise code sits at the edge of the instruction cache: its unroll
@@ -736,8 +767,33 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
                         topk_insert<3>(norm1d<0>(__fsub_rn(q.x, p.x), __fsub_rn(q.y, p.y), __fsub_rn(q.z, p.z)), j, nd, nj);
                     }
                 }
-                pair_hit = nd[0] <= P.thr_pair;  // nearest drone decides (:202-207)
-                form_n = N - 1;
+                if (!masked) {
+                    pair_hit = nd[0] <= P.thr_pair;  // nearest drone decides (:202-207)
+                    form_n = N - 1;
+                } else {
+                    // collisions count among ACTIVE drones only (:202-207): an active pick within the threshold settles
+                    // it; three parked picks within the threshold leave it open -> scan the active drones
+                    const unsigned env_alive = alive_mask >> e_base;
+                    bool open = alive;
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        const bool within = nd[q] <= P.thr_pair;
+                        pair_hit = pair_hit || (within && ((env_alive >> nj[q]) & 1u));
+                        open = open && within;
+                    }
+                    open = open && !pair_hit;
+                    if (__any_sync(FULL_MASK, open)) {
+                        const float4* te = tab2 + 2 * e_base;
+#pragma unroll 1
+                        for (int j = 0; j < N; ++j) {
+                            if (j == i || !((env_alive >> j) & 1u)) continue;
+                            const float4 q = te[j];
+                            pair_hit = pair_hit || norm1d<0>(__fsub_rn(q.x, p.x), __fsub_rn(q.y, p.y), __fsub_rn(q.z, p.z)) <= P.thr_pair;
+                        }
+                    }
+                    pair_hit = pair_hit && alive;
+                    form_n = alive ? n_alive_env - 1 : 0;
+                }
 
                 // ---- obstacles: _nearest_obstacle_features (:273-291) + obstacle part of _collision_mask
                 unsigned o0, o1, o2, o3, o4;
@@ -827,7 +883,7 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
                 }
                 bad = bad && mine;
             }
-            if (alive_mask != ok_lanes || __any_sync(FULL_MASK, bad)) {
+            if ((alive_mask != ok_lanes && !masked) || __any_sync(FULL_MASK, bad)) {
                 // ============ exact path: parked drones, coincident drones, or a detected near-tie ============
                 // the reference's loops as written: ascending j, strict '<' (lowest index wins ties),
                 // collision / formation over ACTIVE pairs only, np.mean's pairwise summation order

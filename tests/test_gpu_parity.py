@@ -122,8 +122,9 @@ def test_rotation_and_general_kernels_agree_under_randomisation(monkeypatch, N, 
     assert engines[0].launch_count <= engines[1].launch_count   # rotation pass: auto-reset fused into the step launch
 
 
-@pytest.mark.parametrize("N,world", [(64, 60.0), (128, 90.0), (32, 40.0)])
-def test_parked_drones_masked_rotation_pass(N, world):
+@pytest.mark.parametrize("N,world,dr", [(64, 60.0, False), (128, 90.0, False), (32, 40.0, False), (16, 30.0, False),
+                                        (8, 24.0, False), (32, 40.0, True), (8, 24.0, True), (128, 90.0, True)])
+def test_parked_drones_masked_rotation_pass(N, world, dr):
     """Envs with parked drones (they reached the goal earlier) stay on the rotation-pass kernels: neighbour blocks
     see every drone, formation error and collisions only the ACTIVE ones (drone_swarm_env.py:185-224).  Injected
     states: random subsets parked, parked drones sitting inside an active drone's collision sphere, and an active
@@ -133,8 +134,12 @@ def test_parked_drones_masked_rotation_pass(N, world):
 
     cfg = {"num_drones": N, "num_obstacles": 8, "world_size": world, "max_steps": 50}
     E, T = 96, 10
-    b = _backend(E, cfg)
-    o = so.OracleSwarm(E, cfg)
+    dr_cfg = None
+    if dr:   # the DR instantiations carry the same masked pass (sensor noise: rows must then agree exactly)
+        from test_domain_randomization import DR_DELAY
+        dr_cfg = DR_DELAY
+    b = _backend(E, cfg, **(dict(domain_randomization=dr_cfg, dr_seed=11) if dr else {}))
+    o = so.OracleSwarm(E, cfg, dr=dr_cfg, dr_seed=11)
     seeds = np.arange(50, 50 + E, dtype=np.uint64)
     b.seed(seeds); o.seed(seeds)
     b.reset(); o.reset()
@@ -173,13 +178,14 @@ def test_parked_drones_masked_rotation_pass(N, world):
         valid = o.obs_valid.astype(bool)
         bo, oo = b.obs, o.obs
         for e, i in np.argwhere((pu.bits(bo) != pu.bits(oo)).any(axis=2) & valid):
+            assert not dr, f"obs row differs under randomisation at step {t} env {e} drone {i}"
             assert obs_row_ok_up_to_ties("swarm", {**so.DEFAULTS, **cfg}, o.positions[e], o.velocities[e], o.goal[e],
                                          o.obstacles[e], i, bo[e, i]), f"obs row beyond ties at step {t} env {e} drone {i}"
             ties += 1
         if t == 0:   # the injected layouts did what they were built for
-            assert len(behind) > 3 and len(touching) > 3
+            assert len(behind) >= 3 and len(touching) >= 3
             assert (o.collision[behind, 0] == 1).all()       # the active 4th-nearest behind three parked ones counts
-            assert (o.collision[touching, 0] == 0).sum() > 3  # parked neighbours alone never collide
+            assert (o.collision[touching, 0] == 0).sum() >= 3  # parked neighbours alone never collide
     assert int(o.active.sum()) < E * N and ties < 10
 
 
