@@ -612,8 +612,12 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
                 const f32x2 p_xy = pack2(p.x, p.y), p_z0 = pack2(p.z, 0.0f);
                 constexpr unsigned KEYMASK = ~IDX & 0x7fffffffu;
                 const unsigned env_alive = alive_mask >> e_base;   // bit j: drone j of this lane's env is active
+                // masked_tag: integral_constant<int, 0> = every drone active, 1 = masked, 2 = decided at run time (ONE copy
+                // of the loop serves both: for instantiations whose loop is rolled anyway and which sit at the edge of the
+                // instruction cache)
                 auto full_round = [&](auto masked_tag, int r, const float4& q, float ndf) {
-                    constexpr bool MASKED = decltype(masked_tag)::value;
+                    constexpr int MT_ = decltype(masked_tag)::value;
+                    const bool MASKED = MT_ == 2 ? masked : (MT_ == 1);
                     const int src = lane + N - r;                                   // (i - r) mod N in the low bits
                     const float ndb = __shfl_sync(FULL_MASK, ndf, src, N);          // -d((i - r) mod N, i)
                     srow[r] = ndf;
@@ -640,7 +644,7 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
 #define SWARM_ROT_UNROLL_PAIRS 8
 #endif
 #ifndef SWARM_ROT_UNROLL_PAIRS_DR
-#define SWARM_ROT_UNROLL_PAIRS_DR 2
+#define SWARM_ROT_UNROLL_PAIRS_DR 1   // (2 until the masked pass was added; re-measured: 1 0.1469 ms, 2 0.1485, 3 0.1484, 4 0.1559)
 #endif
                 // (the unroll factors are tuning knobs: the loop body must stay inside the instruction cache)
                 // (the fused instantiation carries the reset code as well and misses the instruction cache -- 89 % hit rate,
@@ -651,8 +655,9 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
                 constexpr int kUnrollWant = kFused ? SWARM_ROT_UNROLL_PAIRS_FUSED : (DR ? SWARM_ROT_UNROLL_PAIRS_DR : SWARM_ROT_UNROLL_PAIRS);
                 constexpr int kUnroll = kPairs > kUnrollWant ? kUnrollWant : kPairs;
                 auto pair_rounds = [&](auto masked_tag) {
-                    constexpr bool MASKED = decltype(masked_tag)::value;
-                    constexpr int kUnrollHere = MASKED ? 1 : kUnroll;
+                    constexpr int MT_ = decltype(masked_tag)::value;
+                    const bool MASKED = MT_ == 2 ? masked : (MT_ == 1);
+                    constexpr int kUnrollHere = MT_ != 0 ? 1 : kUnroll;
 #pragma unroll kUnrollHere
                     for (int u = 0; u < kPairs - 1; ++u) {
                         const int ra = 2 * u + 1, rb = 2 * u + 2;
@@ -686,8 +691,12 @@ __global__ void __launch_bounds__(rot_warps(NT, DR) * 32, rot_min_blocks(NT, DR)
                         }
                     }
                 };
-                if (!masked) pair_rounds(std::false_type{});
-                else pair_rounds(std::true_type{});
+#ifndef SWARM_ROT_MASKED_RUNTIME_DR
+#define SWARM_ROT_MASKED_RUNTIME_DR 0
+#endif
+                if (SWARM_ROT_MASKED_RUNTIME_DR && DR && kUnroll == 1) pair_rounds(std::integral_constant<int, 2>{});
+                else if (!masked) pair_rounds(std::integral_constant<int, 0>{});
+                else pair_rounds(std::integral_constant<int, 1>{});
 #else
                 float4 qn = tp[1];
                 // (the DR variant's loop + noise code sits at the edge of the instruction cache: its unroll
