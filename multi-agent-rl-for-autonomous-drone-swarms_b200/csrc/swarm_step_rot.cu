@@ -142,13 +142,16 @@ __global__ void __launch_bounds__(rot_warps(NT, DRM != 0) * 32, rot_min_blocks(N
                                                        (size_t)kRotWarps * SWARM_STATS_WORDS * sizeof(unsigned long long) +
                                                        (size_t)kRotWarps * kLocalList * sizeof(int));
     // per-env outputs by lane (see SWARM_ROT_LANE_OUT): pointer / stride table of this warp, filled once
-    // (not in the DR instantiations: they sit at the edge of the instruction cache and measured 1.3 % slower with it,
-    //  the plain ones 1.0 % faster)
-    constexpr bool kLaneOut = SWARM_ROT_LANE_OUT && MODE == kRotStep && NT == 32 && !DR;
+    // (the DR instantiations sit at the edge of the instruction cache: while they still carried the command-ring code they
+    //  measured 1.3 % slower with it -- the plain ones 1.0 % faster; without that code, DRM = 1, 0.1455 -> 0.1433 ms)
+#ifndef SWARM_ROT_LANE_OUT_DR
+#define SWARM_ROT_LANE_OUT_DR 1
+#endif
+    constexpr bool kLaneOut = SWARM_ROT_LANE_OUT && MODE == kRotStep && NT == 32 && (DRM == 0 || (DRM == 1 && SWARM_ROT_LANE_OUT_DR));
     unsigned char* const lane_out = smem_raw + (size_t)kRotWarps * per_warp +
                                     (size_t)kRotWarps * SWARM_STATS_WORDS * sizeof(unsigned long long) +
                                     (size_t)kRotWarps * kLocalList * sizeof(int) +
-                                    (size_t)warp * kLaneOutBytes;   // (DR off only: no quantile table in front)
+                                    ((DR && !SWARM_ROT_DR_QTAB_GLOBAL) ? 2048 : 0) + (size_t)warp * kLaneOutBytes;
     unsigned long long* const optr = reinterpret_cast<unsigned long long*>(lane_out);
     unsigned* const ostride = reinterpret_cast<unsigned*>(lane_out + 8 * kLaneOutputs);
     unsigned* const ostage = reinterpret_cast<unsigned*>(lane_out + 12 * kLaneOutputs);
@@ -1260,7 +1263,7 @@ size_t rot_smem_bytes(const DevParams& p) {
     return (size_t)rot_warps(p.N, p.dr_enabled != 0) * rot_smem_per_warp(32 / p.N, p.M, p.dr_enabled != 0) +
            (size_t)rot_warps(p.N, p.dr_enabled != 0) * (SWARM_STATS_WORDS * sizeof(unsigned long long) + 8 * sizeof(int)) +
            ((p.dr_enabled && !SWARM_ROT_DR_QTAB_GLOBAL) ? 2048 : 0) +
-           (p.dr_enabled ? 0 : (size_t)rot_warps(p.N, false) * kLaneOutBytes);
+           ((p.dr_enabled && !SWARM_ROT_LANE_OUT_DR) ? 0 : (size_t)rot_warps(p.N, p.dr_enabled != 0) * kLaneOutBytes);
 }
 
 cudaError_t launch_rot_kernel(const DevParams& p, int grid, cudaStream_t stream) {
