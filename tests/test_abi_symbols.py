@@ -66,3 +66,21 @@ def test_config_mirror_matches_reference_defaults_and_drops_unknown_keys():
     c = swarm_b200.DroneEnvConfig.from_dict({"world_size": 28.0, "num_drones": 8, "bogus": 1, "seed": 3})
     assert c.world_size == 28.0 and c.seed == 3 and c.max_steps == 400 and c.neighbor_k == 3
     assert swarm_b200.DroneEnvConfig.from_dict(None) == swarm_b200.DroneEnvConfig()
+
+
+def test_unpack_flags_is_the_inverse_of_the_packing_rule():
+    """SwarmHostOut.flags (ABI 5): bit k of the byte is FLAG_FIELDS[k]; `SwarmEngine.unpack_flags` splits it (host side)."""
+    import numpy as np
+    import swarm_b200
+    from swarm_b200 import _abi
+    rng = np.random.default_rng(0)
+    fields = {n: rng.integers(0, 2, size=(7, 5)).astype(np.uint8) for n in _abi.FLAG_FIELDS}
+    packed = sum(fields[n] << k for k, n in enumerate(_abi.FLAG_FIELDS)).astype(np.uint8)
+    assert packed.max() < 32
+    un = swarm_b200.SwarmEngine.unpack_flags(packed)
+    assert set(un) == set(_abi.FLAG_FIELDS)
+    for n in _abi.FLAG_FIELDS:
+        assert np.array_equal(un[n], fields[n].astype(bool)), n
+    assert (_abi.FLAG_TERMINATED, _abi.FLAG_TRUNCATED, _abi.FLAG_REACHED, _abi.FLAG_COLLISION, _abi.FLAG_OBS_VALID) == (1, 2, 4, 8, 16)
+    assert set(swarm_b200.SwarmEngine.OUTPUT_SETS) == {"packed", "lean"}
+    assert "flags" in swarm_b200.SwarmEngine.OUTPUT_SETS["lean"] and "global_state" not in swarm_b200.SwarmEngine.OUTPUT_SETS["lean"]
